@@ -1,0 +1,305 @@
+// fps.cu -- furthest point sampling for sm_100a.
+//
+// Replaces pointrcnn/pointnet2_lib/pointnet2/src/sampling_gpu.cu:93-253
+// (furthest_point_sampling_kernel + launcher) behind pn2_fps_f32 (include/pn2_b200.h).
+//
+// Design (see DESIGN.md "FPS"): the reference runs one 1024-thread CTA per cloud and re-reads
+// xyz + the running min-distance from global memory every round (20 B/point/round), with a
+// 2*log2(bs)-barrier shared-memory tree per round.  Here a cloud is owned by a thread-block
+// CLUSTER of up to 8 CTAs (8 x 256 threads).  Every thread keeps its P points and their running
+// min-distance in registers for the whole kernel, so after the initial load the kernel touches
+// HBM only to write one index per round.  Per round:
+//   1. P distance updates per thread (FMA order identical to the reference),
+//   2. warp argmax with two redux.sync (max on the float bits, min on the tie-break rank),
+//   3. the winning lane of every warp publishes a 32-byte record {d2, rank, k, x, y, z} to ALL
+//      CTAs of the cluster with st.async (DSMEM, completes on the destination's mbarrier),
+//   4. every warp waits on its own CTA's mbarrier, reduces the CLUSTER*8 records redundantly
+//      (again two redux.sync) and thereby knows the next centre without a second exchange.
+// There is no __syncthreads and no cluster barrier inside the round loop.
+//
+// Bit-exactness: the reference's winner among equal distances is decided by its launch shape:
+// thread tid scans k = tid, tid+bs, ... keeping the FIRST maximum (strict >, sampling_gpu.cu:
+// 136-137) and the tree (__update, :86-91) keeps the lower slot on ties at every level, which
+// orders threads by the BIT-REVERSED thread id.  So the reference picks
+//   max d2, then min bitrev_{log2 bs}(k mod bs), then min k      with bs = opt_n_threads(N).
+// rank(k) = bitrev(k mod bs) * ceil(N/bs) + k / bs encodes the last two keys in one integer.
+#include "common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct __align__(16) FpsRecord {
+    uint32_t d2bits;  // running min distance of the candidate (non-negative float: bits are monotone)
+    uint32_t rinv;    // ~rank: larger is better, 0 = "no valid point"
+    int32_t k;        // point index
+    uint32_t pad;
+    float x, y, z, w;  // its coordinates, so nobody has to fetch them
+};
+static_assert(sizeof(FpsRecord) == 32, "record is two 16-byte stores");
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pn2_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(pn2_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     remote_addr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// P points per thread, CLUSTER CTAs per cloud.  grid = (CLUSTER, B).
+template <int P, int CLUSTER>
+__global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
+                                                       int32_t *__restrict__ idx, int n, int m, int log2bs, int cnt) {
+    constexpr int S = CLUSTER * kWarps;  // records per round
+    __shared__ FpsRecord slots[2][S];
+    __shared__ __align__(8) uint64_t bars[2];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t crank = (CLUSTER > 1) ? cluster_ctarank() : 0u;
+    const int cloud = blockIdx.y;
+
+    xyz += (size_t)cloud * n * 3;
+    idx += (size_t)cloud * m;
+    if (temp) temp += (size_t)cloud * n;
+
+    // ---- resident state: P points, their running min distance and their tie-break rank ----
+    float px[P], py[P], pz[P], pt[P];
+    uint32_t prank[P];
+    const int kbase = (int)crank * (P * kThreads) + tid;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int k = kbase + p * kThreads;
+        if (k < n) {
+            px[p] = __ldg(xyz + (size_t)k * 3 + 0);
+            py[p] = __ldg(xyz + (size_t)k * 3 + 1);
+            pz[p] = __ldg(xyz + (size_t)k * 3 + 2);
+            pt[p] = temp ? temp[k] : 1e10f;
+            const uint32_t tref = (uint32_t)k & ((1u << log2bs) - 1u);
+            const uint32_t rev = log2bs ? (__brev(tref) >> (32 - log2bs)) : 0u;
+            prank[p] = rev * (uint32_t)cnt + ((uint32_t)k >> log2bs);
+        } else {  // padding slot: distance 0 and the worst rank, can never win against a real point
+            px[p] = py[p] = pz[p] = 0.f;
+            pt[p] = 0.f;
+            prank[p] = 0xFFFFFFFFu;
+        }
+    }
+
+    if (CLUSTER > 1) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();  // barriers initialised everywhere before any remote store
+    }
+
+    float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // idx[0] = 0 always
+    if (crank == 0 && tid == 0) idx[0] = 0;
+
+    for (int r = 0; r < m - 1; ++r) {
+        const int par = r & 1;
+        if (CLUSTER > 1 && tid == 0) mbar_arrive_expect_tx(&bars[par], S * (uint32_t)sizeof(FpsRecord));
+
+        // 1. distance update, thread max
+        float tmax = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float d = pn2_sqdist(px[p] - cx, py[p] - cy, pz[p] - cz);
+            pt[p] = fminf(d, pt[p]);
+            tmax = fmaxf(tmax, pt[p]);
+        }
+        // 2. warp argmax: max distance bits, then min rank among the lanes that hold it
+        const uint32_t vb = __float_as_uint(tmax);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, vb);
+        uint32_t rk = 0xFFFFFFFFu;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        int sk = 0;
+        if (vb == wmax) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (__float_as_uint(pt[p]) == wmax && prank[p] < rk) {
+                    rk = prank[p];
+                    sx = px[p]; sy = py[p]; sz = pz[p];
+                    sk = kbase + p * kThreads;
+                }
+            }
+        }
+        const uint32_t wrk = __reduce_min_sync(0xffffffffu, rk);
+        const uint32_t winners = __ballot_sync(0xffffffffu, rk == wrk);
+        // 3. publish the warp's record
+        if (lane == __ffs(winners) - 1) {
+            const uint32_t rinv = ~wrk;
+            if (CLUSTER == 1) {
+                FpsRecord rec;
+                rec.d2bits = wmax; rec.rinv = rinv; rec.k = sk; rec.pad = 0;
+                rec.x = sx; rec.y = sy; rec.z = sz; rec.w = 0.f;
+                slots[par][warp] = rec;
+            } else {
+                const uint32_t local = pn2_smem_u32(&slots[par][crank * kWarps + warp]);
+                const uint32_t lbar = pn2_smem_u32(&bars[par]);
+#pragma unroll
+                for (int c = 0; c < CLUSTER; ++c) {
+                    const uint32_t dst = mapa(local, c);
+                    const uint32_t dbar = mapa(lbar, c);
+                    st_async_v4(dst, wmax, rinv, (uint32_t)sk, 0u, dbar);
+                    st_async_v4(dst + 16, __float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), 0u, dbar);
+                }
+            }
+        }
+        if (CLUSTER == 1) __syncthreads();
+        else mbar_wait(&bars[par], (uint32_t)(r >> 1) & 1u);
+
+        // 4. every warp reduces the S records (redundantly) -> next centre
+        unsigned long long kA = 0ull, kB = 0ull;
+        if (lane < S) kA = ((unsigned long long)slots[par][lane].d2bits << 32) | slots[par][lane].rinv;
+        if (S > 32 && lane + 32 < S)
+            kB = ((unsigned long long)slots[par][lane + 32].d2bits << 32) | slots[par][lane + 32].rinv;
+        const unsigned long long km = kA > kB ? kA : kB;
+        const int myslot = (kA >= kB) ? lane : lane + 32;
+        const uint32_t hi = (uint32_t)(km >> 32), lo = (uint32_t)km;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const uint32_t who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+        const int wslot = __shfl_sync(0xffffffffu, myslot, __ffs(who) - 1);
+        const float4 c4 = *reinterpret_cast<const float4 *>(&slots[par][wslot].x);
+        cx = c4.x; cy = c4.y; cz = c4.z;
+        if (crank == 0 && tid == 0) idx[r + 1] = slots[par][wslot].k;
+    }
+
+    if (temp) {  // the reference leaves the running min distances in the caller's scratch
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int k = kbase + p * kThreads;
+            if (k < n) temp[k] = pt[p];
+        }
+    }
+    if (CLUSTER > 1) cluster_sync_all();  // nobody exits while a peer may still target its smem
+}
+
+template <int P, int CLUSTER>
+cudaError_t launch_fps(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
+                       cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CLUSTER, b, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fps_kernel<P, CLUSTER>, xyz, temp, idx, n, m, log2bs, cnt);
+}
+
+template <int CLUSTER>
+cudaError_t dispatch_p(int p, const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
+                       cudaStream_t s) {
+    switch (p) {
+        case 1: return launch_fps<1, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+        case 2: return launch_fps<2, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+        case 4: return launch_fps<4, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+        case 8: return launch_fps<8, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+        case 16: return launch_fps<16, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+        default: return launch_fps<32, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, s);
+    }
+}
+
+}  // namespace
+
+// Block size the reference launcher would have used (cuda_utils.h:10-14); it only matters
+// here because it fixes the tie-break order.  Same double-precision expression.
+PN2_API int pn2_fps_ref_block_size(int n) {
+    const int pow_2 = (int)(std::log((double)n) / std::log(2.0));
+    int v = 1 << pow_2;
+    if (v > 1024) v = 1024;
+    if (v < 1) v = 1;
+    return v;
+}
+
+static int g_fps_cluster_override = 0;
+PN2_API void pn2_fps_set_cluster(int c) { g_fps_cluster_override = c; }
+
+// xyz (B,N,3) f32 ; temp (B,N) f32 scratch or NULL (NULL = implicit 1e10, nothing written
+// back) ; idx (B,M) int32.  Enqueues on `stream`, never synchronises.
+PN2_API int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0 || (!xyz && b * n > 0) || (!idx && b * m > 0)) {
+        pn2_set_last_error("pn2_fps_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (b == 0 || m == 0) return PN2_OK;
+    if (n == 0) {
+        pn2_set_last_error("pn2_fps_f32: empty cloud with m > 0");
+        return PN2_ERR_INVALID;
+    }
+    const int bs = pn2_fps_ref_block_size(n);
+    int log2bs = 0;
+    while ((1 << log2bs) < bs) ++log2bs;
+    const int cnt = (n + bs - 1) / bs;
+
+    int cluster = n >= 8192 ? 8 : (n > 4096 ? 4 : 1);
+    if (g_fps_cluster_override) cluster = g_fps_cluster_override;
+    int p = (n + cluster * kThreads - 1) / (cluster * kThreads);
+    while (p > 32 && cluster < 8) {
+        cluster *= 2;
+        p = (n + cluster * kThreads - 1) / (cluster * kThreads);
+    }
+    if (p > 32) {
+        pn2_set_last_error("pn2_fps_f32: N > 65536 points per cloud is not supported");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    int pp = 1;
+    while (pp < p) pp *= 2;
+    cudaError_t e;
+    switch (cluster) {
+        case 1: e = dispatch_p<1>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, stream); break;
+        case 2: e = dispatch_p<2>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, stream); break;
+        case 4: e = dispatch_p<4>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, stream); break;
+        case 8: e = dispatch_p<8>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, stream); break;
+        default: pn2_set_last_error("pn2_fps_f32: cluster must be 1, 2, 4 or 8"); return PN2_ERR_INVALID;
+    }
+    if (e != cudaSuccess) {
+        pn2_set_last_error(cudaGetErrorString(e));
+        return PN2_ERR_LAUNCH;
+    }
+    return PN2_OK;
+}

@@ -1,0 +1,88 @@
+/*
+ * pn2_b200.h -- C ABI of libpn2_b200.so, the sm_100a implementation of the PointRCNN
+ * inference hot path of cxy1997/3D_adapt_auto_driving.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name
+ *     starts with h_; the caller owns every buffer including scratch (nothing is allocated,
+ *     freed or synchronised inside, unlike the reference's roipool3d_kernel.cu:214 /
+ *     iou3d.cpp:87 which cudaMalloc per call and block on cudaMemcpy);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call
+ *     returns immediately;
+ *   - the return value is a status: 0 ok, 1 invalid argument, 2 launch failure,
+ *     3 unsupported size.  pn2_last_error() gives the message.  Nothing ever calls exit()
+ *     (the reference does: e.g. sampling_gpu.cu:249-252);
+ *   - the library is stateless and re-entrant apart from the thread-local error string.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).  INTEGRATION.md shows the binding a maintainer adds.
+ */
+#ifndef PN2_B200_H
+#define PN2_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_OK 0
+#define PN2_ERR_INVALID 1
+#define PN2_ERR_LAUNCH 2
+#define PN2_ERR_UNSUPPORTED 3
+
+const char *pn2_last_error(void);
+int pn2_abi_version(void);
+
+/* ---- pointnet2_cuda (pointrcnn/pointnet2_lib/pointnet2/src/pointnet2_api.cpp:10-24) ---- */
+
+/* furthest_point_sampling_wrapper(b,n,m,points,temp,idx)  sampling.cpp:36-46,
+ * kernel sampling_gpu.cu:93-253.  xyz (B,N,3) f32, temp (B,N) f32 caller scratch pre-filled
+ * with 1e10 (mutated like the reference; NULL = implicit 1e10, not written back),
+ * idx (B,M) int32.  Bit-exact incl. the reference's tie order. */
+int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, void *stream);
+/* cuda_utils.h:10-14 opt_n_threads: the reference block size that fixes the tie order. */
+int pn2_fps_ref_block_size(int n);
+/* tuning hook: force the CTAs-per-cloud cluster size (0 = heuristic). */
+void pn2_fps_set_cluster(int c);
+
+/* gather_points_wrapper(b,c,n,npoints,points,idx,out)  sampling.cpp:11-21, sampling_gpu.cu:8-44.
+ * points (B,C,N), idx (B,M) int32 -> out (B,C,M). */
+int pn2_gather_points_f32(const float *points, const int32_t *idx, float *out, int b, int c, int n, int m, void *stream);
+/* gather_points_grad_wrapper  sampling.cpp:24-34, sampling_gpu.cu:46-84. grad_points pre-zeroed. */
+int pn2_gather_points_grad_f32(const float *grad_out, const int32_t *idx, float *grad_points, int b, int c, int n,
+                               int m, void *stream);
+
+/* ball_query_wrapper(b,n,m,radius,nsample,new_xyz,xyz,idx)  ball_query.cpp:14-24,
+ * ball_query_gpu.cu:9-67.  idx (B,M,nsample) int32 must be zero-initialised by the caller
+ * (pointnet2_utils.py:218): rows without a neighbour are not written.  Bit-exact. */
+int pn2_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int b, int n, int m, float radius,
+                       int nsample, void *stream);
+/* Both MSG scales of one SA layer (pointnet2_modules.py:37-38 loops over groupers) in one scan. */
+int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int b, int n, int m,
+                            float radius0, int nsample0, float radius1, int nsample1, void *stream);
+
+/* group_points_wrapper(b,c,n,npoints,nsample,points,idx,out)  group_points.cpp:24-35,
+ * group_points_gpu.cu:47-86.  points (B,C,N), idx (B,M,ns) -> out (B,C,M,ns). */
+int pn2_group_points_f32(const float *points, const int32_t *idx, float *out, int b, int c, int n, int m, int nsample,
+                         void *stream);
+/* group_points_grad_wrapper  group_points.cpp:11-21, group_points_gpu.cu:8-44. */
+int pn2_group_points_grad_f32(const float *grad_out, const int32_t *idx, float *grad_points, int b, int c, int n, int m,
+                              int nsample, void *stream);
+
+/* three_nn_wrapper(b,n,m,unknown,known,dist2,idx)  interpolate.cpp:14-24,
+ * interpolate_gpu.cu:9-74.  unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 SQUARED,
+ * idx (B,n,3) int32.  Bit-exact. */
+int pn2_three_nn_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int b, int n, int m,
+                     void *stream);
+/* three_interpolate_wrapper(b,c,m,n,points,idx,weight,out)  interpolate.cpp:27-38,
+ * interpolate_gpu.cu:77-117.  points (B,C,m) -> out (B,C,n).  Bit-exact. */
+int pn2_three_interpolate_f32(const float *points, const int32_t *idx, const float *weight, float *out, int b, int c,
+                              int m, int n, void *stream);
+/* three_interpolate_grad_wrapper(b,c,n,m,...)  interpolate.cpp:40-53, interpolate_gpu.cu:120-160. */
+int pn2_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx, const float *weight, float *grad_points,
+                                   int b, int c, int n, int m, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_B200_H */

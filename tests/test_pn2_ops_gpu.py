@@ -1,0 +1,160 @@
+"""GPU parity of the sm_100a pointnet2 ops, called through the reference-shaped API
+(pointnet2_utils -> pointnet2_cuda -> C-ABI), against
+  (1) the CPU oracle on seeded inputs at sizes it finishes in seconds, and
+  (2) the reference's own kernels (oracle/_ref/libpn2_legacy.so) at BASELINE.json's full sizes.
+Index outputs and the f32 values that are pure copies / fixed-order FMAs must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load
+
+pytestmark = pytest.mark.gpu
+synthetic = load("synthetic")
+
+
+def p2u():
+    return load("pointnet2_utils")
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+@pytest.mark.parametrize("n,m,b", [(2048, 512, 2), (512, 128, 5), (128, 32, 3), (300, 77, 2), (4096, 256, 1)])
+def test_fps_vs_oracle(cuda, oracle, kind, n, m, b):
+    xyz_h = synthetic.make_clouds(kind, b, n, seed=1024 + n)
+    idx = p2u().furthest_point_sample(torch.from_numpy(xyz_h).to(cuda), m)
+    ref, _ = oracle.fps(xyz_h, m)
+    assert idx.dtype == torch.int32 and idx.shape == (b, m)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_fps_every_cluster_size_and_temp_writeback(cuda, oracle, cluster):
+    cabi = load("cabi")
+    p2c = load("pointnet2_cuda")
+    xyz_h = synthetic.make_clouds("ties", 3, 3000, seed=666)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    temp = torch.full((3, 3000), 1e10, device=cuda)
+    idx = torch.empty((3, 200), dtype=torch.int32, device=cuda)
+    cabi.lib().pn2_fps_set_cluster(cluster)
+    try:
+        p2c.furthest_point_sampling_wrapper(3, 3000, 200, xyz, temp, idx)
+    finally:
+        cabi.lib().pn2_fps_set_cluster(0)
+    ref, ref_temp = oracle.fps(xyz_h, 200)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(temp.cpu().numpy(), ref_temp)  # caller scratch mutated like the reference
+
+
+def test_fps_edge_cases(cuda, oracle):
+    f = p2u().furthest_point_sample
+    one = torch.zeros((2, 1, 3), device=cuda)
+    assert f(one, 1).cpu().tolist() == [[0], [0]]
+    same = torch.ones((1, 64, 3), device=cuda)  # all points identical: every distance ties at 0
+    ref, _ = oracle.fps(same.cpu().numpy(), 8)
+    assert np.array_equal(f(same, 8).cpu().numpy(), ref)
+    assert f(torch.zeros((0, 16, 3), device=cuda), 4).shape == (0, 4)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+def test_fps_full_size_vs_legacy(cuda, legacy, kind):
+    # config 3 of BASELINE.json: 16384 -> 4096, batch 8 ; plus the RCNN shapes 512->128, 128->32
+    for b, n, m in [(8, 16384, 4096), (64, 512, 128), (64, 128, 32), (2, 32768, 1024)]:
+        xyz = torch.from_numpy(synthetic.make_clouds(kind, b, n, seed=1024)).to(cuda)
+        got = p2u().furthest_point_sample(xyz, m)
+        ref, _ = legacy.fps(xyz, m)
+        assert torch.equal(got, ref), (kind, b, n, m, int((got != ref).sum()))
+
+
+@pytest.mark.parametrize("r,ns", [(0.1, 16), (0.5, 32), (1.0, 64), (4.0, 16)])
+def test_ball_query_vs_oracle(cuda, oracle, r, ns):
+    xyz_h = synthetic.make_clouds("lidar", 2, 3000, seed=5)
+    new_h = xyz_h[:, ::7].copy()
+    new_h[:, :3] += 500.0  # no neighbour at all -> rows stay zero
+    got = p2u().ball_query(r, ns, torch.from_numpy(xyz_h).to(cuda), torch.from_numpy(new_h).to(cuda))
+    assert np.array_equal(got.cpu().numpy(), oracle.ball_query(r, ns, xyz_h, new_h))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+def test_ball_query_full_size_vs_legacy_and_dual(cuda, legacy, kind):
+    cabi = load("cabi")
+    xyz = torch.from_numpy(synthetic.make_clouds(kind, 4, 16384, seed=1024)).to(cuda)
+    idx, _ = legacy.fps(xyz, 4096)
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    refs = {}
+    for r, ns in [(0.1, 16), (0.5, 32), (0.1, 64)]:
+        refs[(r, ns)] = legacy.ball_query(r, ns, xyz, new_xyz)
+        assert torch.equal(p2u().ball_query(r, ns, xyz, new_xyz), refs[(r, ns)]), (kind, r, ns)
+    i0 = torch.zeros((4, 4096, 16), dtype=torch.int32, device=cuda)
+    i1 = torch.zeros((4, 4096, 32), dtype=torch.int32, device=cuda)
+    cabi.call("pn2_ball_query_dual_f32", cabi.ptr(new_xyz), cabi.ptr(xyz), cabi.ptr(i0), cabi.ptr(i1), cabi.i32(4),
+              cabi.i32(16384), cabi.i32(4096), cabi.f32(0.1), cabi.i32(16), cabi.f32(0.5), cabi.i32(32))
+    assert torch.equal(i0, refs[(0.1, 16)]) and torch.equal(i1, refs[(0.5, 32)])
+
+
+def test_gather_group_vs_oracle_and_backward(cuda, oracle):
+    rng = np.random.RandomState(0)
+    feats_h = rng.randn(3, 19, 700).astype(np.float32)
+    idx_h = rng.randint(0, 700, size=(3, 130)).astype(np.int32)
+    gidx_h = rng.randint(0, 700, size=(3, 130, 9)).astype(np.int32)
+    feats = torch.from_numpy(feats_h).to(cuda).requires_grad_(True)
+    out = p2u().gather_operation(feats, torch.from_numpy(idx_h).to(cuda))
+    assert np.array_equal(out.detach().cpu().numpy(), oracle.gather_points(feats_h, idx_h))
+    g = p2u().grouping_operation(feats, torch.from_numpy(gidx_h).to(cuda))
+    assert np.array_equal(g.detach().cpu().numpy(), oracle.group_points(feats_h, gidx_h))
+    go_h = rng.randn(*g.shape).astype(np.float32)
+    g.backward(torch.from_numpy(go_h).to(cuda))
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), oracle.group_points_grad(go_h, gidx_h, 700), rtol=1e-5, atol=1e-5)
+    feats.grad = None
+    go2 = rng.randn(*out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(go2).to(cuda))
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), oracle.gather_points_grad(go2, idx_h, 700), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,m", [(1024, 256), (999, 5), (64, 2), (4096, 1024)])
+def test_three_nn_and_interpolate_vs_oracle(cuda, oracle, n, m):
+    known_h = synthetic.make_clouds("ties", 2, m, seed=n)
+    unknown_h = synthetic.make_clouds("ties", 2, n, seed=n + 1)
+    dist, idx = p2u().three_nn(torch.from_numpy(unknown_h).to(cuda), torch.from_numpy(known_h).to(cuda))
+    d2_ref, idx_ref = oracle.three_nn(unknown_h, known_h)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(d2_ref))  # the Python wrapper returns sqrt (pointnet2_utils.py:98)
+    rng = np.random.RandomState(1)
+    feats_h = rng.randn(2, 21, m).astype(np.float32)
+    w_h = rng.rand(2, n, 3).astype(np.float32)
+    feats = torch.from_numpy(feats_h).to(cuda).requires_grad_(True)
+    out = p2u().three_interpolate(feats, idx, torch.from_numpy(w_h).to(cuda))
+    assert np.array_equal(out.detach().cpu().numpy(), oracle.three_interpolate(feats_h, idx_ref, w_h))
+    go = rng.randn(*out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(go).to(cuda))
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), oracle.three_interpolate_grad(go, idx_ref, w_h, m), rtol=1e-4, atol=1e-4)
+
+
+def test_three_nn_interpolate_full_size_vs_legacy(cuda, legacy):
+    # FP0 of the RPN backbone: 16384 unknown <- 4096 known, 256 channels
+    xyz = torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=1024)).to(cuda)
+    known = xyz[:, :4096].contiguous()
+    dist, idx = p2u().three_nn(xyz, known)
+    d2_ref, idx_ref = legacy.three_nn(xyz, known)
+    assert torch.equal(idx, idx_ref) and torch.equal(dist, torch.sqrt(d2_ref))
+    feats = torch.randn((2, 256, 4096), device=cuda)
+    w = torch.rand((2, 16384, 3), device=cuda)
+    assert torch.equal(p2u().three_interpolate(feats, idx, w), legacy.three_interpolate(feats, idx, w))
+    assert torch.equal(p2u().grouping_operation(feats, idx), legacy.group(feats, idx))
+    assert torch.equal(p2u().gather_operation(feats, idx[:, :, 0].contiguous()), legacy.gather(feats, idx[:, :, 0].contiguous()))
+
+
+def test_legacy_pins_the_oracle(cuda, legacy, oracle):
+    """The CPU restatement agrees with the reference's real kernels (the oracle's pin)."""
+    for kind in ["uniform", "lidar", "ties"]:
+        xyz_h = synthetic.make_clouds(kind, 2, 4096, seed=1024)
+        xyz = torch.from_numpy(xyz_h).to(cuda)
+        idx, temp = legacy.fps(xyz, 512)
+        ref_idx, ref_temp = oracle.fps(xyz_h, 512)
+        assert np.array_equal(idx.cpu().numpy(), ref_idx) and np.array_equal(temp.cpu().numpy(), ref_temp)
+        new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        for r, ns in [(0.5, 16), (1.0, 32)]:
+            assert np.array_equal(legacy.ball_query(r, ns, xyz, new_xyz).cpu().numpy(),
+                                  oracle.ball_query(r, ns, xyz_h, new_xyz.cpu().numpy()))
+        d2, i3 = legacy.three_nn(xyz, new_xyz)
+        d2o, i3o = oracle.three_nn(xyz_h, new_xyz.cpu().numpy())
+        assert np.array_equal(i3.cpu().numpy(), i3o) and np.array_equal(d2.cpu().numpy(), d2o)
