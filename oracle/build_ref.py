@@ -68,6 +68,8 @@ def build_legacy(verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # the numba rotated-IoU reference is a Python file: it travels as a git-ignored copy
+    shutil.copyfile(os.path.join(REF, "evaluate/rotate_iou.py"), os.path.join(out_dir, "rotate_iou.py"))
     return dst
 
 

@@ -255,9 +255,9 @@ static inline int pt_in_box3d(float x, float y, float z, float cx, float by, flo
                               float cosa, float sina, float max_dis) {
     float cy = (float)((double)by - (double)h / 2.0);
     if ((fabsf(x - cx) > max_dis) || ((double)fabsf(y - cy) > (double)h / 2.0) || (fabsf(z - cz) > max_dis)) return 0;
-    /* as compiled: x_rot = fl(dx*cos) - fl(dz*sin) (two mul, one sub, NOT fused);
-     *              z_rot = fma(dz, cos, fl(dx*sin)) */
-    float x_rot = (x - cx) * cosa - (z - cz) * sina;
+    /* as compiled (SASS of the unmodified reference, nvcc/ptxas 12.9): ptxas fuses the PTX
+     * mul/sub pair, so  x_rot = fma(dx, cos, -fl(dz*sin)) ;  z_rot = fma(dz, cos, fl(dx*sin)) */
+    float x_rot = fmaf(x - cx, cosa, -((z - cz) * sina));
     float z_rot = fmaf(z - cz, cosa, (x - cx) * sina);
     return ((double)x_rot >= -(double)l / 2.0) & ((double)x_rot <= (double)l / 2.0) &
            ((double)z_rot >= -(double)w / 2.0) & ((double)z_rot <= (double)w / 2.0);
