@@ -1,0 +1,75 @@
+"""Mirror of pointrcnn/lib/utils/bbox_transform.py: decode_bbox_target (:24-121) and
+rotate_pc_along_y_torch (:5-21).  Bin-based box decoding; the float operation ORDER follows
+the reference statement by statement so that decoded boxes are bit-identical (they feed
+threshold tests and NMS)."""
+import numpy as np
+import torch
+
+
+def rotate_pc_along_y_torch(pc, rot_angle):
+    """pc (N,3+C) rotated about y by rot_angle (N): [x',z'] = [x,z] @ [[c,-s],[s,c]]^T, in place."""
+    cosa = torch.cos(rot_angle).view(-1, 1)
+    sina = torch.sin(rot_angle).view(-1, 1)
+    R = torch.stack((torch.cat([cosa, -sina], dim=1), torch.cat([sina, cosa], dim=1)), dim=1)  # (N,2,2)
+    xz = pc[:, [0, 2]].unsqueeze(dim=1)  # (N,1,2)
+    pc[:, [0, 2]] = torch.matmul(xz, R.permute(0, 2, 1)).squeeze(dim=1)
+    return pc
+
+
+def _bin_and_residual(pred, bin_lo, n_bins, res_lo):
+    b = torch.argmax(pred[:, bin_lo:bin_lo + n_bins], dim=1)
+    res = torch.gather(pred[:, res_lo:res_lo + n_bins], dim=1, index=b.unsqueeze(dim=1)).squeeze(dim=1)
+    return b, res
+
+
+def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size,
+                       get_xz_fine=True, get_y_by_bin=False, loc_y_scope=0.5, loc_y_bin_size=0.25, get_ry_fine=False):
+    """roi_box3d (N,3) point xyz or (N,7) roi; pred_reg (N,C) -> (N,7) [x,y,z,h,w,l,ry]."""
+    anchor_size = anchor_size.to(roi_box3d.device)
+    nb = int(loc_scope / loc_bin_size) * 2
+    nby = int(loc_y_scope / loc_y_bin_size) * 2
+
+    x_bin = torch.argmax(pred_reg[:, 0:nb], dim=1)
+    z_bin = torch.argmax(pred_reg[:, nb:nb * 2], dim=1)
+    pos_x = x_bin.float() * loc_bin_size + loc_bin_size / 2 - loc_scope
+    pos_z = z_bin.float() * loc_bin_size + loc_bin_size / 2 - loc_scope
+    off = nb * 2
+    if get_xz_fine:
+        x_res = torch.gather(pred_reg[:, nb * 2:nb * 3], dim=1, index=x_bin.unsqueeze(dim=1)).squeeze(dim=1)
+        z_res = torch.gather(pred_reg[:, nb * 3:nb * 4], dim=1, index=z_bin.unsqueeze(dim=1)).squeeze(dim=1)
+        pos_x += x_res * loc_bin_size
+        pos_z += z_res * loc_bin_size
+        off = nb * 4
+
+    if get_y_by_bin:
+        y_bin, y_res = _bin_and_residual(pred_reg, off, nby, off + nby)
+        pos_y = y_bin.float() * loc_y_bin_size + loc_y_bin_size / 2 - loc_y_scope + y_res * loc_y_bin_size
+        pos_y = pos_y + roi_box3d[:, 1]
+        off += 2 * nby
+    else:
+        pos_y = roi_box3d[:, 1] + pred_reg[:, off]
+        off += 1
+
+    ry_bin, ry_res_norm = _bin_and_residual(pred_reg, off, num_head_bin, off + num_head_bin)
+    if get_ry_fine:
+        angle_per_class = (np.pi / 2) / num_head_bin
+        ry_res = ry_res_norm * (angle_per_class / 2)
+        ry = (ry_bin.float() * angle_per_class + angle_per_class / 2) + ry_res - np.pi / 4
+    else:
+        angle_per_class = (2 * np.pi) / num_head_bin
+        ry_res = ry_res_norm * (angle_per_class / 2)
+        ry = (ry_bin.float() * angle_per_class + ry_res) % (2 * np.pi)
+        ry[ry > np.pi] -= 2 * np.pi
+    off += 2 * num_head_bin
+
+    assert off + 3 == pred_reg.shape[1]
+    size_res_norm = pred_reg[:, off:off + 3]
+    hwl = size_res_norm * anchor_size + anchor_size
+
+    ret = torch.cat((pos_x.view(-1, 1), pos_y.view(-1, 1), pos_z.view(-1, 1), hwl, ry.view(-1, 1)), dim=1)
+    if roi_box3d.shape[1] == 7:
+        roi_ry = roi_box3d[:, 6]
+        ret = rotate_pc_along_y_torch(ret, -roi_ry)
+        ret[:, 6] += roi_ry
+    ret[:, [0, 2]] += roi_box3d[:, [0, 2]]
+    return ret

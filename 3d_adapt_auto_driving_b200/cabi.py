@@ -59,9 +59,44 @@ def check(status, what):
         raise Pn2Error("%s failed (status %d): %s" % (what, status, lib().pn2_last_error().decode()))
 
 
-def call(name, *args):
-    """Call lib.<name>(*args, current_stream) and raise on a non-zero status."""
+# ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) ----
+launch_count = 0
+_profile = None   # None, or {"names": set() | None (= all), "records": [(name, work, start_evt, end_evt)]}
+
+
+def profile_start(names=None):
+    """Bracket every C-ABI launch (or only `names`) with CUDA events on the launching stream."""
+    global _profile
+    _profile = {"names": set(names) if names else None, "records": []}
+
+
+def profile_stop():
+    """-> {name: {"launches", "ms", "work"}} ; synchronises."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, work, s, e in prof["records"]:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+        d["launches"] += 1
+        d["ms"] += s.elapsed_time(e)
+        d["work"] += float(work or 0.0)
+    return out
+
+
+def call(name, *args, work=None):
+    """Call lib.<name>(*args, current_stream) and raise on a non-zero status.  `work` is the
+    algorithmic FLOPs or bytes of this launch (only used by the profiler)."""
+    global launch_count
     fn = getattr(lib(), name)
+    launch_count += 1
+    if _profile is not None and (_profile["names"] is None or name in _profile["names"]):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(fn(*args, stream_ptr()), name)
+        e.record()
+        _profile["records"].append((name, work, s, e))
+        return
     check(fn(*args, stream_ptr()), name)
 
 

@@ -168,3 +168,47 @@ PN2_API int pn2_three_interpolate_grad_f32(const float *grad_out, const int32_t 
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
+
+// ---- point-major 3-tap interpolation (internal layout of the fused FP path) ----
+// feats (B, m, ldf) rows of C channels ; idx / weight (B, n, 3) ; out rows (B*n, ldo) cols [0,C).
+// Same arithmetic order as the channel-major kernel; a row gather is three contiguous reads.
+namespace {
+__global__ void __launch_bounds__(256) three_interpolate_pm_kernel(const float *__restrict__ feats, int ldf,
+                                                                  const int32_t *__restrict__ idx,
+                                                                  const float *__restrict__ weight,
+                                                                  float *__restrict__ out, int ldo, int c, int m,
+                                                                  int n, long long total) {
+    // one warp per unknown point, lanes stride over channels
+    const long long pt = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= total) return;
+    const long long cloud = pt / n;
+    const int32_t *id = idx + pt * 3;
+    const float *w = weight + pt * 3;
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const float *r0 = feats + (cloud * m + __ldg(id)) * ldf;
+    const float *r1 = feats + (cloud * m + __ldg(id + 1)) * ldf;
+    const float *r2 = feats + (cloud * m + __ldg(id + 2)) * ldf;
+    float *o = out + pt * ldo;
+    for (int ch = lane; ch < c; ch += 32) {
+        float t = __fmul_rn(w1, __ldg(r1 + ch));
+        t = __fmaf_rn(w0, __ldg(r0 + ch), t);
+        t = __fmaf_rn(w2, __ldg(r2 + ch), t);
+        o[ch] = t;
+    }
+}
+}  // namespace
+
+PN2_API int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx, const float *weight,
+                                         float *out, int ldo, int b, int c, int m, int n, cudaStream_t stream) {
+    if (b < 0 || c < 0 || n < 0 || m < 0 || ldf < c || ldo < c) {
+        pn2_set_last_error("pn2_three_interpolate_pm_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    const long long total = (long long)b * n;
+    if (total == 0 || c == 0) return PN2_OK;
+    three_interpolate_pm_kernel<<<pn2_divup(total * 32, 256), 256, 0, stream>>>(feats, ldf, idx, weight, out, ldo, c, m,
+                                                                               n, total);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

@@ -1,0 +1,300 @@
+// iou3d.cu -- rotated / axis-aligned BEV overlap and NMS for sm_100a.
+//
+// Replaces pointrcnn/lib/utils/iou3d/src/iou3d_kernel.cu:223-348 (boxes_overlap_kernel,
+// boxes_iou_bev_kernel, nms_kernel, nms_normal_kernel) and the host greedy pass of
+// iou3d.cpp:73-169 behind pn2_boxes_overlap_bev_f32 / pn2_boxes_iou_bev_f32 / pn2_nms_bev_f32.
+//
+// NMS design.  The reference materialises the full n x n/64 suppression bit matrix
+// (n = 6300: 39.7 M IoU evaluations, 5 MB), cudaMalloc's it per call, copies it to the host
+// with a blocking cudaMemcpy and runs the greedy pass on the CPU (iou3d.cpp:87-116) -- 32
+// times per batch in the proposal layer, which then keeps only the first 70 / 30 survivors
+// (proposal_layer.py:112).  Here one CTA per NMS problem runs the greedy pass ON THE DEVICE
+// and evaluates a suppression row lazily, only for boxes that are actually kept, and stops
+// after `max_keep` survivors: 70 x 6300 IoUs instead of 39.7 M, no scratch, no host round
+// trip, data-dependent sizes stay on the device (counts[] in, num[] out) so the whole
+// proposal stage can be enqueued without a synchronisation.  The result is identical to the
+// mask + greedy formulation: box j is suppressed iff some kept i < j has iou(i, j) > thresh,
+// and iou(i, j) is evaluated with the same operand order (row box first).
+//
+// Overlap arithmetic: same formulas, same expression shapes and the same default FMA
+// contraction as the reference so that areas agree bit for bit (checked against the
+// reference kernels on the GPU, tests/test_iou3d_gpu.py).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr float kEps = 1e-8f;
+
+struct P2 {
+    float x, y;
+};
+
+__device__ __forceinline__ float cross3(const P2 &p1, const P2 &p2, const P2 &p0) {
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+
+__device__ __forceinline__ bool boxes_apart(const P2 &p1, const P2 &p2, const P2 &q1, const P2 &q2) {
+    const bool touch = min(p1.x, p2.x) <= max(q1.x, q2.x) && min(q1.x, q2.x) <= max(p1.x, p2.x) &&
+                       min(p1.y, p2.y) <= max(q1.y, q2.y) && min(q1.y, q2.y) <= max(p1.y, p2.y);
+    return !touch;
+}
+
+// proper intersection of segment p0-p1 with q0-q1 (iou3d_kernel.cu:66-96)
+__device__ __forceinline__ bool seg_intersect(const P2 &p1, const P2 &p0, const P2 &q1, const P2 &q0, P2 &ans) {
+    if (boxes_apart(p0, p1, q0, q1)) return false;
+    const float s1 = cross3(q0, p1, p0);
+    const float s2 = cross3(p1, q1, p0);
+    const float s3 = cross3(p0, q1, q0);
+    const float s4 = cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return false;
+    const float s5 = cross3(q1, p1, p0);
+    if (fabsf(s5 - s1) > kEps) {
+        ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        const float D = a0 * b1 - a1 * b0;
+        ans.x = (b0 * c1 - b1 * c0) / D;
+        ans.y = (a1 * c0 - a0 * c1) / D;
+    }
+    return true;
+}
+
+// point inside the (un-rotated extent of the) box after rotating it back (iou3d_kernel.cu:50-64)
+__device__ __forceinline__ bool inside_box(const float *box, const P2 &p) {
+    const float margin = 1e-5f;
+    const float center_x = (box[0] + box[2]) / 2;
+    const float center_y = (box[1] + box[3]) / 2;
+    const float angle_cos = cosf(-box[4]), angle_sin = sinf(-box[4]);
+    const float rot_x = (p.x - center_x) * angle_cos + (p.y - center_y) * angle_sin + center_x;
+    const float rot_y = -(p.x - center_x) * angle_sin + (p.y - center_y) * angle_cos + center_y;
+    return rot_x > box[0] - margin && rot_x < box[2] + margin && rot_y > box[1] - margin && rot_y < box[3] + margin;
+}
+
+__device__ __forceinline__ void spin(const P2 &c, float angle_cos, float angle_sin, P2 &p) {
+    const float nx = (p.x - c.x) * angle_cos + (p.y - c.y) * angle_sin + c.x;
+    const float ny = -(p.x - c.x) * angle_sin + (p.y - c.y) * angle_cos + c.y;
+    p.x = nx;
+    p.y = ny;
+}
+
+// intersection area of two rotated rectangles [x1,y1,x2,y2,angle] (iou3d_kernel.cu:108-212)
+__device__ float rot_overlap(const float *box_a, const float *box_b) {
+    const float ax1 = box_a[0], ay1 = box_a[1], ax2 = box_a[2], ay2 = box_a[3], aang = box_a[4];
+    const float bx1 = box_b[0], by1 = box_b[1], bx2 = box_b[2], by2 = box_b[3], bang = box_b[4];
+    P2 ca, cb;
+    ca.x = (ax1 + ax2) / 2; ca.y = (ay1 + ay2) / 2;
+    cb.x = (bx1 + bx2) / 2; cb.y = (by1 + by2) / 2;
+    P2 A[5], B[5];
+    A[0] = {ax1, ay1}; A[1] = {ax2, ay1}; A[2] = {ax2, ay2}; A[3] = {ax1, ay2};
+    B[0] = {bx1, by1}; B[1] = {bx2, by1}; B[2] = {bx2, by2}; B[3] = {bx1, by2};
+    const float a_cos = cosf(aang), a_sin = sinf(aang);
+    const float b_cos = cosf(bang), b_sin = sinf(bang);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        spin(ca, a_cos, a_sin, A[k]);
+        spin(cb, b_cos, b_sin, B[k]);
+    }
+    A[4] = A[0];
+    B[4] = B[0];
+
+    P2 poly[16];
+    P2 centre = {0.f, 0.f};
+    int cnt = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (seg_intersect(A[i + 1], A[i], B[j + 1], B[j], poly[cnt])) {
+                centre.x = centre.x + poly[cnt].x;
+                centre.y = centre.y + poly[cnt].y;
+                ++cnt;
+            }
+    for (int k = 0; k < 4; ++k) {
+        if (inside_box(box_a, B[k])) {
+            centre.x = centre.x + B[k].x;
+            centre.y = centre.y + B[k].y;
+            poly[cnt++] = B[k];
+        }
+        if (inside_box(box_b, A[k])) {
+            centre.x = centre.x + A[k].x;
+            centre.y = centre.y + A[k].y;
+            poly[cnt++] = A[k];
+        }
+    }
+    centre.x /= cnt;
+    centre.y /= cnt;
+    // order the vertices by polar angle about the centroid: the same adjacent-swap passes as
+    // the reference (:187-196), with each vertex's atan2f evaluated once instead of per compare
+    float ang[16];
+    for (int i = 0; i < cnt; ++i) ang[i] = atan2f(poly[i].y - centre.y, poly[i].x - centre.x);
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (ang[i] > ang[i + 1]) {
+                const P2 tp = poly[i]; poly[i] = poly[i + 1]; poly[i + 1] = tp;
+                const float ta = ang[i]; ang[i] = ang[i + 1]; ang[i + 1] = ta;
+            }
+    float area = 0;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ux = poly[k].x - poly[0].x, uy = poly[k].y - poly[0].y;
+        const float vx = poly[k + 1].x - poly[0].x, vy = poly[k + 1].y - poly[0].y;
+        area += ux * vy - uy * vx;
+    }
+    return fabsf(area) / 2.0f;
+}
+
+__device__ __forceinline__ float rot_iou(const float *a, const float *b) {
+    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
+    const float sb = (b[2] - b[0]) * (b[3] - b[1]);
+    const float s = rot_overlap(a, b);
+    return s / fmaxf(sa + sb - s, kEps);
+}
+
+// iou3d_kernel.cu:295-303
+__device__ __forceinline__ float flat_iou(const float *a, const float *b) {
+    const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+    const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+    const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+    const float inter = width * height;
+    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
+    const float sb = (b[2] - b[0]) * (b[3] - b[1]);
+    return inter / fmaxf(sa + sb - inter, kEps);
+}
+
+template <bool IOU>
+__global__ void __launch_bounds__(256) pairwise_kernel(int na, const float *__restrict__ a, int nb,
+                                                      const float *__restrict__ b, float *__restrict__ out) {
+    // 16 x 16 pairs per CTA, b index fastest so the result rows are written coalesced
+    const int ia = blockIdx.y * 16 + threadIdx.y;
+    const int ib = blockIdx.x * 16 + threadIdx.x;
+    __shared__ float sa[16][5], sb[16][5];
+    const int t = threadIdx.y * 16 + threadIdx.x;
+    if (t < 80) {
+        const int r = t / 5, c = t % 5;
+        const int ga = blockIdx.y * 16 + r;
+        sa[r][c] = ga < na ? a[ga * 5 + c] : 0.f;
+    } else if (t < 160) {
+        const int r = (t - 80) / 5, c = (t - 80) % 5;
+        const int gb = blockIdx.x * 16 + r;
+        sb[r][c] = gb < nb ? b[gb * 5 + c] : 0.f;
+    }
+    __syncthreads();
+    if (ia >= na || ib >= nb) return;
+    out[(size_t)ia * nb + ib] = IOU ? rot_iou(sa[threadIdx.y], sb[threadIdx.x]) : rot_overlap(sa[threadIdx.y], sb[threadIdx.x]);
+}
+
+constexpr int kNmsThreads = 256;
+constexpr int kNmsMaxWords = 1024;  // up to 32768 boxes per problem
+
+// One CTA per problem.  boxes (P, stride, 5) sorted by descending score; counts[P] (device) or n.
+template <bool ROTATED>
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const float *__restrict__ boxes, int stride, int n_fixed,
+                                                         const int32_t *__restrict__ counts, float thresh,
+                                                         int max_keep, long long *__restrict__ keep,
+                                                         int32_t *__restrict__ num_out) {
+    __shared__ uint32_t remv[kNmsMaxWords];
+    __shared__ int cur;
+    __shared__ float cur_box[5];
+    const int prob = blockIdx.x;
+    const int n = counts ? counts[prob] : n_fixed;
+    boxes += (size_t)prob * stride * 5;
+    keep += (size_t)prob * max_keep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int words = (n + 31) >> 5;
+    for (int w = tid; w < words; w += kNmsThreads) remv[w] = 0u;
+    __syncthreads();
+
+    int kept = 0;
+    int pos = 0;  // first candidate index not yet examined (uniform)
+    while (kept < max_keep && pos < n) {
+        // warp 0 finds the first unsuppressed box at index >= pos
+        if (warp == 0) {
+            int found = n;
+            for (int w0 = pos >> 5; w0 < words && found == n; w0 += 32) {
+                const int w = w0 + lane;
+                uint32_t freeb = 0u;
+                if (w < words) {
+                    freeb = ~remv[w];
+                    if (w == (pos >> 5)) freeb &= 0xffffffffu << (pos & 31);
+                    const int hi = n - w * 32;  // valid bits in this word
+                    if (hi < 32) freeb &= (1u << hi) - 1u;
+                }
+                const unsigned any = __ballot_sync(0xffffffffu, freeb != 0u);
+                if (any) {
+                    const int src = __ffs(any) - 1;
+                    const uint32_t fb = __shfl_sync(0xffffffffu, freeb, src);
+                    found = (w0 + src) * 32 + (__ffs(fb) - 1);
+                }
+            }
+            if (lane == 0) cur = found;
+            if (found < n && lane < 5) cur_box[lane] = boxes[(size_t)found * 5 + lane];
+        }
+        __syncthreads();
+        const int i = cur;
+        if (i >= n) break;
+        if (tid == 0) keep[kept] = i;
+        ++kept;
+        pos = i + 1;
+        if (kept < max_keep) {
+            // suppression row of box i, only for j > i; one 32-box word per warp step
+            float bi[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) bi[c] = cur_box[c];
+            for (int w = (pos >> 5) + warp; w < words; w += kNmsThreads / 32) {
+                const int j = w * 32 + lane;
+                bool sup = false;
+                if (j >= pos && j < n && !((remv[w] >> lane) & 1u)) {
+                    float bj[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) bj[c] = __ldg(boxes + (size_t)j * 5 + c);
+                    sup = (ROTATED ? rot_iou(bi, bj) : flat_iou(bi, bj)) > thresh;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0 && bal) remv[w] |= bal;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) num_out[prob] = kept;
+}
+
+}  // namespace
+
+// boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap)  iou3d.cpp:31-50 / iou3d_kernel.cu:223-234.
+// a (na,5), b (nb,5) [x1,y1,x2,y2,ry] -> out (na,nb) intersection AREA.
+PN2_API int pn2_boxes_overlap_bev_f32(const float *a, int na, const float *b, int nb, float *out, cudaStream_t stream) {
+    if (na < 0 || nb < 0) { pn2_set_last_error("pn2_boxes_overlap_bev_f32: bad argument"); return PN2_ERR_INVALID; }
+    if (na == 0 || nb == 0) return PN2_OK;
+    dim3 grid(pn2_divup(nb, 16), pn2_divup(na, 16)), block(16, 16);
+    pairwise_kernel<false><<<grid, block, 0, stream>>>(na, a, nb, b, out);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// boxes_iou_bev_gpu  iou3d.cpp:52-71 / iou3d_kernel.cu:236-248.
+PN2_API int pn2_boxes_iou_bev_f32(const float *a, int na, const float *b, int nb, float *out, cudaStream_t stream) {
+    if (na < 0 || nb < 0) { pn2_set_last_error("pn2_boxes_iou_bev_f32: bad argument"); return PN2_ERR_INVALID; }
+    if (na == 0 || nb == 0) return PN2_OK;
+    dim3 grid(pn2_divup(nb, 16), pn2_divup(na, 16)), block(16, 16);
+    pairwise_kernel<true><<<grid, block, 0, stream>>>(na, a, nb, b, out);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// nms_gpu / nms_normal_gpu (iou3d.cpp:73-169, kernels iou3d_kernel.cu:250-348), batched and
+// entirely on the device.  boxes (problems, stride, 5) sorted by descending score; problem p
+// uses its first counts[p] boxes (counts may be NULL: all use n).  keep (problems, max_keep)
+// int64 indices into the sorted list in ascending order; num (problems) int32 survivors
+// (<= max_keep; pass max_keep = n for the reference's full list).
+PN2_API int pn2_nms_bev_f32(const float *boxes, int problems, int stride, int n, const int32_t *counts, float thresh,
+                            int rotated, int max_keep, long long *keep, int32_t *num, cudaStream_t stream) {
+    if (problems < 0 || stride < 0 || n < 0 || n > stride || max_keep < 0 || stride > kNmsMaxWords * 32) {
+        pn2_set_last_error("pn2_nms_bev_f32: bad argument (at most 32768 boxes per problem)");
+        return PN2_ERR_INVALID;
+    }
+    if (problems == 0) return PN2_OK;
+    if (rotated) nms_kernel<true><<<problems, kNmsThreads, 0, stream>>>(boxes, stride, n, counts, thresh, max_keep, keep, num);
+    else nms_kernel<false><<<problems, kNmsThreads, 0, stream>>>(boxes, stride, n, counts, thresh, max_keep, keep, num);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

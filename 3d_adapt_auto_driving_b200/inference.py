@@ -1,0 +1,101 @@
+"""The eval hot loop of pointrcnn/tools/eval_rcnn.py:493-635 (eval_one_epoch_joint) as a callable:
+pinned host clouds -> H2D -> PointRCNN forward -> decode_bbox_target -> sigmoid score threshold ->
+rotated NMS -> fixed-width detection records -> D2H.
+
+The reference walks the scenes of a batch in a Python loop and, per scene, indexes the
+selected boxes, sorts, runs NMS with a blocking D2H of the suppression matrix, and copies
+the survivors to the host (eval_rcnn.py:614-629).  Here the whole batch is post-processed
+with a constant number of launches and NO host synchronisation: the score mask becomes a
+per-scene count, one batched sort orders the candidates, one batched device NMS
+(pn2_nms_bev_f32 with device-side counts) yields the keep lists, and a single D2H copy
+returns (B, M, 8) records [x, y, z, h, w, l, ry, raw_score] plus the number of valid rows per
+scene -- the same boxes in the same (descending score) order the reference writes to its KITTI
+files.  The record tensor is also what the multi-GPU path all-gathers (parallel.py)."""
+import numpy as np
+import torch
+
+from . import iou3d_cuda
+from . import kitti_utils
+from .bbox_transform import decode_bbox_target
+from .config import cfg
+
+
+class Detector:
+    def __init__(self, model, device=None):
+        self.model = model.eval()
+        self.device = device if device is not None else next(model.parameters()).device
+        self.mean_size = torch.from_numpy(cfg.CLS_MEAN_SIZE[0]).to(self.device)
+        self._stage = {}
+
+    # ---- eval_rcnn.py:516-535, 611-627, batched and sync-free ----
+    def postprocess(self, ret_dict, batch_size):
+        """-> records (B, M, 8) float32 [box7, raw score] sorted by descending score with the
+        suppressed / below-threshold rows zeroed, counts (B,) int32; all on the device."""
+        rois = ret_dict['rois']
+        rcnn_cls = ret_dict['rcnn_cls'].view(batch_size, -1, ret_dict['rcnn_cls'].shape[1])
+        rcnn_reg = ret_dict['rcnn_reg'].view(batch_size, -1, ret_dict['rcnn_reg'].shape[1])
+        if rcnn_cls.shape[2] != 1:
+            raise NotImplementedError("multi-class RCNN head (eval_rcnn.py:536-540) is not on the default.yaml path")
+        M = rois.shape[1]
+        pred = decode_bbox_target(rois.view(-1, 7), rcnn_reg.view(-1, rcnn_reg.shape[-1]), anchor_size=self.mean_size,
+                                  loc_scope=cfg.RCNN.LOC_SCOPE, loc_bin_size=cfg.RCNN.LOC_BIN_SIZE,
+                                  num_head_bin=cfg.RCNN.NUM_HEAD_BIN, get_xz_fine=True,
+                                  get_y_by_bin=cfg.RCNN.LOC_Y_BY_BIN, loc_y_scope=cfg.RCNN.LOC_Y_SCOPE,
+                                  loc_y_bin_size=cfg.RCNN.LOC_Y_BIN_SIZE, get_ry_fine=True).view(batch_size, M, 7)
+        raw = rcnn_cls[:, :, 0]
+        sel = torch.sigmoid(raw) > cfg.RCNN.SCORE_THRESH                      # eval_rcnn.py:612
+        counts = sel.sum(dim=1).to(torch.int32)
+        # selected boxes first, by descending raw score (iou3d_utils.py:63 sorts the selection)
+        key = torch.where(sel, raw, torch.full_like(raw, -float('inf')))
+        order = torch.sort(key, dim=1, descending=True, stable=True)[1]
+        boxes_sorted = torch.gather(pred, 1, order.unsqueeze(-1).expand(-1, -1, 7))
+        scores_sorted = torch.gather(raw, 1, order)
+        bev = kitti_utils.boxes3d_to_bev_torch(boxes_sorted.view(-1, 7)).view(batch_size, M, 5).contiguous()
+        keep, num = iou3d_cuda.nms_device(bev, cfg.RCNN.NMS_THRESH, rotated=True, max_keep=M, counts=counts)
+        valid = torch.arange(M, device=keep.device).unsqueeze(0) < num.unsqueeze(1)
+        keep = torch.where(valid, keep, torch.zeros_like(keep))
+        rec = torch.cat((torch.gather(boxes_sorted, 1, keep.unsqueeze(-1).expand(-1, -1, 7)),
+                         torch.gather(scores_sorted, 1, keep).unsqueeze(-1)), dim=2)
+        rec = rec * valid.unsqueeze(-1).to(rec.dtype)
+        return rec, num
+
+    @torch.no_grad()
+    def detect_device(self, pts_input):
+        """pts_input (B, N, 3) on the device -> (records (B,M,8), counts (B,)) on the device."""
+        ret = self.model({'pts_input': pts_input})
+        return self.postprocess(ret, pts_input.shape[0])
+
+    @torch.no_grad()
+    def detect(self, pts_host, out_records=None, out_counts=None):
+        """pts_host: (B, N, 3) float32 HOST tensor (pinned for an async copy) or ndarray.
+        Returns host tensors (records (B,M,8), counts (B,)); pass pinned `out_*` buffers to
+        avoid an allocation per call.  One H2D, one D2H pair, one synchronisation."""
+        if isinstance(pts_host, np.ndarray):
+            pts_host = torch.from_numpy(pts_host)
+        pts = pts_host.to(self.device, non_blocking=True).float()             # eval_rcnn.py:498
+        rec, num = self.detect_device(pts)
+        if out_records is None:
+            out_records = torch.empty(rec.shape, dtype=rec.dtype, pin_memory=True)
+            out_counts = torch.empty(num.shape, dtype=num.dtype, pin_memory=True)
+        out_records.copy_(rec, non_blocking=True)
+        out_counts.copy_(num, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_records, out_counts
+
+
+def records_to_lists(records, counts):
+    """host (B,M,8), (B,) -> per scene (boxes3d (k,7), scores (k,)) ndarrays, the arguments of
+    eval_rcnn.py:76 save_kitti_format."""
+    rec = records.numpy() if isinstance(records, torch.Tensor) else records
+    cnt = counts.numpy() if isinstance(counts, torch.Tensor) else counts
+    return [(rec[b, :int(cnt[b]), :7].copy(), rec[b, :int(cnt[b]), 7].copy()) for b in range(rec.shape[0])]
+
+
+def build_model(seed=0, eval_mode="rcnn", device="cuda"):
+    """default.yaml PointRCNN with seeded random-init weights (no checkpoint is available offline)."""
+    from .config import use_default_yaml
+    from .net.point_rcnn import PointRCNN
+    use_default_yaml(eval_mode)
+    torch.manual_seed(seed)
+    model = PointRCNN(num_classes=2, use_xyz=True, mode='TEST')
+    return model.to(device).eval()

@@ -1,0 +1,52 @@
+"""Mirror of pointrcnn/lib/utils/iou3d/iou3d_utils.py: boxes_iou_bev, boxes_iou3d_gpu, nms_gpu,
+nms_normal_gpu with the reference's signatures and return values (keep = indices into the
+ORIGINAL box order, on the device).  Unlike the reference (iou3d_utils.py:68-70: CPU keep
+tensor, blocking copy of the whole suppression matrix, `.cuda()` re-upload) the NMS result
+never leaves the GPU."""
+import torch
+
+from . import iou3d_cuda
+from . import kitti_utils
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """(M,5),(N,5) [x1,y1,x2,y2,ry] -> (M,N) rotated BEV IoU."""
+    ans_iou = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    iou3d_cuda.boxes_iou_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans_iou)
+    return ans_iou
+
+
+def boxes_iou3d_gpu(boxes_a, boxes_b):
+    """(N,7),(M,7) [x,y,z,h,w,l,ry] -> (N,M) 3D IoU = BEV overlap x height overlap / union
+    (iou3d_utils.py:21-53; the elementwise part is torch in the reference too)."""
+    boxes_a_bev = kitti_utils.boxes3d_to_bev_torch(boxes_a)
+    boxes_b_bev = kitti_utils.boxes3d_to_bev_torch(boxes_b)
+    overlaps_bev = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    iou3d_cuda.boxes_overlap_bev_gpu(boxes_a_bev.contiguous(), boxes_b_bev.contiguous(), overlaps_bev)
+    a_min = (boxes_a[:, 1] - boxes_a[:, 3]).view(-1, 1)
+    a_max = boxes_a[:, 1].view(-1, 1)
+    b_min = (boxes_b[:, 1] - boxes_b[:, 3]).view(1, -1)
+    b_max = boxes_b[:, 1].view(1, -1)
+    overlaps_h = torch.clamp(torch.min(a_max, b_max) - torch.max(a_min, b_min), min=0)
+    overlaps_3d = overlaps_bev * overlaps_h
+    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
+    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(1, -1)
+    return overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-7)
+
+
+def _nms(boxes, scores, thresh, rotated, max_keep=None):
+    order = scores.sort(0, descending=True)[1]
+    sorted_boxes = boxes[order].contiguous()
+    keep, num = iou3d_cuda.nms_device(sorted_boxes, thresh, rotated, max_keep=max_keep)
+    return order[keep[0, :int(num.item())]].contiguous()
+
+
+def nms_gpu(boxes, scores, thresh, max_keep=None):
+    """rotated-IoU NMS (iou3d_utils.py:56-70). boxes (N,5), scores (N) -> kept original indices.
+    max_keep (extension): stop after that many survivors."""
+    return _nms(boxes, scores, thresh, True, max_keep)
+
+
+def nms_normal_gpu(boxes, scores, thresh, max_keep=None):
+    """axis-aligned NMS (iou3d_utils.py:73-87)."""
+    return _nms(boxes, scores, thresh, False, max_keep)

@@ -1,0 +1,53 @@
+"""The torch helpers of pointrcnn/lib/utils/kitti_utils.py that sit on the inference path:
+boxes3d_to_bev_torch (:134-147), enlarge_box3d (:150-160), rotate_pc_along_y_torch (:45-63),
+boxes3d_to_corners3d_torch / boxes3d_to_corners3d (numpy, used by eval_rcnn.py:78)."""
+import numpy as np
+import torch
+
+
+def boxes3d_to_bev_torch(boxes3d):
+    """(N,7) [x,y,z,h,w,l,ry] -> (N,5) [x1,y1,x2,y2,ry] in the x-z plane."""
+    cu, cv = boxes3d[:, 0], boxes3d[:, 2]
+    half_l, half_w = boxes3d[:, 5] / 2, boxes3d[:, 4] / 2
+    return torch.stack((cu - half_l, cv - half_w, cu + half_l, cv + half_w, boxes3d[:, 6]), dim=1)
+
+
+def enlarge_box3d(boxes3d, extra_width):
+    large = boxes3d.copy() if isinstance(boxes3d, np.ndarray) else boxes3d.clone()
+    large[:, 3:6] += extra_width * 2
+    large[:, 1] += extra_width
+    return large
+
+
+def rotate_pc_along_y_torch(pc, rot_angle):
+    """pc (N,S,3+C) rotated about y by rot_angle (N); in place on columns 0 and 2 like the
+    reference: [x', z'] = [x, z] @ [[cos, -sin], [sin, cos]]^T."""
+    cosa = torch.cos(rot_angle).view(-1, 1, 1)
+    sina = torch.sin(rot_angle).view(-1, 1, 1)
+    x = pc[:, :, 0:1].clone()
+    z = pc[:, :, 2:3].clone()
+    pc[:, :, 0:1] = x * cosa - z * sina
+    pc[:, :, 2:3] = x * sina + z * cosa
+    return pc
+
+
+# corner order of the KITTI convention (kitti_utils.py:72-77): bottom face first (y = 0), then
+# the top face (y = -h); signs of (l/2, w/2) per corner
+_CORNER_SX = np.array([1, 1, -1, -1, 1, 1, -1, -1], np.float32)
+_CORNER_SZ = np.array([1, -1, -1, 1, 1, -1, -1, 1], np.float32)
+_CORNER_TOP = np.array([0, 0, 0, 0, 1, 1, 1, 1], np.float32)
+
+
+def boxes3d_to_corners3d(boxes3d, rotate=True):
+    """numpy (N,7) [x,y,z,h,w,l,ry] -> (N,8,3) corners in rect-camera coordinates
+    (kitti_utils.py:66-98; y points down, the box origin is the bottom-face centre)."""
+    b = np.asarray(boxes3d)
+    h, w, l, ry = b[:, 3:4], b[:, 4:5], b[:, 5:6], b[:, 6]
+    xc = (l / 2.0).astype(np.float32) * _CORNER_SX          # (N,8)
+    zc = (w / 2.0).astype(np.float32) * _CORNER_SZ
+    yc = (-h).astype(np.float32) * _CORNER_TOP
+    if rotate:
+        c, s = np.cos(ry)[:, None], np.sin(ry)[:, None]
+        xc, zc = xc * c + zc * s, -xc * s + zc * c
+    out = np.stack((b[:, 0:1] + xc, b[:, 1:2] + yc, b[:, 2:3] + zc), axis=2)
+    return out.astype(np.float32)

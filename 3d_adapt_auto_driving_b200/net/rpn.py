@@ -1,0 +1,78 @@
+"""Mirror of pointrcnn/lib/net/rpn.py: backbone + per-point classification / box-regression
+heads + the proposal layer (rpn.py:11-83).  Same attribute names (backbone_net, rpn_cls_layer,
+rpn_reg_layer, proposal_layer), Dropout kept at index 1 of each head so state-dict indices
+match (rpn.py:26-27,44-45), same init (rpn.py:60-66), same output dict."""
+import importlib
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import pytorch_utils as pt_utils
+from .. import fused as fz
+from ..config import cfg
+from ..proposal_layer import ProposalLayer
+
+
+class RPN(nn.Module):
+    def __init__(self, use_xyz=True, mode='TRAIN'):
+        super().__init__()
+        self.training_mode = (mode == 'TRAIN')
+        MODEL = importlib.import_module('.' + cfg.RPN.BACKBONE, package=__package__)
+        self.backbone_net = MODEL.get_model(input_channels=int(cfg.RPN.USE_INTENSITY), use_xyz=use_xyz)
+
+        def head(fc_list, out_channels):
+            layers, pre = [], cfg.RPN.FP_MLPS[0][-1]
+            for c in fc_list:
+                layers.append(pt_utils.Conv1d(pre, c, bn=cfg.RPN.USE_BN))
+                pre = c
+            layers.append(pt_utils.Conv1d(pre, out_channels, activation=None))
+            if cfg.RPN.DP_RATIO >= 0:
+                layers.insert(1, nn.Dropout(cfg.RPN.DP_RATIO))
+            return nn.Sequential(*layers)
+
+        per_loc_bin_num = int(cfg.RPN.LOC_SCOPE / cfg.RPN.LOC_BIN_SIZE) * 2
+        reg_channel = per_loc_bin_num * (4 if cfg.RPN.LOC_XZ_FINE else 2) + cfg.RPN.NUM_HEAD_BIN * 2 + 3
+        reg_channel += 1  # y offset
+        self.rpn_cls_layer = head(cfg.RPN.CLS_FC, 1)
+        self.rpn_reg_layer = head(cfg.RPN.REG_FC, reg_channel)
+        self.rpn_cls_loss_func = None  # training only (rpn.py:48-56); not part of the inference path
+        self.proposal_layer = ProposalLayer(mode=mode)
+        self.init_weights()
+        self._packed = None
+
+    def init_weights(self):
+        if cfg.RPN.LOSS_CLS in ['SigmoidFocalLoss']:
+            pi = 0.01
+            nn.init.constant_(self.rpn_cls_layer[2].conv.bias, -np.log((1 - pi) / pi))
+        nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
+
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def forward(self, input_data):
+        pts_input = input_data['pts_input']
+        if self.backbone_net.can_fuse(pts_input):
+            backbone_xyz, feats_pm = self.backbone_net.forward_pm(pts_input)          # (B,N,3), (B,N,C)
+            if self._packed is None:
+                self._packed = (fz.pack_sequential(self.rpn_cls_layer), fz.pack_sequential(self.rpn_reg_layer))
+            B, N, _ = feats_pm.shape
+            outs = []
+            for layers in self._packed:
+                cur = feats_pm.view(B * N, -1)
+                for layer in layers:
+                    cur = fz.linear(cur, layer)
+                outs.append(cur.view(B, N, -1))
+            rpn_cls, rpn_reg = outs
+            backbone_features = feats_pm.transpose(1, 2)  # (B,C,N) view, as the reference returns it
+        else:
+            backbone_xyz, backbone_features = self.backbone_net(pts_input)  # (B,N,3), (B,C,N)
+            rpn_cls = self.rpn_cls_layer(backbone_features).transpose(1, 2).contiguous()  # (B,N,1)
+            rpn_reg = self.rpn_reg_layer(backbone_features).transpose(1, 2).contiguous()  # (B,N,C)
+        return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,
+                'backbone_features': backbone_features}

@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- PointRCNN inference throughput (scenes/sec) on synthetic 16384-point KITTI-shaped
+clouds; BASELINE.json's metric on its config 4 (full RPN+RCNN forward, batch 16, random-init
+default.yaml weights) plus the eval post-processing of eval_rcnn.py:516-627.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one batch of 16 scenes through the whole hot path (H2D-free for `value`, from pinned
+host buffers with the detections copied back for `e2e`).  Scenes shard across ranks (weak
+scaling); the only collective is one all_gather of the detection records at the end of the e2e
+region.  One JSON line on stdout (rank 0).
+
+--impl reference runs the REFERENCE implementation of the same path: its own CUDA kernels
+(oracle/_ref/libpn2_legacy.so = the reference .cu files compiled unchanged) under the
+reference's op-by-op Python composition and per-scene host-greedy NMS, on the same GPU, and
+next to it the CPU port (oracle/cpu_forward.py) on a bounded sample.  The reference has no CPU
+implementation of this path; see DESIGN.md "Reference arm".
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "3d_adapt_auto_driving_b200"
+
+METRIC = "pointrcnn_inference_scenes_per_sec"
+UNIT = "scenes/s"
+NPOINTS = 16384
+FLOPS_PER_SCENE = 130.0e9  # 2*MAC of every SharedMLP layer of RPN + RCNN at default.yaml
+
+
+def load(sub):
+    return importlib.import_module(PKG + "." + sub)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+    if local < len(vis) and vis[local].strip().isdigit():
+        return int(vis[local])
+    return local
+
+
+def make_batches(torch, syn, batch, nbatches, seed):
+    return [torch.from_numpy(syn.make_clouds("lidar", batch, NPOINTS, seed=seed + 17 * i)).pin_memory()
+            for i in range(nbatches)]
+
+
+def dist_setup(torch, gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist, world, rank, local
+    torch.cuda.set_device(0)
+    return None, 1, 0, 0
+
+
+def cpu_port_sample(torch, batch_seed, max_scenes=4, budget_s=12.0):
+    """The CPU port (oracle/cpu_forward.py) on a bounded sample of the same workload: scenes of
+    the first benchmark batch, one at a time, all host threads for the torch part."""
+    from oracle import cpu_forward as cf
+    syn = load("synthetic")
+    inf = load("inference")
+    model = inf.build_model(seed=0, device="cpu")
+    pkg = {"cfg": load("config").cfg, "decode_bbox_target": load("bbox_transform").decode_bbox_target}
+    pts = torch.from_numpy(syn.make_clouds("lidar", max_scenes, NPOINTS, seed=batch_seed))
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(max_scenes):
+        out = cf.pointrcnn_forward(pkg, model, pts[i:i + 1])
+        cf.postprocess(pkg, out, 1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d scene(s) of batch 0 (16384 pts, 100 ROIs each), %.1f s; C restatement of the reference "
+                      "kernels single-threaded + torch CPU fp32 convs on %d threads" % (done, dt, torch.get_num_threads())}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    cabi = load("cabi")
+    cabi.lib()  # fail loudly if the CUDA extension is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    dist, world, rank, local = dist_setup(torch, args.gpus)
+    dev = torch.device("cuda", local)
+    syn, inf = load("synthetic"), load("inference")
+    model = inf.build_model(seed=0, device=dev)
+    det = inf.Detector(model, dev)
+    B, K, W = args.batch, args.steps, args.warmup
+    host = make_batches(torch, syn, B, 4, seed=1024 + 1000 * rank)
+    resident = [h.to(dev) for h in host]
+    out_rec = torch.empty((B, 100, 8), dtype=torch.float32).pin_memory()
+    out_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(W):
+        det.detect_device(resident[i % 4])
+    torch.cuda.synchronize()
+
+    # which C-ABI kernel dominates a step (one profiled step, untimed)
+    cabi.profile_start()
+    det.detect_device(resident[0])
+    breakdown = cabi.profile_stop()
+    step_kernel_ms = sum(v["ms"] for v in breakdown.values())
+    top = max(breakdown, key=lambda k: breakdown[k]["ms"])
+    mlp_names = {"pn2_linear_f32", "pn2_sa_group_linear_f32"}
+    prof_names = mlp_names if top in mlp_names else {top}
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+
+    # ---- value: K steps, inputs resident in HBM ----
+    barrier()
+    l0 = cabi.launch_count
+    cabi.profile_start(prof_names)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(K):
+        det.detect_device(resident[i % 4])
+    e.record()
+    barrier()
+    dom = cabi.profile_stop()
+    ms_total = max_over_ranks(s.elapsed_time(e))
+    launches = (cabi.launch_count - l0) // K
+
+    # ---- e2e: host buffers in, detections out, every step; one all_gather at the end ----
+    for i in range(2):
+        det.detect(host[i % 4], out_rec, out_cnt)
+    keep_rec = torch.empty((K, B, 100, 8), dtype=torch.float32, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        pts = host[i % 4].to(dev, non_blocking=True)
+        rec, num = det.detect_device(pts)
+        keep_rec[i].copy_(rec)
+        out_rec.copy_(rec, non_blocking=True)
+        out_cnt.copy_(num, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the host reads the detections of every step
+    if dist is not None:
+        gathered = [torch.empty_like(keep_rec) for _ in range(world)]
+        dist.all_gather(gathered, keep_rec)                 # the single collective: detection boxes
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+
+    scenes = B * K * world
+    value = scenes / (ms_total * 1e-3)
+    peaks = measured_peaks()
+    dom_ms = sum(v["ms"] for v in dom.values())
+    dom_work = sum(v["work"] for v in dom.values())
+    dom_launches = sum(v["launches"] for v in dom.values())
+    if top in mlp_names:
+        # dense contraction with fp32 semantics: quoted against the TF32 dense tensor peak
+        # (= half the measured bf16 figure; a 3xTF32 split needs 3 tensor FLOPs per useful one)
+        peak = peaks["bf16_tflops_sustained"] / 2.0
+        roof = {"bound": "tensor", "kernel": "+".join(sorted(dom)), "achieved": dom_work / (dom_ms * 1e-3) / 1e12,
+                "peak": peak, "unit": "TFLOP/s", "peak_source": "%s bf16 sustained / 2 (TF32 dense)" % peaks["source"],
+                "traffic": None}
+    else:
+        roof = {"bound": "hbm", "kernel": top, "achieved": dom_work / (dom_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "peak_source": peaks["source"], "traffic": None}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["launches_per_step"] = dom_launches // K
+    roof["share_of_step"] = dom_ms / (s.elapsed_time(e))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[3]: full PointRCNN RPN+RCNN forward (default.yaml, random-init "
+                               "weights seed 0) + eval_rcnn.py decode/score/rotated-NMS, batch=16 synthetic KITTI-shaped "
+                               "clouds of 16384 points per GPU",
+                   "batch_per_gpu": B, "npoints": NPOINTS, "rois_per_scene": 100, "parallelism": "scene-shard x%d" % world,
+                   "l2": "per-step working set (pooled ROI tensor 0.44 GB + SA activations) >> 126 MB L2; inputs rotate over 4 batches"},
+        "e2e": {"value": scenes / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * NPOINTS * 3 * 4,
+                "d2h_bytes_per_step": B * 100 * 8 * 4 + B * 4,
+                "collective": "one all_gather of (K,B,100,8) f32 detection records" if world > 1 else None},
+        "gpu_launches": int(launches * K),
+        "gpu_launches_per_step": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernel_breakdown_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernel_ms_per_step_sum": round(step_kernel_ms, 3),
+        "mlp_tflops_effective": FLOPS_PER_SCENE * scenes / (ms_total * 1e-3) / 1e12,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_sample(torch, 1024)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, K, W = args.batch, args.steps, args.warmup
+    from oracle import legacy
+    have_gpu = torch.cuda.is_available() and legacy.available()
+    cpu = cpu_port_sample(torch, 1024)
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if not have_gpu:
+        base.update({"value": cpu["value"], "ms_per_step": 1e3 * B / cpu["value"], "cpu_baseline": cpu,
+                     "config": {"workload": "CPU port (oracle/) of the same workload; legacy-CUDA library unavailable"},
+                     "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base), flush=True)
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    legacy.install(PKG)
+    syn, inf = load("synthetic"), load("inference")
+    cfg = load("config").cfg
+    ku, iu = load("kitti_utils"), load("iou3d_utils")
+    decode = load("bbox_transform").decode_bbox_target
+    model = inf.build_model(seed=0, device=dev)
+    for m in model.modules():
+        if hasattr(m, "fused"):
+            m.fused = False       # the reference's op-by-op composition (cuDNN convs, torch defaults)
+    host = make_batches(torch, syn, B, 4, seed=1024)
+    mean_size = torch.from_numpy(cfg.CLS_MEAN_SIZE[0]).to(dev)
+
+    def step(pts_host):
+        """eval_rcnn.py:498-629 for one batch."""
+        with torch.no_grad():
+            inputs = pts_host.cuda(non_blocking=True).float()
+            ret = model({'pts_input': inputs})
+            bs = inputs.shape[0]
+            rois = ret['rois']
+            rcnn_cls = ret['rcnn_cls'].view(bs, -1, ret['rcnn_cls'].shape[1])
+            rcnn_reg = ret['rcnn_reg'].view(bs, -1, ret['rcnn_reg'].shape[1])
+            pred = decode(rois.view(-1, 7), rcnn_reg.view(-1, rcnn_reg.shape[-1]), anchor_size=mean_size,
+                          loc_scope=cfg.RCNN.LOC_SCOPE, loc_bin_size=cfg.RCNN.LOC_BIN_SIZE,
+                          num_head_bin=cfg.RCNN.NUM_HEAD_BIN, get_xz_fine=True, get_y_by_bin=cfg.RCNN.LOC_Y_BY_BIN,
+                          loc_y_scope=cfg.RCNN.LOC_Y_SCOPE, loc_y_bin_size=cfg.RCNN.LOC_Y_BIN_SIZE,
+                          get_ry_fine=True).view(bs, -1, 7)
+            raw = rcnn_cls
+            norm = torch.sigmoid(raw)
+            inds = norm > cfg.RCNN.SCORE_THRESH
+            outs = []
+            for k in range(bs):
+                cur = inds[k].view(-1)
+                if cur.sum() == 0:
+                    continue
+                bsel, ssel = pred[k, cur], raw[k, cur]
+                keep = iu.nms_gpu(ku.boxes3d_to_bev_torch(bsel), ssel.view(-1), cfg.RCNN.NMS_THRESH).view(-1)
+                outs.append((bsel[keep].cpu().numpy(), ssel[keep].cpu().numpy()))
+            return outs
+
+    for i in range(W):
+        step(host[i % 4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(host[i % 4])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    value = B * K / dt
+    base.update({
+        "value": value, "ms_per_step": 1e3 * dt / K,
+        "config": {"workload": "same as the b200 arm (configs[3], batch 16), executed by the REFERENCE implementation: "
+                               "its CUDA kernels (oracle/_ref/libpn2_legacy.so, reference .cu compiled unchanged for sm_100a) "
+                               "+ the reference's op-by-op module composition with cuDNN 1x1 convs (torch defaults, "
+                               "cudnn.allow_tf32=%s) + per-scene host-greedy NMS, host buffers in / detections out"
+                               % torch.backends.cudnn.allow_tf32, "batch_per_gpu": B, "npoints": NPOINTS},
+        "cpu_baseline": dict(cpu, note="the reference has no CPU implementation of this path; `value` above is its "
+                                       "CUDA path on the same B200, this is the CPU port on the host cores"),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
+    print(json.dumps(base), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,48 @@ int pn2_three_interpolate_f32(const float *points, const int32_t *idx, const flo
 int pn2_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx, const float *weight, float *grad_points,
                                    int b, int c, int n, int m, void *stream);
 
+/* ---- roipool3d_cuda (pointrcnn/lib/utils/roipool3d/src/roipool3d.cpp:198-203) ---- */
+
+/* forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag)  roipool3d.cpp:17-45,
+ * kernels roipool3d_kernel.cu:97-232.  xyz (B,N,3), boxes3d (B,M,7) already enlarged
+ * (roipool3d_utils.py:18), feat (B,N,C) -> pooled (B,M,sampled,3+C) f32 and empty (B,M) int32,
+ * both pre-zeroed by the caller (roipool3d_utils.py:20-22).  Indices bit-exact. */
+int pn2_roipool3d_f32(const float *xyz, const float *boxes3d, const float *feat, float *pooled, int32_t *empty, int b,
+                      int n, int m, int c, int sampled, void *stream);
+
+/* ---- iou3d_cuda (pointrcnn/lib/utils/iou3d/src/iou3d.cpp:174-179) ---- */
+
+/* boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap)  iou3d.cpp:31-50, iou3d_kernel.cu:223-234.
+ * a (na,5), b (nb,5) [x1,y1,x2,y2,ry] -> out (na,nb) intersection area. */
+int pn2_boxes_overlap_bev_f32(const float *a, int na, const float *b, int nb, float *out, void *stream);
+/* boxes_iou_bev_gpu  iou3d.cpp:52-71, iou3d_kernel.cu:236-248. */
+int pn2_boxes_iou_bev_f32(const float *a, int na, const float *b, int nb, float *out, void *stream);
+/* nms_gpu / nms_normal_gpu (boxes, keep, thresh) -> num  iou3d.cpp:73-169 (mask kernels
+ * iou3d_kernel.cu:250-348 + host greedy pass), batched and device-resident: boxes
+ * (problems, stride, 5) sorted by descending score, problem p uses its first counts[p] boxes
+ * (counts NULL: n for all); keep (problems, max_keep) int64, num (problems) int32.
+ * max_keep = n gives the reference's full keep list; keep indices are bit-exact. */
+int pn2_nms_bev_f32(const float *boxes, int problems, int stride, int n, const int32_t *counts, float thresh,
+                    int rotated, int max_keep, long long *keep, int32_t *num, void *stream);
+
+/* ---- shared-MLP layers (pointnet2_lib/pointnet2/pytorch_utils.py:5-101 SharedMLP/Conv1d/Conv2d,
+ *      pointnet2_modules.py:37-48 group -> MLP -> max_pool2d), point-major activations ---- */
+
+/* Y[r,0:cout] = act(X[r,0:cin] . W[c,0:cin]^T + bias[c] [+ R[r,c]]), optional max over `pool`
+ * consecutive rows (pool = nsample: F.max_pool2d of pointnet2_modules.py:42).  Within 1e-4 rel
+ * of the cuDNN fp32 result. */
+int pn2_linear_f32(const float *x, int ldx, const float *w, int ldw, const float *bias, const float *res, int ldr,
+                   float *y, int ldy, long long rows, int cin, int cout, int relu, int pool, void *stream);
+/* QueryAndGroup.forward (pointnet2_utils.py:241-264) + SharedMLP layers 1 and 2 fused: the
+ * grouped tensor is never materialised.  h (clouds*n, ldh) = per-point part of layer 1. */
+int pn2_sa_group_linear_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                            const float *wxyz, const float *w, int ldw, const float *bias, float *y, int ldy, int clouds,
+                            int n, int m, int ns, int c1, int cout, int relu, int pool, void *stream);
+/* three_interpolate on point-major features (internal layout of the fused FP module,
+ * pointnet2_modules.py:139-149). */
+int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx, const float *weight, float *out,
+                                 int ldo, int b, int c, int m, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,73 @@ def roipool3d(xyz, feat, boxes_enlarged, sampled=512):
     lib().legacy_roipool3d(B, N, M, C, int(sampled), _p(xyz), _p(boxes_enlarged), _p(feat), _p(pooled), _p(empty))
     torch.cuda.synchronize()
     return pooled, empty
+
+
+# ------------------------------------------------------------------------------------------
+# The legacy-CUDA arm of bench.py (--impl reference): route the product's reference-shaped
+# Python modules (fused = False: the reference's own composition) onto the REFERENCE kernels.
+# Runs in its own process; nothing is restored.
+# ------------------------------------------------------------------------------------------
+def nms_reference(boxes, scores, thresh, normal, max_keep=None):
+    """iou3d_utils.py:56-87 as the reference executes it: sort on the device, mask kernel,
+    blocking D2H of the (n, n/64) u64 matrix, greedy pass on the host (C, like iou3d.cpp),
+    keep list re-uploaded."""
+    import numpy as np
+    from . import oracle as orc
+    order = scores.sort(0, descending=True)[1]
+    b = boxes[order].contiguous()
+    n = b.shape[0]
+    if n == 0:
+        return order[:0]
+    mask = nms_mask(b, thresh, normal=normal).cpu().numpy()
+    keep = np.zeros((n,), np.int64)
+    orc.lib().orc_nms_greedy_from_mask.restype = ctypes.c_int
+    k = orc.lib().orc_nms_greedy_from_mask(mask.ctypes.data_as(ctypes.c_void_p), n, keep.ctypes.data_as(ctypes.c_void_p))
+    return order[torch.from_numpy(keep[:k]).to(boxes.device)].contiguous()
+
+
+def install(pkg_name):
+    """Monkey-patch <pkg>.pointnet2_cuda / iou3d_utils / roipool3d_cuda to call libpn2_legacy.so."""
+    import importlib
+    L = lib()
+    p2 = importlib.import_module(pkg_name + ".pointnet2_cuda")
+    iu = importlib.import_module(pkg_name + ".iou3d_utils")
+    rp = importlib.import_module(pkg_name + ".roipool3d_cuda")
+
+    def fps_w(b, n, m, points, temp, idx):
+        L.legacy_fps(b, n, m, _p(points), _p(temp), _p(idx), _s()); return 1
+
+    def gather_w(b, c, n, npoints, points, idx, out):
+        L.legacy_gather(b, c, n, npoints, _p(points), _p(idx), _p(out), _s()); return 1
+
+    def bq_w(b, n, m, radius, nsample, new_xyz, xyz, idx):
+        L.legacy_ball_query(b, n, m, ctypes.c_float(radius), nsample, _p(new_xyz), _p(xyz), _p(idx), _s()); return 1
+
+    def group_w(b, c, n, npoints, nsample, points, idx, out):
+        L.legacy_group(b, c, n, npoints, nsample, _p(points), _p(idx), _p(out), _s()); return 1
+
+    def nn_w(b, n, m, unknown, known, dist2, idx):
+        L.legacy_three_nn(b, n, m, _p(unknown), _p(known), _p(dist2), _p(idx), _s())
+
+    def interp_w(b, c, m, n, points, idx, weight, out):
+        L.legacy_three_interpolate(b, c, m, n, _p(points), _p(idx), _p(weight), _p(out), _s())
+
+    p2.furthest_point_sampling_wrapper = fps_w
+    p2.gather_points_wrapper = gather_w
+    p2.ball_query_wrapper = bq_w
+    p2.group_points_wrapper = group_w
+    p2.three_nn_wrapper = nn_w
+    p2.three_interpolate_wrapper = interp_w
+
+    iu.nms_gpu = lambda boxes, scores, thresh, max_keep=None: nms_reference(boxes, scores, thresh, False)
+    iu.nms_normal_gpu = lambda boxes, scores, thresh, max_keep=None: nms_reference(boxes, scores, thresh, True)
+
+    def roipool_fw(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
+        B, N, _ = xyz.shape
+        # the reference launcher runs on the legacy default stream and cudaMallocs inside
+        torch.cuda.current_stream().synchronize()
+        L.legacy_roipool3d(B, N, boxes3d.size(1), pts_feature.size(2), pooled_features.size(2), _p(xyz), _p(boxes3d),
+                           _p(pts_feature), _p(pooled_features), _p(pooled_empty_flag))
+        return 1
+
+    rp.forward = roipool_fw

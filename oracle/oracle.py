@@ -20,6 +20,7 @@ def lib():
         _lib = ctypes.CDLL(build_ref.build_oracle())
         _lib.orc_opt_n_threads.restype = ctypes.c_int
         _lib.orc_nms_normal.restype = ctypes.c_int
+        _lib.orc_nms_rotated.restype = ctypes.c_int
     return _lib
 
 
@@ -140,3 +141,19 @@ def roipool3d(xyz, feat, boxes3d_enlarged, sampled=512, trig=None):
     lib().orc_roipool3d(px, pb, pf, pooled.ctypes.data_as(ctypes.c_void_p), empty.ctypes.data_as(ctypes.c_void_p), pt,
                         B, N, M, C, int(sampled))
     return pooled, empty
+
+
+# ---- geom_oracle.c: rotated BEV overlap / IoU / NMS (iou3d_kernel.cu + iou3d.cpp) ----
+def boxes_overlap_bev(a, b, iou=False):
+    a, pa = _f(a); b, pb = _f(b)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    lib().orc_boxes_overlap_bev(pa, a.shape[0], pb, b.shape[0], out.ctypes.data_as(ctypes.c_void_p), 1 if iou else 0)
+    return out
+
+
+def nms_rotated(boxes_sorted, thresh):
+    boxes, pb = _f(boxes_sorted)
+    n = boxes.shape[0]
+    keep = np.zeros((max(n, 1),), np.int64)
+    k = lib().orc_nms_rotated(pb, keep.ctypes.data_as(ctypes.c_void_p), n, ctypes.c_float(thresh))
+    return keep[:k].copy()

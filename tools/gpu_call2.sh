@@ -1,0 +1,13 @@
+#!/bin/bash
+# second GPU contact: all GPU parity tests, both bench arms, launch list of one bench step
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_b200.json 2> gpurun_out/bench_b200.err; echo "bench exit $?"
+cat gpurun_out/bench_b200.json; tail -5 gpurun_out/bench_b200.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"
+cat gpurun_out/bench_ref.json; tail -5 gpurun_out/bench_ref.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "ncu exit $?"
+tail -3 gpurun_out/bench_ncu.log
