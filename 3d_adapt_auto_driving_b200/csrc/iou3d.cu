@@ -16,9 +16,9 @@
 // mask + greedy formulation: box j is suppressed iff some kept i < j has iou(i, j) > thresh,
 // and iou(i, j) is evaluated with the same operand order (row box first).
 //
-// Overlap arithmetic: same formulas, same expression shapes and the same default FMA
-// contraction as the reference so that areas agree bit for bit (checked against the
-// reference kernels on the GPU, tests/test_iou3d_gpu.py).
+// Overlap arithmetic: same formulas with every rounding pinned by _rn intrinsics to what nvcc
+// emits for the reference source, so that areas agree bit for bit (checked against the
+// reference kernels on the GPU, tests/test_iou3d_roipool_gpu.py).
 #include "common.cuh"
 #include <math.h>
 
@@ -30,13 +30,25 @@ struct P2 {
     float x, y;
 };
 
+// Arithmetic pinning.  The bits of an overlap area depend on which products get fused into
+// FMAs when the reference source is compiled -- by nvcc's front end AND by ptxas, which fuses
+// non-.rn mul/sub pairs of the PTX.  Read from the SASS of the unmodified iou3d_kernel.cu (nvcc 12.9
+// -O2, sm_100a; oracle/_ref/libpn2_legacy.so) every "a*b - c*d" and "a*b + c*d" is executed as
+//   fma(a, b, -+rn(c*d))       (minuend product fused, the other product rounded first)
+// with one exception: s2 = cross(p1,q1,p0) and s5 = cross(q1,p1,p0) of a segment test share
+// their two products, which are therefore both rounded and then subtracted.  Centre +- terms
+// fused with *0.5 are exact either way.  Everything below is written with _rn intrinsics so
+// that no compiler version can contract or re-associate it differently.
+__device__ __forceinline__ float diffprod(float a, float b, float c, float d) {   // a*b - c*d as compiled
+    return __fmaf_rn(a, b, -__fmul_rn(c, d));
+}
 __device__ __forceinline__ float cross3(const P2 &p1, const P2 &p2, const P2 &p0) {
-    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+    return diffprod(__fsub_rn(p1.x, p0.x), __fsub_rn(p2.y, p0.y), __fsub_rn(p2.x, p0.x), __fsub_rn(p1.y, p0.y));
 }
 
 __device__ __forceinline__ bool boxes_apart(const P2 &p1, const P2 &p2, const P2 &q1, const P2 &q2) {
-    const bool touch = min(p1.x, p2.x) <= max(q1.x, q2.x) && min(q1.x, q2.x) <= max(p1.x, p2.x) &&
-                       min(p1.y, p2.y) <= max(q1.y, q2.y) && min(q1.y, q2.y) <= max(p1.y, p2.y);
+    const bool touch = fminf(p1.x, p2.x) <= fmaxf(q1.x, q2.x) && fminf(q1.x, q2.x) <= fmaxf(p1.x, p2.x) &&
+                       fminf(p1.y, p2.y) <= fmaxf(q1.y, q2.y) && fminf(q1.y, q2.y) <= fmaxf(p1.y, p2.y);
     return !touch;
 }
 
@@ -44,40 +56,46 @@ __device__ __forceinline__ bool boxes_apart(const P2 &p1, const P2 &p2, const P2
 __device__ __forceinline__ bool seg_intersect(const P2 &p1, const P2 &p0, const P2 &q1, const P2 &q0, P2 &ans) {
     if (boxes_apart(p0, p1, q0, q1)) return false;
     const float s1 = cross3(q0, p1, p0);
-    const float s2 = cross3(p1, q1, p0);
+    // s2 = (p1.x-p0.x)(q1.y-p0.y) - (q1.x-p0.x)(p1.y-p0.y) and s5 = -s2 share both products
+    const float pa = __fmul_rn(__fsub_rn(p1.x, p0.x), __fsub_rn(q1.y, p0.y));
+    const float pb = __fmul_rn(__fsub_rn(q1.x, p0.x), __fsub_rn(p1.y, p0.y));
+    const float s2 = __fsub_rn(pa, pb);
     const float s3 = cross3(p0, q1, q0);
     const float s4 = cross3(q1, p1, q0);
-    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return false;
-    const float s5 = cross3(q1, p1, p0);
-    if (fabsf(s5 - s1) > kEps) {
-        ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
-        ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    if (!(__fmul_rn(s1, s2) > 0 && __fmul_rn(s3, s4) > 0)) return false;
+    const float s5 = __fsub_rn(pb, pa);
+    const float den = __fsub_rn(s5, s1);
+    if (fabsf(den) > kEps) {
+        ans.x = __fdiv_rn(diffprod(s5, q0.x, s1, q1.x), den);
+        ans.y = __fdiv_rn(diffprod(s5, q0.y, s1, q1.y), den);
     } else {
-        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
-        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
-        const float D = a0 * b1 - a1 * b0;
-        ans.x = (b0 * c1 - b1 * c0) / D;
-        ans.y = (a1 * c0 - a0 * c1) / D;
+        const float a0 = __fsub_rn(p0.y, p1.y), b0 = __fsub_rn(p1.x, p0.x);
+        const float c0 = diffprod(p0.x, p1.y, p1.x, p0.y);
+        const float a1 = __fsub_rn(q0.y, q1.y), b1 = __fsub_rn(q1.x, q0.x);
+        const float c1 = diffprod(q0.x, q1.y, q1.x, q0.y);
+        const float D = diffprod(a0, b1, a1, b0);
+        ans.x = __fdiv_rn(diffprod(b0, c1, b1, c0), D);
+        ans.y = __fdiv_rn(diffprod(a1, c0, a0, c1), D);
     }
     return true;
+}
+
+// rotation about a centre with the reference's rounding
+__device__ __forceinline__ void spin(const P2 &c, float angle_cos, float angle_sin, P2 &p) {
+    const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y);
+    p.x = __fadd_rn(__fmaf_rn(angle_cos, dx, __fmul_rn(angle_sin, dy)), c.x);
+    p.y = __fadd_rn(diffprod(angle_cos, dy, angle_sin, dx), c.y);
 }
 
 // point inside the (un-rotated extent of the) box after rotating it back (iou3d_kernel.cu:50-64)
 __device__ __forceinline__ bool inside_box(const float *box, const P2 &p) {
     const float margin = 1e-5f;
-    const float center_x = (box[0] + box[2]) / 2;
-    const float center_y = (box[1] + box[3]) / 2;
-    const float angle_cos = cosf(-box[4]), angle_sin = sinf(-box[4]);
-    const float rot_x = (p.x - center_x) * angle_cos + (p.y - center_y) * angle_sin + center_x;
-    const float rot_y = -(p.x - center_x) * angle_sin + (p.y - center_y) * angle_cos + center_y;
-    return rot_x > box[0] - margin && rot_x < box[2] + margin && rot_y > box[1] - margin && rot_y < box[3] + margin;
-}
-
-__device__ __forceinline__ void spin(const P2 &c, float angle_cos, float angle_sin, P2 &p) {
-    const float nx = (p.x - c.x) * angle_cos + (p.y - c.y) * angle_sin + c.x;
-    const float ny = -(p.x - c.x) * angle_sin + (p.y - c.y) * angle_cos + c.y;
-    p.x = nx;
-    p.y = ny;
+    P2 c, q = p;
+    c.x = __fmul_rn(__fadd_rn(box[0], box[2]), 0.5f);
+    c.y = __fmul_rn(__fadd_rn(box[1], box[3]), 0.5f);
+    spin(c, cosf(-box[4]), sinf(-box[4]), q);
+    return q.x > __fsub_rn(box[0], margin) && q.x < __fadd_rn(box[2], margin) && q.y > __fsub_rn(box[1], margin) &&
+           q.y < __fadd_rn(box[3], margin);
 }
 
 // intersection area of two rotated rectangles [x1,y1,x2,y2,angle] (iou3d_kernel.cu:108-212)
@@ -85,8 +103,8 @@ __device__ float rot_overlap(const float *box_a, const float *box_b) {
     const float ax1 = box_a[0], ay1 = box_a[1], ax2 = box_a[2], ay2 = box_a[3], aang = box_a[4];
     const float bx1 = box_b[0], by1 = box_b[1], bx2 = box_b[2], by2 = box_b[3], bang = box_b[4];
     P2 ca, cb;
-    ca.x = (ax1 + ax2) / 2; ca.y = (ay1 + ay2) / 2;
-    cb.x = (bx1 + bx2) / 2; cb.y = (by1 + by2) / 2;
+    ca.x = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f); ca.y = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+    cb.x = __fmul_rn(__fadd_rn(bx1, bx2), 0.5f); cb.y = __fmul_rn(__fadd_rn(by1, by2), 0.5f);
     P2 A[5], B[5];
     A[0] = {ax1, ay1}; A[1] = {ax2, ay1}; A[2] = {ax2, ay2}; A[3] = {ax1, ay2};
     B[0] = {bx1, by1}; B[1] = {bx2, by1}; B[2] = {bx2, by2}; B[3] = {bx1, by2};
@@ -106,28 +124,28 @@ __device__ float rot_overlap(const float *box_a, const float *box_b) {
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j)
             if (seg_intersect(A[i + 1], A[i], B[j + 1], B[j], poly[cnt])) {
-                centre.x = centre.x + poly[cnt].x;
-                centre.y = centre.y + poly[cnt].y;
+                centre.x = __fadd_rn(centre.x, poly[cnt].x);
+                centre.y = __fadd_rn(centre.y, poly[cnt].y);
                 ++cnt;
             }
     for (int k = 0; k < 4; ++k) {
         if (inside_box(box_a, B[k])) {
-            centre.x = centre.x + B[k].x;
-            centre.y = centre.y + B[k].y;
+            centre.x = __fadd_rn(centre.x, B[k].x);
+            centre.y = __fadd_rn(centre.y, B[k].y);
             poly[cnt++] = B[k];
         }
         if (inside_box(box_b, A[k])) {
-            centre.x = centre.x + A[k].x;
-            centre.y = centre.y + A[k].y;
+            centre.x = __fadd_rn(centre.x, A[k].x);
+            centre.y = __fadd_rn(centre.y, A[k].y);
             poly[cnt++] = A[k];
         }
     }
-    centre.x /= cnt;
-    centre.y /= cnt;
+    centre.x = __fdiv_rn(centre.x, (float)cnt);
+    centre.y = __fdiv_rn(centre.y, (float)cnt);
     // order the vertices by polar angle about the centroid: the same adjacent-swap passes as
     // the reference (:187-196), with each vertex's atan2f evaluated once instead of per compare
     float ang[16];
-    for (int i = 0; i < cnt; ++i) ang[i] = atan2f(poly[i].y - centre.y, poly[i].x - centre.x);
+    for (int i = 0; i < cnt; ++i) ang[i] = atan2f(__fsub_rn(poly[i].y, centre.y), __fsub_rn(poly[i].x, centre.x));
     for (int j = 0; j < cnt - 1; ++j)
         for (int i = 0; i < cnt - j - 1; ++i)
             if (ang[i] > ang[i + 1]) {
@@ -136,29 +154,29 @@ __device__ float rot_overlap(const float *box_a, const float *box_b) {
             }
     float area = 0;
     for (int k = 0; k < cnt - 1; ++k) {
-        const float ux = poly[k].x - poly[0].x, uy = poly[k].y - poly[0].y;
-        const float vx = poly[k + 1].x - poly[0].x, vy = poly[k + 1].y - poly[0].y;
-        area += ux * vy - uy * vx;
+        const float ux = __fsub_rn(poly[k].x, poly[0].x), uy = __fsub_rn(poly[k].y, poly[0].y);
+        const float vx = __fsub_rn(poly[k + 1].x, poly[0].x), vy = __fsub_rn(poly[k + 1].y, poly[0].y);
+        area = __fadd_rn(area, diffprod(ux, vy, uy, vx));
     }
-    return fabsf(area) / 2.0f;
+    return __fmul_rn(fabsf(area), 0.5f);
 }
 
 __device__ __forceinline__ float rot_iou(const float *a, const float *b) {
-    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
-    const float sb = (b[2] - b[0]) * (b[3] - b[1]);
+    const float sb = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
     const float s = rot_overlap(a, b);
-    return s / fmaxf(sa + sb - s, kEps);
+    const float uni = __fsub_rn(__fmaf_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]), sb), s);
+    return __fdiv_rn(s, fmaxf(uni, kEps));
 }
 
-// iou3d_kernel.cu:295-303
+// iou3d_kernel.cu:295-303 as compiled inside nms_normal_kernel (the row box's area is the plain product)
 __device__ __forceinline__ float flat_iou(const float *a, const float *b) {
     const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
     const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
-    const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
-    const float inter = width * height;
-    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
-    const float sb = (b[2] - b[0]) * (b[3] - b[1]);
-    return inter / fmaxf(sa + sb - inter, kEps);
+    const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
+    const float inter = __fmul_rn(width, height);
+    const float sa = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
+    const float uni = __fsub_rn(__fmaf_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]), sa), inter);
+    return __fdiv_rn(inter, fmaxf(uni, kEps));
 }
 
 template <bool IOU>

@@ -1,0 +1,151 @@
+// tc_common.cuh -- raw-PTX building blocks for the tcgen05 (5th-gen tensor core) kernels:
+// mbarrier, TMEM allocation, UMMA shared-memory / instruction descriptors, tcgen05.mma /
+// commit / ld / st, proxy fences, and the 128-byte-swizzle K-major operand layout.
+// sm_100a only.  No CUTLASS: everything below is the PTX the hardware guide
+// (/opt/skills/guides/blackwell_cuda_programming.md) and cute/arch/mma_sm100_desc.hpp describe.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace tc {
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pn2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pn2_smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must abort the kernel (launch error on the next sync), never hang
+// the GPU.  The limit is ~2 s of SM clock, far beyond any legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = pn2_smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spin & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// named barrier among a subset of warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------ TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // whole warp, ncols pow2 >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pn2_smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ------------------------------------------------------------------ descriptors
+// K-major operand tile, 128-byte swizzle: rows of 128 B (64 bf16 along K), 8-row groups of 1 KB,
+// the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  SBO = 1024 B between
+// 8-row groups, LBO unused (one swizzle atom along K), descriptor version 1 (sm_100),
+// layout type 2 = SWIZZLE_128B (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // LBO (ignored)  [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // SBO            [32,46)
+    d |= (uint64_t)1 << 46;                              // version = 1    [46,48)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B   [61,64)
+    return d;
+}
+// byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a [rows][64 bf16] swizzled tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+    return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4));
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4)                       // c_format  = F32
+           | (1u << 7)                     // a_format  = BF16
+           | (1u << 10)                    // b_format  = BF16
+           | ((uint32_t)(n >> 3) << 17)    // n_dim
+           | ((uint32_t)(m >> 4) << 24);   // m_dim
+}
+
+// ------------------------------------------------------------------ MMA issue (one thread)
+// D[tmem] (+)= A[smem] . B[smem]^T   (both operands K-major)
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T   (A: lane = row, 32-bit column j holds k = 2j (low half), 2j+1)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all prior tcgen05.mma of this thread complete -> arrive on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(pn2_smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ TMEM <-> registers
+// 32 lanes x 32 bit, 16 consecutive columns: thread t of warp w reads lane 32*(w%4)+t
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ bf16 hi/lo split
+// x = hi + lo + O(2^-17 |x|): hi = bf16(x), lo = bf16(x - hi).  Packs two values per 32-bit
+// word with the FIRST (lower k) value in the low half, the order the MMA reads K in.
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+}  // namespace tc

@@ -5,6 +5,8 @@ weight folding/packing caches, output allocation.  No arithmetic is done in torc
 three_nn weight normalisation, which the reference itself does in torch
 (pointnet2_modules.py:140-142).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -30,8 +32,22 @@ def _rows2d(x):
     return x2, x2.shape[0], (x2.stride(0) if x2.shape[0] > 1 else max(c, x2.stride(0))), c
 
 
+# Which engine runs the shared-MLP layers: "tc" = tcgen05 tensor cores with BF16x3 split operands
+# (default; ~1e-5 of the tensor scale per layer), "ffma" = exact-fp32 CUDA-core kernels.
+MLP_ENGINE = os.environ.get("PN2_MLP", "tc")
+_TC_POOLS = (1, 16, 32, 64, 128)
+
+
+def set_mlp_engine(name):
+    global MLP_ENGINE
+    if name not in ("tc", "ffma"):
+        raise ValueError(name)
+    MLP_ENGINE = name
+
+
 class PackedLayer:
-    """Folded (conv + eval BN) layer: w (cout, kpad) zero-padded to a multiple of 4, bias, relu."""
+    """Folded (conv + eval BN) layer: w (cout, kpad) zero-padded to a multiple of 4, bias, relu;
+    `.tc` is the same layer packed for the tensor-core kernel (built on first use)."""
 
     def __init__(self, w, b, relu):
         cout, cin = w.shape
@@ -39,6 +55,13 @@ class PackedLayer:
         wp = torch.zeros((cout, kpad), dtype=torch.float32, device=w.device)
         wp[:, :cin] = w
         self.w, self.b, self.relu, self.cin, self.cout, self.ldw = wp, b.contiguous(), bool(relu), cin, cout, kpad
+        self._tc = None
+
+    @property
+    def tc(self):
+        if self._tc is None:
+            self._tc = PackedLayerTC(self.w[:, :self.cin], self.b, self.relu)
+        return self._tc
 
     @staticmethod
     def from_block(block):
@@ -57,6 +80,9 @@ def pack_sequential(seq):
 
 def linear(x, layer, out=None, pool=1, res=None, relu=None):
     """y = act(x @ W^T + b [+ res]) on rows; x (rows, cin) view, out optional (rows/pool, cout) view."""
+    use_relu = layer.relu if relu is None else relu
+    if MLP_ENGINE == "tc" and pool in _TC_POOLS and (pool == 1 or use_relu):
+        return linear_tc(x, layer.tc, out=out, pool=pool, res=res, relu=use_relu)
     x2, rows, ldx, cin = _rows2d(x)
     if cin != layer.cin:
         raise cabi.Pn2Error("linear: input has %d channels, layer expects %d" % (cin, layer.cin))
@@ -80,6 +106,8 @@ def linear(x, layer, out=None, pool=1, res=None, relu=None):
 
 def sa_group_linear(h, idx, xyz, centres, wxyz, layer, out=None, pool=1):
     """second SA layer with the gather + split first layer fused in (pn2_sa_group_linear_f32)."""
+    if MLP_ENGINE == "tc" and pool in _TC_POOLS and (pool == 1 or layer.relu) and layer.cin <= 512:
+        return sa_group_linear_tc(h, idx, xyz, centres, wxyz, layer.tc, out=out, pool=pool)
     B, M, ns = idx.shape
     N = xyz.shape[1]
     h2, hrows, ldh, c1 = _rows2d(h)
@@ -125,3 +153,83 @@ def fps_gather(xyz, npoint):
               work=16.0 * B * max(npoint - 1, 0) * N)
     new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     return idx, new_xyz
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) path: weights split into bf16 hi/lo and pre-arranged in the exact shared
+# memory image the MMA reads (linear_tc.cu): [nchunks][nkb][hi tile | lo tile], each tile
+# ntile rows x 64 bf16 (128 B), 16-byte chunk c of row r stored at chunk position c ^ (r & 7).
+# ---------------------------------------------------------------------------------------------
+def tc_tiling(cout):
+    """-> (ntile, nchunks): UMMA N (multiple of 16, <= 256) and the number of N chunks."""
+    if cout <= 256:
+        return (cout + 15) // 16 * 16, 1
+    nchunks = (cout + 255) // 256
+    per = (cout + nchunks - 1) // nchunks
+    return (per + 15) // 16 * 16, nchunks
+
+
+def pack_tc(w):
+    """w (cout, cin) f32 -> (blob uint8 tensor, ntile, nchunks, nkb)."""
+    cout, cin = w.shape
+    ntile, nchunks = tc_tiling(cout)
+    nkb = (cin + 63) // 64
+    wp = torch.zeros((nchunks * ntile, nkb * 64), dtype=torch.float32, device=w.device)
+    wp[:cout, :cin] = w
+    hi = wp.to(torch.bfloat16)
+    lo = (wp - hi.float()).to(torch.bfloat16)
+    both = torch.stack((hi, lo), dim=0)                                      # (2, N, K)
+    t = both.view(2, nchunks, ntile // 8, 8, nkb, 8, 8)                       # (h, chunk, grp, r, kb, c, e)
+    r = torch.arange(8, device=w.device).view(8, 1)
+    c = torch.arange(8, device=w.device).view(1, 8)
+    src_c = (c ^ r)                                                          # position p holds chunk p ^ r
+    t = torch.gather(t, 5, src_c.view(1, 1, 1, 8, 1, 8, 1).expand(2, nchunks, ntile // 8, 8, nkb, 8, 8))
+    blob = t.permute(1, 4, 0, 2, 3, 5, 6).contiguous()                       # (chunk, kb, h, grp, r, pos, e)
+    return blob.view(torch.uint8).reshape(-1), ntile, nchunks, nkb
+
+
+class PackedLayerTC:
+    def __init__(self, w, b, relu):
+        self.cout, self.cin = w.shape
+        self.blob, self.ntile, self.nchunks, self.nkb = pack_tc(w)
+        self.b, self.relu = b.contiguous(), bool(relu)
+
+
+def linear_tc(x, layer, out=None, pool=1, res=None, relu=None):
+    """tensor-core twin of linear(): y = act(x @ W^T + b [+ res]) [max over pool rows]."""
+    x2, rows, ldx, cin = _rows2d(x)
+    if cin != layer.cin:
+        raise cabi.Pn2Error("linear_tc: input has %d channels, layer expects %d" % (cin, layer.cin))
+    if rows % pool:
+        raise cabi.Pn2Error("linear_tc: rows not divisible by pool")
+    if out is None:
+        out = torch.empty((rows // pool, layer.cout), dtype=torch.float32, device=x.device)
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == rows // pool and oc == layer.cout
+    rp, ldr = ptr(None), 0
+    if res is not None:
+        r2, rrows, ldr, rc = _rows2d(res)
+        assert rrows == rows and rc == layer.cout
+        rp = ptr(r2)
+    use_relu = layer.relu if relu is None else relu
+    cabi.call("pn2_linear_tc_f32", ptr(x2), i32(ldx), ptr(layer.blob), i32(layer.ntile), i32(layer.nchunks),
+              i32(layer.nkb), ptr(layer.b), rp, i32(ldr), ptr(o2), i32(ldy), _i64(rows), i32(cin), i32(layer.cout),
+              i32(1 if use_relu else 0), i32(pool), work=2.0 * rows * cin * layer.cout)
+    return out
+
+
+def sa_group_linear_tc(h, idx, xyz, centres, wxyz, layer, out=None, pool=1):
+    B, M, ns = idx.shape
+    N = xyz.shape[1]
+    h2, hrows, ldh, c1 = _rows2d(h)
+    assert hrows == B * N and c1 == layer.cin
+    rows = B * M * ns
+    if out is None:
+        out = torch.empty((rows // pool, layer.cout), dtype=torch.float32, device=h.device)
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == rows // pool and oc == layer.cout
+    cabi.call("pn2_sa_group_linear_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz),
+              ptr(layer.blob), i32(layer.ntile), i32(layer.nchunks), i32(layer.nkb), ptr(layer.b), ptr(o2), i32(ldy),
+              i32(B), i32(N), i32(M), i32(ns), i32(c1), i32(layer.cout), i32(1 if layer.relu else 0), i32(pool),
+              work=2.0 * rows * c1 * (layer.cout + 3))
+    return out

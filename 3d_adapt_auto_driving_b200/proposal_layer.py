@@ -1,7 +1,16 @@
 """Mirror of pointrcnn/lib/rpn/proposal_layer.py: ProposalLayer.forward / distance_based_proposal
-/ score_based_proposal.  Decoding and band selection are the reference's torch statements; the
-NMS runs on the device and stops after the post-NMS quota (the reference computes the full
-keep list on the host and then slices it, proposal_layer.py:107-112 -- same first-k result)."""
+/ score_based_proposal.  Decoding is the reference's torch statements (bit-identical boxes).
+
+Two execution paths with identical results:
+  * `fused = False`: the reference's control flow -- Python loop over scenes and depth bands,
+    boolean-mask indexing (a host synchronisation each), one NMS call per band;
+  * default on CUDA: the whole batch at once and without any host synchronisation.  Band
+    membership becomes a rank by a cumulative sum along the score-sorted order, the first
+    6300 / 2700 members of each band are scattered into fixed-width candidate arrays with
+    device-side counts, one batched device NMS per band (pn2_nms_bev_f32, one CTA per scene,
+    stops at the post-NMS quota of 70 / 30) and a final scatter assembles the zero-padded
+    (B, 100, 7) ROIs.  The reference computes full keep lists on the host and slices them
+    (proposal_layer.py:107-112): same first-k result."""
 import torch
 import torch.nn as nn
 
@@ -18,6 +27,7 @@ class ProposalLayer(nn.Module):
         self.MEAN_SIZE = torch.from_numpy(cfg.CLS_MEAN_SIZE[0])
         if torch.cuda.is_available():
             self.MEAN_SIZE = self.MEAN_SIZE.cuda()
+        self.fused = True
 
     def forward(self, rpn_scores, rpn_reg, xyz):
         """rpn_scores (B,N), rpn_reg (B,N,C), xyz (B,N,3) -> rois (B,M,7), roi scores (B,M)."""
@@ -31,6 +41,8 @@ class ProposalLayer(nn.Module):
 
         scores = rpn_scores
         _, sorted_idxs = torch.sort(scores, dim=1, descending=True)
+        if self.fused and scores.is_cuda and cfg.TEST.RPN_DISTANCE_BASED_PROPOSE and cfg.RPN.NMS_TYPE in ('normal', 'rotate'):
+            return self._forward_batched(scores, proposals, sorted_idxs)
         top_n = cfg[self.mode].RPN_POST_NMS_TOP_N
         ret_bbox3d = scores.new_zeros((batch_size, top_n, 7))
         ret_scores = scores.new_zeros((batch_size, top_n))
@@ -43,6 +55,60 @@ class ProposalLayer(nn.Module):
             ret_bbox3d[k, :tot] = p
             ret_scores[k, :tot] = s
         return ret_bbox3d, ret_scores
+
+    def _forward_batched(self, scores, proposals, order):
+        """distance_based_proposal (proposal_layer.py:58-119) for all scenes, sync-free."""
+        from . import iou3d_cuda
+        B, N = scores.shape
+        dev = scores.device
+        pre_tot = cfg[self.mode].RPN_PRE_NMS_TOP_N
+        post_tot = cfg[self.mode].RPN_POST_NMS_TOP_N
+        pre_n = [int(pre_tot * 0.7), pre_tot - int(pre_tot * 0.7)]
+        post_n = [int(post_tot * 0.7), post_tot - int(post_tot * 0.7)]
+        thresh = cfg[self.mode].RPN_NMS_THRESH
+        rotated = cfg.RPN.NMS_TYPE == 'rotate'
+
+        s_ord = torch.gather(scores, 1, order)                                           # (B,N) descending
+        p_ord = torch.gather(proposals, 1, order.unsqueeze(-1).expand(-1, -1, 7))         # (B,N,7)
+        dist = p_ord[:, :, 2]
+        near = (dist > 0) & (dist <= 40.0)
+        far = (dist > 40.0) & (dist <= 80.0)
+        near_rank = torch.cumsum(near, dim=1) - 1                                        # rank inside the band
+        far_rank = torch.cumsum(far, dim=1) - 1
+        far_total = far_rank[:, -1:] + 1
+        # an empty far band borrows the near-band candidates that follow the near quota (:92-100)
+        borrow = far_total == 0
+        far_sel = torch.where(borrow, near & (near_rank >= pre_n[0]), far)
+        far_rank = torch.where(borrow, near_rank - pre_n[0], far_rank)
+
+        outs = []
+        for sel, rank, pre, post in ((near, near_rank, pre_n[0], post_n[0]), (far_sel, far_rank, pre_n[1], post_n[1])):
+            take = sel & (rank < pre)
+            cnt = take.sum(dim=1).to(torch.int32)                                        # (B,) on the device
+            slot = torch.where(take, rank, torch.full_like(rank, pre))                   # dump slot = pre
+            cand = p_ord.new_zeros((B, pre + 1, 7))
+            cand.scatter_(1, slot.unsqueeze(-1).expand(-1, -1, 7), p_ord)
+            cs = s_ord.new_zeros((B, pre + 1))
+            cs.scatter_(1, slot, s_ord)
+            cand, cs = cand[:, :pre].contiguous(), cs[:, :pre]
+            bev = kitti_utils.boxes3d_to_bev_torch(cand.view(-1, 7)).view(B, pre, 5).contiguous()
+            keep, num = iou3d_cuda.nms_device(bev, thresh, rotated=rotated, max_keep=post, counts=cnt)
+            outs.append((cand, cs, keep, num.to(torch.int64)))
+
+        ret_bbox3d = scores.new_zeros((B, post_tot + 1, 7))
+        ret_scores = scores.new_zeros((B, post_tot + 1))
+        base = torch.zeros((B, 1), dtype=torch.int64, device=dev)
+        for (cand, cs, keep, num), post in zip(outs, post_n):
+            ar = torch.arange(post, device=dev).unsqueeze(0)
+            valid = ar < num.unsqueeze(1)
+            keep = torch.where(valid, keep, torch.zeros_like(keep))
+            kb = torch.gather(cand, 1, keep.unsqueeze(-1).expand(-1, -1, 7))
+            ks = torch.gather(cs, 1, keep)
+            dst = torch.where(valid, base + ar, torch.full_like(keep, post_tot))          # dump slot = post_tot
+            ret_bbox3d.scatter_(1, dst.unsqueeze(-1).expand(-1, -1, 7), kb)
+            ret_scores.scatter_(1, dst, ks)
+            base = base + num.unsqueeze(1)
+        return ret_bbox3d[:, :post_tot].contiguous(), ret_scores[:, :post_tot].contiguous()
 
     def _nms(self, boxes_bev, scores, keep_n):
         thresh = cfg[self.mode].RPN_NMS_THRESH

@@ -180,6 +180,16 @@ def run_b200(args):
         det.detect_device(resident[i % 4])
     torch.cuda.synchronize()
 
+    if args.minimal:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(K):
+            det.detect_device(resident[i % 4])
+        e.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"minimal": True, "ms_per_step": s.elapsed_time(e) / K, "steps": K}), flush=True)
+        return
+
     # which C-ABI kernel dominates a step (one profiled step, untimed)
     cabi.profile_start()
     det.detect_device(resident[0])
@@ -363,6 +373,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--minimal", action="store_true",
+                    help="warm-up + timed steps only (no profiled step, e2e or CPU legs): the command ncu wraps")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

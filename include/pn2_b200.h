@@ -124,6 +124,16 @@ int pn2_sa_group_linear_f32(const float *h, int ldh, const int32_t *idx, const f
 int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx, const float *weight, float *out,
                                  int ldo, int b, int c, int m, int n, void *stream);
 
+/* ---- the same shared-MLP layers on the tcgen05 tensor cores (BF16x3 split, fp32 accumulation in
+ *      TMEM); wblob is the host-packed weight image described in csrc/linear_tc.cu ---- */
+int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
+                      const float *res, int ldr, float *y, int ldy, long long rows, int cin, int cout, int relu,
+                      int pool, void *stream);
+int pn2_sa_group_linear_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                               const float *wxyz, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
+                               float *y, int ldy, int clouds, int n, int m, int ns, int c1, int cout, int relu, int pool,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,9 +5,10 @@
  * TEST INFRASTRUCTURE ONLY (tests/, __graft_entry__.smoke(), bench.py cpu_baseline /
  * --impl reference).  The product never links this file.
  *
- * Float expressions use explicit fmaf() where nvcc 12.9 contracts the reference source
- * (a*b - c*d -> fma(a, b, -(c*d)); a*b + c*d -> fma(a, b, c*d)); build with
- * -ffp-contract=off.  sinf/cosf/atan2f come from the host libm, which can differ from the
+ * Float expressions use explicit fmaf() exactly where the COMPILED reference fuses (nvcc front
+ * end + ptxas; read from the SASS of oracle/_ref/libpn2_legacy.so): a*b -+ c*d runs as
+ * fma(a, b, -+rn(c*d)) everywhere except the s2 / s5 pair of a segment test, whose two shared
+ * products are rounded first.  Build with -ffp-contract=off.  sinf/cosf/atan2f come from the host libm, which can differ from the
  * CUDA math library in the last ulp: the pin (tests/test_golden_cpu.py) therefore checks
  * areas against the reference-kernel goldens to 5e-5 m^2 (the shoelace sum amplifies the trig ulp),
  * the zero pattern and the NMS keep lists exactly.
@@ -19,12 +20,15 @@
 
 typedef struct { float x, y; } Pt;
 
+/* a*b - c*d as the compiled reference executes it (SASS of the unmodified kernel): the minuend
+ * product is fused, the other product is rounded first */
+static inline float diffprod(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }
+
 static const float EPS = 1e-8f;
 
 /* iou3d_kernel.cu:38-40 cross(p1, p2, p0) */
 static inline float cross3(Pt p1, Pt p2, Pt p0) {
-    const float t = (p2.x - p0.x) * (p1.y - p0.y);
-    return fmaf(p1.x - p0.x, p2.y - p0.y, -t);
+    return diffprod(p1.x - p0.x, p2.y - p0.y, p2.x - p0.x, p1.y - p0.y);
 }
 
 /* iou3d_kernel.cu:42-48 */
@@ -40,25 +44,27 @@ static inline int check_in_box2d(const float *box, Pt p) {
     const float angle_cos = cosf(-box[4]), angle_sin = sinf(-box[4]);
     const float dx = p.x - center_x, dy = p.y - center_y;
     const float rot_x = fmaf(dx, angle_cos, dy * angle_sin) + center_x;
-    const float rot_y = fmaf(-dx, angle_sin, dy * angle_cos) + center_y;
+    const float rot_y = diffprod(angle_cos, dy, angle_sin, dx) + center_y;
     return rot_x > box[0] - MARGIN && rot_x < box[2] + MARGIN && rot_y > box[1] - MARGIN && rot_y < box[3] + MARGIN;
 }
 
 /* iou3d_kernel.cu:66-96 */
 static inline int intersection(Pt p1, Pt p0, Pt q1, Pt q0, Pt *ans) {
     if (!check_rect_cross(p0, p1, q0, q1)) return 0;
-    const float s1 = cross3(q0, p1, p0), s2 = cross3(p1, q1, p0), s3 = cross3(p0, q1, q0), s4 = cross3(q1, p1, q0);
+    /* s2 and s5 = -s2 share their two products: both rounded, then subtracted */
+    const float pa = (p1.x - p0.x) * (q1.y - p0.y), pb = (q1.x - p0.x) * (p1.y - p0.y);
+    const float s1 = cross3(q0, p1, p0), s2 = pa - pb, s3 = cross3(p0, q1, q0), s4 = cross3(q1, p1, q0);
     if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
-    const float s5 = cross3(q1, p1, p0);
+    const float s5 = pb - pa;
     if (fabsf(s5 - s1) > EPS) {
-        ans->x = fmaf(s5, q0.x, -(s1 * q1.x)) / (s5 - s1);
-        ans->y = fmaf(s5, q0.y, -(s1 * q1.y)) / (s5 - s1);
+        ans->x = diffprod(s5, q0.x, s1, q1.x) / (s5 - s1);
+        ans->y = diffprod(s5, q0.y, s1, q1.y) / (s5 - s1);
     } else {
-        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = fmaf(p0.x, p1.y, -(p1.x * p0.y));
-        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = fmaf(q0.x, q1.y, -(q1.x * q0.y));
-        const float D = fmaf(a0, b1, -(a1 * b0));
-        ans->x = fmaf(b0, c1, -(b1 * c0)) / D;
-        ans->y = fmaf(a1, c0, -(a0 * c1)) / D;
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = diffprod(p0.x, p1.y, p1.x, p0.y);
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = diffprod(q0.x, q1.y, q1.x, q0.y);
+        const float D = diffprod(a0, b1, a1, b0);
+        ans->x = diffprod(b0, c1, b1, c0) / D;
+        ans->y = diffprod(a1, c0, a0, c1) / D;
     }
     return 1;
 }
@@ -68,7 +74,7 @@ static inline Pt rotate_around_center(Pt c, float angle_cos, float angle_sin, Pt
     const float dx = p.x - c.x, dy = p.y - c.y;
     Pt r;
     r.x = fmaf(dx, angle_cos, dy * angle_sin) + c.x;
-    r.y = fmaf(-dx, angle_sin, dy * angle_cos) + c.y;
+    r.y = diffprod(angle_cos, dy, angle_sin, dx) + c.y;
     return r;
 }
 
@@ -117,17 +123,16 @@ float orc_box_overlap(const float *box_a, const float *box_b) {
     for (int k = 0; k < cnt - 1; ++k) {
         const float ux = cp[k].x - cp[0].x, uy = cp[k].y - cp[0].y;
         const float vx = cp[k + 1].x - cp[0].x, vy = cp[k + 1].y - cp[0].y;
-        area += fmaf(ux, vy, -(uy * vx));
+        area += diffprod(ux, vy, uy, vx);
     }
     return (float)(fabs((double)area) / 2.0);
 }
 
 /* iou3d_kernel.cu:214-221 iou_bev */
 float orc_iou_bev(const float *a, const float *b) {
-    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
     const float sb = (b[2] - b[0]) * (b[3] - b[1]);
     const float s = orc_box_overlap(a, b);
-    return s / fmaxf(sa + sb - s, EPS);
+    return s / fmaxf(fmaf(a[2] - a[0], a[3] - a[1], sb) - s, EPS);
 }
 
 /* boxes_overlap_kernel :223-234 / boxes_iou_bev_kernel :236-248 */
