@@ -23,20 +23,20 @@
 //               one cp.async.bulk (TMA bulk copy) per stage on the same mbarrier.
 // The accumulator is double-buffered in TMEM (2 x N <= 512 columns), so the epilogue of tile i
 // overlaps the main loop of tile i+1.
-#include "tc_common.cuh"
+#include "tc_producer.cuh"
+#include "tc_epilogue.cuh"
 
 namespace {
 using namespace tc;
 
-constexpr int BM = 128;          // rows per tile = UMMA M
-constexpr int BK = 64;           // bf16 per K-block row = one 128-byte swizzle atom
-constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 8;
+constexpr int BM = kBM;          // rows per tile = UMMA M
+constexpr int BK = kBK;          // bf16 per K-block row = one 128-byte swizzle atom
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;
-constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kMetaWarp = kEpiWarps + 1;
+constexpr int kFirstProdWarp = kEpiWarps + 2;
+constexpr int kThreads = (kEpiWarps + 2 + kProdWarps) * 32;   // 26 warps
 constexpr int kMaxStages = 4;
-constexpr int kABytes = BM * BK * 2;  // one bf16 A tile (hi or lo) = 16 KB
+constexpr int kABytes = kTileBytes;   // one bf16 A tile (hi or lo) = 16 KB
 constexpr int kStgLd = 17;            // epilogue staging row stride (floats)
 
 struct TcParams {
@@ -50,11 +50,6 @@ struct TcParams {
     int vec_ok;             // rows of x are 16-byte aligned (ldx % 4 == 0, base aligned)
 };
 
-struct RowMeta {
-    int src;                // source row of x, or -1 (row beyond the end: zeros)
-    float dx, dy, dz;
-};
-
 // shared memory carve-up (dynamic, 1024-aligned base)
 struct SmemLayout {
     uint32_t stage_bytes, off_meta, off_wx, off_bias, off_stg, off_part, off_bars, off_tmem, total;
@@ -63,19 +58,19 @@ __host__ __device__ inline SmemLayout make_layout(int ntile, int stages, int kpa
     SmemLayout L;
     L.stage_bytes = 2 * kABytes + 2 * ntile * 128;
     uint32_t o = L.stage_bytes * stages;
-    L.off_meta = o; o += 2 * BM * sizeof(RowMeta);
+    L.off_meta = o; o += gather ? kMetaDepth * BM * sizeof(RowMeta) : 0;
     L.off_wx = o;   o += gather ? 3 * kpad * 4 : 0;
     L.off_bias = o; o += 256 * 4;
-    L.off_stg = o;  o += kEpiWarps * 32 * kStgLd * 4;
-    L.off_part = o; o += 8 * 256 * 4;
-    L.off_bars = o; o += (2 * kMaxStages + 4) * 8;
+    L.off_stg = o;  L.off_part = o;   // staging (un-pooled store) and partial maxima (pooled) share space
+    o += (kEpiWarps * 32 * kStgLd * 4 > 8 * 256 * 4) ? kEpiWarps * 32 * kStgLd * 4 : 8 * 256 * 4;
+    L.off_bars = o; o += (2 * kMaxStages + 4 + 2 * kMetaDepth) * 8;
     L.off_tmem = o; o += 16;
     L.total = o;
     return L;
 }
 
 template <bool GATHER>
-__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const TcParams p) {
+__global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled operand tiles need 1 KB alignment in the shared window (1 KB of slack is allocated)
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -86,16 +81,22 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const TcParams p
     uint64_t *empty = full + kMaxStages;
     uint64_t *acc_full = empty + kMaxStages;
     uint64_t *acc_empty = acc_full + 2;
+    uint64_t *meta_full = acc_empty + 2;
+    uint64_t *meta_empty = meta_full + kMetaDepth;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_tmem);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], kProdWarps + 1);
+            mbar_init(&full[s], kGroupWarps + 1);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], kEpiWarps);
+        }
+        for (int q = 0; q < kMetaDepth; ++q) {
+            mbar_init(&meta_full[q], 1);
+            mbar_init(&meta_empty[q], kProdWarps);
         }
         fence_barrier_init();
     }
@@ -112,149 +113,30 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const TcParams p
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= kMmaWarp + 1) {
-        // =============================== producers ===============================
-        const int ptid = threadIdx.x - (kMmaWarp + 1) * 32;   // 0..255
-        const int pw = ptid >> 5;
-        const int rsub = pw * 2 + (lane >> 4);                 // row within a 16-row pass
-        const int kq = (lane & 15) * 4;                        // first k of this thread's float4 in a K-block
-        RowMeta *meta = reinterpret_cast<RowMeta *>(smem + L.off_meta);
-        const float *wxs = reinterpret_cast<const float *>(smem + L.off_wx);
+    ProducerArgs pa;
+    pa.x = p.x; pa.ldx = p.ldx; pa.cin = p.cin; pa.rows = p.rows; pa.vec_ok = p.vec_ok;
+    pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
+    pa.nkb = p.nkb; pa.stages = p.stages; pa.nchunks = p.nchunks; pa.items = p.items;
+    pa.ring = smem; pa.stage_bytes = L.stage_bytes; pa.full = full; pa.empty = empty;
+    pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad;
 
-        auto fill_meta = [&](long long item, int buf) {
-            if (ptid < BM) {
-                RowMeta mt;
-                mt.src = -1; mt.dx = mt.dy = mt.dz = 0.f;
-                if (item < p.items) {
-                    const long long r = (item / p.nchunks) * BM + ptid;
-                    if (r < p.rows) {
-                        if (GATHER) {
-                            const long long centre = r / p.ns, cloud = centre / p.m;
-                            const int j = __ldg(p.idx + r);
-                            const long long src = cloud * p.n + j;
-                            const float *pj = p.xyz + src * 3, *pc = p.centres + centre * 3;
-                            mt.src = (int)src;
-                            mt.dx = __ldg(pj) - __ldg(pc);
-                            mt.dy = __ldg(pj + 1) - __ldg(pc + 1);
-                            mt.dz = __ldg(pj + 2) - __ldg(pc + 2);
-                        } else {
-                            mt.src = (int)r;
-                        }
-                    }
-                }
-                meta[buf * BM + ptid] = mt;
-            }
-        };
-        // flat sequence of steps t = (item iteration, kb); loads run two steps ahead of stores
-        const long long first = blockIdx.x, stride = gridDim.x;
-        const long long my_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
-        const long long total_steps = my_items * p.nkb;
-
-        float4 areg0[8], areg1[8];   // two K-blocks of loads in flight; kept in registers (static slot)
-        auto issue_loads = [&](long long t, float4 (&areg)[8]) {
-            const long long it = t / p.nkb;
-            const int kb = (int)(t % p.nkb);
-            const RowMeta *mt = meta + (it & 1) * BM;
-            const int k = kb * BK + kq;
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int src = mt[ps * 16 + rsub].src;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src >= 0 && k < p.cin) {
-                    const float *px = p.x + (long long)src * p.ldx + k;
-                    if (p.vec_ok && k + 3 < p.cin) {
-                        v = __ldg(reinterpret_cast<const float4 *>(px));
-                    } else {
-                        v.x = __ldg(px);
-                        if (k + 1 < p.cin) v.y = __ldg(px + 1);
-                        if (k + 2 < p.cin) v.z = __ldg(px + 2);
-                        if (k + 3 < p.cin) v.w = __ldg(px + 3);
-                    }
-                }
-                areg[ps] = v;
-            }
-        };
-
-        if (my_items > 0) {
-            fill_meta(first, 0);
-            fill_meta(first + stride, 1);
-            named_bar_sync(1, kProdThreads);
-            issue_loads(0, areg0);
-            if (total_steps > 1) issue_loads(1, areg1);
-        }
-        int stage = 0;
-        uint32_t phase = 0;
-        auto do_step = [&](long long t, float4 (&areg)[8]) {
-            const long long it = t / p.nkb;
-            const int kb = (int)(t % p.nkb);
-            const long long item = first + it * stride;
-            uint8_t *sbase = smem + (size_t)stage * L.stage_bytes;
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (ptid == 0) {
-                // weight K-block: one bulk copy, completes on the same barrier as the A rows
-                const uint32_t bytes = 2u * p.ntile * 128u;
-                const uint8_t *src = p.wblob + ((size_t)(item % p.nchunks) * p.nkb + kb) * bytes;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(&full[stage])),
-                             "r"(bytes)
-                             : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        pn2_smem_u32(sbase + 2 * kABytes)),
-                    "l"(src), "r"(bytes), "r"(pn2_smem_u32(&full[stage]))
-                    : "memory");
-            }
-            // transform + store this thread's 8 row segments
-            const RowMeta *mt = meta + (it & 1) * BM;
-            const int k = kb * BK + kq;
-            float4 w0, w1, w2;
-            if (GATHER) {
-                w0 = *reinterpret_cast<const float4 *>(wxs + k);
-                w1 = *reinterpret_cast<const float4 *>(wxs + kpad + k);
-                w2 = *reinterpret_cast<const float4 *>(wxs + 2 * kpad + k);
-            }
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int r = ps * 16 + rsub;
-                float4 v = areg[ps];
-                if (GATHER) {
-                    const RowMeta q = mt[r];
-                    if (q.src >= 0) {
-                        v.x = fmaxf(fmaf(w2.x, q.dz, fmaf(w1.x, q.dy, fmaf(w0.x, q.dx, v.x))), 0.f);
-                        v.y = fmaxf(fmaf(w2.y, q.dz, fmaf(w1.y, q.dy, fmaf(w0.y, q.dx, v.y))), 0.f);
-                        v.z = fmaxf(fmaf(w2.z, q.dz, fmaf(w1.z, q.dy, fmaf(w0.z, q.dx, v.z))), 0.f);
-                        v.w = fmaxf(fmaf(w2.w, q.dz, fmaf(w1.w, q.dy, fmaf(w0.w, q.dx, v.w))), 0.f);
-                        if (k + 3 >= p.cin) {   // zero the K padding again (bias-like terms must not leak)
-                            if (k + 0 >= p.cin) v.x = 0.f;
-                            if (k + 1 >= p.cin) v.y = 0.f;
-                            if (k + 2 >= p.cin) v.z = 0.f;
-                            v.w = 0.f;
-                        }
-                    }
-                }
-                uint2 hi, lo;
-                split2(v.x, v.y, hi.x, lo.x);
-                split2(v.z, v.w, hi.y, lo.y);
-                const uint32_t off = sw128_offset(r, (lane & 15) >> 1) + ((lane & 1) << 3);
-                *reinterpret_cast<uint2 *>(sbase + off) = hi;
-                *reinterpret_cast<uint2 *>(sbase + kABytes + off) = lo;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[stage]);
-            // refill: loads of step t+2; at an item boundary publish the meta of the item after next
-            if (kb == p.nkb - 1) {
-                // every producer is done reading meta[it&1] once it passes this barrier
-                named_bar_sync(1, kProdThreads);
-                fill_meta(first + (it + 2) * stride, (int)(it & 1));
-                named_bar_sync(1, kProdThreads);
-            }
-            if (t + 2 < total_steps) issue_loads(t + 2, areg);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        };
-        for (long long t = 0; t < total_steps; t += 2) {
-            do_step(t, areg0);
-            if (t + 1 < total_steps) do_step(t + 1, areg1);
-        }
+    if (warp >= kFirstProdWarp) {
+        // =============================== producers (tc_producer.cuh) ===============================
+        const uint32_t bbytes = 2u * p.ntile * 128u;
+        producer_run<GATHER>(pa, (int)threadIdx.x - kFirstProdWarp * 32, [&](long long item, int kb, int stage) {
+            // weight K-block: one bulk copy (TMA), completes on the same barrier as the A rows
+            const uint8_t *src = p.wblob + ((size_t)(item % p.nchunks) * p.nkb + kb) * bbytes;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(&full[stage])),
+                         "r"(bbytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             pn2_smem_u32(smem + (size_t)stage * L.stage_bytes + 2 * kABytes)),
+                         "l"(src), "r"(bbytes), "r"(pn2_smem_u32(&full[stage]))
+                         : "memory");
+        });
+    } else if (warp == kMetaWarp) {
+        if (GATHER) meta_run(pa, lane);
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
@@ -292,11 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const TcParams p
         }
         __syncwarp();
     } else {
-        // =============================== epilogue ===============================
+        // =============================== epilogue (tc_epilogue.cuh) ===============================
         float *bias_s = reinterpret_cast<float *>(smem + L.off_bias);
         float *stg = reinterpret_cast<float *>(smem + L.off_stg) + warp * 32 * kStgLd;
         float *part = reinterpret_cast<float *>(smem + L.off_part);
-        const int etid = threadIdx.x;   // 0..127
+        const int etid = threadIdx.x;   // 0..255
+        const int q = warp & 3, half = warp >> 2;
         long long it = 0;
         int cur_chunk = -1;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -305,82 +188,54 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const TcParams p
             const int chunk = (int)(item % p.nchunks);
             const int col_base = chunk * p.ntile;
             if (chunk != cur_chunk) {
-                named_bar_sync(2, kEpiWarps * 32);
-                for (int c = etid; c < p.ntile; c += kEpiWarps * 32)
+                named_bar_sync(2, kEpiThreads);
+                for (int c = etid; c < p.ntile; c += kEpiThreads)
                     bias_s[c] = (p.bias && col_base + c < p.cout) ? __ldg(p.bias + col_base + c) : 0.f;
-                named_bar_sync(2, kEpiWarps * 32);
+                named_bar_sync(2, kEpiThreads);
                 cur_chunk = chunk;
             }
             mbar_wait(&acc_full[a], (uint32_t)((it >> 1) & 1));
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.ntile);
-            const long long row0 = tile * BM + warp * 32;
-            for (int c0 = 0; c0 < p.ntile; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                if (p.pool <= 1) {
-                    // transpose through shared memory: lane = row  ->  lanes = 2 rows x 16 columns
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.ntile);
+            const long long row0 = tile * BM + q * 32;
+            if (p.pool > 1) {
+                pool_tile(taddr, p.ntile, half, bias_s, row0 + lane < p.rows, p.pool, lane, q, part);
+            } else {
+                // 16-column chunks: transpose through shared memory (lane = row -> lanes = 2 rows x 16
+                // columns) so that every store instruction writes two full 64-byte row segments
+                for (int c0 = half * 16; c0 < p.ntile; c0 += 32) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) stg[lane * kStgLd + j] = __uint_as_float(v[j]);
                     __syncwarp();
                     const int cc = lane & 15;
                     const int col = col_base + c0 + cc;
                     const float bj = bias_s[c0 + cc];
+                    if (col < p.cout) {
 #pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = i * 2 + (lane >> 4);
-                        const long long r = row0 + rr;
-                        if (r < p.rows && col < p.cout) {
-                            float o = stg[rr * kStgLd + cc] + bj;
-                            if (p.res) o += __ldg(p.res + r * p.ldr + col);
-                            if (p.relu) o = fmaxf(o, 0.f);
-                            p.y[r * p.ldy + col] = o;
+                        for (int i = 0; i < 16; ++i) {
+                            const int rr = i * 2 + (lane >> 4);
+                            const long long r = row0 + rr;
+                            if (r < p.rows) {
+                                float o = stg[rr * kStgLd + cc] + bj;
+                                if (p.res) o += __ldg(p.res + r * p.ldr + col);
+                                if (p.relu) o = fmaxf(o, 0.f);
+                                p.y[r * p.ldy + col] = o;
+                            }
                         }
                     }
                     __syncwarp();
-                } else {
-                    // max over the rows of a group; values are >= 0 after ReLU so the float order is
-                    // the unsigned order of the bits (redux.sync has no float form on sm_100)
-                    const bool live = row0 + lane < p.rows;
-                    uint32_t mine = 0u;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float o = fmaxf(__uint_as_float(v[j]) + bias_s[c0 + j], 0.f);
-                        const uint32_t u = live ? __float_as_uint(o) : 0u;
-                        uint32_t mx;
-                        if (p.pool == 16) {
-                            const uint32_t lo16 = __reduce_max_sync(0xffffffffu, lane < 16 ? u : 0u);
-                            const uint32_t hi16 = __reduce_max_sync(0xffffffffu, lane >= 16 ? u : 0u);
-                            mx = (lane & 16) ? hi16 : lo16;
-                        } else {
-                            mx = __reduce_max_sync(0xffffffffu, u);
-                        }
-                        if ((lane & 15) == j) mine = mx;
-                    }
-                    // lane j (< 16) holds column c0+j of segment 0, lane 16+j of segment 1 (pool 16)
-                    if (p.pool == 16) part[(warp * 2 + (lane >> 4)) * 256 + c0 + (lane & 15)] = __uint_as_float(mine);
-                    else if (lane < 16) part[warp * 256 + c0 + lane] = __uint_as_float(mine);
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
             if (p.pool > 1) {
-                named_bar_sync(2, kEpiWarps * 32);
-                const int groups = BM / p.pool;                    // per tile: 8, 4, 2 or 1
-                const int parts_per_group = p.pool <= 32 ? 1 : p.pool / 32;
-                for (int e = etid; e < groups * p.ntile; e += kEpiWarps * 32) {
-                    const int g = e / p.ntile, c = e % p.ntile;
-                    const long long orow = tile * groups + g;
-                    if (orow * p.pool >= p.rows || col_base + c >= p.cout) continue;
-                    float mx = 0.f;
-                    if (p.pool == 16) mx = part[g * 256 + c];
-                    else
-                        for (int q = 0; q < parts_per_group; ++q) mx = fmaxf(mx, part[(g * parts_per_group + q) * 256 + c]);
-                    p.y[orow * p.ldy + col_base + c] = mx;
-                }
-                named_bar_sync(2, kEpiWarps * 32);
+                named_bar_sync(2, kEpiThreads);
+                pool_combine(part, p.pool, p.ntile, tile, p.rows, p.cout, col_base, p.y, p.ldy, etid);
+                named_bar_sync(2, kEpiThreads);
             }
         }
     }

@@ -1,0 +1,341 @@
+// sa_fused_tc.cu -- one whole set-abstraction MLP per kernel on the tcgen05 tensor cores, sm_100a.
+//
+// Replaces, for one (SA module, scale), the reference chain
+//   QueryAndGroup (pointnet2_utils.py:241-264)  ->  SharedMLP layer 1, 2, 3 (pytorch_utils.py:5-101)
+//   ->  F.max_pool2d over nsample (pointnet2_modules.py:42)
+// given the per-point half of layer 1 (H = W1f f + b1, one small GEMM over the SOURCE points).
+// Nothing between the gathered H rows and the pooled (centres, c3) output touches HBM: for RCNN
+// SA1 at batch 16 the two (13.1 M x 128) fp32 activations of the layer-by-layer path (6.7 GB
+// written + 6.7 GB read each) never exist.
+//
+// Per 128-row tile (= 128 / nsample centres), one persistent CTA per SM:
+//   meta warp            row metadata (source row, xyz offset to the centre) a few tiles ahead;
+//   producers (16 warps) gather H rows, add the xyz half of layer 1, ReLU, split to bf16 hi/lo,
+//                        store the layer-2 operand K-block by K-block into a swizzled smem ring;
+//   MMA thread           layer 2:  acc2[b] (TMEM) = A1 (smem) x W2 (smem, resident), BF16x3;
+//                        layer 3:  acc3   (TMEM) = A2 (TMEM)  x W3 (smem, resident), BF16x3;
+//                        the layer-2 MMAs of tile i+1 are issued before layer 3 of tile i so the
+//                        tensor pipe works while the epilogue converts tile i;
+//   epilogue (8 warps)   E2: tcgen05.ld acc2 -> +b2, ReLU, bf16 hi/lo -> tcgen05.st into the TMEM
+//                            A-operand region of layer 3 (the activation never leaves the SM);
+//                        E3: tcgen05.ld acc3 -> +b3, ReLU -> max over nsample rows (redux.sync on
+//                            the non-negative float bits) -> pooled output.
+// TMEM columns: acc2[0] | acc2[1] | A2.hi | A2.lo | acc3  =  3 * N2 + N3 <= 512.
+// Shared memory: W2 and W3 (pre-split, pre-swizzled by fused.pack_tc) resident, a 2-4 stage ring
+// of 32 KB operand K-blocks.
+#include "tc_producer.cuh"
+#include "tc_epilogue.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int BM = kBM;
+constexpr int BK = kBK;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kMetaWarp = kEpiWarps + 1;
+constexpr int kFirstProdWarp = kEpiWarps + 2;
+constexpr int kThreads = (kEpiWarps + 2 + kProdWarps) * 32;   // 26 warps
+constexpr int kMaxStages = 4;
+constexpr int kABytes = kTileBytes;
+
+struct SaParams {
+    const float *h; int ldh; int c1;
+    const int32_t *idx; const float *xyz; const float *centres; const float *wxyz;
+    int n, m, ns;
+    long long rows, tiles;
+    const uint8_t *w2blob; int n2, nkb1;     // layer 2: N = n2 (multiple of 16), K-blocks of c1
+    const uint8_t *w3blob; int n3, nkb2;     // layer 3: N = n3, K-blocks of c2
+    const float *b2; const float *b3; int c2, c3;
+    float *y; int ldy;
+    int stages, dbuf;
+};
+
+struct SmemLayout {
+    uint32_t off_w2, off_w3, off_ring, off_meta, off_wx, off_bias, off_part, off_bars, off_tmem, total;
+};
+__host__ __device__ inline SmemLayout make_layout(const SaParams &p, int stages) {
+    SmemLayout L;
+    uint32_t o = 0;
+    L.off_w2 = o;   o += (uint32_t)p.nkb1 * 2u * p.n2 * 128u;
+    L.off_w3 = o;   o += (uint32_t)p.nkb2 * 2u * p.n3 * 128u;
+    L.off_ring = o; o += (uint32_t)stages * 2u * kABytes;
+    L.off_meta = o; o += kMetaDepth * BM * sizeof(RowMeta);
+    L.off_wx = o;   o += 3u * p.nkb1 * BK * 4u;
+    L.off_bias = o; o += 2 * 256 * 4;
+    L.off_part = o; o += 8 * 256 * 4;
+    L.off_bars = o; o += (2 * kMaxStages + 8 + 2 * kMetaDepth) * 8;
+    L.off_tmem = o; o += 16;
+    L.total = o;
+    return L;
+}
+
+__global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kpad = p.nkb1 * BK;
+    const SmemLayout L = make_layout(p, p.stages);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+    uint64_t *empty = full + kMaxStages;
+    uint64_t *acc2_full = empty + kMaxStages;   // [2]
+    uint64_t *acc2_empty = acc2_full + 2;       // [2]
+    uint64_t *a2_full = acc2_empty + 2;
+    uint64_t *a2_empty = a2_full + 1;
+    uint64_t *acc3_full = a2_empty + 1;
+    uint64_t *acc3_empty = acc3_full + 1;
+    uint64_t *meta_full = acc3_empty + 1;
+    uint64_t *meta_empty = meta_full + kMetaDepth;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_tmem);
+    uint64_t *w_full = reinterpret_cast<uint64_t *>(smem + L.off_tmem + 8);
+
+    const uint32_t w2_bytes = (uint32_t)p.nkb1 * 2u * p.n2 * 128u;
+    const uint32_t w3_bytes = (uint32_t)p.nkb2 * 2u * p.n3 * 128u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], kGroupWarps);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc2_full[a], 1);
+            mbar_init(&acc2_empty[a], kEpiWarps);
+        }
+        mbar_init(a2_full, kEpiWarps);
+        mbar_init(a2_empty, 1);
+        mbar_init(acc3_full, 1);
+        mbar_init(acc3_empty, kEpiWarps);
+        mbar_init(w_full, 1);
+        for (int q = 0; q < kMetaDepth; ++q) {
+            mbar_init(&meta_full[q], 1);
+            mbar_init(&meta_empty[q], kProdWarps);
+        }
+        fence_barrier_init();
+        // resident weights: two bulk copies, one barrier
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(w_full)),
+                     "r"(w2_bytes + w3_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pn2_smem_u32(smem + L.off_w2)),
+                     "l"(p.w2blob), "r"(w2_bytes), "r"(pn2_smem_u32(w_full))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pn2_smem_u32(smem + L.off_w3)),
+                     "l"(p.w3blob), "r"(w3_bytes), "r"(pn2_smem_u32(w_full))
+                     : "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+    {
+        float *wxs = reinterpret_cast<float *>(smem + L.off_wx);
+        for (int i = threadIdx.x; i < 3 * kpad; i += kThreads) {
+            const int c = i / kpad, k = i % kpad;
+            wxs[i] = k < p.c1 ? __ldg(p.wxyz + c * p.c1 + k) : 0.f;
+        }
+        float *bias_s = reinterpret_cast<float *>(smem + L.off_bias);
+        for (int i = threadIdx.x; i < 512; i += kThreads) {
+            const int c = i & 255;
+            bias_s[i] = i < 256 ? (c < p.c2 ? __ldg(p.b2 + c) : 0.f) : (c < p.c3 ? __ldg(p.b3 + c) : 0.f);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t col_acc2 = 0;
+    const uint32_t col_a2 = (uint32_t)(p.dbuf ? 2 : 1) * p.n2;   // hi at col_a2, lo at col_a2 + n2/2
+    const uint32_t col_acc3 = col_a2 + p.n2;
+
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_tiles = first < p.tiles ? (p.tiles - first + stride - 1) / stride : 0;
+
+    ProducerArgs pa;
+    pa.x = p.h; pa.ldx = p.ldh; pa.cin = p.c1; pa.rows = p.rows;
+    pa.vec_ok = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.h) & 15) == 0);
+    pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
+    pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = p.tiles;
+    pa.ring = smem + L.off_ring; pa.stage_bytes = 2 * kABytes; pa.full = full; pa.empty = empty;
+    pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad;
+
+    if (warp >= kFirstProdWarp) {
+        // =============================== producers (tc_producer.cuh) ===============================
+        producer_run<true>(pa, (int)threadIdx.x - kFirstProdWarp * 32, [](long long, int, int) {});
+    } else if (warp == kMetaWarp) {
+        meta_run(pa, lane);
+    } else if (warp == kMmaWarp) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && my_tiles > 0) {
+            const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
+            const uint32_t idesc3 = make_idesc_bf16(BM, p.n3);
+            const uint32_t w2a = pn2_smem_u32(smem + L.off_w2), w3a = pn2_smem_u32(smem + L.off_w3);
+            int stage = 0;
+            uint32_t phase = 0;
+            mbar_wait(w_full, 0);
+            auto issue_m2 = [&](long long it) {
+                const int b = p.dbuf ? (int)(it & 1) : 0;
+                const uint32_t use = p.dbuf ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(&acc2_empty[b], (use & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d = tmem_base + col_acc2 + (uint32_t)b * p.n2;
+                for (int kb = 0; kb < p.nkb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t sa = pn2_smem_u32(smem + L.off_ring + (size_t)stage * 2 * kABytes);
+                    const uint64_t a_hi = make_smem_desc_sw128(sa), a_lo = make_smem_desc_sw128(sa + kABytes);
+                    const uint32_t wb = w2a + (uint32_t)kb * 2u * p.n2 * 128u;
+                    const uint64_t b_hi = make_smem_desc_sw128(wb), b_lo = make_smem_desc_sw128(wb + p.n2 * 128u);
+                    const int krem = p.c1 - kb * BK;
+                    const int ksteps = krem >= BK ? 4 : (krem + 15) >> 4;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        mma_ss(d, a_hi + adv, b_hi + adv, idesc2, (kb | ks) ? 1u : 0u);
+                        mma_ss(d, a_hi + adv, b_lo + adv, idesc2, 1u);
+                        mma_ss(d, a_lo + adv, b_hi + adv, idesc2, 1u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc2_full[b]);
+            };
+            if (p.dbuf) issue_m2(0);
+            for (long long it = 0; it < my_tiles; ++it) {
+                if (p.dbuf) {
+                    if (it + 1 < my_tiles) issue_m2(it + 1);
+                } else {
+                    issue_m2(it);
+                }
+                // layer 3: A2 (TMEM, written by the epilogue) x W3
+                mbar_wait(a2_full, (uint32_t)(it & 1));
+                mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d3 = tmem_base + col_acc3;
+                const uint32_t a2hi = tmem_base + col_a2, a2lo = a2hi + (uint32_t)(p.n2 >> 1);
+                const int ksteps3 = p.c2 >> 4;
+                for (int ks = 0; ks < ksteps3; ++ks) {
+                    const uint32_t wb = w3a + (uint32_t)(ks >> 2) * 2u * p.n3 * 128u;
+                    const uint64_t adv = (uint64_t)((ks & 3) * 2);
+                    const uint64_t b_hi = make_smem_desc_sw128(wb) + adv;
+                    const uint64_t b_lo = make_smem_desc_sw128(wb + p.n3 * 128u) + adv;
+                    mma_ts(d3, a2hi + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
+                    mma_ts(d3, a2hi + ks * 8, b_lo, idesc3, 1u);
+                    mma_ts(d3, a2lo + ks * 8, b_hi, idesc3, 1u);
+                }
+                mma_commit(acc3_full);
+                mma_commit(a2_empty);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue (tc_epilogue.cuh) ===============================
+        const float *bias2 = reinterpret_cast<const float *>(smem + L.off_bias);
+        const float *bias3 = bias2 + 256;
+        float *part = reinterpret_cast<float *>(smem + L.off_part);
+        const int etid = threadIdx.x;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (long long it = 0; it < my_tiles; ++it) {
+            const long long tile = first + it * stride;
+            const int b = p.dbuf ? (int)(it & 1) : 0;
+            const uint32_t use = p.dbuf ? (uint32_t)(it >> 1) : (uint32_t)it;
+            // ---- E2: acc2 -> bias, ReLU, bf16 hi/lo -> TMEM operand of layer 3 ----
+            mbar_wait(&acc2_full[b], use & 1);
+            mbar_wait(a2_empty, (uint32_t)(it & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t t_acc2 = lane_addr + col_acc2 + (uint32_t)b * p.n2;
+            const uint32_t t_hi = lane_addr + col_a2, t_lo = t_hi + (uint32_t)(p.n2 >> 1);
+            for (int c0 = half * 16; c0 < p.n2; c0 += 32) {
+                uint32_t v[16];
+                tmem_ld16(t_acc2 + c0, v);
+                tmem_ld_wait();
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float x0 = fmaxf(__uint_as_float(v[2 * j]) + bias2[c0 + 2 * j], 0.f);
+                    const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bias2[c0 + 2 * j + 1], 0.f);
+                    split2(x0, x1, hi[j], lo[j]);
+                }
+                tmem_st8(t_hi + (c0 >> 1), hi);
+                tmem_st8(t_lo + (c0 >> 1), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(a2_full);
+                mbar_arrive(&acc2_empty[b]);
+            }
+            // ---- E3: acc3 -> bias, ReLU -> max over the nsample rows of each centre ----
+            mbar_wait(acc3_full, (uint32_t)(it & 1));
+            tc_fence_after_sync();
+            const long long row0 = tile * BM + q * 32;
+            pool_tile(lane_addr + col_acc3, p.n3, half, bias3, row0 + lane < p.rows, p.ns, lane, q, part);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc3_empty);
+            named_bar_sync(2, kEpiThreads);
+            pool_combine(part, p.ns, p.n3, tile, p.rows, p.c3, 0, p.y, p.ldy, etid);
+            named_bar_sync(2, kEpiThreads);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+// One SA scale, layers 1(pair-wise half) + 2 + 3 + max over nsample, fully on chip.
+//   h (clouds*n, ldh): per-point half of layer 1 (bias / BN folded in), c1 channels
+//   idx (clouds, m, ns) from ball_query; xyz (clouds, n, 3); centres (clouds, m, 3); wxyz (3, c1)
+//   w2blob / w3blob: fused.pack_tc images of W2 (c2 x c1) and W3 (c3 x c2); n2 / n3 their padded N
+//   y (clouds*m, ldy) columns [0, c3): pooled output.  Both layers are ReLU layers.
+// Supported: ns in {16, 32, 64, 128}; c2 a multiple of 16; 2*n2 + n3 <= 512 TMEM columns; weights +
+// a 2-stage operand ring within 227 KB of shared memory.  Returns PN2_ERR_UNSUPPORTED otherwise
+// (callers fall back to the layer-by-layer kernels).
+PN2_API int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                                const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2,
+                                const void *w3blob, int n3, int nkb2, const float *b3, float *y, int ldy, int clouds,
+                                int n, int m, int ns, int c1, int c2, int c3, cudaStream_t stream) {
+    if (!h || !idx || !xyz || !centres || !wxyz || !w2blob || !w3blob || !b2 || !b3 || !y || clouds < 0 || n <= 0 ||
+        m < 0 || c1 <= 0 || c2 <= 0 || c3 <= 0 || ldh < c1 || ldy < c3 || (long long)clouds * n > 2147483647LL) {
+        pn2_set_last_error("pn2_sa_fused_tc_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (!(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || n2 < c2 || n3 < c3 || (n2 & 15) || (n3 & 15) ||
+        n2 > 256 || n3 > 256 || nkb1 * BK < c1 || nkb2 * BK < c2 || 2 * n2 + n3 > 512 || n2 != c2) {
+        pn2_set_last_error("pn2_sa_fused_tc_f32: unsupported shape");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    SaParams p = {};
+    p.h = h; p.ldh = ldh; p.c1 = c1; p.idx = idx; p.xyz = xyz; p.centres = centres; p.wxyz = wxyz;
+    p.n = n; p.m = m; p.ns = ns;
+    p.rows = (long long)clouds * m * ns;
+    p.tiles = (p.rows + BM - 1) / BM;
+    p.w2blob = static_cast<const uint8_t *>(w2blob); p.n2 = n2; p.nkb1 = nkb1;
+    p.w3blob = static_cast<const uint8_t *>(w3blob); p.n3 = n3; p.nkb2 = nkb2;
+    p.b2 = b2; p.b3 = b3; p.c2 = c2; p.c3 = c3; p.y = y; p.ldy = ldy;
+    p.dbuf = (3 * n2 + n3 <= 512) ? 1 : 0;
+    if (p.rows == 0) return PN2_OK;
+    int stages = kMaxStages;
+    SmemLayout L = make_layout(p, stages);
+    while (stages > 2 && L.total + 1024 > 227 * 1024) L = make_layout(p, --stages);
+    if (L.total + 1024 > 227 * 1024) {
+        pn2_set_last_error("pn2_sa_fused_tc_f32: weights do not fit in shared memory");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    p.stages = stages;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(sa_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long grid = p.tiles < sms ? p.tiles : sms;
+    sa_fused_tc_kernel<<<(unsigned)grid, kThreads, L.total + 1024, stream>>>(p);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

@@ -1,0 +1,211 @@
+// tc_producer.cuh -- the operand producer shared by the tcgen05 shared-MLP kernels.
+//
+// Sixteen producer warps turn fp32 activation rows in global memory (plain rows, or rows gathered
+// through ball-query indices with the xyz half of the first SA layer and its ReLU applied on the
+// fly) into the bf16 hi/lo, 128-byte-swizzled K-major tiles the MMA reads from shared memory.
+//
+// The design target is memory-level parallelism: a 128 x 64 K-block is 32 KB of fp32 and the
+// tensor pipe consumes one every ~770 cycles, against ~1500 cycles of L2/HBM latency.  Two groups
+// of eight warps fill two ring stages concurrently, each thread with 8 x 16 B of loads in
+// flight in registers (the register file, otherwise idle in a TMEM-accumulator kernel, is the
+// landing zone: 64 KB outstanding per SM) and no shared-memory staging.
+// Row metadata for gathered tiles (source row, xyz offset to the centre) is produced by a
+// separate meta warp running up to four tiles ahead through its own mbarrier ring, so the
+// dependent idx -> xyz loads never sit on the producers' critical path.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int kBM = 128;               // rows per tile (UMMA M)
+constexpr int kBK = 64;                // bf16 per K-block row (one 128-byte swizzle atom)
+constexpr int kTileBytes = kBM * kBK * 2;   // one bf16 operand tile (hi or lo): 16 KB
+constexpr int kProdWarps = 16;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kMetaDepth = 4;          // tiles of row metadata in flight
+
+struct RowMeta {
+    int src;                           // source row of x, or -1 (row beyond the end: zeros)
+    float dx, dy, dz;
+};
+
+struct ProducerArgs {
+    const float *x; int ldx; int cin; long long rows; int vec_ok;
+    const int32_t *idx; const float *xyz; const float *centres; int n, m, ns;   // gather only
+    int nkb, stages, nchunks;
+    long long items;                   // work items of the whole grid; item -> tile = item / nchunks
+    uint8_t *ring; uint32_t stage_bytes;   // A.hi at ring + s * stage_bytes, A.lo kTileBytes after it
+    uint64_t *full, *empty;            // per stage
+    RowMeta *meta; uint64_t *meta_full, *meta_empty;   // [kMetaDepth] x kBM, gather only
+    const float *wxs; int kpad;        // (3, kpad) xyz coefficients of layer 1 in shared memory
+};
+
+// volatile 16-byte shared load (so the compiler re-reads instead of pinning 12 registers)
+__device__ __forceinline__ void lds128(const float *p, float4 &v) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(pn2_smem_u32(p)));
+}
+
+// ---- meta warp (gather only): RowMeta of tile `it` into slot it % kMetaDepth ----
+__device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
+    const long long first = blockIdx.x, stride = gridDim.x;
+    long long it = 0;
+    for (long long item = first; item < a.items; item += stride, ++it) {
+        const int slot = (int)(it % kMetaDepth);
+        mbar_wait(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1);
+        const long long row0 = (item / a.nchunks) * kBM;
+#pragma unroll
+        for (int q = 0; q < kBM / 32; ++q) {
+            const int r = q * 32 + lane;
+            const long long row = row0 + r;
+            RowMeta mt;
+            mt.src = -1; mt.dx = mt.dy = mt.dz = 0.f;
+            if (row < a.rows) {
+                const long long centre = row / a.ns, cloud = centre / a.m;
+                const int j = __ldg(a.idx + row);
+                const long long src = cloud * a.n + j;
+                const float *pj = a.xyz + src * 3, *pc = a.centres + centre * 3;
+                mt.src = (int)src;
+                mt.dx = __ldg(pj) - __ldg(pc);
+                mt.dy = __ldg(pj + 1) - __ldg(pc + 1);
+                mt.dz = __ldg(pj + 2) - __ldg(pc + 2);
+            }
+            a.meta[slot * kBM + r] = mt;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a.meta_full[slot]);
+    }
+}
+
+// ---- producer warps.  hook(item, kb, stage) runs on the first thread of the group that owns the
+//      step once the stage is free (linear_tc.cu launches the weight K-block's bulk copy there).
+//
+// The sixteen warps form kGroups = 2 groups that take alternate K-block steps, so two ring stages
+// are being filled concurrently and a warp has exactly ONE batch of loads (8 x 16 B per lane) in
+// flight: deeper per-warp queues do not work, a warp has six scoreboard slots and later short
+// loads end up waiting on the slot of the oldest global batch (profiled: long_scoreboard stalls
+// on the shared-memory reads that follow the prefetch).  A group issues the loads of its next step
+// right after storing the current one, i.e. before it waits for that step's stage to drain, so
+// the flight time overlaps the MMA of the other group's stage. ----
+constexpr int kGroups = 2;
+constexpr int kGroupWarps = kProdWarps / kGroups;          // 8
+constexpr int kRowsPerPass = 2 * kGroupWarps;               // 16
+constexpr int kPasses = kBM / kRowsPerPass;                 // 8 float4 per thread per K-block
+
+template <bool GATHER, class StageHook>
+__device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, StageHook hook) {
+    const int lane = ptid & 31, pw = ptid >> 5;
+    const int group = pw % kGroups, wg = pw / kGroups;
+    const int rsub = wg * 2 + (lane >> 4);     // row inside a 16-row pass
+    const int kq = (lane & 15) * 4;            // first k of this thread's float4 inside a K-block
+    const uint32_t soff = ((uint32_t)((lane & 15) >> 1) << 4) + ((lane & 1) << 3);   // chunk / half inside a row
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_items = first < a.items ? (a.items - first + stride - 1) / stride : 0;
+    const long long total_steps = my_items * a.nkb;
+
+    // position of the step whose loads are issued next (L*) and of the step stored next (S*)
+    long long l_t = group, s_t = group;
+    long long l_it = group / a.nkb, s_it = l_it;
+    int l_kb = group % a.nkb, s_kb = l_kb;
+    long long meta_seen = -1, meta_freed = 0;   // tiles whose meta this warp has waited for / released
+    int stage = group % a.stages;
+    uint32_t phase = (uint32_t)((group / a.stages) & 1);
+
+    float4 areg[kPasses];
+    auto issue_loads = [&]() {
+        const int k = l_kb * kBK + kq;
+        const RowMeta *mt = a.meta + (l_it % kMetaDepth) * kBM;
+        long long row0 = 0;
+        if (GATHER) {
+            if (l_it != meta_seen) {
+                mbar_wait(&a.meta_full[l_it % kMetaDepth], (uint32_t)((l_it / kMetaDepth) & 1));
+                meta_seen = l_it;
+            }
+        } else {
+            row0 = ((first + l_it * stride) / a.nchunks) * kBM;
+        }
+        const bool kvec = a.vec_ok && k + 3 < a.cin;
+#pragma unroll
+        for (int ps = 0; ps < kPasses; ++ps) {
+            const int r = ps * kRowsPerPass + rsub;
+            long long src;
+            if (GATHER) src = mt[r].src;
+            else src = (row0 + r < a.rows) ? row0 + r : -1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src >= 0 && k < a.cin) {
+                const float *px = a.x + src * a.ldx + k;
+                if (kvec) {
+                    v = __ldg(reinterpret_cast<const float4 *>(px));
+                } else {
+                    v.x = __ldg(px);
+                    if (k + 1 < a.cin) v.y = __ldg(px + 1);
+                    if (k + 2 < a.cin) v.z = __ldg(px + 2);
+                    if (k + 3 < a.cin) v.w = __ldg(px + 3);
+                }
+            }
+            areg[ps] = v;
+        }
+        l_t += kGroups;
+        l_kb += kGroups;
+        while (l_kb >= a.nkb) { l_kb -= a.nkb; ++l_it; }
+    };
+
+    if (l_t < total_steps) issue_loads();
+    while (s_t < total_steps) {
+        uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes;
+        mbar_wait(&a.empty[stage], phase ^ 1);
+        if (wg == 0 && lane == 0) hook(first + s_it * stride, s_kb, stage);
+        const int k = s_kb * kBK + kq;
+        const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM;
+        const bool ktail = k + 3 >= a.cin;
+#pragma unroll
+        for (int ps = 0; ps < kPasses; ++ps) {
+            const int r = ps * kRowsPerPass + rsub;
+            float4 v = areg[ps];
+            if (GATHER) {
+                // layer-1 output of this (centre, neighbour) pair: relu(H_j + W1x . (x_j - centre));
+                // the coefficients are re-read from shared memory every other row: registers are
+                // reserved for the loads in flight
+                const RowMeta q = mt[r];
+                float4 w0, w1, w2;
+                lds128(a.wxs + k, w0);
+                lds128(a.wxs + a.kpad + k, w1);
+                lds128(a.wxs + 2 * a.kpad + k, w2);
+                if (q.src >= 0) {
+                    v.x = fmaxf(fmaf(w2.x, q.dz, fmaf(w1.x, q.dy, fmaf(w0.x, q.dx, v.x))), 0.f);
+                    v.y = fmaxf(fmaf(w2.y, q.dz, fmaf(w1.y, q.dy, fmaf(w0.y, q.dx, v.y))), 0.f);
+                    v.z = fmaxf(fmaf(w2.z, q.dz, fmaf(w1.z, q.dy, fmaf(w0.z, q.dx, v.z))), 0.f);
+                    v.w = fmaxf(fmaf(w2.w, q.dz, fmaf(w1.w, q.dy, fmaf(w0.w, q.dx, v.w))), 0.f);
+                    if (ktail) {               // keep the K padding at zero
+                        if (k + 0 >= a.cin) v.x = 0.f;
+                        if (k + 1 >= a.cin) v.y = 0.f;
+                        if (k + 2 >= a.cin) v.z = 0.f;
+                        v.w = 0.f;
+                    }
+                }
+            }
+            uint2 hi, lo;
+            split2(v.x, v.y, hi.x, lo.x);
+            split2(v.z, v.w, hi.y, lo.y);
+            // sw128_offset(r, chunk) with the per-thread chunk / half folded into soff
+            const uint32_t off = (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7)) + (soff ^ ((uint32_t)(r & 7) << 4));
+            *reinterpret_cast<uint2 *>(sbase + off) = hi;
+            *reinterpret_cast<uint2 *>(sbase + kTileBytes + off) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a.full[stage]);
+        // advance to this group's next step; release the metadata of the tiles left behind
+        s_t += kGroups;
+        s_kb += kGroups;
+        while (s_kb >= a.nkb) { s_kb -= a.nkb; ++s_it; }
+        if (GATHER && lane == 0) {
+            const long long upto = s_t < total_steps ? s_it : my_items;
+            for (; meta_freed < upto; ++meta_freed) mbar_arrive(&a.meta_empty[meta_freed % kMetaDepth]);
+        }
+        stage += kGroups;
+        while (stage >= a.stages) { stage -= a.stages; phase ^= 1; }
+        if (l_t < total_steps) issue_loads();
+    }
+}
+
+}  // namespace tc

@@ -233,3 +233,32 @@ def sa_group_linear_tc(h, idx, xyz, centres, wxyz, layer, out=None, pool=1):
               i32(B), i32(N), i32(M), i32(ns), i32(c1), i32(layer.cout), i32(1 if layer.relu else 0), i32(pool),
               work=2.0 * rows * c1 * (layer.cout + 3))
     return out
+
+
+def sa_fused_supported(l2, l3, ns):
+    """shape test mirroring pn2_sa_fused_tc_f32 (csrc/sa_fused_tc.cu): TMEM columns and shared memory."""
+    t2, t3 = l2.tc, l3.tc
+    if MLP_ENGINE != "tc" or ns not in (16, 32, 64, 128) or not (l2.relu and l3.relu):
+        return False
+    if t2.nchunks != 1 or t3.nchunks != 1 or l2.cout % 16 or t2.ntile != l2.cout or 2 * t2.ntile + t3.ntile > 512:
+        return False
+    smem = (t2.nkb * 2 * t2.ntile * 128 + t3.nkb * 2 * t3.ntile * 128 + 2 * 32768 + 4 * 128 * 16 + 3 * t2.nkb * 64 * 4
+            + 2048 + 8192 + 256 + 1024)
+    return smem <= 227 * 1024
+
+
+def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
+    """gather + pair-wise half of layer 1 + layer 2 + layer 3 + max over nsample in one kernel."""
+    B, M, ns = idx.shape
+    N = xyz.shape[1]
+    h2, hrows, ldh, c1 = _rows2d(h)
+    assert hrows == B * N and c1 == l2.cin and l3.cin == l2.cout
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == B * M and oc == l3.cout
+    t2, t3 = l2.tc, l3.tc
+    rows = B * M * ns
+    cabi.call("pn2_sa_fused_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
+              i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(t3.blob), i32(t3.ntile), i32(t3.nkb), ptr(t3.b), ptr(o2),
+              i32(ldy), i32(B), i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout),
+              work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
+    return out

@@ -134,6 +134,15 @@ int pn2_sa_group_linear_tc_f32(const float *h, int ldh, const int32_t *idx, cons
                                float *y, int ldy, int clouds, int n, int m, int ns, int c1, int cout, int relu, int pool,
                                void *stream);
 
+/* One SA scale end to end on chip: QueryAndGroup (pointnet2_utils.py:241-264) + SharedMLP layers 1-3
+ * (pytorch_utils.py:5-101) + F.max_pool2d over nsample (pointnet2_modules.py:42), given the per-point
+ * half h of layer 1.  Returns PN2_ERR_UNSUPPORTED when the shape does not fit TMEM / shared memory
+ * (callers then use the layer-by-layer entry points above).  csrc/sa_fused_tc.cu. */
+int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                        const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3blob,
+                        int n3, int nkb2, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
+                        int c2, int c3, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,43 @@
+"""Small driver for ncu: the RCNN SA1 shared-MLP layers in isolation (gather layer 2, pooled layer 3)
+at a quarter of the batch-16 size.  python tools/prof_tc.py [iters]"""
+import importlib, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "3d_adapt_auto_driving_b200"
+fz = importlib.import_module(PKG + ".fused")
+p2u = importlib.import_module(PKG + ".pointnet2_utils")
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+torch.manual_seed(0)
+R, S, M, ns, C = 400, 512, 128, 64, 128
+xyz = (torch.rand((R, S, 3), device="cuda") - 0.5) * torch.tensor([4.0, 2.0, 6.0], device="cuda")
+idx_c, centres = fz.fps_gather(xyz, M)
+idx = p2u.ball_query(0.2, ns, xyz, centres)
+h = torch.randn((R * S, C), device="cuda")
+wxyz = torch.randn((3, C), device="cuda")
+g = torch.Generator(device="cpu").manual_seed(1)
+l2w = (torch.randn((C, C), generator=g) / C ** 0.5).cuda()
+l3w = (torch.randn((C, C), generator=g) / C ** 0.5).cuda()
+l2 = fz.PackedLayerTC(l2w, torch.randn(C, generator=g).cuda(), True)
+l3 = fz.PackedLayerTC(l3w, torch.randn(C, generator=g).cuda(), True)
+out2 = torch.empty((R * M, C), device="cuda")
+mid = torch.empty((R * M * ns, C), device="cuda")
+out = torch.empty((R * M, C), device="cuda")
+for i in range(iters):
+    s, e, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    s.record()
+    fz.sa_group_linear_tc(h, idx, xyz, centres, wxyz, l2, out=mid)
+    e.record()
+    fz.linear_tc(mid, l3, out=out, pool=ns)
+    e2.record()
+    torch.cuda.synchronize()
+    e3 = torch.cuda.Event(enable_timing=True)
+    L2, L3 = fz.PackedLayer(l2w, l2.b, True), fz.PackedLayer(l3w, l3.b, True)
+    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
+    e2.record()
+    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
+    e3.record()
+    torch.cuda.synchronize()
+    print("gather layer %.3f ms   pooled layer %.3f ms   fused SA %.3f ms  (rows %d)  fused==layered: %.2e" % (
+        s.elapsed_time(e), e.elapsed_time(e2), e2.elapsed_time(e3), R * M * ns,
+        float((out - out2).abs().max() / out.abs().max())))
