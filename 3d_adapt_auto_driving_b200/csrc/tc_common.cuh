@@ -38,6 +38,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
     __trap();
 }
+// Optional in-kernel stopwatch (tools/prof_tc.py): cycles a role spends blocked on a barrier.
+// `prof` is a device buffer of 32 u64 per CTA or nullptr (the default).
+__device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, const unsigned long long *prof,
+                                                unsigned long long &acc) {
+    if (prof == nullptr) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -86,6 +99,38 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            | (1u << 10)                    // b_format  = BF16
            | ((uint32_t)(n >> 3) << 17)    // n_dim
            | ((uint32_t)(m >> 4) << 24);   // m_dim
+}
+
+// The same descriptor as two 32-bit halves: the high word is a constant, advancing along K inside
+// the swizzle atom is a 32-bit add on the low word.  The MMA-issuing thread shares its scheduler
+// with six other warps, so every instruction it does not execute is tensor-pipe time gained.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %5};\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
 }
 
 // ------------------------------------------------------------------ MMA issue (one thread)

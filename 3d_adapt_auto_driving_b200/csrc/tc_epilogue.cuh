@@ -15,50 +15,73 @@ constexpr int kBM_ = 128;           // rows per tile
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
-// max over the rows of each pooling group of act(acc + bias), for the chunks of this warp.
-// Values are >= 0 after ReLU, so the float order is the unsigned order of the bits
-// (redux.sync has no float form on sm_100).  part: [8][256] floats; for pool 16 the row index is
-// 2*q + half-warp, otherwise q (pool 64 / 128 are combined across quadrants by pool_combine).
-__device__ __forceinline__ void pool_tile(uint32_t taddr, int ncols, int half, const float *bias_s, bool live, int pool,
-                                          int lane, int q, float *part) {
-    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        uint32_t mine = 0u;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float o = fmaxf(__uint_as_float(v[j]) + bias_s[c0 + j], 0.f);
-            const uint32_t u = live ? __float_as_uint(o) : 0u;
-            uint32_t mx;
-            if (pool == 16) {
-                const uint32_t lo16 = __reduce_max_sync(0xffffffffu, lane < 16 ? u : 0u);
-                const uint32_t hi16 = __reduce_max_sync(0xffffffffu, lane >= 16 ? u : 0u);
-                mx = (lane & 16) ? hi16 : lo16;
-            } else {
-                mx = __reduce_max_sync(0xffffffffu, u);
-            }
-            if ((lane & 15) == j) mine = mx;
-        }
-        if (pool == 16) part[(q * 2 + (lane >> 4)) * 256 + c0 + (lane & 15)] = __uint_as_float(mine);
-        else if (lane < 16) part[q * 256 + c0 + lane] = __uint_as_float(mine);
-    }
+// ---- pooled epilogue: max over the rows of each pooling group of ReLU(acc + bias) ----
+// relu(. + b) is monotone, so the max runs on the raw accumulators and bias / ReLU are applied to
+// the one surviving value per lane.  The cross-lane maximum is a butterfly that exchanges half of
+// the remaining values at every step (16 columns over 32 lanes: 8 + 4 + 2 + 1 + 1 shuffles), after
+// which lane l holds column (l >> 1) of the chunk (pool >= 32) or column (l & 15) of its half-warp's
+// group (pool 16).  redux.sync was tried first: ~60 cycles each through the uniform datapath, 16
+// per chunk, 4.7 k cycles per tile.
+__device__ __forceinline__ float bfly_max_pair(float keep, float send, int mask) {
+    return fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, mask));
 }
 
-// after a barrier among the epilogue warps: combine the quadrant maxima and write the pooled rows
-__device__ __forceinline__ void pool_combine(const float *part, int pool, int ncols, long long tile, long long rows,
-                                             int cout, int col_base, float *y, int ldy, int etid) {
-    const int groups = kBM_ / pool;                       // per tile: 8, 4, 2 or 1
-    const int parts_per_group = pool <= 32 ? 1 : pool / 32;
-    for (int e = etid; e < groups * ncols; e += kEpiThreads) {
-        const int g = e / ncols, c = e % ncols;
-        const long long orow = tile * groups + g;
-        if (orow * pool >= rows || col_base + c >= cout) continue;
-        float mx = 0.f;
-        if (pool == 16) mx = part[g * 256 + c];
-        else
-            for (int qq = 0; qq < parts_per_group; ++qq) mx = fmaxf(mx, part[(g * parts_per_group + qq) * 256 + c]);
-        y[orow * ldy + col_base + c] = mx;
+// Results go straight to global memory: a group that lives in one warp (pool 16 / 32) is stored,
+// a group spread over 2 or 4 warps (pool 64 / 128) is combined with atomicMax on the float bits
+// (all values >= 0 after ReLU; the caller zero-fills y first).
+__device__ __forceinline__ void pool_tile(uint32_t taddr, int ncols, int half, const float *bias_s, bool live, int pool,
+                                          int lane, int q, long long tile, long long rows, int cout, int col_base,
+                                          float *y, int ldy) {
+    const bool all_live = __all_sync(0xffffffffu, live);
+    // pooled row this lane writes, its validity and the lane's column inside a 16-column chunk (no
+    // divisions: pool is 16, 32, 64 or 128)
+    long long orow;
+    int c;
+    bool writer;
+    if (pool == 16) { orow = tile * 8 + q * 2 + (lane >> 4); c = lane & 15; writer = true; }
+    else {
+        orow = pool == 32 ? tile * 4 + q : (pool == 64 ? tile * 2 + (q >> 1) : tile);
+        c = lane >> 1;
+        writer = (lane & 1) == 0;
+    }
+    writer = writer && orow * pool < rows;
+    float *yrow = y + orow * ldy + col_base + c;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    for (int c0 = half * 16; c0 < ncols; c0 += 32) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + c0, raw);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        if (!all_live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = live ? v[j] : -INFINITY;
+        }
+        float w8[8], w4[4], w2[2], r;
+        if (pool == 16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = bfly_max_pair(b3 ? v[i + 8] : v[i], b3 ? v[i] : v[i + 8], 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w4[i] = bfly_max_pair(b2 ? w8[i + 4] : w8[i], b2 ? w8[i] : w8[i + 4], 4);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) w2[i] = bfly_max_pair(b1 ? w4[i + 2] : w4[i], b1 ? w4[i] : w4[i + 2], 2);
+            r = bfly_max_pair(b0 ? w2[1] : w2[0], b0 ? w2[0] : w2[1], 1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = bfly_max_pair(b4 ? v[i + 8] : v[i], b4 ? v[i] : v[i + 8], 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w4[i] = bfly_max_pair(b3 ? w8[i + 4] : w8[i], b3 ? w8[i] : w8[i + 4], 8);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) w2[i] = bfly_max_pair(b2 ? w4[i + 2] : w4[i], b2 ? w4[i] : w4[i + 2], 4);
+            r = bfly_max_pair(b1 ? w2[1] : w2[0], b1 ? w2[0] : w2[1], 2);
+            r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        }
+        const float o = fmaxf(r + bias_s[c0 + c], 0.f);
+        if (writer && col_base + c0 + c < cout) {
+            if (pool <= 32) yrow[c0] = o;
+            else atomicMax(reinterpret_cast<unsigned int *>(yrow + c0), __float_as_uint(o));
+        }
     }
 }
 

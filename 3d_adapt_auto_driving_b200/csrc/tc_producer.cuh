@@ -25,7 +25,7 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kMetaDepth = 4;          // tiles of row metadata in flight
 
 struct RowMeta {
-    int src;                           // source row of x, or -1 (row beyond the end: zeros)
+    int src;                           // source row of x (rows beyond the end point at row 0; the epilogue masks them)
     float dx, dy, dz;
 };
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
             const int r = q * 32 + lane;
             const long long row = row0 + r;
             RowMeta mt;
-            mt.src = -1; mt.dx = mt.dy = mt.dz = 0.f;
+            mt.src = 0; mt.dx = mt.dy = mt.dz = 0.f;   // rows beyond the end: any valid row (masked by the epilogue)
             if (row < a.rows) {
                 const long long centre = row / a.ns, cloud = centre / a.m;
                 const int j = __ldg(a.idx + row);
@@ -91,18 +91,21 @@ constexpr int kGroupWarps = kProdWarps / kGroups;          // 8
 constexpr int kRowsPerPass = 2 * kGroupWarps;               // 16
 constexpr int kPasses = kBM / kRowsPerPass;                 // 8 float4 per thread per K-block
 
-template <bool GATHER, class StageHook>
-__device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, StageHook hook) {
+template <bool GATHER, bool FAST, class StageHook>
+__device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, StageHook hook) {
     const int lane = ptid & 31, pw = ptid >> 5;
     const int group = pw % kGroups, wg = pw / kGroups;
-    const int rsub = wg * 2 + (lane >> 4);     // row inside a 16-row pass
+    const int rsub = wg * 2 + (lane >> 4);     // row inside a 16-row pass: row r = ps * 16 + rsub
     const int kq = (lane & 15) * 4;            // first k of this thread's float4 inside a K-block
-    const uint32_t soff = ((uint32_t)((lane & 15) >> 1) << 4) + ((lane & 1) << 3);   // chunk / half inside a row
+    // byte offset of this thread's 8 bytes inside a swizzled tile, pass 0; pass ps adds ps * 2048
+    // (r >> 3 = 2 ps + (rsub >> 3), r & 7 = rsub & 7: the swizzle term does not depend on ps)
+    const uint32_t toff = (uint32_t)(((rsub >> 3) << 10) + ((rsub & 7) << 7)) +
+                          ((((uint32_t)((lane & 15) >> 1) ^ (uint32_t)(rsub & 7)) << 4) | ((uint32_t)(lane & 1) << 3));
     const long long first = blockIdx.x, stride = gridDim.x;
     const long long my_items = first < a.items ? (a.items - first + stride - 1) / stride : 0;
     const long long total_steps = my_items * a.nkb;
 
-    // position of the step whose loads are issued next (L*) and of the step stored next (S*)
+    // position of the step whose loads are issued next (l_*) and of the step stored next (s_*)
     long long l_t = group, s_t = group;
     long long l_it = group / a.nkb, s_it = l_it;
     int l_kb = group % a.nkb, s_kb = l_kb;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, St
     float4 areg[kPasses];
     auto issue_loads = [&]() {
         const int k = l_kb * kBK + kq;
-        const RowMeta *mt = a.meta + (l_it % kMetaDepth) * kBM;
+        const RowMeta *mt = a.meta + (l_it % kMetaDepth) * kBM + rsub;
         long long row0 = 0;
         if (GATHER) {
             if (l_it != meta_seen) {
@@ -121,28 +124,38 @@ __device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, St
                 meta_seen = l_it;
             }
         } else {
-            row0 = ((first + l_it * stride) / a.nchunks) * kBM;
+            row0 = ((first + l_it * stride) / a.nchunks) * kBM + rsub;
         }
-        const bool kvec = a.vec_ok && k + 3 < a.cin;
+        const float *xk = a.x + k;
+        if (FAST) {
 #pragma unroll
-        for (int ps = 0; ps < kPasses; ++ps) {
-            const int r = ps * kRowsPerPass + rsub;
-            long long src;
-            if (GATHER) src = mt[r].src;
-            else src = (row0 + r < a.rows) ? row0 + r : -1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src >= 0 && k < a.cin) {
-                const float *px = a.x + src * a.ldx + k;
-                if (kvec) {
-                    v = __ldg(reinterpret_cast<const float4 *>(px));
-                } else {
-                    v.x = __ldg(px);
-                    if (k + 1 < a.cin) v.y = __ldg(px + 1);
-                    if (k + 2 < a.cin) v.z = __ldg(px + 2);
-                    if (k + 3 < a.cin) v.w = __ldg(px + 3);
-                }
+            for (int ps = 0; ps < kPasses; ++ps) {
+                long long src;
+                if (GATHER) src = mt[ps * kRowsPerPass].src;
+                else src = min(row0 + ps * kRowsPerPass, a.rows - 1);
+                areg[ps] = __ldg(reinterpret_cast<const float4 *>(xk + src * a.ldx));
             }
-            areg[ps] = v;
+        } else {
+            const bool kvec = a.vec_ok && k + 3 < a.cin;
+#pragma unroll
+            for (int ps = 0; ps < kPasses; ++ps) {
+                long long src;
+                if (GATHER) src = mt[ps * kRowsPerPass].src;
+                else src = min(row0 + ps * kRowsPerPass, a.rows - 1);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < a.cin) {
+                    const float *px = xk + src * a.ldx;
+                    if (kvec) {
+                        v = __ldg(reinterpret_cast<const float4 *>(px));
+                    } else {
+                        v.x = __ldg(px);
+                        if (k + 1 < a.cin) v.y = __ldg(px + 1);
+                        if (k + 2 < a.cin) v.z = __ldg(px + 2);
+                        if (k + 3 < a.cin) v.w = __ldg(px + 3);
+                    }
+                }
+                areg[ps] = v;
+            }
         }
         l_t += kGroups;
         l_kb += kGroups;
@@ -151,45 +164,39 @@ __device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, St
 
     if (l_t < total_steps) issue_loads();
     while (s_t < total_steps) {
-        uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes;
+        uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
         mbar_wait(&a.empty[stage], phase ^ 1);
         if (wg == 0 && lane == 0) hook(first + s_it * stride, s_kb, stage);
         const int k = s_kb * kBK + kq;
-        const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM;
-        const bool ktail = k + 3 >= a.cin;
+        const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM + rsub;
+        float4 w0, w1, w2;
+        if (GATHER) {
+            w0 = *reinterpret_cast<const float4 *>(a.wxs + k);
+            w1 = *reinterpret_cast<const float4 *>(a.wxs + a.kpad + k);
+            w2 = *reinterpret_cast<const float4 *>(a.wxs + 2 * a.kpad + k);
+        }
 #pragma unroll
         for (int ps = 0; ps < kPasses; ++ps) {
-            const int r = ps * kRowsPerPass + rsub;
             float4 v = areg[ps];
             if (GATHER) {
-                // layer-1 output of this (centre, neighbour) pair: relu(H_j + W1x . (x_j - centre));
-                // the coefficients are re-read from shared memory every other row: registers are
-                // reserved for the loads in flight
-                const RowMeta q = mt[r];
-                float4 w0, w1, w2;
-                lds128(a.wxs + k, w0);
-                lds128(a.wxs + a.kpad + k, w1);
-                lds128(a.wxs + 2 * a.kpad + k, w2);
-                if (q.src >= 0) {
-                    v.x = fmaxf(fmaf(w2.x, q.dz, fmaf(w1.x, q.dy, fmaf(w0.x, q.dx, v.x))), 0.f);
-                    v.y = fmaxf(fmaf(w2.y, q.dz, fmaf(w1.y, q.dy, fmaf(w0.y, q.dx, v.y))), 0.f);
-                    v.z = fmaxf(fmaf(w2.z, q.dz, fmaf(w1.z, q.dy, fmaf(w0.z, q.dx, v.z))), 0.f);
-                    v.w = fmaxf(fmaf(w2.w, q.dz, fmaf(w1.w, q.dy, fmaf(w0.w, q.dx, v.w))), 0.f);
-                    if (ktail) {               // keep the K padding at zero
-                        if (k + 0 >= a.cin) v.x = 0.f;
-                        if (k + 1 >= a.cin) v.y = 0.f;
-                        if (k + 2 >= a.cin) v.z = 0.f;
-                        v.w = 0.f;
-                    }
+                // layer-1 output of this (centre, neighbour) pair: relu(H_j + W1x . (x_j - centre))
+                const float4 q = *reinterpret_cast<const float4 *>(mt + ps * kRowsPerPass);   // (src bits, dx, dy, dz)
+                v.x = fmaxf(fmaf(w2.x, q.w, fmaf(w1.x, q.z, fmaf(w0.x, q.y, v.x))), 0.f);
+                v.y = fmaxf(fmaf(w2.y, q.w, fmaf(w1.y, q.z, fmaf(w0.y, q.y, v.y))), 0.f);
+                v.z = fmaxf(fmaf(w2.z, q.w, fmaf(w1.z, q.z, fmaf(w0.z, q.y, v.z))), 0.f);
+                v.w = fmaxf(fmaf(w2.w, q.w, fmaf(w1.w, q.z, fmaf(w0.w, q.y, v.w))), 0.f);
+                if (!FAST && k + 3 >= a.cin) {     // keep the K padding at zero
+                    if (k + 0 >= a.cin) v.x = 0.f;
+                    if (k + 1 >= a.cin) v.y = 0.f;
+                    if (k + 2 >= a.cin) v.z = 0.f;
+                    v.w = 0.f;
                 }
             }
             uint2 hi, lo;
             split2(v.x, v.y, hi.x, lo.x);
             split2(v.z, v.w, hi.y, lo.y);
-            // sw128_offset(r, chunk) with the per-thread chunk / half folded into soff
-            const uint32_t off = (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7)) + (soff ^ ((uint32_t)(r & 7) << 4));
-            *reinterpret_cast<uint2 *>(sbase + off) = hi;
-            *reinterpret_cast<uint2 *>(sbase + kTileBytes + off) = lo;
+            *reinterpret_cast<uint2 *>(sbase + ps * 2048) = hi;
+            *reinterpret_cast<uint2 *>(sbase + kTileBytes + ps * 2048) = lo;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -206,6 +213,13 @@ __device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, St
         while (stage >= a.stages) { stage -= a.stages; phase ^= 1; }
         if (l_t < total_steps) issue_loads();
     }
+}
+
+// FAST: 16-byte aligned rows and K a multiple of 64 -- no per-element bounds in the inner loops
+template <bool GATHER, class StageHook>
+__device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, StageHook hook) {
+    if (a.vec_ok && (a.cin & (kBK - 1)) == 0) producer_body<GATHER, true>(a, ptid, hook);
+    else producer_body<GATHER, false>(a, ptid, hook);
 }
 
 }  // namespace tc

@@ -212,6 +212,8 @@ def linear_tc(x, layer, out=None, pool=1, res=None, relu=None):
         assert rrows == rows and rc == layer.cout
         rp = ptr(r2)
     use_relu = layer.relu if relu is None else relu
+    if pool >= 64:
+        o2.zero_()      # groups spread over several warps are combined with atomicMax on the output
     cabi.call("pn2_linear_tc_f32", ptr(x2), i32(ldx), ptr(layer.blob), i32(layer.ntile), i32(layer.nchunks),
               i32(layer.nkb), ptr(layer.b), rp, i32(ldr), ptr(o2), i32(ldy), _i64(rows), i32(cin), i32(layer.cout),
               i32(1 if use_relu else 0), i32(pool), work=2.0 * rows * cin * layer.cout)
@@ -228,6 +230,8 @@ def sa_group_linear_tc(h, idx, xyz, centres, wxyz, layer, out=None, pool=1):
         out = torch.empty((rows // pool, layer.cout), dtype=torch.float32, device=h.device)
     o2, orows, ldy, oc = _rows2d(out)
     assert orows == rows // pool and oc == layer.cout
+    if pool >= 64:
+        o2.zero_()
     cabi.call("pn2_sa_group_linear_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz),
               ptr(layer.blob), i32(layer.ntile), i32(layer.nchunks), i32(layer.nkb), ptr(layer.b), ptr(o2), i32(ldy),
               i32(B), i32(N), i32(M), i32(ns), i32(c1), i32(layer.cout), i32(1 if layer.relu else 0), i32(pool),
@@ -257,6 +261,8 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
     assert orows == B * M and oc == l3.cout
     t2, t3 = l2.tc, l3.tc
     rows = B * M * ns
+    if ns >= 64:
+        o2.zero_()
     cabi.call("pn2_sa_fused_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
               i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(t3.blob), i32(t3.ntile), i32(t3.nkb), ptr(t3.b), ptr(o2),
               i32(ldy), i32(B), i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout),

@@ -125,7 +125,9 @@ int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx
                                  int ldo, int b, int c, int m, int n, void *stream);
 
 /* ---- the same shared-MLP layers on the tcgen05 tensor cores (BF16x3 split, fp32 accumulation in
- *      TMEM); wblob is the host-packed weight image described in csrc/linear_tc.cu ---- */
+ *      TMEM); wblob is the host-packed weight image described in csrc/linear_tc.cu.  When pool (nsample)
+ *      is 64 or 128 the pooled output y must be ZERO-FILLED by the caller: pooling groups that span
+ *      several warps are combined with atomicMax on the (non-negative) float bits. ---- */
 int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
                       const float *res, int ldr, float *y, int ldy, long long rows, int cin, int cout, int relu,
                       int pool, void *stream);
@@ -142,6 +144,9 @@ int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, const float
                         const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3blob,
                         int n3, int nkb2, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
                         int c2, int c3, void *stream);
+
+/* tuning hook: per-CTA stopwatch buffer (32 u64 per CTA, device memory) for the fused SA kernel, NULL = off */
+void pn2_sa_fused_tc_set_profile(void *buf);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 300 python tools/prof_tc.py 2

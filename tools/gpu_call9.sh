@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_linear_tc_gpu.py -q -x > gpurun_out/pytest_tc.log 2>&1; echo "pytest tc exit $?"; tail -3 gpurun_out/pytest_tc.log
+timeout 300 python tools/prof_tc.py 3
