@@ -276,7 +276,10 @@ PN2_API int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int 
     while ((1 << log2bs) < bs) ++log2bs;
     const int cnt = (n + bs - 1) / bs;
 
-    int cluster = n >= 8192 ? 8 : (n > 4096 ? 4 : 1);
+    // CTAs per cloud.  An 8-CTA cluster must sit inside one GPC (~18 SMs: two clusters per GPC), so
+    // more than ~12 big clouds no longer run in a single wave with clusters of 8 (measured, B = 16,
+    // 16384 -> 4096: 4.79 ms with 8, 3.53 ms with 4); 4-CTA clusters keep 32 points per thread.
+    int cluster = n >= 8192 ? (b <= 12 ? 8 : 4) : (n > 4096 ? 4 : 1);
     if (g_fps_cluster_override) cluster = g_fps_cluster_override;
     int p = (n + cluster * kThreads - 1) / (cluster * kThreads);
     while (p > 32 && cluster < 8) {

@@ -20,14 +20,17 @@ def enlarge_box3d(boxes3d, extra_width):
 
 
 def rotate_pc_along_y_torch(pc, rot_angle):
-    """pc (N,S,3+C) rotated about y by rot_angle (N); in place on columns 0 and 2 like the
-    reference: [x', z'] = [x, z] @ [[cos, -sin], [sin, cos]]^T."""
-    cosa = torch.cos(rot_angle).view(-1, 1, 1)
-    sina = torch.sin(rot_angle).view(-1, 1, 1)
-    x = pc[:, :, 0:1].clone()
-    z = pc[:, :, 2:3].clone()
-    pc[:, :, 0:1] = x * cosa - z * sina
-    pc[:, :, 2:3] = x * sina + z * cosa
+    """pc (N,S,3+C) rotated about y by rot_angle (N), in place on columns 0 and 2 -- the batched
+    matmul of the reference (kitti_utils.py:45-63): [x', z'] = [x, z] @ [[cos, -sin], [sin, cos]]^T.
+    The reference calls it once per scene in a Python loop (rcnn_net.py:150-152); rows are
+    independent, so one call over all B*M ROIs gives the same values."""
+    cosa = torch.cos(rot_angle).view(-1, 1)
+    sina = torch.sin(rot_angle).view(-1, 1)
+    R = torch.cat((torch.cat([cosa, -sina], dim=1).unsqueeze(dim=1), torch.cat([sina, cosa], dim=1).unsqueeze(dim=1)), dim=1)
+    xz = torch.stack((pc[:, :, 0], pc[:, :, 2]), dim=2)                   # (N,S,2)
+    out = torch.matmul(xz, R.permute(0, 2, 1))
+    pc[:, :, 0] = out[:, :, 0]
+    pc[:, :, 2] = out[:, :, 1]
     return pc
 
 
