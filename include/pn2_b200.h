@@ -145,6 +145,12 @@ int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, const float
                         int n3, int nkb2, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
                         int c2, int c3, void *stream);
 
+/* ---- evaluate/rotate_iou.py:294-329 rotate_iou_gpu_eval (numba kernel rotate_iou_kernel_eval :261-291) ----
+ * boxes (n,5), qboxes (k,5) rows [cx, cy, w, h, angle] f32 -> out (n,k) f32; criterion -1 IoU,
+ * 0 inter/area(query), 1 inter/area(box), 2 inter.  Bit-exact with the numba build. */
+int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int k, float *out, int criterion,
+                            void *stream);
+
 /* tuning hook: per-CTA stopwatch buffer (32 u64 per CTA, device memory) for the fused SA kernel, NULL = off */
 void pn2_sa_fused_tc_set_profile(void *buf);
 

@@ -174,3 +174,103 @@ int orc_nms_greedy_from_mask(const unsigned long long *mask, int n, int64_t *kee
     free(remv);
     return num_to_keep;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * evaluate/rotate_iou.py:16-291 (numba.cuda kernel rotate_iou_kernel_eval and device functions),
+ * restated with the float32 / float64 mix numba infers and the FMA fusions of the compiled
+ * kernel (PTX from numba 0.65 on a B200 + the SASS ptxas 12.9 makes of it; see
+ * csrc/rotate_iou.cu for the list).  npts_out (optional) receives the number of polygon
+ * vertices per pair: the reference keeps them in a local array of 8 points (rotate_iou.py:233),
+ * so pairs with more than 8 are out-of-bounds writes there -- undefined, not reproducible.
+ * ------------------------------------------------------------------------------------------ */
+static void riou_corners(const float *rb, float *c) {            /* :203-227 */
+    const float a_cos = cosf(rb[4]), a_sin = sinf(rb[4]);
+    const float xh = rb[2] * 0.5f, yh = rb[3] * 0.5f;
+    const float px[4] = {-xh, -xh, xh, xh}, py[4] = {-yh, yh, yh, -yh};
+    for (int i = 0; i < 4; ++i) {
+        c[2 * i] = fmaf(px[i], a_cos, a_sin * py[i]) + rb[0];
+        c[2 * i + 1] = fmaf(py[i], a_cos, -(px[i] * a_sin)) + rb[1];
+    }
+}
+static int riou_point_in_quad(float x, float y, const float *q) { /* :160-176 */
+    const float ab0 = q[2] - q[0], ab1 = q[3] - q[1], ad0 = q[6] - q[0], ad1 = q[7] - q[1];
+    const float ap0 = x - q[0], ap1 = y - q[1];
+    const float abab = fmaf(ab0, ab0, ab1 * ab1), abap = fmaf(ab1, ap1, ab0 * ap0);
+    const float adad = fmaf(ad0, ad0, ad1 * ad1), adap = fmaf(ad1, ap1, ad0 * ap0);
+    return abab >= abap && abap >= 0.f && adad >= adap && adap >= 0.f;
+}
+static int riou_segment(const float *p1, const float *p2, int i, int j, float *out) { /* :72-115 */
+    const float A0 = p1[2 * i], A1 = p1[2 * i + 1], B0 = p1[2 * ((i + 1) % 4)], B1 = p1[2 * ((i + 1) % 4) + 1];
+    const float C0 = p2[2 * j], C1 = p2[2 * j + 1], D0 = p2[2 * ((j + 1) % 4)], D1 = p2[2 * ((j + 1) % 4) + 1];
+    const float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1, CA1 = C1 - A1;
+    const int acd = DA1 * CA0 > CA1 * DA0;
+    const int bcd = (D1 - B1) * (C0 - B0) > (C1 - B1) * (D0 - B0);
+    if (acd == bcd) return 0;
+    const int abc = CA1 * BA0 > BA1 * CA0, abd = DA1 * BA0 > BA1 * DA0;
+    if (abc == abd) return 0;
+    const float DC0 = D0 - C0, DC1 = D1 - C1;
+    const float ABBA = fmaf(A0, B1, -(B0 * A1)), CDDC = fmaf(C0, D1, -(D0 * C1));
+    const float DH = fmaf(BA1, DC0, -(BA0 * DC1));
+    out[0] = fmaf(ABBA, DC0, -(BA0 * CDDC)) / DH;
+    out[1] = fmaf(ABBA, DC1, -(BA1 * CDDC)) / DH;
+    return 1;
+}
+static double riou_inter(const float *r1, const float *r2, int *npts) {  /* :230-244 */
+    float c1[8], c2[8], pts[48], vs[24];
+    riou_corners(r1, c1);
+    riou_corners(r2, c2);
+    int n = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (riou_point_in_quad(c1[2 * i], c1[2 * i + 1], c2)) { pts[2 * n] = c1[2 * i]; pts[2 * n + 1] = c1[2 * i + 1]; ++n; }
+        if (riou_point_in_quad(c2[2 * i], c2[2 * i + 1], c1)) { pts[2 * n] = c2[2 * i]; pts[2 * n + 1] = c2[2 * i + 1]; ++n; }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float t[2];
+            if (riou_segment(c1, c2, i, j, t)) { pts[2 * n] = t[0]; pts[2 * n + 1] = t[1]; ++n; }
+        }
+    if (npts) *npts = n;
+    if (n > 0) {                                                      /* :32-69 */
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = 0; i < n; ++i) { s0 += pts[2 * i]; s1 += pts[2 * i + 1]; }
+        const float m0 = (float)((double)s0 / (double)n), m1 = (float)((double)s1 / (double)n);
+        for (int i = 0; i < n; ++i) {
+            float v0 = pts[2 * i] - m0, v1 = pts[2 * i + 1] - m1;
+            const float d = sqrtf(fmaf(v0, v0, v1 * v1));
+            v0 = v0 / d; v1 = v1 / d;
+            if (v1 < 0.f) v0 = -2.f - v0;
+            vs[i] = v0;
+        }
+        for (int i = 1; i < n; ++i)
+            if (vs[i - 1] > vs[i]) {
+                const float temp = vs[i], tx = pts[2 * i], ty = pts[2 * i + 1];
+                int j = i;
+                while (j > 0 && vs[j - 1] > temp) { vs[j] = vs[j - 1]; pts[2 * j] = pts[2 * j - 2]; pts[2 * j + 1] = pts[2 * j - 1]; --j; }
+                vs[j] = temp; pts[2 * j] = tx; pts[2 * j + 1] = ty;
+            }
+    }
+    double area = 0.0;                                                /* :16-29 */
+    for (int i = 0; i < n - 2; ++i) {
+        const float *a = pts, *b = pts + 2 * i + 2, *c = pts + 2 * i + 4;
+        const float cr = fmaf(a[0] - c[0], b[1] - c[1], -((a[1] - c[1]) * (b[0] - c[0])));
+        area += fabs((double)cr * 0.5);
+    }
+    return area;
+}
+/* :247-291.  boxes (n,5), qboxes (k,5) -> out (n,k); rbox1 = query box, rbox2 = box */
+void orc_rotate_iou_eval(const float *boxes, int n, const float *qboxes, int k, float *out, int criterion, int32_t *npts_out) {
+    for (int ib = 0; ib < n; ++ib)
+        for (int iq = 0; iq < k; ++iq) {
+            const float *r1 = qboxes + (size_t)iq * 5, *r2 = boxes + (size_t)ib * 5;
+            const float area1 = r1[2] * r1[3], area2 = r2[2] * r2[3];
+            int np = 0;
+            const double ai = riou_inter(r1, r2, &np);
+            double r;
+            if (criterion == -1) r = ai / ((double)(area1 + area2) - ai);
+            else if (criterion == 0) r = ai / (double)area1;
+            else if (criterion == 1) r = ai / (double)area2;
+            else r = ai;
+            out[(size_t)ib * k + iq] = (float)r;
+            if (npts_out) npts_out[(size_t)ib * k + iq] = np;
+        }
+}

@@ -157,3 +157,14 @@ def nms_rotated(boxes_sorted, thresh):
     keep = np.zeros((max(n, 1),), np.int64)
     k = lib().orc_nms_rotated(pb, keep.ctypes.data_as(ctypes.c_void_p), n, ctypes.c_float(thresh))
     return keep[:k].copy()
+
+
+def rotate_iou_eval(boxes, query_boxes, criterion=-1, return_npts=False):
+    """geom_oracle.c restatement of evaluate/rotate_iou.py's kernel -> (N,K) float32 [, vertex counts]."""
+    b, pb = _f(boxes); q, pq = _f(query_boxes)
+    n, k = b.shape[0], q.shape[0]
+    out = np.zeros((n, k), np.float32)
+    npts = np.zeros((n, k), np.int32)
+    lib().orc_rotate_iou_eval(pb, n, pq, k, out.ctypes.data_as(ctypes.c_void_p), int(criterion),
+                              npts.ctypes.data_as(ctypes.c_void_p))
+    return (out, npts) if return_npts else out
