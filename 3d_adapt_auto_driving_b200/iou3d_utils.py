@@ -35,6 +35,7 @@ def boxes_iou3d_gpu(boxes_a, boxes_b):
 
 
 def _nms(boxes, scores, thresh, rotated, max_keep=None):
+    scores = scores.reshape(-1)      # eval_rcnn.py:626 passes (n, 1) scores; the result is .view(-1)'ed there
     order = scores.sort(0, descending=True)[1]
     sorted_boxes = boxes[order].contiguous()
     keep, num = iou3d_cuda.nms_device(sorted_boxes, thresh, rotated, max_keep=max_keep)

@@ -54,3 +54,16 @@ def boxes3d_to_corners3d(boxes3d, rotate=True):
         xc, zc = xc * c + zc * s, -xc * s + zc * c
     out = np.stack((b[:, 0:1] + xc, b[:, 1:2] + yc, b[:, 2:3] + zc), axis=2)
     return out.astype(np.float32)
+
+
+def objs_to_boxes3d(obj_list):
+    """[Object3d] -> (N,7) float32 [x, y, z, h, w, l, ry] (kitti_utils.py:180-185)"""
+    boxes3d = np.zeros((len(obj_list), 7), dtype=np.float32)
+    for k, obj in enumerate(obj_list):
+        boxes3d[k, 0:3], boxes3d[k, 3], boxes3d[k, 4], boxes3d[k, 5], boxes3d[k, 6] = obj.pos, obj.h, obj.w, obj.l, obj.ry
+    return boxes3d
+
+
+def get_objects_from_label(label_file):
+    from . import object3d
+    return object3d.get_objects_from_label(label_file)

@@ -73,6 +73,18 @@ def build_legacy(verbose=False):
     return dst
 
 
+def stage_reference_scripts():
+    """git-ignored verbatim copies of reference Python files the GPU box needs (it has no /root/reference):
+    evaluate/rotate_iou.py (numba goldens) and pointrcnn/tools/eval_rcnn.py, the unmodified driver that
+    tests/test_eval_rcnn_dropin_gpu.py runs on top of the package."""
+    out_dir = os.path.join(HERE, "_ref")
+    if not os.path.isdir(REF):
+        return
+    os.makedirs(out_dir, exist_ok=True)
+    for rel, name in (("evaluate/rotate_iou.py", "rotate_iou.py"), ("pointrcnn/tools/eval_rcnn.py", "eval_rcnn.py")):
+        shutil.copyfile(os.path.join(REF, rel), os.path.join(out_dir, name))
+
+
 if __name__ == "__main__":
     print(build_oracle(verbose=True))
     print(build_legacy(verbose=True))
