@@ -47,6 +47,12 @@ class KittiRCNNDataset(KittiDataset):
         rank, world = int(os.environ.get("PN2_SHARD_RANK", "0")), int(os.environ.get("PN2_SHARD_WORLD", "1"))
         if world > 1:
             self.sample_id_list = self.sample_id_list[rank::world]
+        # The reference draws every scene's subsampling from ONE np.random stream in scene order
+        # (eval_rcnn.py:467 seeds it once), so which points a scene keeps depends on all scenes before
+        # it -- impossible to reproduce on a shard without loading every other shard's scenes.  Sharded
+        # runs (and PN2_PER_SCENE_SEED=1) therefore re-seed per scene: results are then identical for
+        # every world size, and differ from the single-stream order only in which points are sampled.
+        self.per_scene_seed = world > 1 or os.environ.get("PN2_PER_SCENE_SEED", "0") == "1"
         if self.logger is not None:
             self.logger.info('Load testing samples from %s' % self.imageset_dir)
             self.logger.info('Done: total test samples %d' % len(self.sample_id_list))
@@ -120,6 +126,8 @@ class KittiRCNNDataset(KittiDataset):
         pts_rect = pts_rect[pts_valid_flag][:, 0:3]
         pts_intensity = pts_intensity[pts_valid_flag]
         if self.random_select:
+            if self.per_scene_seed:
+                np.random.seed((666 * 1000003 + sample_id) % (2 ** 32))
             choice = self._sample_indices(pts_rect)
             ret_pts_rect = pts_rect[choice, :]
             ret_pts_intensity = pts_intensity[choice] - 0.5          # intensity to [-0.5, 0.5]
