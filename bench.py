@@ -275,6 +275,14 @@ def run_b200(args):
     else:
         roof = {"bound": "hbm", "kernel": top, "achieved": dom_work / (dom_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "peak_source": peaks["source"], "traffic": None}
+    # dram bytes of the same kernel family from the committed ncu --set full capture (per launch, like `achieved`)
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if top in mlp_names and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        roof["traffic"] = tj["mlp_family"]["dram_bytes_per_launch"]
+        roof["traffic_source"] = tj["source"]
+        roof["algorithmic_flop_per_launch"] = dom_work / max(dom_launches, 1)
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["launches_per_step"] = dom_launches // K
     roof["share_of_step"] = dom_ms / s.elapsed_time(e)
