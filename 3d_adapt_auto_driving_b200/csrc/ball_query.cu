@@ -17,6 +17,7 @@
 // non-negative term; the full distance is evaluated only for the ~2r/extent fraction that
 // survives.  A CTA leaves the tile loop as soon as all its centres are full.
 #include "common.cuh"
+#include "spatial_order.cuh"
 
 namespace {
 
@@ -85,6 +86,135 @@ __global__ void __launch_bounds__(kThreads) ball_query_kernel(const float *__res
     }
 }
 
+
+// =================================================================================================
+// Culled variant (large clouds).  The brute-force scan above tests every (centre, point) pair; with
+// KITTI extents (70 m x 80 m) and radii of 0.1 - 1 m more than 95 % of those tests fail on the
+// first axis.  Here the centres of a cloud are first put in Hilbert-curve order of their ground-plane
+// cell (spatial_order.cuh: one CTA per cloud, counting sort in shared memory), so that the 32
+// centres of a WARP share a small bounding box.  Each warp works on its own: it streams the cloud
+// 512 points at a time, compacts with a ballot the points inside its box grown by the larger
+// radius (ascending index order is preserved), and its lanes then scan only that short list with
+// the exact test of the reference.  Warps are the unit of work because lidar clouds are very
+// unevenly dense: the few warps whose centres sit in the dense near field keep thousands of
+// candidates, the rest a few hundred, and 128 small units per cloud balance over the SMs.  The cull is conservative (box grown by r * 1.001 plus rounding slack; a hit needs
+// |d| < r on every axis because the squared distance is a sum of non-negative, monotonically
+// rounded terms), so the set and order of accepted candidates -- and hence idx -- is unchanged.
+// =================================================================================================
+constexpr int kCullWarps = kThreads / 32;         // 4 autonomous warps per CTA
+constexpr int kWarpList = 512;                    // candidates a warp culls per pass (16 rounds of 32)
+
+template <bool DUAL>
+__global__ void __launch_bounds__(kThreads) ball_query_culled_kernel(const float *__restrict__ new_xyz,
+                                                                    const float *__restrict__ xyz,
+                                                                    const int32_t *__restrict__ order,
+                                                                    int32_t *__restrict__ idx0, int32_t *__restrict__ idx1,
+                                                                    int n, int m, float radius0, int ns0, float radius1,
+                                                                    int ns1) {
+    __shared__ float4 cand[kCullWarps][kWarpList];
+    const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wfirst = (blockIdx.x * kCullWarps + warp) * 32;
+    if (wfirst >= m) return;                      // warps never meet at a CTA barrier
+    const bool active = wfirst + lane < m;
+    // inactive lanes mirror the warp's first centre so they do not widen the box
+    const int c = __ldg(order + (size_t)cloud * m + (active ? wfirst + lane : wfirst));
+    xyz += (size_t)cloud * n * 3;
+    const float *q = new_xyz + ((size_t)cloud * m + c) * 3;
+    const float qx = __ldg(q + 0), qy = __ldg(q + 1), qz = __ldg(q + 2);
+
+    const float r2_0 = __fmul_rn(radius0, radius0);
+    const float r2_1 = DUAL ? __fmul_rn(radius1, radius1) : 0.f;
+    const float rmax = DUAL ? fmaxf(fabsf(radius0), fabsf(radius1)) : fabsf(radius0);
+    const float grow = rmax * 1.001f;
+
+    float lx = qx, hx = qx, ly = qy, hy = qy, lz = qz, hz = qz;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+        ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+        lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    {   // grown box, plus the rounding slack of the box arithmetic itself (relative to the coordinate magnitude)
+        const float ex = grow + 1e-4f + 1e-6f * fmaxf(fabsf(lx), fabsf(hx)), ey = grow + 1e-4f + 1e-6f * fmaxf(fabsf(ly), fabsf(hy)),
+                    ez = grow + 1e-4f + 1e-6f * fmaxf(fabsf(lz), fabsf(hz));
+        lx -= ex; hx += ex; ly -= ey; hy += ey; lz -= ez; hz += ez;
+    }
+    // a NaN centre makes the box NaN and every cull test false: fall back to "keep everything"
+    const bool keep_all = __any_sync(0xffffffffu, !(qx == qx) || !(qy == qy) || !(qz == qz)) || !(lx <= hx) ||
+                          !(ly <= hy) || !(lz <= hz);
+
+    int32_t *row0 = idx0 + ((size_t)cloud * m + c) * ns0;
+    int32_t *row1 = DUAL ? idx1 + ((size_t)cloud * m + c) * ns1 : nullptr;
+    int cnt0 = active ? 0 : ns0;
+    int cnt1 = (DUAL && active) ? 0 : ns1;
+    if (!DUAL) cnt1 = 0x7fffffff;
+
+    float4 *mine = cand[warp];
+    for (int base = 0; base < n; base += kWarpList) {
+        const bool done = (cnt0 >= ns0) && (!DUAL || cnt1 >= ns1);
+        if (__all_sync(0xffffffffu, done)) break;
+        // ---- cull the next 512 candidates, 32 per round, compacted in index order ----
+        int wn = 0;
+#pragma unroll 4
+        for (int rd = 0; rd < kWarpList / 32; ++rd) {
+            const int k = base + rd * 32 + lane;
+            bool in = false;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (k < n) {
+                px = __ldg(xyz + (size_t)k * 3); py = __ldg(xyz + (size_t)k * 3 + 1); pz = __ldg(xyz + (size_t)k * 3 + 2);
+                in = keep_all || (px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) mine[wn + __popc(bal & ((1u << lane) - 1u))] = make_float4(px, py, pz, __int_as_float(k));
+            wn += __popc(bal);
+        }
+        __syncwarp();
+        // ---- scan the list: the reference's test and fill rule ----
+        if (!done) {
+#pragma unroll 2
+            for (int i = 0; i < wn; ++i) {
+                const float4 p = mine[i];
+                const float dx = qx - p.x;
+                if (fabsf(dx) < rmax) {
+                    const float d2 = pn2_sqdist(dx, qy - p.y, qz - p.z);
+                    const int k = __float_as_int(p.w);
+                    if (d2 < r2_0 && cnt0 < ns0) {
+                        if (cnt0 == 0)
+                            for (int l = 0; l < ns0; ++l) row0[l] = k;
+                        else
+                            row0[cnt0] = k;
+                        ++cnt0;
+                    }
+                    if (DUAL && d2 < r2_1 && cnt1 < ns1) {
+                        if (cnt1 == 0)
+                            for (int l = 0; l < ns1; ++l) row1[l] = k;
+                        else
+                            row1[cnt1] = k;
+                        ++cnt1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool DUAL>
+int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n, int m,
+                  float r0, int ns0, float r1, int ns1, cudaStream_t stream) {
+    if (launch_spatial_order(new_xyz, order, b, m, stream) != cudaSuccess) {
+        pn2_set_last_error("pn2_ball_query_culled_f32: ordering kernel launch failed");
+        return PN2_ERR_LAUNCH;
+    }
+    dim3 grid(pn2_divup(m, kThreads), b);   // 4 warps x 32 centres per CTA
+    ball_query_culled_kernel<DUAL><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// the culled path pays off once the scan dominates the extra sort launch
+inline bool use_culled(const int32_t *order, int n, int m) { return order && m >= 256 && n >= 1024; }
+
 }  // namespace
 
 PN2_API int pn2_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int b, int n, int m, float radius,
@@ -113,4 +243,25 @@ PN2_API int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int3
                                                            nsample1);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
+}
+
+// The same results as pn2_ball_query_f32 (nsample1 == 0) / pn2_ball_query_dual_f32 through the
+// spatially culled scan.  `order` is caller-provided scratch of b * m int32 (the Morton order of
+// the centres is left there); with order == NULL or a small problem the brute-force kernels run.
+PN2_API int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
+                                      int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
+                                      int nsample1, cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0 || nsample0 <= 0 || nsample1 < 0 || (nsample1 > 0 && !idx1)) {
+        pn2_set_last_error("pn2_ball_query_culled_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (b == 0 || m == 0 || n == 0) return PN2_OK;
+    if (!use_culled(order, n, m)) {
+        if (nsample1 > 0)
+            return pn2_ball_query_dual_f32(new_xyz, xyz, idx0, idx1, b, n, m, radius0, nsample0, radius1, nsample1, stream);
+        return pn2_ball_query_f32(new_xyz, xyz, idx0, b, n, m, radius0, nsample0, stream);
+    }
+    if (nsample1 > 0)
+        return launch_culled<true>(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, stream);
+    return launch_culled<false>(new_xyz, xyz, idx0, nullptr, order, b, n, m, radius0, nsample0, 0.f, 0, stream);
 }

@@ -17,6 +17,7 @@
 // the reference expression (interpolate_gpu.cu:96).  One thread per unknown point loops over
 // a block of channels so idx/weight are read once per 8 channels instead of once per channel.
 #include "common.cuh"
+#include "spatial_order.cuh"
 #include <math.h>
 
 namespace {
@@ -64,6 +65,104 @@ __global__ void __launch_bounds__(kThreads) three_nn_kernel(const float *__restr
                 }
             }
         }
+    }
+    if (active) {
+        float *d = dist2 + ((size_t)cloud * n + i) * 3;
+        int32_t *o = idx + ((size_t)cloud * n + i) * 3;
+        d[0] = b1; d[1] = b2; d[2] = b3;
+        o[0] = i1; o[1] = i2; o[2] = i3;
+    }
+}
+
+
+// ---- culled three_nn (large levels) ----
+// The unknown points are walked in Hilbert-curve order (spatial_order.cuh), so the 32 of a warp
+// share a small bounding box.  Every warp works on its own: known points are streamed 256 at a
+// time; before each pass the warp takes the largest current third-neighbour distance B of its
+// lanes, and a known point can only improve some lane's top three if it lies inside the box grown
+// by sqrt(B) (every axis term of the squared distance is non-negative and monotonically rounded;
+// the box is grown by a further 0.1 % plus rounding slack).  The warp compacts the survivors with
+// a ballot, in index order, and its lanes run the reference's strict-< insertion over the short
+// list.  Ties are therefore resolved exactly as in the full scan and dist2 / idx are unchanged.
+constexpr int kNnWarps = kThreads / 32;
+constexpr int kNnList = 256;                     // known points a warp culls per pass (8 rounds of 32)
+
+__global__ void __launch_bounds__(kThreads) three_nn_culled_kernel(const float *__restrict__ unknown,
+                                                                  const float *__restrict__ known,
+                                                                  const int32_t *__restrict__ order,
+                                                                  float *__restrict__ dist2, int32_t *__restrict__ idx,
+                                                                  int n, int m) {
+    __shared__ float4 cand[kNnWarps][kNnList];
+    const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wfirst = (blockIdx.x * kNnWarps + warp) * 32;
+    if (wfirst >= n) return;                     // warps never meet at a CTA barrier
+    const bool active = wfirst + lane < n;
+    // inactive lanes mirror the warp's first point: they neither widen the box nor raise the bound
+    const int i = __ldg(order + (size_t)cloud * n + (active ? wfirst + lane : wfirst));
+    known += (size_t)cloud * m * 3;
+    const float *u = unknown + ((size_t)cloud * n + i) * 3;
+    const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
+
+    float lx = ux, hx = ux, ly = uy, hy = uy, lz = uz, hz = uz;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+        ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+        lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    // a NaN coordinate anywhere in the warp disables the cull (every comparison below would be false)
+    const bool box_ok = !__any_sync(0xffffffffu, !(ux == ux) || !(uy == uy) || !(uz == uz)) && (lx <= hx) && (ly <= hy) &&
+                        (lz <= hz);
+    // rounding slack of the box arithmetic itself, relative to the coordinate magnitude
+    const float ex = 1e-4f + 1e-6f * fmaxf(fabsf(lx), fabsf(hx)), ey = 1e-4f + 1e-6f * fmaxf(fabsf(ly), fabsf(hy)),
+                ez = 1e-4f + 1e-6f * fmaxf(fabsf(lz), fabsf(hz));
+
+    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+    int i1 = 0, i2 = 0, i3 = 0;
+    float4 *mine = cand[warp];
+    for (int base = 0; base < m; base += kNnList) {
+        // ---- bound: largest third-neighbour distance in the warp ----
+        float bm = b3;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        const bool keep_all = !box_ok || !(bm < 1.0e30f);
+        const float g = keep_all ? 0.f : sqrtf(bm) * 1.001f;
+        const float clx = lx - (g + ex), chx = hx + (g + ex), cly = ly - (g + ey), chy = hy + (g + ey),
+                    clz = lz - (g + ez), chz = hz + (g + ez);
+        // ---- cull the next 256 known points, 32 per round, compacted in index order ----
+        int wn = 0;
+#pragma unroll
+        for (int rd = 0; rd < kNnList / 32; ++rd) {
+            const int k = base + rd * 32 + lane;
+            bool in = false;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (k < m) {
+                px = __ldg(known + (size_t)k * 3); py = __ldg(known + (size_t)k * 3 + 1); pz = __ldg(known + (size_t)k * 3 + 2);
+                in = keep_all || (px >= clx && px <= chx && py >= cly && py <= chy && pz >= clz && pz <= chz);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) mine[wn + __popc(bal & ((1u << lane) - 1u))] = make_float4(px, py, pz, __int_as_float(k));
+            wn += __popc(bal);
+        }
+        __syncwarp();
+        // ---- the reference's insertion over the list ----
+#pragma unroll 2
+        for (int t = 0; t < wn; ++t) {
+            const float4 p = mine[t];
+            const float dx = ux - p.x;
+            if (__fmul_rn(dx, dx) < b3) {
+                const float d = pn2_sqdist(dx, uy - p.y, uz - p.z);
+                const int k = __float_as_int(p.w);
+                if (d < b1) {
+                    b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
+                } else if (d < b2) {
+                    b3 = b2; i3 = i2; b2 = d; i2 = k;
+                } else if (d < b3) {
+                    b3 = d; i3 = k;
+                }
+            }
+        }
+        __syncwarp();
     }
     if (active) {
         float *d = dist2 + ((size_t)cloud * n + i) * 3;
@@ -139,6 +238,27 @@ PN2_API int pn2_three_nn_f32(const float *unknown, const float *known, float *di
     if (b == 0 || n == 0) return PN2_OK;
     dim3 grid(pn2_divup(n, kThreads), b);
     three_nn_kernel<<<grid, kThreads, 0, stream>>>(unknown, known, dist2, idx, n, m);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// pn2_three_nn_f32 through the spatially culled scan; `order` is caller scratch of b * n int32
+// (left holding the Morton order of the unknown points).  order == NULL or a small level runs the
+// brute-force kernel.  Same dist2 / idx bit for bit.
+PN2_API int pn2_three_nn_culled_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int32_t *order,
+                                    int b, int n, int m, cudaStream_t stream) {
+    if (!order || n < 1024 || m < 512) return pn2_three_nn_f32(unknown, known, dist2, idx, b, n, m, stream);
+    if (b < 0) {
+        pn2_set_last_error("pn2_three_nn_culled_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (b == 0) return PN2_OK;
+    if (launch_spatial_order(unknown, order, b, n, stream) != cudaSuccess) {
+        pn2_set_last_error("pn2_three_nn_culled_f32: ordering kernel launch failed");
+        return PN2_ERR_LAUNCH;
+    }
+    dim3 grid(pn2_divup(n, kThreads), b);
+    three_nn_culled_kernel<<<grid, kThreads, 0, stream>>>(unknown, known, order, dist2, idx, n, m);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -44,6 +44,7 @@ constexpr int kStgLd = 17;            // epilogue staging row stride (floats)
 
 struct TcParams {
     const float *x; int ldx; int cin; long long rows;
+    const float *x2; int ldx2; int kb_split;   // optional second source of the input columns (see pn2_linear_tc2_f32)
     const int32_t *idx; const float *xyz; const float *centres; const float *wxyz; int n, m, ns;
     const uint8_t *wblob;   // [nchunks][nkb][hi tile | lo tile], each ntile x 128 B, swizzled
     const float *bias; const float *res; int ldr; int cout; int relu;
@@ -118,6 +119,7 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
 
     ProducerArgs pa;
     pa.x = p.x; pa.ldx = p.ldx; pa.cin = p.cin; pa.rows = p.rows; pa.vec_ok = p.vec_ok;
+    pa.x2 = p.x2; pa.ldx2 = p.ldx2; pa.kb_split = p.kb_split;
     pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
     pa.nkb = p.nkb; pa.stages = p.stages; pa.nchunks = p.nchunks; pa.items = p.items;
     pa.ring = smem; pa.stage_bytes = L.stage_bytes; pa.full = full; pa.empty = empty;
@@ -234,6 +236,21 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
                                 if (p.relu) o = fmaxf(o, 0.f);
                                 yp[i * ystep] = o;
                             }
+                        } else if (full_rows) {   // residual: all sixteen loads in flight before the first store
+                            const float *rp = p.res + (row0 + rh) * p.ldr + col;
+                            const size_t rstep = (size_t)2 * p.ldr;
+#pragma unroll
+                            for (int h8 = 0; h8 < 2; ++h8) {
+                                float rv[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) rv[i] = __ldg(rp + (h8 * 8 + i) * rstep);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float o = sp[(h8 * 8 + i) * 2 * kStgLd] + bj + rv[i];
+                                    if (p.relu) o = fmaxf(o, 0.f);
+                                    yp[(h8 * 8 + i) * ystep] = o;
+                                }
+                            }
                         } else {
                             for (int i = 0; i < 16; ++i) {
                                 const long long r = row0 + i * 2 + rh;
@@ -315,6 +332,7 @@ int fill_common(TcParams &p, const void *wblob, int ntile, int nchunks, int nkb,
     p.ntile = ntile; p.nchunks = nchunks; p.nkb = nkb;
     p.bias = bias; p.res = res; p.ldr = ldr; p.cout = cout; p.relu = relu;
     p.y = y; p.ldy = ldy; p.pool = pool; p.cin = cin; p.rows = rows;
+    p.x2 = nullptr; p.ldx2 = 0; p.kb_split = 0x7fffffff;
     p.items = ((rows + BM - 1) / BM) * nchunks;
     return PN2_OK;
 }
@@ -341,6 +359,36 @@ PN2_API int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int nt
     }
     p.x = x; p.ldx = ldx;
     p.vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    return launch_tc<false>(p, stream);
+}
+
+// pn2_linear_tc_f32 on a column-wise concatenation [x | x2] that is never materialised: the first
+// c_a input columns are read from x (row stride ldx), the remaining cin - c_a from x2 (row stride
+// ldx2).  The split must sit on a K-block boundary and both sources must be 16-byte aligned
+// (c_a % 64 == 0, cin % 64 == 0, ldx % 4 == ldx2 % 4 == 0).  Used for merge_down_layer on
+// cat[xyz_feature, rpn_feature] (rcnn_net.py:174-176) without the torch.cat.
+PN2_API int pn2_linear_tc2_f32(const float *x, int ldx, int c_a, const float *x2, int ldx2, const void *wblob, int ntile,
+                               int nchunks, int nkb, const float *bias, const float *res, int ldr, float *y, int ldy,
+                               long long rows, int cin, int cout, int relu, int pool, cudaStream_t stream) {
+    TcParams p = {};
+    if (!x || !x2 || c_a <= 0 || c_a >= cin || ldx < c_a || ldx2 < cin - c_a) {
+        pn2_set_last_error("pn2_linear_tc2_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if ((c_a % BK) || (cin % BK) || (ldx & 3) || (ldx2 & 3) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+        (reinterpret_cast<uintptr_t>(x2) & 15)) {
+        pn2_set_last_error("pn2_linear_tc2_f32: sources must be 16-byte aligned and split on a 64-column boundary");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    const int rc = fill_common(p, wblob, ntile, nchunks, nkb, bias, res, ldr, y, ldy, rows, cin, cout, relu, pool);
+    if (rc) return rc;
+    if (rows == 0) return PN2_OK;
+    if (rows > 2147483647LL) {
+        pn2_set_last_error("pn2_linear_tc2_f32: too many rows");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    p.x = x; p.ldx = ldx; p.vec_ok = 1;
+    p.x2 = x2; p.ldx2 = ldx2; p.kb_split = c_a / BK;
     return launch_tc<false>(p, stream);
 }
 

@@ -44,17 +44,18 @@ __device__ __forceinline__ bool in_box(const BoxTest &b, float x, float y, float
 __global__ void __launch_bounds__(kThreads) roipool3d_kernel(const float *__restrict__ xyz,
                                                             const float *__restrict__ boxes3d,
                                                             const float *__restrict__ feat,
+                                                            const float *__restrict__ feat2,
                                                             float *__restrict__ pooled, int32_t *__restrict__ empty,
-                                                            int n, int m, int c, int sampled) {
+                                                            int n, int m, int c, int c2, int off2, int row, int sampled) {
     extern __shared__ int32_t list[];  // sampled entries
     __shared__ int warp_cnt[kWarps];
-    __shared__ int total;
 
     const int roi = blockIdx.x, cloud = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *bx = boxes3d + ((size_t)cloud * m + roi) * 7;
     xyz += (size_t)cloud * n * 3;
     feat += (size_t)cloud * n * c;
+    if (feat2) feat2 += (size_t)cloud * n * c2;
 
     BoxTest b;
     {
@@ -68,7 +69,6 @@ __global__ void __launch_bounds__(kThreads) roipool3d_kernel(const float *__rest
         b.cosa = cosf(ang);
         b.sina = sinf(ang);
     }
-    if (tid == 0) total = 0;
     __syncthreads();
 
     int cnt = 0;  // uniform across the CTA
@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(kThreads) roipool3d_kernel(const float *__rest
         return;
     }
     const int have = min(cnt, sampled);
-    const int row = 3 + c;
     float *dst_base = pooled + ((size_t)cloud * m + roi) * (size_t)sampled * row;
     for (int s = warp; s < sampled; s += kWarps) {
         const int src = list[s < have ? s : s % have];
@@ -105,6 +104,11 @@ __global__ void __launch_bounds__(kThreads) roipool3d_kernel(const float *__rest
         const float *f = feat + (size_t)src * c;
         if (lane < 3) dst[lane] = __ldg(xyz + (size_t)src * 3 + lane);
         for (int j = lane; j < c; j += 32) dst[3 + j] = __ldg(f + j);
+        if (feat2) {   // second feature block at a 16-byte aligned column: 128-bit copies
+            const float4 *f2 = reinterpret_cast<const float4 *>(feat2 + (size_t)src * c2);
+            float4 *d2 = reinterpret_cast<float4 *>(dst + off2);
+            for (int j = lane; j < (c2 >> 2); j += 32) d2[j] = __ldg(f2 + j);
+        }
     }
 }
 
@@ -121,8 +125,35 @@ PN2_API int pn2_roipool3d_f32(const float *xyz, const float *boxes3d, const floa
     }
     if (b == 0 || m == 0) return PN2_OK;
     dim3 grid(m, b);
-    roipool3d_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(xyz, boxes3d, feat, pooled, empty, n, m, c,
-                                                                           sampled);
+    roipool3d_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(xyz, boxes3d, feat, nullptr, pooled, empty, n,
+                                                                           m, c, 0, 0, 3 + c, sampled);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// The same pooling with the per-point feature vector given in two pieces and a padded output
+// row, so that the wide piece lands 16-byte aligned for the tensor-core MLP that consumes it:
+//   pooled row (ld_out floats) = [x y z | feat (c) | zero pad ... | feat2 (c2) at column off2 | pad]
+// feat (B,N,c) may be NULL when c == 0.  Needs c2 % 4 == 0, off2 % 4 == 0, off2 >= 3 + c,
+// ld_out % 4 == 0, ld_out >= off2 + c2 and 16-byte aligned feat2 / pooled.  `pooled` pre-zeroed.
+// Selection and order of the sampled points are those of pn2_roipool3d_f32.
+PN2_API int pn2_roipool3d_split_f32(const float *xyz, const float *boxes3d, const float *feat, int c, const float *feat2,
+                                    int c2, float *pooled, int ld_out, int off2, int32_t *empty, int b, int n, int m,
+                                    int sampled, cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0 || c < 0 || c2 <= 0 || !feat2 || (c > 0 && !feat) || sampled <= 0 || sampled > 8192 ||
+        off2 < 3 + c || ld_out < off2 + c2) {
+        pn2_set_last_error("pn2_roipool3d_split_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if ((c2 & 3) || (off2 & 3) || (ld_out & 3) || (reinterpret_cast<uintptr_t>(feat2) & 15) ||
+        (reinterpret_cast<uintptr_t>(pooled) & 15)) {
+        pn2_set_last_error("pn2_roipool3d_split_f32: feat2 block must be 16-byte aligned");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    if (b == 0 || m == 0) return PN2_OK;
+    dim3 grid(m, b);
+    roipool3d_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(xyz, boxes3d, feat, feat2, pooled, empty, n,
+                                                                           m, c, c2, off2, ld_out, sampled);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -154,6 +154,7 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
 
     ProducerArgs pa;
     pa.x = p.h; pa.ldx = p.ldh; pa.cin = p.c1; pa.rows = p.rows;
+    pa.x2 = nullptr; pa.ldx2 = 0; pa.kb_split = 0x7fffffff;
     pa.vec_ok = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.h) & 15) == 0);
     pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
     pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = p.tiles;

@@ -31,6 +31,7 @@ struct RowMeta {
 
 struct ProducerArgs {
     const float *x; int ldx; int cin; long long rows; int vec_ok;
+    const float *x2; int ldx2; int kb_split;   // K-blocks >= kb_split come from x2 (plain rows, FAST path only)
     const int32_t *idx; const float *xyz; const float *centres; int n, m, ns;   // gather only
     int nkb, stages, nchunks;
     long long items;                   // work items of the whole grid; item -> tile = item / nchunks
@@ -128,12 +129,17 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
         }
         const float *xk = a.x + k;
         if (FAST) {
+            long long ld = a.ldx;
+            if (!GATHER && l_kb >= a.kb_split) {   // second operand source (concatenated input)
+                xk = a.x2 + (k - a.kb_split * kBK);
+                ld = a.ldx2;
+            }
 #pragma unroll
             for (int ps = 0; ps < kPasses; ++ps) {
                 long long src;
                 if (GATHER) src = mt[ps * kRowsPerPass].src;
                 else src = min(row0 + ps * kRowsPerPass, a.rows - 1);
-                areg[ps] = __ldg(reinterpret_cast<const float4 *>(xk + src * a.ldx));
+                areg[ps] = __ldg(reinterpret_cast<const float4 *>(xk + src * ld));
             }
         } else {
             const bool kvec = a.vec_ok && k + 3 < a.cin;

@@ -140,8 +140,9 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
     M = new_xyz.shape[1]
     i0 = torch.zeros((B, M, ns0), dtype=torch.int32, device=xyz.device)
     i1 = torch.zeros((B, M, ns1), dtype=torch.int32, device=xyz.device)
-    cabi.call("pn2_ball_query_dual_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), i32(B), i32(N), i32(M), f32(r0),
-              i32(ns0), f32(r1), i32(ns1), work=12.0 * B * M * N)
+    order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)    # scratch: Morton order of the centres
+    cabi.call("pn2_ball_query_culled_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), ptr(order), i32(B), i32(N), i32(M),
+              f32(r0), i32(ns0), f32(r1), i32(ns1), work=12.0 * B * M * N)
     return i0, i1
 
 
@@ -217,6 +218,28 @@ def linear_tc(x, layer, out=None, pool=1, res=None, relu=None):
     cabi.call("pn2_linear_tc_f32", ptr(x2), i32(ldx), ptr(layer.blob), i32(layer.ntile), i32(layer.nchunks),
               i32(layer.nkb), ptr(layer.b), rp, i32(ldr), ptr(o2), i32(ldy), _i64(rows), i32(cin), i32(layer.cout),
               i32(1 if use_relu else 0), i32(pool), work=2.0 * rows * cin * layer.cout)
+    return out
+
+
+def linear_cat(xa, xb, layer, out=None):
+    """y = act(cat[xa, xb] @ W^T + b) without materialising the concatenation on the tensor-core engine
+    (pn2_linear_tc2_f32); the exact-fp32 engine concatenates and calls linear()."""
+    a2, rows, lda, ca = _rows2d(xa)
+    b2, rows_b, ldb, cb = _rows2d(xb)
+    if rows != rows_b or ca + cb != layer.cin:
+        raise cabi.Pn2Error("linear_cat: shapes do not match the layer")
+    aligned = (ca % 64 == 0 and cb % 64 == 0 and lda % 4 == 0 and ldb % 4 == 0 and a2.data_ptr() % 16 == 0
+               and b2.data_ptr() % 16 == 0)
+    if MLP_ENGINE != "tc" or not aligned:
+        return linear(torch.cat((a2, b2), dim=1), layer, out=out)
+    tc = layer.tc
+    if out is None:
+        out = torch.empty((rows, layer.cout), dtype=torch.float32, device=xa.device)
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == rows and oc == layer.cout
+    cabi.call("pn2_linear_tc2_f32", ptr(a2), i32(lda), i32(ca), ptr(b2), i32(ldb), ptr(tc.blob), i32(tc.ntile),
+              i32(tc.nchunks), i32(tc.nkb), ptr(tc.b), ptr(None), i32(0), ptr(o2), i32(ldy), _i64(rows), i32(layer.cin),
+              i32(layer.cout), i32(1 if layer.relu else 0), i32(1), work=2.0 * rows * layer.cin * layer.cout)
     return out
 
 

@@ -98,18 +98,52 @@ class RCNNNet(nn.Module):
         kitti_utils.rotate_pc_along_y_torch(flat, batch_rois.view(-1, 7)[:, 6])
         return flat
 
+    _PAD = 8   # column of the rpn feature block in the padded pooled rows (16-byte aligned)
+
+    def _pool_rois_padded(self, input_data):
+        """_pool_rois for the fused path: no torch.cat of the per-point features, and pooled rows laid
+        out [x y z | mask, depth (| intensity) | 0-pad to column 8 | 128 rpn features] so that the wide
+        block is aligned for the tensor-core MLP (pn2_roipool3d_split_f32).  Same sampled points."""
+        rpn_xyz, batch_rois = input_data['rpn_xyz'].contiguous(), input_data['roi_boxes3d']
+        rpn_features = input_data['rpn_features'].contiguous()
+        extra = []
+        if cfg.RCNN.USE_INTENSITY:
+            extra.append(input_data['rpn_intensity'])
+        extra.append(input_data['seg_mask'])
+        if cfg.RCNN.USE_DEPTH:
+            extra.append(input_data['pts_depth'] / 70.0 - 0.5)
+        head = torch.stack(extra, dim=2).contiguous()
+        B, N, C2 = rpn_features.shape
+        M, S, ld = batch_rois.shape[1], cfg.RCNN.NUM_POINTS, self._PAD + C2
+        boxes = kitti_utils.enlarge_box3d(batch_rois.view(-1, 7), cfg.RCNN.POOL_EXTRA_WIDTH).view(B, -1, 7).contiguous()
+        pooled = torch.zeros((B, M, S, ld), dtype=torch.float32, device=rpn_xyz.device)
+        empty = torch.zeros((B, M), dtype=torch.int32, device=rpn_xyz.device)
+        fz.cabi.call("pn2_roipool3d_split_f32", fz.ptr(rpn_xyz), fz.ptr(boxes), fz.ptr(head), fz.i32(head.shape[2]),
+                     fz.ptr(rpn_features), fz.i32(C2), fz.ptr(pooled), fz.i32(ld), fz.i32(self._PAD), fz.ptr(empty),
+                     fz.i32(B), fz.i32(N), fz.i32(M), fz.i32(S))
+        pooled[:, :, :, 0:3] -= batch_rois[:, :, 0:3].unsqueeze(dim=2)
+        flat = pooled.view(B * M, S, ld)
+        kitti_utils.rotate_pc_along_y_torch(flat, batch_rois.view(-1, 7)[:, 6])
+        return flat
+
+    def _fusable(self, probe):
+        return (self.fused and not self.training and probe.is_cuda and cfg.RCNN.USE_RPN_FEATURES
+                and all(m._can_fuse(probe) for m in self.SA_modules[:-1]))
+
     def forward(self, input_data):
         if cfg.RCNN.ROI_SAMPLE_JIT:
             if self.training:
                 raise NotImplementedError("training (proposal_target_layer) is out of scope of the inference package")
+            rf = input_data['rpn_features']
+            if (self._fusable(input_data['rpn_xyz']) and rf.shape[2] % 64 == 0
+                    and self.rcnn_input_channel <= self._PAD):
+                return self._forward_fused(self._pool_rois_padded(input_data), self._PAD)
             pts_input = self._pool_rois(input_data)
         else:
             pts_input = input_data['pts_input']
 
-        use_fused = (self.fused and not self.training and pts_input.is_cuda and cfg.RCNN.USE_RPN_FEATURES
-                     and all(m._can_fuse(pts_input) for m in self.SA_modules[:-1]))
-        if use_fused:
-            return self._forward_fused(pts_input)
+        if self._fusable(pts_input):
+            return self._forward_fused(pts_input, self.rcnn_input_channel)
 
         xyz, features = self._break_up_pc(pts_input)
         if cfg.RCNN.USE_RPN_FEATURES:
@@ -128,15 +162,16 @@ class RCNNNet(nn.Module):
         rcnn_reg = self.reg_layer(l_features[-1]).transpose(1, 2).contiguous().squeeze(dim=1)
         return {'rcnn_cls': rcnn_cls, 'rcnn_reg': rcnn_reg}
 
-    def _forward_fused(self, pts_input):
-        """pts_input (R, S, 3 + extra + C_rpn) point-major rows, R = B * rois."""
+    def _forward_fused(self, pts_input, feat_off):
+        """pts_input (R, S, ld) point-major rows, R = B * rois: columns [0, rcnn_input_channel) are
+        xyz + extras, the rpn features start at column feat_off."""
         if self._packed is None:
             up = fz.pack_sequential(self.xyz_up_layer)
             merge = fz.pack_sequential(self.merge_down_layer)[0]
             c = up[-1].cout
             wm = merge.w[:, :merge.cin]
             self._packed = {
-                "up": up,
+                "up": up, "merge": merge,
                 # merge_down on cat[xyz_feature, rpn_feature] = W_a xyz_feature + (W_b rpn_feature + b)
                 "merge_a": fz.PackedLayer(wm[:, :c], torch.zeros_like(merge.b), merge.relu),
                 "merge_b": fz.PackedLayer(wm[:, c:], merge.b, False),
@@ -150,8 +185,12 @@ class RCNNNet(nn.Module):
         cur = rows[:, 0:nin]
         for layer in pk["up"]:
             cur = fz.linear(cur, layer)
-        side = fz.linear(rows[:, nin:], pk["merge_b"])                    # W_b rpn_feature + b
-        merged = fz.linear(cur, pk["merge_a"], res=side)                  # relu(W_a xyz_feature + side)
+        rpn_feat = rows[:, feat_off:]
+        if fz.MLP_ENGINE == "tc" and feat_off % 4 == 0 and C % 4 == 0 and rpn_feat.shape[1] % 64 == 0:
+            merged = fz.linear_cat(cur, rpn_feat, pk["merge"])            # one GEMM over the virtual concatenation
+        else:
+            side = fz.linear(rpn_feat, pk["merge_b"])                     # W_b rpn_feature + b
+            merged = fz.linear(cur, pk["merge_a"], res=side)              # relu(W_a xyz_feature + side)
         l_xyz, l_feats = xyz, merged.view(R, S, -1)
         for sa in self.SA_modules:
             l_xyz, l_feats = sa.forward_pm(l_xyz, l_feats)

@@ -62,7 +62,10 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_poi
 def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     _chk(unknown, torch.float32, "unknown"); _chk(known, torch.float32, "known")
     _chk(dist2, torch.float32, "dist2"); _chk(idx, torch.int32, "idx")
-    cabi.call("pn2_three_nn_f32", ptr(unknown), ptr(known), ptr(dist2), ptr(idx), i32(b), i32(n), i32(m))
+    # large levels take the spatially culled scan (same outputs); it needs b*n int32 of scratch
+    order = torch.empty((b, n), dtype=torch.int32, device=unknown.device) if (n >= 1024 and m >= 512) else None
+    cabi.call("pn2_three_nn_culled_f32", ptr(unknown), ptr(known), ptr(dist2), ptr(idx), ptr(order), i32(b), i32(n),
+              i32(m), work=9.0 * b * n * m)
 
 
 def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):

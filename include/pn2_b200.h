@@ -60,6 +60,12 @@ int pn2_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int
 /* Both MSG scales of one SA layer (pointnet2_modules.py:37-38 loops over groupers) in one scan. */
 int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int b, int n, int m,
                             float radius0, int nsample0, float radius1, int nsample1, void *stream);
+/* Same idx as the two entries above (nsample1 == 0: single radius) through a spatially culled scan:
+ * centres Morton-ordered per cloud into `order` (caller scratch, b*m int32), candidates compacted by
+ * warp ballot against the CTA's grown bounding box.  order == NULL or a small problem -> brute force. */
+int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order,
+                              int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
+                              void *stream);
 
 /* group_points_wrapper(b,c,n,npoints,nsample,points,idx,out)  group_points.cpp:24-35,
  * group_points_gpu.cu:47-86.  points (B,C,N), idx (B,M,ns) -> out (B,C,M,ns). */
@@ -74,6 +80,11 @@ int pn2_group_points_grad_f32(const float *grad_out, const int32_t *idx, float *
  * idx (B,n,3) int32.  Bit-exact. */
 int pn2_three_nn_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int b, int n, int m,
                      void *stream);
+/* Same dist2 / idx through a spatially culled scan (unknown points Morton-ordered into `order`,
+ * caller scratch of b*n int32; known points compacted by warp ballot against the CTA's bounding box
+ * grown by the current third-neighbour bound).  order == NULL or a small level -> brute force. */
+int pn2_three_nn_culled_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int32_t *order, int b,
+                            int n, int m, void *stream);
 /* three_interpolate_wrapper(b,c,m,n,points,idx,weight,out)  interpolate.cpp:27-38,
  * interpolate_gpu.cu:77-117.  points (B,C,m) -> out (B,C,n).  Bit-exact. */
 int pn2_three_interpolate_f32(const float *points, const int32_t *idx, const float *weight, float *out, int b, int c,
@@ -90,6 +101,13 @@ int pn2_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx, co
  * both pre-zeroed by the caller (roipool3d_utils.py:20-22).  Indices bit-exact. */
 int pn2_roipool3d_f32(const float *xyz, const float *boxes3d, const float *feat, float *pooled, int32_t *empty, int b,
                       int n, int m, int c, int sampled, void *stream);
+/* The same pooling (same sampled points, same order) with the per-point features given in two
+ * pieces and a padded output row [x y z | feat (c) | 0.. | feat2 (c2) at column off2 | 0..] of
+ * ld_out floats, so the rpn feature block is 16-byte aligned for the tensor-core MLP that reads
+ * it (replaces the torch.cat of rcnn_net.py:137-139 plus roipool3d_utils.py:7-28 on the fused path). */
+int pn2_roipool3d_split_f32(const float *xyz, const float *boxes3d, const float *feat, int c, const float *feat2, int c2,
+                            float *pooled, int ld_out, int off2, int32_t *empty, int b, int n, int m, int sampled,
+                            void *stream);
 
 /* ---- iou3d_cuda (pointrcnn/lib/utils/iou3d/src/iou3d.cpp:174-179) ---- */
 
@@ -131,6 +149,11 @@ int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx
 int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
                       const float *res, int ldr, float *y, int ldy, long long rows, int cin, int cout, int relu,
                       int pool, void *stream);
+/* pn2_linear_tc_f32 on the never-materialised concatenation [x (c_a columns) | x2 (cin - c_a columns)]:
+ * merge_down_layer on cat[xyz_feature, rpn_feature] (rcnn_net.py:174-176) without the cat. */
+int pn2_linear_tc2_f32(const float *x, int ldx, int c_a, const float *x2, int ldx2, const void *wblob, int ntile,
+                       int nchunks, int nkb, const float *bias, const float *res, int ldr, float *y, int ldy,
+                       long long rows, int cin, int cout, int relu, int pool, void *stream);
 int pn2_sa_group_linear_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                                const float *wxyz, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
                                float *y, int ldy, int clouds, int n, int m, int ns, int c1, int cout, int relu, int pool,

@@ -146,3 +146,31 @@ def test_roipool3d_utils_full_size_vs_legacy(cuda, legacy):
     assert torch.equal(empty, ref_empty)
     assert torch.equal(pooled, ref_pooled)
     assert pooled.shape == (B, M, 512, 3 + C) and int(empty.sum()) < B * M
+
+
+def test_roipool3d_split_padded_rows_equal_plain_pooling(cuda):
+    """pn2_roipool3d_split_f32 (two feature sources, padded rows) pools the same points in the same order"""
+    cabi = load("cabi")
+    B, N, M, S = 2, 16384, 40, 512
+    xyz_h = synthetic.make_clouds("lidar", B, N, seed=31)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    head = torch.randn((B, N, 2), device=cuda)
+    wide = torch.randn((B, N, 128), device=cuda)
+    rng = np.random.RandomState(2)
+    rois = np.zeros((B, M, 7), np.float32)
+    for b in range(B):
+        for m in range(M - 5):            # the last five boxes stay all-zero (empty)
+            p = xyz_h[b, rng.randint(0, N)]
+            rois[b, m] = [p[0], p[1] + 0.8, p[2], 2.5, 2.6, 4.9, rng.uniform(-np.pi, np.pi)]
+    boxes = torch.from_numpy(rois).to(cuda)
+    ref = torch.zeros((B, M, S, 3 + 130), device=cuda)
+    ref_empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
+    load("roipool3d_cuda").forward(xyz, boxes, torch.cat((head, wide), dim=2).contiguous(), ref, ref_empty)
+    got = torch.zeros((B, M, S, 136), device=cuda)
+    empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
+    cabi.call("pn2_roipool3d_split_f32", cabi.ptr(xyz), cabi.ptr(boxes), cabi.ptr(head), cabi.i32(2), cabi.ptr(wide),
+              cabi.i32(128), cabi.ptr(got), cabi.i32(136), cabi.i32(8), cabi.ptr(empty), cabi.i32(B), cabi.i32(N),
+              cabi.i32(M), cabi.i32(S))
+    assert torch.equal(empty, ref_empty) and int(empty.sum()) >= 5 * B
+    assert torch.equal(got[..., :5], ref[..., :5]) and torch.equal(got[..., 8:], ref[..., 5:])
+    assert float(got[..., 5:8].abs().max()) == 0.0

@@ -63,6 +63,31 @@ def test_linear_tc_strided_residual_pool(cuda):
     assert rel_err(y, r) < 3e-5
 
 
+def test_linear_cat_two_sources_equals_concatenated(cuda):
+    """pn2_linear_tc2_f32 reads [xa | xb] from two strided sources; same K order as the one-source
+    kernel on the materialised concatenation, so the results are identical bit for bit."""
+    fz = load("fused")
+    fz.set_mlp_engine("tc")
+    w, b, _ = _layer(fz, 128, 256, True, 3)
+    layer = fz.PackedLayer(w, b, True)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for rows in (128 * 40, 1000):
+        xa = torch.randn((rows, 128), generator=g).cuda()
+        wide = torch.randn((rows, 136), generator=g).cuda()       # padded pooled rows: features at column 8
+        xb = wide[:, 8:]
+        got = fz.linear_cat(xa, xb, layer)
+        cat = torch.cat((xa, xb), dim=1)
+        assert torch.equal(got, fz.linear(cat, layer))
+        assert rel_err(got, torch.relu(cat.double() @ w.double().t() + b.double())) < 3e-5
+    # residual epilogue (prefetched loads) on full and ragged tiles
+    w2, b2, l2 = _layer(fz, 64, 128, True, 4)
+    for rows in (128 * 33, 777):
+        x = torch.randn((rows, 128), generator=g).cuda()
+        res = torch.randn((rows, 64), generator=g).cuda()
+        got = fz.linear_tc(x, l2, res=res)
+        assert rel_err(got, torch.relu(x.double() @ w2.double().t() + b2.double() + res.double())) < 3e-5
+
+
 @pytest.mark.parametrize("c1,cout,ns,pool", [(128, 128, 64, 1), (128, 256, 64, 64), (16, 16, 16, 1), (32, 64, 32, 32), (196, 256, 16, 16)])
 def test_sa_group_linear_tc_vs_fp64(cuda, c1, cout, ns, pool):
     fz = load("fused")

@@ -91,6 +91,57 @@ def test_ball_query_full_size_vs_legacy_and_dual(cuda, legacy, kind):
     assert torch.equal(i0, refs[(0.1, 16)]) and torch.equal(i1, refs[(0.5, 32)])
 
 
+def _culled(cabi, xyz, new_xyz, r0, ns0, r1=0.0, ns1=0, order=True):
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    i0 = torch.zeros((B, M, ns0), dtype=torch.int32, device=xyz.device)
+    i1 = torch.zeros((B, M, max(ns1, 1)), dtype=torch.int32, device=xyz.device)
+    scratch = torch.empty((B, M), dtype=torch.int32, device=xyz.device) if order else None
+    cabi.call("pn2_ball_query_culled_f32", cabi.ptr(new_xyz), cabi.ptr(xyz), cabi.ptr(i0), cabi.ptr(i1 if ns1 else None),
+              cabi.ptr(scratch), cabi.i32(B), cabi.i32(N), cabi.i32(M), cabi.f32(r0), cabi.i32(ns0), cabi.f32(r1),
+              cabi.i32(ns1))
+    return i0, i1, scratch
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+@pytest.mark.parametrize("n,m", [(3000, 700), (1024, 256), (4096, 1024)])
+def test_ball_query_culled_vs_oracle(cuda, oracle, kind, n, m):
+    """the Morton-ordered, ballot-compacted scan returns the reference's idx bit for bit"""
+    cabi = load("cabi")
+    xyz_h = synthetic.make_clouds(kind, 2, n, seed=77 + n)
+    sel = np.random.RandomState(n).permutation(n)[:m]
+    new_h = xyz_h[:, sel].copy()
+    new_h[:, :5] += 500.0                 # centres without any neighbour: rows stay zero
+    xyz, new_xyz = torch.from_numpy(xyz_h).to(cuda), torch.from_numpy(new_h).to(cuda)
+    for (r0, ns0, r1, ns1) in [(0.1, 16, 0.5, 32), (1.0, 16, 2.0, 32), (0.5, 64, 0.0, 0), (100.0, 8, 0.05, 4)]:
+        i0, i1, order = _culled(cabi, xyz, new_xyz, r0, ns0, r1, ns1)
+        assert np.array_equal(i0.cpu().numpy(), oracle.ball_query(r0, ns0, xyz_h, new_h)), (kind, n, m, r0)
+        if ns1:
+            assert np.array_equal(i1.cpu().numpy(), oracle.ball_query(r1, ns1, xyz_h, new_h)), (kind, n, m, r1)
+        # the scratch holds a permutation of the centres of every cloud
+        assert torch.equal(torch.sort(order, dim=1)[0], torch.arange(m, device=cuda, dtype=torch.int32).expand(2, m))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+def test_ball_query_culled_full_size_vs_brute_force(cuda, legacy, kind):
+    cabi = load("cabi")
+    xyz = torch.from_numpy(synthetic.make_clouds(kind, 4, 16384, seed=1024)).to(cuda)
+    idx, _ = legacy.fps(xyz, 4096)
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    i0, i1, _ = _culled(cabi, xyz, new_xyz, 0.1, 16, 0.5, 32)
+    assert torch.equal(i0, legacy.ball_query(0.1, 16, xyz, new_xyz))
+    assert torch.equal(i1, legacy.ball_query(0.5, 32, xyz, new_xyz))
+    # no scratch -> brute-force path, same answer; fused.ball_query_dual is the product caller
+    j0, j1, _ = _culled(cabi, xyz, new_xyz, 0.1, 16, 0.5, 32, order=False)
+    assert torch.equal(i0, j0) and torch.equal(i1, j1)
+    k0, k1 = load("fused").ball_query_dual(xyz, new_xyz, 0.1, 16, 0.5, 32)
+    assert torch.equal(i0, k0) and torch.equal(i1, k1)
+    # degenerate cloud: every point identical (zero-size bounding box)
+    same = torch.ones((1, 2048, 3), device=cuda)
+    d0, _, _ = _culled(cabi, same, same[:, :512].contiguous(), 0.1, 16)
+    assert torch.equal(d0, torch.arange(16, device=cuda, dtype=torch.int32).expand(1, 512, 16))
+
+
 def test_gather_group_vs_oracle_and_backward(cuda, oracle):
     rng = np.random.RandomState(0)
     feats_h = rng.randn(3, 19, 700).astype(np.float32)
@@ -141,6 +192,26 @@ def test_three_nn_interpolate_full_size_vs_legacy(cuda, legacy):
     assert torch.equal(p2u().three_interpolate(feats, idx, w), legacy.three_interpolate(feats, idx, w))
     assert torch.equal(p2u().grouping_operation(feats, idx), legacy.group(feats, idx))
     assert torch.equal(p2u().gather_operation(feats, idx[:, :, 0].contiguous()), legacy.gather(feats, idx[:, :, 0].contiguous()))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "ties"])
+@pytest.mark.parametrize("n,m,b", [(16384, 4096, 3), (4096, 1024, 2), (2001, 601, 2)])
+def test_three_nn_culled_equals_brute_force(cuda, kind, n, m, b):
+    """Morton-ordered, bound-culled three_nn: dist2 and idx (ties included) identical to the full scan"""
+    cabi = load("cabi")
+    unknown = torch.from_numpy(synthetic.make_clouds(kind, b, n, seed=9 + n)).to(cuda)
+    sel = torch.randperm(n, generator=torch.Generator().manual_seed(m))[:m].to(cuda)
+    known = unknown[:, sel].contiguous()          # known points coincide with unknown ones: zero distances and ties
+    outs = []
+    for culled in (False, True):
+        d2 = torch.empty((b, n, 3), device=cuda)
+        idx = torch.empty((b, n, 3), dtype=torch.int32, device=cuda)
+        order = torch.empty((b, n), dtype=torch.int32, device=cuda) if culled else None
+        cabi.call("pn2_three_nn_culled_f32", cabi.ptr(unknown), cabi.ptr(known), cabi.ptr(d2), cabi.ptr(idx),
+                  cabi.ptr(order), cabi.i32(b), cabi.i32(n), cabi.i32(m))
+        outs.append((d2, idx))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(torch.sort(order, dim=1)[0], torch.arange(n, device=cuda, dtype=torch.int32).expand(b, n))
 
 
 def test_legacy_pins_the_oracle(cuda, legacy, oracle):
