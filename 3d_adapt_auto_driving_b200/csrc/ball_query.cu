@@ -97,27 +97,115 @@ __global__ void __launch_bounds__(kThreads) ball_query_kernel(const float *__res
 // radius (ascending index order is preserved), and its lanes then scan only that short list with
 // the exact test of the reference.  Warps are the unit of work because lidar clouds are very
 // unevenly dense: the few warps whose centres sit in the dense near field keep thousands of
-// candidates, the rest a few hundred, and 128 small units per cloud balance over the SMs.  The cull is conservative (box grown by r * 1.001 plus rounding slack; a hit needs
+// candidates, the rest a few hundred, and 128 small units per cloud balance over the SMs.
+// The list is scanned cooperatively (scan_list): 32 candidates at a time against one centre, hits
+// ordered by a ballot and appended with consecutive stores -- no divergent per-lane insertion,
+// whose serial latency otherwise dominates in the dense warps.  The cull is conservative (box grown by r * 1.001 plus rounding slack; a hit needs
 // |d| < r on every axis because the squared distance is a sum of non-negative, monotonically
 // rounded terms), so the set and order of accepted candidates -- and hence idx -- is unchanged.
 // =================================================================================================
-constexpr int kCullWarps = kThreads / 32;         // 4 autonomous warps per CTA
-constexpr int kWarpList = 512;                    // candidates a warp culls per pass (16 rounds of 32)
+constexpr int kCullThreads = 64;                  // 2 autonomous warps per CTA
+constexpr int kCullWarps = kCullThreads / 32;
+constexpr int kWarpList = 1024;                   // capacity of a warp's candidate list (16 KB)
+constexpr int kScanUnroll = 8;                    // groups of 32 list entries evaluated per scan step
+constexpr int kCullBatch = 8;                     // rounds of 32 candidates whose loads are in flight together
+
+// One pass of the cooperative scan: the 32 lanes test 32 list entries at a time against ONE centre,
+// a ballot orders the hits, and they are appended to the centre's row with consecutive stores.
+// cnt / first live in the lane that owns the centre and are exchanged by shuffle.
+template <bool DUAL>
+__device__ __forceinline__ void scan_list(const float4 *__restrict__ list, int wn, int lane, float qx, float qy, float qz,
+                                          int c, float r2_0, float r2_1, int ns0, int ns1, int32_t *__restrict__ idx0,
+                                          int32_t *__restrict__ idx1, size_t row_base, int &cnt0, int &cnt1, int &first0,
+                                          int &first1) {
+    const unsigned lt = (1u << lane) - 1u;
+    for (int j = 0; j < 32; ++j) {
+        int n0 = __shfl_sync(0xffffffffu, cnt0, j);
+        int n1 = DUAL ? __shfl_sync(0xffffffffu, cnt1, j) : ns1;
+        if (n0 >= ns0 && n1 >= ns1) continue;     // this centre is full (or an inactive lane)
+        const float cx = __shfl_sync(0xffffffffu, qx, j), cy = __shfl_sync(0xffffffffu, qy, j),
+                    cz = __shfl_sync(0xffffffffu, qz, j);
+        const int cj = __shfl_sync(0xffffffffu, c, j);
+        int32_t *row0 = idx0 + (row_base + cj) * ns0;
+        int32_t *row1 = DUAL ? idx1 + (row_base + cj) * ns1 : nullptr;
+        int f0 = __shfl_sync(0xffffffffu, first0, j), f1 = DUAL ? __shfl_sync(0xffffffffu, first1, j) : 0;
+        // kScanUnroll groups of 32 candidates per step: their loads, distances and ballots are
+        // independent and overlap; only the cheap integer appends are sequential
+        for (int i0 = 0; i0 < wn; i0 += 32 * kScanUnroll) {
+            unsigned b0[kScanUnroll], b1[kScanUnroll];
+            int kk[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int i = i0 + u * 32 + lane;
+                const bool live = i < wn;
+                const float4 p = list[live ? i : 0];
+                const float d2 = pn2_sqdist(cx - p.x, cy - p.y, cz - p.z);
+                kk[u] = __float_as_int(p.w);
+                b0[u] = __ballot_sync(0xffffffffu, live && d2 < r2_0);
+                b1[u] = DUAL ? __ballot_sync(0xffffffffu, live && d2 < r2_1) : 0u;
+            }
+            // appends: the slot of a hit is n + (hits of earlier groups) + (hits of lower lanes), so
+            // the stores are predicated and independent of each other -- no serial chain through n
+            if (n0 < ns0) {
+                if (n0 == 0) {               // first hit of this centre so far: remember it for the fill rule
+                    unsigned fb = 0u;
+                    int fk = 0;
+#pragma unroll
+                    for (int u = kScanUnroll - 1; u >= 0; --u)
+                        if (b0[u]) { fb = b0[u]; fk = kk[u]; }
+                    if (fb) f0 = __shfl_sync(0xffffffffu, fk, __ffs(fb) - 1);
+                }
+                int at = n0;
+#pragma unroll
+                for (int u = 0; u < kScanUnroll; ++u) {
+                    const int pos = at + __popc(b0[u] & lt);
+                    if (((b0[u] >> lane) & 1u) && pos < ns0) row0[pos] = kk[u];
+                    at += __popc(b0[u]);
+                }
+                n0 = at;
+            }
+            if (DUAL && n1 < ns1) {
+                if (n1 == 0) {
+                    unsigned fb = 0u;
+                    int fk = 0;
+#pragma unroll
+                    for (int u = kScanUnroll - 1; u >= 0; --u)
+                        if (b1[u]) { fb = b1[u]; fk = kk[u]; }
+                    if (fb) f1 = __shfl_sync(0xffffffffu, fk, __ffs(fb) - 1);
+                }
+                int at = n1;
+#pragma unroll
+                for (int u = 0; u < kScanUnroll; ++u) {
+                    const int pos = at + __popc(b1[u] & lt);
+                    if (((b1[u] >> lane) & 1u) && pos < ns1) row1[pos] = kk[u];
+                    at += __popc(b1[u]);
+                }
+                n1 = at;
+            }
+            if (n0 >= ns0 && n1 >= ns1) break;
+        }
+        if (lane == j) {
+            cnt0 = min(n0, ns0); first0 = f0;
+            if (DUAL) { cnt1 = min(n1, ns1); first1 = f1; }
+        }
+    }
+}
 
 template <bool DUAL>
-__global__ void __launch_bounds__(kThreads) ball_query_culled_kernel(const float *__restrict__ new_xyz,
-                                                                    const float *__restrict__ xyz,
-                                                                    const int32_t *__restrict__ order,
-                                                                    int32_t *__restrict__ idx0, int32_t *__restrict__ idx1,
-                                                                    int n, int m, float radius0, int ns0, float radius1,
-                                                                    int ns1) {
+__global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const float *__restrict__ new_xyz,
+                                                                        const float *__restrict__ xyz,
+                                                                        const int32_t *__restrict__ order,
+                                                                        int32_t *__restrict__ idx0,
+                                                                        int32_t *__restrict__ idx1, int n, int m,
+                                                                        float radius0, int ns0, float radius1, int ns1) {
     __shared__ float4 cand[kCullWarps][kWarpList];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wfirst = (blockIdx.x * kCullWarps + warp) * 32;
     if (wfirst >= m) return;                      // warps never meet at a CTA barrier
     const bool active = wfirst + lane < m;
     // inactive lanes mirror the warp's first centre so they do not widen the box
-    const int c = __ldg(order + (size_t)cloud * m + (active ? wfirst + lane : wfirst));
+    const int slot = active ? wfirst + lane : wfirst;
+    const int c = order ? __ldg(order + (size_t)cloud * m + slot) : slot;
     xyz += (size_t)cloud * n * 3;
     const float *q = new_xyz + ((size_t)cloud * m + c) * 3;
     const float qx = __ldg(q + 0), qy = __ldg(q + 1), qz = __ldg(q + 2);
@@ -143,77 +231,72 @@ __global__ void __launch_bounds__(kThreads) ball_query_culled_kernel(const float
     const bool keep_all = __any_sync(0xffffffffu, !(qx == qx) || !(qy == qy) || !(qz == qz)) || !(lx <= hx) ||
                           !(ly <= hy) || !(lz <= hz);
 
-    int32_t *row0 = idx0 + ((size_t)cloud * m + c) * ns0;
-    int32_t *row1 = DUAL ? idx1 + ((size_t)cloud * m + c) * ns1 : nullptr;
-    int cnt0 = active ? 0 : ns0;
-    int cnt1 = (DUAL && active) ? 0 : ns1;
-    if (!DUAL) cnt1 = 0x7fffffff;
+    const size_t row_base = (size_t)cloud * m;
+    int cnt0 = active ? 0 : ns0, cnt1 = (DUAL && active) ? 0 : ns1, first0 = 0, first1 = 0;
 
     float4 *mine = cand[warp];
-    for (int base = 0; base < n; base += kWarpList) {
-        const bool done = (cnt0 >= ns0) && (!DUAL || cnt1 >= ns1);
-        if (__all_sync(0xffffffffu, done)) break;
-        // ---- cull the next 512 candidates, 32 per round, compacted in index order ----
-        int wn = 0;
-#pragma unroll 4
-        for (int rd = 0; rd < kWarpList / 32; ++rd) {
+    int wn = 0;
+    for (int base = 0; base < n; base += kCullBatch * 32) {
+        // ---- cull: kCullBatch rounds of 32 candidates, all loads issued first; survivors are
+        //      appended in index order ----
+        float px[kCullBatch], py[kCullBatch], pz[kCullBatch];
+#pragma unroll
+        for (int rd = 0; rd < kCullBatch; ++rd) {
+            const int k = min(base + rd * 32 + lane, n - 1);
+            px[rd] = __ldg(xyz + (size_t)k * 3); py[rd] = __ldg(xyz + (size_t)k * 3 + 1); pz[rd] = __ldg(xyz + (size_t)k * 3 + 2);
+        }
+#pragma unroll
+        for (int rd = 0; rd < kCullBatch; ++rd) {
             const int k = base + rd * 32 + lane;
-            bool in = false;
-            float px = 0.f, py = 0.f, pz = 0.f;
-            if (k < n) {
-                px = __ldg(xyz + (size_t)k * 3); py = __ldg(xyz + (size_t)k * 3 + 1); pz = __ldg(xyz + (size_t)k * 3 + 2);
-                in = keep_all || (px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz);
-            }
+            const bool in = k < n && (keep_all || (px[rd] >= lx && px[rd] <= hx && py[rd] >= ly && py[rd] <= hy &&
+                                                   pz[rd] >= lz && pz[rd] <= hz));
             const unsigned bal = __ballot_sync(0xffffffffu, in);
-            if (in) mine[wn + __popc(bal & ((1u << lane) - 1u))] = make_float4(px, py, pz, __int_as_float(k));
+            if (in) mine[wn + __popc(bal & ((1u << lane) - 1u))] = make_float4(px[rd], py[rd], pz[rd], __int_as_float(k));
             wn += __popc(bal);
         }
-        __syncwarp();
-        // ---- scan the list: the reference's test and fill rule ----
-        if (!done) {
-#pragma unroll 2
-            for (int i = 0; i < wn; ++i) {
-                const float4 p = mine[i];
-                const float dx = qx - p.x;
-                if (fabsf(dx) < rmax) {
-                    const float d2 = pn2_sqdist(dx, qy - p.y, qz - p.z);
-                    const int k = __float_as_int(p.w);
-                    if (d2 < r2_0 && cnt0 < ns0) {
-                        if (cnt0 == 0)
-                            for (int l = 0; l < ns0; ++l) row0[l] = k;
-                        else
-                            row0[cnt0] = k;
-                        ++cnt0;
-                    }
-                    if (DUAL && d2 < r2_1 && cnt1 < ns1) {
-                        if (cnt1 == 0)
-                            for (int l = 0; l < ns1; ++l) row1[l] = k;
-                        else
-                            row1[cnt1] = k;
-                        ++cnt1;
-                    }
-                }
-            }
+        // ---- scan when the list cannot take another batch, or at the end of the cloud ----
+        if (wn > kWarpList - kCullBatch * 32 || base + kCullBatch * 32 >= n) {
+            __syncwarp();
+            scan_list<DUAL>(mine, wn, lane, qx, qy, qz, c, r2_0, r2_1, ns0, ns1, idx0, idx1, row_base, cnt0, cnt1, first0,
+                            first1);
+            __syncwarp();
+            wn = 0;
+            const bool done = (cnt0 >= ns0) && (!DUAL || cnt1 >= ns1);
+            if (__all_sync(0xffffffffu, done)) break;
         }
-        __syncwarp();
+    }
+    // ---- fill rule of the reference: the first hit occupies every slot a later hit did not take ----
+    for (int j = 0; j < 32; ++j) {
+        if (!__shfl_sync(0xffffffffu, (int)active, j)) continue;
+        const int cj = __shfl_sync(0xffffffffu, c, j);
+        const int n0 = __shfl_sync(0xffffffffu, cnt0, j), f0 = __shfl_sync(0xffffffffu, first0, j);
+        if (n0 > 0)
+            for (int l = n0 + lane; l < ns0; l += 32) idx0[(row_base + cj) * ns0 + l] = f0;
+        if (DUAL) {
+            const int n1 = __shfl_sync(0xffffffffu, cnt1, j), f1 = __shfl_sync(0xffffffffu, first1, j);
+            if (n1 > 0)
+                for (int l = n1 + lane; l < ns1; l += 32) idx1[(row_base + cj) * ns1 + l] = f1;
+        }
     }
 }
 
 template <bool DUAL>
 int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n, int m,
                   float r0, int ns0, float r1, int ns1, cudaStream_t stream) {
-    if (launch_spatial_order(new_xyz, order, b, m, stream) != cudaSuccess) {
+    // few centres per cloud: the ordering launch costs more than it saves, warps take the centres as they come
+    const bool sorted = m >= 256;
+    if (sorted && launch_spatial_order(new_xyz, order, b, m, stream) != cudaSuccess) {
         pn2_set_last_error("pn2_ball_query_culled_f32: ordering kernel launch failed");
         return PN2_ERR_LAUNCH;
     }
-    dim3 grid(pn2_divup(m, kThreads), b);   // 4 warps x 32 centres per CTA
-    ball_query_culled_kernel<DUAL><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1);
+    if (!sorted) order = nullptr;
+    dim3 grid(pn2_divup(m, kCullThreads), b);   // 2 warps x 32 centres per CTA
+    ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
 
-// the culled path pays off once the scan dominates the extra sort launch
-inline bool use_culled(const int32_t *order, int n, int m) { return order && m >= 256 && n >= 1024; }
+inline bool use_culled(const int32_t *order, int n, int m) { return order && n >= 128; }
 
 }  // namespace
 
@@ -246,8 +329,8 @@ PN2_API int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int3
 }
 
 // The same results as pn2_ball_query_f32 (nsample1 == 0) / pn2_ball_query_dual_f32 through the
-// spatially culled scan.  `order` is caller-provided scratch of b * m int32 (the Morton order of
-// the centres is left there); with order == NULL or a small problem the brute-force kernels run.
+// spatially culled scan.  `order` is caller-provided scratch of b * m int32 (the Hilbert order of
+// the centres is left there when m >= 256); with order == NULL or a tiny cloud the brute-force kernels run.
 PN2_API int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
                                       int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
                                       int nsample1, cudaStream_t stream) {

@@ -145,22 +145,35 @@ __global__ void __launch_bounds__(kThreads) three_nn_culled_kernel(const float *
             wn += __popc(bal);
         }
         __syncwarp();
-        // ---- the reference's insertion over the list ----
-#pragma unroll 2
-        for (int t = 0; t < wn; ++t) {
-            const float4 p = mine[t];
-            const float dx = ux - p.x;
-            if (__fmul_rn(dx, dx) < b3) {
-                const float d = pn2_sqdist(dx, uy - p.y, uz - p.z);
-                const int k = __float_as_int(p.w);
+        // ---- the reference's insertion over the list; four distances are evaluated together so
+        //      their latencies overlap, the (rarely taken) insertions stay in index order ----
+        auto insert = [&](float d, int k) {
+            if (d < b3) {
                 if (d < b1) {
                     b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
                 } else if (d < b2) {
                     b3 = b2; i3 = i2; b2 = d; i2 = k;
-                } else if (d < b3) {
+                } else {
                     b3 = d; i3 = k;
                 }
             }
+        };
+        int t = 0;
+        for (; t + 4 <= wn; t += 4) {
+            float dd[4];
+            int kk[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 p = mine[t + v];
+                dd[v] = pn2_sqdist(ux - p.x, uy - p.y, uz - p.z);
+                kk[v] = __float_as_int(p.w);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) insert(dd[v], kk[v]);
+        }
+        for (; t < wn; ++t) {
+            const float4 p = mine[t];
+            insert(pn2_sqdist(ux - p.x, uy - p.y, uz - p.z), __float_as_int(p.w));
         }
         __syncwarp();
     }
@@ -243,7 +256,7 @@ PN2_API int pn2_three_nn_f32(const float *unknown, const float *known, float *di
 }
 
 // pn2_three_nn_f32 through the spatially culled scan; `order` is caller scratch of b * n int32
-// (left holding the Morton order of the unknown points).  order == NULL or a small level runs the
+// (left holding the Hilbert order of the unknown points).  order == NULL or a small level runs the
 // brute-force kernel.  Same dist2 / idx bit for bit.
 PN2_API int pn2_three_nn_culled_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int32_t *order,
                                     int b, int n, int m, cudaStream_t stream) {

@@ -140,7 +140,7 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
     M = new_xyz.shape[1]
     i0 = torch.zeros((B, M, ns0), dtype=torch.int32, device=xyz.device)
     i1 = torch.zeros((B, M, ns1), dtype=torch.int32, device=xyz.device)
-    order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)    # scratch: Morton order of the centres
+    order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)    # scratch: Hilbert order of the centres
     cabi.call("pn2_ball_query_culled_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), ptr(order), i32(B), i32(N), i32(M),
               f32(r0), i32(ns0), f32(r1), i32(ns1), work=12.0 * B * M * N)
     return i0, i1

@@ -48,7 +48,8 @@ class RPN(nn.Module):
         nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
 
     def train(self, mode=True):
-        self._packed = None
+        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
+            self._packed = None
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):

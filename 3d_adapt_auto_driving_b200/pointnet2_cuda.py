@@ -43,7 +43,10 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out, idx, grad_points):
 
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx):
     _chk(new_xyz, torch.float32, "new_xyz"); _chk(xyz, torch.float32, "xyz"); _chk(idx, torch.int32, "idx")
-    cabi.call("pn2_ball_query_f32", ptr(new_xyz), ptr(xyz), ptr(idx), i32(b), i32(n), i32(m), f32(radius), i32(nsample))
+    # same idx through the culled / ballot-append scan (ball_query.cu); it needs b*m int32 of scratch
+    order = torch.empty((b, m), dtype=torch.int32, device=xyz.device) if n >= 128 else None
+    cabi.call("pn2_ball_query_culled_f32", ptr(new_xyz), ptr(xyz), ptr(idx), ptr(None), ptr(order), i32(b), i32(n), i32(m),
+              f32(radius), i32(nsample), f32(0.0), i32(0), work=12.0 * b * m * n)
     return 1
 
 

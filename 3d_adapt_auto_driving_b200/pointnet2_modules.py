@@ -36,7 +36,8 @@ class _PointnetSAModuleBase(nn.Module):
 
     # ---- cache of folded weights for the fused path ----
     def train(self, mode=True):
-        self._packed = None
+        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
+            self._packed = None
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):
@@ -190,7 +191,8 @@ class PointnetFPModule(nn.Module):
         self._packed = None
 
     def train(self, mode=True):
-        self._packed = None
+        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
+            self._packed = None
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):

@@ -61,8 +61,9 @@ int pn2_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int
 int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int b, int n, int m,
                             float radius0, int nsample0, float radius1, int nsample1, void *stream);
 /* Same idx as the two entries above (nsample1 == 0: single radius) through a spatially culled scan:
- * centres Morton-ordered per cloud into `order` (caller scratch, b*m int32), candidates compacted by
- * warp ballot against the CTA's grown bounding box.  order == NULL or a small problem -> brute force. */
+ * centres put in Hilbert-curve order per cloud into `order` (caller scratch, b*m int32), candidates
+ * compacted by warp ballot against each warp's grown bounding box, hits appended by ballot too.
+ * order == NULL or n < 128 -> brute force. */
 int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order,
                               int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
                               void *stream);
@@ -80,8 +81,8 @@ int pn2_group_points_grad_f32(const float *grad_out, const int32_t *idx, float *
  * idx (B,n,3) int32.  Bit-exact. */
 int pn2_three_nn_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int b, int n, int m,
                      void *stream);
-/* Same dist2 / idx through a spatially culled scan (unknown points Morton-ordered into `order`,
- * caller scratch of b*n int32; known points compacted by warp ballot against the CTA's bounding box
+/* Same dist2 / idx through a spatially culled scan (unknown points Hilbert-ordered into `order`,
+ * caller scratch of b*n int32; known points compacted by warp ballot against the warp's bounding box
  * grown by the current third-neighbour bound).  order == NULL or a small level -> brute force. */
 int pn2_three_nn_culled_f32(const float *unknown, const float *known, float *dist2, int32_t *idx, int32_t *order, int b,
                             int n, int m, void *stream);

@@ -80,6 +80,28 @@ def test_nms_batched_with_device_counts(cuda, legacy):
         assert np.array_equal(keep[p, :len(ref)].cpu().numpy(), ref), p
 
 
+def test_nms_rotated_dense_mode_and_large_problems(cuda, legacy):
+    """rotated problems of <= 128 boxes take the all-pairs bit-matrix path, larger ones the lazy rows;
+    problems beyond the shared-memory staging budget (9830 boxes) read the boxes from global memory"""
+    ic = load("iou3d_cuda")
+    P, stride = 9, 129
+    sizes = [0, 1, 2, 37, 64, 100, 127, 128, 129]
+    boxes = torch.stack([torch.from_numpy(_bev_boxes(70 + p, stride, spread=6.0)) for p in range(P)]).to(cuda)
+    counts = torch.tensor(sizes, dtype=torch.int32, device=cuda)
+    for thr in (0.1, 0.7):
+        for max_keep in (stride, 10):
+            keep, num = ic.nms_device(boxes, thr, rotated=True, max_keep=max_keep, counts=counts)
+            for p, n in enumerate(sizes):
+                ref = legacy.greedy_from_mask(legacy.nms_mask(boxes[p, :max(n, 1)].contiguous(), thr).cpu(), n) if n else np.zeros(0, np.int64)
+                k = min(max_keep, len(ref))
+                assert int(num[p]) == k, (thr, max_keep, n)
+                assert np.array_equal(keep[p, :k].cpu().numpy(), ref[:k]), (thr, max_keep, n)
+    big = torch.from_numpy(_bev_boxes(5, 12000, spread=60.0)).to(cuda)
+    ref = legacy.greedy_from_mask(legacy.nms_mask(big, 0.8, normal=True).cpu(), 12000)
+    keep, num = ic.nms_device(big, 0.8, rotated=False, max_keep=200)
+    assert int(num) == 200 and np.array_equal(keep[0, :200].cpu().numpy(), ref[:200])
+
+
 def test_nms_utils_returns_original_indices(cuda, legacy):
     iu = load("iou3d_utils")
     boxes = torch.from_numpy(_bev_boxes(7, 500)).to(cuda)
