@@ -17,6 +17,19 @@
 //      (again two redux.sync) and thereby knows the next centre without a second exchange.
 // There is no __syncthreads and no cluster barrier inside the round loop.
 //
+// Round cost is issue slots + one exchange latency, so the per-point work is pared down:
+//   * the P points of a thread sit in registers SORTED by the reference's tie-break rank (a one-time
+//     sorting network at load), so "first strict maximum in register order" IS the reference's
+//     in-thread winner and the update loop only carries (max, index): no second selection pass;
+//   * the distance arithmetic runs two points at a time on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2,
+//     each half IEEE round-to-nearest: bit-identical to the scalar sequence);
+//   * the winner's coordinates come from a shared-memory copy of the CTA's points (one LDS.128 in one
+//     lane) instead of being carried through the selection;
+//   * the rank reduction (second redux) only runs when two lanes / records tie on the distance;
+//   * the mbarrier wait is CTA-scoped: the records arrive through the async proxy (st.async +
+//     complete_tx) straight into shared memory, and a cluster-scoped acquire made ptxas invalidate
+//     the L1 (CCTL.IVALL) in every warp every round.
+//
 // Bit-exactness: the reference's winner among equal distances is decided by its launch shape:
 // thread tid scans k = tid, tid+bs, ... keeping the FIRST maximum (strict >, sampling_gpu.cu:
 // 136-137) and the tree (__update, :86-91) keeps the lower slot on ties at every level, which
@@ -52,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -81,11 +94,21 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// tie-break rank of point k (see the header): bitrev(k mod bs) * ceil(N / bs) + k / bs
+__device__ __forceinline__ uint32_t fps_rank(int k, int log2bs, int cnt) {
+    const uint32_t tref = (uint32_t)k & ((1u << log2bs) - 1u);
+    const uint32_t rev = log2bs ? (__brev(tref) >> (32 - log2bs)) : 0u;
+    return rev * (uint32_t)cnt + ((uint32_t)k >> log2bs);
+}
+
 // P points per thread, CLUSTER CTAs per cloud.  grid = (CLUSTER, B).
+// dynamic shared memory: P * kThreads float4 = this CTA's points, entry p * kThreads + tid = point kbase + p * kThreads
 template <int P, int CLUSTER>
 __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
                                                        int32_t *__restrict__ idx, int n, int m, int log2bs, int cnt) {
     constexpr int S = CLUSTER * kWarps;  // records per round
+    constexpr int P2 = (P + 1) / 2;
+    extern __shared__ float4 pts_s[];
     __shared__ FpsRecord slots[2][S];
     __shared__ __align__(8) uint64_t bars[2];
 
@@ -99,27 +122,52 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
     idx += (size_t)cloud * m;
     if (temp) temp += (size_t)cloud * n;
 
-    // ---- resident state: P points, their running min distance and their tie-break rank ----
-    float px[P], py[P], pz[P], pt[P];
-    uint32_t prank[P];
-    const int kbase = (int)crank * (P * kThreads) + tid;
+    // ---- resident state: P points in tie-break-rank order, their running min distance and index ----
+    const int cta_base = (int)crank * (P * kThreads);
+    const int kbase = cta_base + tid;
+    int ks[P];
+    {
+        uint32_t pr[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const int k = kbase + p * kThreads;
-        if (k < n) {
-            px[p] = __ldg(xyz + (size_t)k * 3 + 0);
-            py[p] = __ldg(xyz + (size_t)k * 3 + 1);
-            pz[p] = __ldg(xyz + (size_t)k * 3 + 2);
-            pt[p] = temp ? temp[k] : 1e10f;
-            const uint32_t tref = (uint32_t)k & ((1u << log2bs) - 1u);
-            const uint32_t rev = log2bs ? (__brev(tref) >> (32 - log2bs)) : 0u;
-            prank[p] = rev * (uint32_t)cnt + ((uint32_t)k >> log2bs);
-        } else {  // padding slot: distance 0 and the worst rank, can never win against a real point
-            px[p] = py[p] = pz[p] = 0.f;
-            pt[p] = 0.f;
-            prank[p] = 0xFFFFFFFFu;
+        for (int p = 0; p < P; ++p) {
+            const int k = kbase + p * kThreads;
+            ks[p] = k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < n) {
+                v.x = __ldg(xyz + (size_t)k * 3 + 0);
+                v.y = __ldg(xyz + (size_t)k * 3 + 1);
+                v.z = __ldg(xyz + (size_t)k * 3 + 2);
+                pr[p] = fps_rank(k, log2bs, cnt);
+            } else {
+                pr[p] = 0xFFFFFFFFu;   // padding: worst rank, sorts last
+            }
+            pts_s[p * kThreads + tid] = v;
+        }
+        // odd-even transposition network on (rank, k): fully unrolled, static register indices
+#pragma unroll
+        for (int pass = 0; pass < P; ++pass) {
+#pragma unroll
+            for (int i = pass & 1; i + 1 < P; i += 2) {
+                const bool sw = pr[i] > pr[i + 1];
+                const uint32_t a = pr[i], b = pr[i + 1];
+                const int ka = ks[i], kb = ks[i + 1];
+                pr[i] = sw ? b : a; pr[i + 1] = sw ? a : b;
+                ks[i] = sw ? kb : ka; ks[i + 1] = sw ? ka : kb;
+            }
         }
     }
+    __syncthreads();   // pts_s complete (read back below in a different order, later by the winner lanes)
+    float2 px[P2], py[P2], pz[P2], pt[P2];
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+        const int k = ks[s];
+        const float4 v = pts_s[k - cta_base];
+        float t = 0.f;   // padding slot: distance 0 and the worst rank, can never win against a real point
+        if (k < n) t = temp ? temp[k] : 1e10f;
+        if (s & 1) { px[s >> 1].y = v.x; py[s >> 1].y = v.y; pz[s >> 1].y = v.z; pt[s >> 1].y = t; }
+        else       { px[s >> 1].x = v.x; py[s >> 1].x = v.y; pz[s >> 1].x = v.z; pt[s >> 1].x = t; }
+    }
+    if (P & 1) { px[P2 - 1].y = 0.f; py[P2 - 1].y = 0.f; pz[P2 - 1].y = 0.f; pt[P2 - 1].y = 0.f; }
 
     if (CLUSTER > 1) {
         if (tid == 0) {
@@ -133,53 +181,63 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
     float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // idx[0] = 0 always
     if (crank == 0 && tid == 0) idx[0] = 0;
 
+    // cluster addresses of this warp's record slot and of the round barrier in every CTA (parity 0)
+    uint32_t rslot[CLUSTER], rbar[CLUSTER];
+#pragma unroll
+    for (int cta = 0; cta < CLUSTER; ++cta) {
+        rslot[cta] = CLUSTER > 1 ? mapa(pn2_smem_u32(&slots[0][crank * kWarps + warp]), cta) : 0u;
+        rbar[cta] = CLUSTER > 1 ? mapa(pn2_smem_u32(&bars[0]), cta) : 0u;
+    }
+
     for (int r = 0; r < m - 1; ++r) {
         const int par = r & 1;
         if (CLUSTER > 1 && tid == 0) mbar_arrive_expect_tx(&bars[par], S * (uint32_t)sizeof(FpsRecord));
 
-        // 1. distance update, thread max
-        float tmax = 0.f;
+        // 1. distance update and thread argmax: the first strict maximum in rank order
+        float tmax = -1.f;
+        int bestk = ks[0];
+        const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const float d = pn2_sqdist(px[p] - cx, py[p] - cy, pz[p] - cz);
-            pt[p] = fminf(d, pt[p]);
-            tmax = fmaxf(tmax, pt[p]);
-        }
-        // 2. warp argmax: max distance bits, then min rank among the lanes that hold it
-        const uint32_t vb = __float_as_uint(tmax);
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, vb);
-        uint32_t rk = 0xFFFFFFFFu;
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        int sk = 0;
-        if (vb == wmax) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                if (__float_as_uint(pt[p]) == wmax && prank[p] < rk) {
-                    rk = prank[p];
-                    sx = px[p]; sy = py[p]; sz = pz[p];
-                    sk = kbase + p * kThreads;
-                }
+        for (int q = 0; q < P2; ++q) {
+            // (p - c) == p + (-c) exactly; t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t) as pn2_sqdist
+            const float2 dx = __fadd2_rn(px[q], ncx), dy = __fadd2_rn(py[q], ncy), dz = __fadd2_rn(pz[q], ncz);
+            float2 t = __fmul2_rn(dy, dy);
+            t = __ffma2_rn(dx, dx, t);
+            t = __ffma2_rn(dz, dz, t);
+            pt[q].x = fminf(t.x, pt[q].x);
+            if (pt[q].x > tmax) { tmax = pt[q].x; bestk = ks[2 * q]; }
+            if (2 * q + 1 < P) {
+                pt[q].y = fminf(t.y, pt[q].y);
+                if (pt[q].y > tmax) { tmax = pt[q].y; bestk = ks[2 * q + 1]; }
             }
         }
-        const uint32_t wrk = __reduce_min_sync(0xffffffffu, rk);
-        const uint32_t winners = __ballot_sync(0xffffffffu, rk == wrk);
+        // 2. warp argmax: max distance bits; the rank decides only if several lanes hold it
+        const uint32_t vb = __float_as_uint(tmax);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, vb);
+        const uint32_t rk = (vb == wmax && bestk < n) ? fps_rank(bestk, log2bs, cnt) : 0xFFFFFFFFu;
+        const uint32_t cand = __ballot_sync(0xffffffffu, vb == wmax);
+        uint32_t winners = cand;
+        if (cand & (cand - 1u)) {
+            const uint32_t wrk = __reduce_min_sync(0xffffffffu, rk);
+            winners = __ballot_sync(0xffffffffu, rk == wrk);
+        }
         // 3. publish the warp's record
         if (lane == __ffs(winners) - 1) {
-            const uint32_t rinv = ~wrk;
+            const float4 c = pts_s[bestk - cta_base];
+            const uint32_t rinv = ~rk;
             if (CLUSTER == 1) {
                 FpsRecord rec;
-                rec.d2bits = wmax; rec.rinv = rinv; rec.k = sk; rec.pad = 0;
-                rec.x = sx; rec.y = sy; rec.z = sz; rec.w = 0.f;
+                rec.d2bits = wmax; rec.rinv = rinv; rec.k = bestk; rec.pad = 0;
+                rec.x = c.x; rec.y = c.y; rec.z = c.z; rec.w = 0.f;
                 slots[par][warp] = rec;
             } else {
-                const uint32_t local = pn2_smem_u32(&slots[par][crank * kWarps + warp]);
-                const uint32_t lbar = pn2_smem_u32(&bars[par]);
+                const uint32_t so = (uint32_t)par * (uint32_t)(S * sizeof(FpsRecord)), bo = (uint32_t)par * 8u;
 #pragma unroll
-                for (int c = 0; c < CLUSTER; ++c) {
-                    const uint32_t dst = mapa(local, c);
-                    const uint32_t dbar = mapa(lbar, c);
-                    st_async_v4(dst, wmax, rinv, (uint32_t)sk, 0u, dbar);
-                    st_async_v4(dst + 16, __float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), 0u, dbar);
+                for (int cta = 0; cta < CLUSTER; ++cta) {
+                    const uint32_t dst = rslot[cta] + so;
+                    const uint32_t dbar = rbar[cta] + bo;
+                    st_async_v4(dst, wmax, rinv, (uint32_t)bestk, 0u, dbar);
+                    st_async_v4(dst + 16, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), 0u, dbar);
                 }
             }
         }
@@ -188,15 +246,19 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
 
         // 4. every warp reduces the S records (redundantly) -> next centre
         unsigned long long kA = 0ull, kB = 0ull;
-        if (lane < S) kA = ((unsigned long long)slots[par][lane].d2bits << 32) | slots[par][lane].rinv;
-        if (S > 32 && lane + 32 < S)
-            kB = ((unsigned long long)slots[par][lane + 32].d2bits << 32) | slots[par][lane + 32].rinv;
+        if (lane < S) kA = *reinterpret_cast<const unsigned long long *>(&slots[par][lane]);   // (rinv | d2bits << 32)
+        if (S > 32 && lane + 32 < S) kB = *reinterpret_cast<const unsigned long long *>(&slots[par][lane + 32]);
+        kA = (kA << 32) | (kA >> 32);
+        kB = (kB << 32) | (kB >> 32);
         const unsigned long long km = kA > kB ? kA : kB;
         const int myslot = (kA >= kB) ? lane : lane + 32;
         const uint32_t hi = (uint32_t)(km >> 32), lo = (uint32_t)km;
         const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-        const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        const uint32_t who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+        uint32_t who = __ballot_sync(0xffffffffu, hi == mh);
+        if (who & (who - 1u)) {
+            const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+        }
         const int wslot = __shfl_sync(0xffffffffu, myslot, __ffs(who) - 1);
         const float4 c4 = *reinterpret_cast<const float4 *>(&slots[par][wslot].x);
         cx = c4.x; cy = c4.y; cz = c4.z;
@@ -205,9 +267,9 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
 
     if (temp) {  // the reference leaves the running min distances in the caller's scratch
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int k = kbase + p * kThreads;
-            if (k < n) temp[k] = pt[p];
+        for (int s = 0; s < P; ++s) {
+            const int k = ks[s];
+            if (k < n) temp[k] = (s & 1) ? pt[s >> 1].y : pt[s >> 1].x;
         }
     }
     if (CLUSTER > 1) cluster_sync_all();  // nobody exits while a peer may still target its smem
@@ -219,7 +281,16 @@ cudaError_t launch_fps(const float *xyz, float *temp, int32_t *idx, int b, int n
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER, b, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)P * kThreads * sizeof(float4);
+    if (cfg.dynamicSmemBytes > 48 * 1024) {
+        static bool attr_done = false;   // per <P, CLUSTER> instantiation
+        if (!attr_done) {
+            cudaError_t ea = cudaFuncSetAttribute(fps_kernel<P, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)cfg.dynamicSmemBytes);
+            if (ea != cudaSuccess) return ea;
+            attr_done = true;
+        }
+    }
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

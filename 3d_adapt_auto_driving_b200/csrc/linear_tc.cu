@@ -124,7 +124,7 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
     pa.nkb = p.nkb; pa.stages = p.stages; pa.nchunks = p.nchunks; pa.items = p.items;
     pa.ring = smem; pa.stage_bytes = L.stage_bytes; pa.full = full; pa.empty = empty;
     pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
-    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = nullptr;
 
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
@@ -307,8 +307,7 @@ int launch_tc(TcParams &p, cudaStream_t stream) {
         cudaFuncSetAttribute(linear_tc_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[GATHER] = true;
     }
-    const long long grid = p.items < sm_count() ? p.items : sm_count();
-    linear_tc_kernel<GATHER><<<(unsigned)grid, kThreads, L.total + 1024, stream>>>(p);
+    linear_tc_kernel<GATHER><<<(unsigned)tc::persistent_grid(p.items, sm_count()), kThreads, L.total + 1024, stream>>>(p);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -160,7 +160,7 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
     pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = p.tiles;
     pa.ring = smem + L.off_ring; pa.stage_bytes = 2 * kABytes; pa.full = full; pa.empty = empty;
     pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
-    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = p.prof;
 
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
@@ -378,8 +378,7 @@ PN2_API int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long grid = p.tiles < sms ? p.tiles : sms;
-    sa_fused_tc_kernel<<<(unsigned)grid, kThreads, L.total + 1024, stream>>>(p);
+    sa_fused_tc_kernel<<<(unsigned)tc::persistent_grid(p.tiles, sms), kThreads, L.total + 1024, stream>>>(p);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

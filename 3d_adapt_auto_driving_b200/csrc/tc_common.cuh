@@ -9,6 +9,20 @@
 
 namespace tc {
 
+// Grid of a "persistent" kernel whose CTAs walk the tiles with stride gridDim.x (one CTA per SM
+// is resident: shared memory).  With batches in flight on several streams (inference.py) part of
+// the SMs can be held by another stream's latency-bound kernel (FPS, NMS) when this one starts; a
+// grid of exactly one CTA per SM would then run the late CTAs alone after the early ones have
+// finished.  Long kernels are therefore cut into up to 4 CTAs per SM (>= 32 tiles each): the hardware
+// block scheduler hands the later CTAs to whichever SM frees up first, for ~1 % of prologue.
+inline long long persistent_grid(long long tiles, int sms) {
+    if (tiles <= sms) return tiles;
+    long long per_sm = tiles / ((long long)sms * 32);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    return (long long)sms * per_sm;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pn2_smem_u32(bar)), "r"(count) : "memory");

@@ -39,6 +39,7 @@ struct ProducerArgs {
     uint64_t *full, *empty;            // per stage
     RowMeta *meta; uint64_t *meta_full, *meta_empty;   // [kMetaDepth] x kBM, gather only
     const float *wxs; int kpad;        // (3, kpad) xyz coefficients of layer 1 in shared memory
+    unsigned long long *prof;          // optional stopwatch buffer (32 u64 per CTA, tools/prof_tc.py) or nullptr
 };
 
 // volatile 16-byte shared load (so the compiler re-reads instead of pinning 12 registers)
@@ -47,33 +48,74 @@ __device__ __forceinline__ void lds128(const float *p, float4 &v) {
 }
 
 // ---- meta warp (gather only): RowMeta of tile `it` into slot it % kMetaDepth ----
+// One warp feeds the sixteen producers, so its two dependent global round trips per tile
+// (idx -> xyz[idx]) are kept off the critical path: the four idx loads of a lane are independent and
+// issued together, the idx loads of the NEXT tile are issued before this tile's coordinates are
+// consumed, and rows past the end are clamped (not branched around) so nothing serialises the loads.
+// Row -> (centre, cloud) uses one 64-bit division per TILE (uniform) and 32-bit ones per row.
 __device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
     const long long first = blockIdx.x, stride = gridDim.x;
+    const uint32_t ns = (uint32_t)a.ns, m = (uint32_t)a.m;
+    const long long last_row = a.rows - 1;
+    constexpr int Q = kBM / 32;
+    unsigned long long w_slot = 0;
+    const long long t_begin = a.prof ? clock64() : 0;
+    int jn[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) jn[q] = 0;
+    if (first < a.items) {
+        const long long row0 = (first / a.nchunks) * kBM;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) jn[q] = __ldg(a.idx + min(row0 + q * 32 + lane, last_row));
+    }
     long long it = 0;
     for (long long item = first; item < a.items; item += stride, ++it) {
         const int slot = (int)(it % kMetaDepth);
-        mbar_wait(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1);
         const long long row0 = (item / a.nchunks) * kBM;
+        const long long centre0 = row0 / ns;                       // tile-uniform 64-bit part
+        const uint32_t rem0 = (uint32_t)(row0 - centre0 * ns);
+        const long long cloud0 = centre0 / m;
+        const uint32_t crem0 = (uint32_t)(centre0 - cloud0 * m);
+        int src[Q];
+        float pj[Q][3], pc[Q][3];
 #pragma unroll
-        for (int q = 0; q < kBM / 32; ++q) {
-            const int r = q * 32 + lane;
-            const long long row = row0 + r;
+        for (int q = 0; q < Q; ++q) {
+            const uint32_t r = (uint32_t)(q * 32 + lane);
+            const bool live = row0 + r <= last_row;
+            const uint32_t rr = live ? r : (uint32_t)(last_row - row0);   // clamp to the last valid row of the tile
+            const uint32_t dc = (rem0 + rr) / ns;
+            const long long centre = centre0 + dc;
+            const long long cloud = cloud0 + (crem0 + dc) / m;
+            const long long s = cloud * a.n + jn[q];
+            src[q] = live ? (int)s : 0;          // rows beyond the end: any valid row (masked by the epilogue)
+            const float *gj = a.xyz + s * 3, *gc = a.centres + centre * 3;
+            pj[q][0] = __ldg(gj); pj[q][1] = __ldg(gj + 1); pj[q][2] = __ldg(gj + 2);
+            pc[q][0] = __ldg(gc); pc[q][1] = __ldg(gc + 1); pc[q][2] = __ldg(gc + 2);
+            if (!live) { pj[q][0] = pc[q][0]; pj[q][1] = pc[q][1]; pj[q][2] = pc[q][2]; }
+        }
+        // next tile's neighbour indices: in flight while this tile's coordinates arrive
+        if (item + stride < a.items) {
+            const long long nrow0 = ((item + stride) / a.nchunks) * kBM;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) jn[q] = __ldg(a.idx + min(nrow0 + q * 32 + lane, last_row));
+        }
+        mbar_wait_timed(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1, a.prof, w_slot);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
             RowMeta mt;
-            mt.src = 0; mt.dx = mt.dy = mt.dz = 0.f;   // rows beyond the end: any valid row (masked by the epilogue)
-            if (row < a.rows) {
-                const long long centre = row / a.ns, cloud = centre / a.m;
-                const int j = __ldg(a.idx + row);
-                const long long src = cloud * a.n + j;
-                const float *pj = a.xyz + src * 3, *pc = a.centres + centre * 3;
-                mt.src = (int)src;
-                mt.dx = __ldg(pj) - __ldg(pc);
-                mt.dy = __ldg(pj + 1) - __ldg(pc + 1);
-                mt.dz = __ldg(pj + 2) - __ldg(pc + 2);
-            }
-            a.meta[slot * kBM + r] = mt;
+            mt.src = src[q];
+            mt.dx = pj[q][0] - pc[q][0];
+            mt.dy = pj[q][1] - pc[q][1];
+            mt.dz = pj[q][2] - pc[q][2];
+            a.meta[slot * kBM + q * 32 + lane] = mt;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&a.meta_full[slot]);
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long *o = a.prof + (size_t)blockIdx.x * 32;
+        o[17] = w_slot;
+        o[18] = (unsigned long long)(clock64() - t_begin);
     }
 }
 
@@ -114,6 +156,8 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     int stage = group % a.stages;
     uint32_t phase = (uint32_t)((group / a.stages) & 1);
 
+    unsigned long long w_meta = 0, w_stage = 0;   // stopwatch (a.prof): cycles blocked on row metadata / on a free stage
+    const long long t_begin = a.prof ? clock64() : 0;
     float4 areg[kPasses];
     auto issue_loads = [&]() {
         const int k = l_kb * kBK + kq;
@@ -121,7 +165,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
         long long row0 = 0;
         if (GATHER) {
             if (l_it != meta_seen) {
-                mbar_wait(&a.meta_full[l_it % kMetaDepth], (uint32_t)((l_it / kMetaDepth) & 1));
+                mbar_wait_timed(&a.meta_full[l_it % kMetaDepth], (uint32_t)((l_it / kMetaDepth) & 1), a.prof, w_meta);
                 meta_seen = l_it;
             }
         } else {
@@ -171,7 +215,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     if (l_t < total_steps) issue_loads();
     while (s_t < total_steps) {
         uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
-        mbar_wait(&a.empty[stage], phase ^ 1);
+        mbar_wait_timed(&a.empty[stage], phase ^ 1, a.prof, w_stage);
         if (wg == 0 && lane == 0) hook(first + s_it * stride, s_kb, stage);
         const int k = s_kb * kBK + kq;
         const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM + rsub;
@@ -218,6 +262,12 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
         stage += kGroups;
         while (stage >= a.stages) { stage -= a.stages; phase ^= 1; }
         if (l_t < total_steps) issue_loads();
+    }
+    if (a.prof && ptid == 0) {
+        unsigned long long *o = a.prof + (size_t)blockIdx.x * 32;
+        o[14] = w_meta;
+        o[15] = w_stage;
+        o[16] = (unsigned long long)(clock64() - t_begin);
     }
 }
 

@@ -26,13 +26,20 @@ class Detector:
     so it is captured once per input shape into a CUDA graph and replayed; `detect_device` then
     returns views of the graph's static output buffers (valid until the next call)."""
 
-    def __init__(self, model, device=None, use_graph=True):
+    def __init__(self, model, device=None, use_graph=True, depth=2):
         self.model = model.eval()
         self.device = device if device is not None else next(model.parameters()).device
         self.mean_size = torch.from_numpy(cfg.CLS_MEAN_SIZE[0]).to(self.device)
         self.use_graph = use_graph
         self._graphs = {}
         self.launches_per_step = None     # C-ABI kernel launches inside one captured step
+        # `depth` batches in flight (submit/collect): every slot owns a stream, a captured graph with its
+        # own static buffers and pinned result buffers.  FPS (a latency chain on <= 64 SMs), the
+        # one-CTA-per-scene NMS and the D2H/host turn-around of batch k then overlap with the
+        # tensor-core MLPs of batch k+1 instead of leaving most of the chip idle.
+        self.depth = max(1, int(depth))
+        self._slots = None
+        self._next = 0
 
     # ---- eval_rcnn.py:516-535, 611-627, batched and sync-free ----
     def postprocess(self, ret_dict, batch_size):
@@ -115,6 +122,89 @@ class Detector:
         out_counts.copy_(num, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_records, out_counts
+
+
+    # ---- pipelined API: `depth` batches in flight ----
+    def _slot_list(self):
+        if self._slots is None:
+            self._slots = [{"stream": torch.cuda.Stream(device=self.device), "graphs": {}, "done": torch.cuda.Event(),
+                            "rec": None, "num": None, "h_rec": None, "h_num": None} for _ in range(self.depth)]
+        return self._slots
+
+    def _slot_capture(self, slot, shape):
+        st = slot["stream"]
+        static_in = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(st):
+            for _ in range(2):
+                self._step(static_in)
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        from . import cabi
+        l0 = cabi.launch_count
+        with torch.cuda.graph(graph, stream=st):
+            rec, num = self._step(static_in)
+        self.launches_per_step = cabi.launch_count - l0
+        slot["graphs"][shape] = (graph, static_in, rec, num)
+        return slot["graphs"][shape]
+
+    @torch.no_grad()
+    def submit(self, pts, to_host=False, keep=None):
+        """Enqueue one batch on the next slot's stream and return a ticket for collect().
+        pts: (B,N,3) float32, a DEVICE tensor produced on the current stream or a (pinned) HOST tensor.
+        to_host: also enqueue the D2H copy of the detections into the slot's pinned buffers.
+        keep: optional device tensor (B,M,8) that receives a copy of the records (multi-GPU gather buffer).
+        The slot's buffers are reused `depth` submits later: collect() the ticket before that."""
+        slots = self._slot_list()
+        slot = slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        st = slot["stream"]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            if self.use_graph:
+                shape = tuple(pts.shape)
+                graph, static_in, rec, num = slot["graphs"].get(shape) or self._slot_capture(slot, shape)
+                static_in.copy_(pts, non_blocking=True)
+                graph.replay()
+            else:
+                rec, num = self._step(pts.to(self.device, non_blocking=True).float())
+            slot["rec"], slot["num"] = rec, num
+            if keep is not None:
+                keep.copy_(rec, non_blocking=True)
+            if to_host:
+                if slot["h_rec"] is None or slot["h_rec"].shape != rec.shape:
+                    slot["h_rec"] = torch.empty(rec.shape, dtype=rec.dtype, pin_memory=True)
+                    slot["h_num"] = torch.empty(num.shape, dtype=num.dtype, pin_memory=True)
+                slot["h_rec"].copy_(rec, non_blocking=True)
+                slot["h_num"].copy_(num, non_blocking=True)
+            slot["done"].record(st)
+        return slot
+
+    def collect(self, ticket, host=True):
+        """Wait for a submitted batch.  host=True: block the host and return the pinned (records, counts)
+        (submit(..., to_host=True)); host=False: make the CURRENT STREAM wait and return the device views."""
+        if host:
+            ticket["done"].synchronize()
+            return ticket["h_rec"], ticket["h_num"]
+        torch.cuda.current_stream().wait_event(ticket["done"])
+        return ticket["rec"], ticket["num"]
+
+    def drain(self):
+        """The current stream waits for every batch in flight."""
+        if self._slots:
+            for slot in self._slots:
+                torch.cuda.current_stream().wait_stream(slot["stream"])
+
+    def detect_stream(self, batches, to_host=True):
+        """Generator over an iterable of host/device batches keeping `depth` of them in flight; yields
+        (records, counts) in submission order (host tensors are views of per-slot pinned buffers, valid
+        until `depth` more batches have been yielded)."""
+        pending = []
+        for pts in batches:
+            if len(pending) == self.depth:
+                yield self.collect(pending.pop(0), host=to_host)
+            pending.append(self.submit(pts, to_host=to_host))
+        while pending:
+            yield self.collect(pending.pop(0), host=to_host)
 
 
 def records_to_lists(records, counts):

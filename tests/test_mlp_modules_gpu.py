@@ -216,6 +216,30 @@ def test_full_forward_runs_and_is_deterministic(cuda, model):
     assert torch.isfinite(o1["rcnn_reg"]).all()
 
 
+def test_detector_pipelined_submit_collect_matches_single_stream(cuda, model):
+    """Detector.submit/collect (two batches in flight, one stream + CUDA graph per slot) returns, batch for
+    batch, exactly the records of the one-at-a-time detect()."""
+    inf = load("inference")
+    batches = [torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=20 + i)).pin_memory() for i in range(5)]
+    ref = inf.Detector(model, cuda, use_graph=False, depth=1)
+    want = []
+    for b in batches:
+        rec, num = ref.detect(b)
+        want.append((rec.clone(), num.clone()))
+    for use_graph in (False, True):
+        det = inf.Detector(model, cuda, use_graph=use_graph, depth=2)
+        got = [(rec.clone(), num.clone()) for rec, num in det.detect_stream(batches)]
+        assert len(got) == len(want)
+        for i, ((r0, n0), (r1, n1)) in enumerate(zip(want, got)):
+            assert torch.equal(n0, n1), (use_graph, i)
+            assert torch.equal(r0, r1), (use_graph, i)
+        # device-side collect: the current stream waits, views of the slot's buffers
+        t = det.submit(batches[0].to(cuda))
+        rec, num = det.collect(t, host=False)
+        assert torch.equal(rec.cpu(), want[0][0]) and torch.equal(num.cpu(), want[0][1])
+        det.drain()
+
+
 def test_proposal_layer_vs_reference_nms_composition(cuda, model, legacy):
     """ProposalLayer with the device NMS == the reference recipe (sort, band split, top-k,
     legacy mask kernel + host greedy, first 70/30) on the same scores / regression."""
