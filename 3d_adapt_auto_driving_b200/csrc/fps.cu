@@ -347,10 +347,11 @@ PN2_API int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int 
     while ((1 << log2bs) < bs) ++log2bs;
     const int cnt = (n + bs - 1) / bs;
 
-    // CTAs per cloud.  An 8-CTA cluster must sit inside one GPC (~18 SMs: two clusters per GPC), so
-    // more than ~12 big clouds no longer run in a single wave with clusters of 8 (measured, B = 16,
-    // 16384 -> 4096: 4.79 ms with 8, 3.53 ms with 4); 4-CTA clusters keep 32 points per thread.
-    int cluster = n >= 8192 ? (b <= 12 ? 8 : 4) : (n > 4096 ? 4 : 1);
+    // CTAs per cloud.  Measured (16384 -> 4096, v2 kernel): 4-CTA clusters 2.74 ms at B = 8 and B = 16;
+    // 8-CTA clusters 3.52 ms at B = 8 (twice the records and remote stores per round for 8 instead of 16
+    // points per thread) and 4.54 ms at B = 16 (an 8-CTA cluster must sit inside one GPC, 16 of them do
+    // not fit in one wave); one CTA is best up to 4096 points (0.53 ms vs 0.62 ms for 4096 -> 1024).
+    int cluster = n > 4096 ? 4 : 1;
     if (g_fps_cluster_override) cluster = g_fps_cluster_override;
     int p = (n + cluster * kThreads - 1) / (cluster * kThreads);
     while (p > 32 && cluster < 8) {

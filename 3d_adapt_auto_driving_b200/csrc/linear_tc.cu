@@ -73,7 +73,7 @@ __host__ __device__ inline SmemLayout make_layout(int ntile, int stages, int kpa
     return L;
 }
 
-template <bool GATHER>
+template <bool GATHER, bool FAST>
 __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled operand tiles need 1 KB alignment in the shared window (1 KB of slack is allocated)
@@ -129,7 +129,7 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
         const uint32_t bbytes = 2u * p.ntile * 128u;
-        producer_run<GATHER>(pa, (int)threadIdx.x, [&](long long item, int kb, int stage) {
+        producer_run<GATHER, FAST, false>(pa, (int)threadIdx.x, [&](long long item, int kb, int stage) {
             // weight K-block: one bulk copy (TMA), completes on the same barrier as the A rows
             const uint8_t *src = p.wblob + ((size_t)(item % p.nchunks) * p.nkb + kb) * bbytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(&full[stage])),
@@ -141,10 +141,11 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
                          : "memory");
         });
     } else if (warp == kMetaWarp) {
-        if (GATHER) meta_run(pa, lane);
+        if (GATHER) meta_run<false>(pa, lane);
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        // all 32 lanes run the loops (uniform operands, see tc::elect_one()); one elected lane issues
+        {
             const uint32_t idesc = make_idesc_bf16(BM, p.ntile);
             int stage = 0;
             uint32_t phase = 0;
@@ -162,24 +163,27 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
                     const uint32_t b_hi = desc_lo(sa + 2 * kABytes), b_lo = desc_lo(sa + 2 * kABytes + p.ntile * 128);
                     const int krem = p.cin - kb * BK;
                     const int ksteps = krem >= BK ? 4 : (krem + 15) >> 4;
-                    if (ksteps == 4 && kb > 0) {   // steady state, fully unrolled: 32 bytes (>> 4) along K per step
+                    if (elect_one()) {
+                        if (ksteps == 4 && kb > 0) {   // steady state, fully unrolled: 32 bytes (>> 4) along K per step
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            mma_ss_lo(d_tmem, a_hi + ks * 2, b_hi + ks * 2, idesc, 1u);
-                            mma_ss_lo(d_tmem, a_hi + ks * 2, b_lo + ks * 2, idesc, 1u);
-                            mma_ss_lo(d_tmem, a_lo + ks * 2, b_hi + ks * 2, idesc, 1u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_ss_lo(d_tmem, a_hi + ks * 2, b_hi + ks * 2, idesc, 1u);
+                                mma_ss_lo(d_tmem, a_hi + ks * 2, b_lo + ks * 2, idesc, 1u);
+                                mma_ss_lo(d_tmem, a_lo + ks * 2, b_hi + ks * 2, idesc, 1u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                mma_ss_lo(d_tmem, a_hi + ks * 2, b_hi + ks * 2, idesc, (kb | ks) ? 1u : 0u);
+                                mma_ss_lo(d_tmem, a_hi + ks * 2, b_lo + ks * 2, idesc, 1u);
+                                mma_ss_lo(d_tmem, a_lo + ks * 2, b_hi + ks * 2, idesc, 1u);
+                            }
                         }
-                    } else {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            mma_ss_lo(d_tmem, a_hi + ks * 2, b_hi + ks * 2, idesc, (kb | ks) ? 1u : 0u);
-                            mma_ss_lo(d_tmem, a_hi + ks * 2, b_lo + ks * 2, idesc, 1u);
-                            mma_ss_lo(d_tmem, a_lo + ks * 2, b_hi + ks * 2, idesc, 1u);
-                        }
+                        mma_commit(&empty[stage]);
+                        if (kb == p.nkb - 1) mma_commit(&acc_full[a]);
                     }
-                    mma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&acc_full[a]);
             }
         }
         __syncwarp();
@@ -304,10 +308,14 @@ int launch_tc(TcParams &p, cudaStream_t stream) {
     p.stages = stages;
     static bool attr_done[2] = {false, false};
     if (!attr_done[GATHER]) {
-        cudaFuncSetAttribute(linear_tc_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(linear_tc_kernel<GATHER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(linear_tc_kernel<GATHER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done[GATHER] = true;
     }
-    linear_tc_kernel<GATHER><<<(unsigned)tc::persistent_grid(p.items, sm_count()), kThreads, L.total + 1024, stream>>>(p);
+    const unsigned grid = (unsigned)tc::persistent_grid(p.items, sm_count());
+    // the second-source (concatenated input) path exists only in the FAST producer; pn2_linear_tc2_f32 guarantees it
+    if (tc::producer_fast(p.vec_ok, p.cin)) linear_tc_kernel<GATHER, true><<<grid, kThreads, L.total + 1024, stream>>>(p);
+    else linear_tc_kernel<GATHER, false><<<grid, kThreads, L.total + 1024, stream>>>(p);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

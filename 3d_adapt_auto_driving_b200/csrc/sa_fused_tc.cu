@@ -52,6 +52,7 @@ struct SaParams {
     float *y; int ldy;
     int stages, dbuf;
     unsigned long long *prof;   // optional stopwatch buffer (32 u64 per CTA) or nullptr
+    int dbg;                    // tools/prof_tc.py only: bit0 E3 skips its TMEM loads, bit1 E2 skips ld/st (results are garbage)
 };
 
 struct SmemLayout {
@@ -73,6 +74,7 @@ __host__ __device__ inline SmemLayout make_layout(const SaParams &p, int stages)
     return L;
 }
 
+template <bool FAST, bool PROF>
 __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -147,7 +149,7 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
     const uint32_t col_acc2 = 0;
     const uint32_t col_a2 = (uint32_t)p.n2;                       // buffer b: hi at col_a2 + b*n2, lo n2/2 after it
     const uint32_t col_acc3 = col_a2 + (uint32_t)(p.dbuf ? 2 : 1) * p.n2;
-    const long long kernel_t0 = clock64();
+    const long long kernel_t0 = PROF ? clock64() : 0;
 
     const long long first = blockIdx.x, stride = gridDim.x;
     const long long my_tiles = first < p.tiles ? (p.tiles - first + stride - 1) / stride : 0;
@@ -164,14 +166,16 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
 
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
-        producer_run<true>(pa, (int)threadIdx.x, [](long long, int, int) {});
+        producer_run<true, FAST, PROF>(pa, (int)threadIdx.x, [](long long, int, int) {});
     } else if (warp == kMetaWarp) {
-        meta_run(pa, lane);
+        meta_run<PROF>(pa, lane);
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
         // Tensor-pipe order  M2(0) | M2(1) M3(0) | M2(2) M3(1) | ...   M2(i+1) only needs E2(i) (acc2 drained),
         // M3(i) also needs E3(i-1) (acc3 drained): layer 2 of the next tile runs under E3, layer 3 under E2.
-        if (lane == 0 && my_tiles > 0) {
+        // All 32 lanes run the loops (uniform control flow and operands, see elect_one()); one elected
+        // lane issues the MMAs and commits.
+        if (my_tiles > 0) {
             const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
             const uint32_t idesc3 = make_idesc_bf16(BM, p.n3);
             const uint32_t w2a = pn2_smem_u32(smem + L.off_w2), w3a = pn2_smem_u32(smem + L.off_w3);
@@ -180,38 +184,41 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
             uint32_t phase = 0;
             mbar_wait(w_full, 0);
             auto issue_m2 = [&](long long it) {
-                mbar_wait_timed(acc2_empty, (uint32_t)(it & 1) ^ 1, p.prof, w_acc2);
+                mbar_wait_timed<PROF>(acc2_empty, (uint32_t)(it & 1) ^ 1, w_acc2);
                 tc_fence_after_sync();
                 const uint32_t d = tmem_base + col_acc2;
                 for (int kb = 0; kb < p.nkb1; ++kb) {
-                    mbar_wait_timed(&full[stage], phase, p.prof, w_ring);
+                    mbar_wait_timed<PROF>(&full[stage], phase, w_ring);
                     tc_fence_after_sync();
-                    const long long tm0 = p.prof ? clock64() : 0;
+                    const long long tm0 = PROF ? clock64() : 0;
                     const uint32_t sa = pn2_smem_u32(smem + L.off_ring + (size_t)stage * 2 * kABytes);
                     const uint32_t a_hi = desc_lo(sa), a_lo = desc_lo(sa + kABytes);
                     const uint32_t wb = w2a + (uint32_t)kb * 2u * p.n2 * 128u;
                     const uint32_t b_hi = desc_lo(wb), b_lo = desc_lo(wb + p.n2 * 128u);
                     const int krem = p.c1 - kb * BK;
                     const int ksteps = krem >= BK ? 4 : (krem + 15) >> 4;
-                    if (ksteps == 4 && kb > 0) {
+                    if (elect_one()) {
+                        if (ksteps == 4 && kb > 0) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, 1u);
-                            mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
-                            mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, (kb | ks) ? 1u : 0u);
+                                mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                            }
                         }
-                    } else {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, (kb | ks) ? 1u : 0u);
-                            mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
-                            mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
-                        }
+                        mma_commit(&empty[stage]);
+                        if (kb == p.nkb1 - 1) mma_commit(acc2_full);
                     }
-                    mma_commit(&empty[stage]);
-                    if (p.prof) t_m2 += (unsigned long long)(clock64() - tm0);
+                    __syncwarp();
+                    if (PROF) t_m2 += (unsigned long long)(clock64() - tm0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(acc2_full);
             };
             issue_m2(0);
             for (long long it = 0; it < my_tiles; ++it) {
@@ -219,26 +226,29 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
                 // layer 3: A2[b] (TMEM, written by the epilogue) x W3
                 const int b = p.dbuf ? (int)(it & 1) : 0;
                 const uint32_t use = p.dbuf ? (uint32_t)(it >> 1) : (uint32_t)it;
-                mbar_wait_timed(&a2_full[b], use & 1, p.prof, w_a2);
-                mbar_wait_timed(acc3_empty, (uint32_t)(it & 1) ^ 1, p.prof, w_acc3);
+                mbar_wait_timed<PROF>(&a2_full[b], use & 1, w_a2);
+                mbar_wait_timed<PROF>(acc3_empty, (uint32_t)(it & 1) ^ 1, w_acc3);
                 tc_fence_after_sync();
-                const long long tm3 = p.prof ? clock64() : 0;
+                const long long tm3 = PROF ? clock64() : 0;
                 const uint32_t d3 = tmem_base + col_acc3;
                 const uint32_t a2hi = tmem_base + col_a2 + (uint32_t)b * p.n2, a2lo = a2hi + (uint32_t)(p.n2 >> 1);
                 const int ksteps3 = p.c2 >> 4;
-                for (int ks = 0; ks < ksteps3; ++ks) {
-                    const uint32_t wb = w3a + (uint32_t)(ks >> 2) * 2u * p.n3 * 128u;
-                    const uint32_t b_hi = desc_lo(wb) + (uint32_t)((ks & 3) * 2);
-                    const uint32_t b_lo = desc_lo(wb + p.n3 * 128u) + (uint32_t)((ks & 3) * 2);
-                    mma_ts_lo(d3, a2hi + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
-                    mma_ts_lo(d3, a2hi + ks * 8, b_lo, idesc3, 1u);
-                    mma_ts_lo(d3, a2lo + ks * 8, b_hi, idesc3, 1u);
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps3; ++ks) {
+                        const uint32_t wb = w3a + (uint32_t)(ks >> 2) * 2u * p.n3 * 128u;
+                        const uint32_t b_hi = desc_lo(wb) + (uint32_t)((ks & 3) * 2);
+                        const uint32_t b_lo = desc_lo(wb + p.n3 * 128u) + (uint32_t)((ks & 3) * 2);
+                        mma_ts_lo(d3, a2hi + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
+                        mma_ts_lo(d3, a2hi + ks * 8, b_lo, idesc3, 1u);
+                        mma_ts_lo(d3, a2lo + ks * 8, b_hi, idesc3, 1u);
+                    }
+                    mma_commit(acc3_full);
+                    mma_commit(&a2_empty[b]);
                 }
-                mma_commit(acc3_full);
-                mma_commit(&a2_empty[b]);
-                if (p.prof) t_m3 += (unsigned long long)(clock64() - tm3);
+                __syncwarp();
+                if (PROF) t_m3 += (unsigned long long)(clock64() - tm3);
             }
-            if (p.prof) {
+            if (PROF && lane == 0) {
                 unsigned long long *o = p.prof + (size_t)blockIdx.x * 32;
                 o[0] = (unsigned long long)(clock64() - kernel_t0); o[1] = w_ring; o[2] = w_acc2; o[3] = w_a2; o[4] = w_acc3;
                 o[5] = (unsigned long long)my_tiles; o[6] = t_m2; o[7] = t_m3;
@@ -257,31 +267,30 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
         auto e3 = [&](long long it) {
             // acc3 -> bias, ReLU -> max over the nsample rows of each centre
             const long long tile = first + it * stride;
-            mbar_wait_timed(acc3_full, (uint32_t)(it & 1), p.prof, w_acc3f);
-            const long long t0 = p.prof ? clock64() : 0;
+            mbar_wait_timed<PROF>(acc3_full, (uint32_t)(it & 1), w_acc3f);
+            const long long t0 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const long long row0 = tile * BM + q * 32;
+            if (!(p.dbg & 1))
             pool_tile(lane_addr + col_acc3, p.n3, half, bias3, row0 + lane < p.rows, p.ns, lane, q, tile, p.rows, p.c3, 0,
                       p.y, p.ldy);
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc3_empty);
-            if (p.prof) t_e3 += (unsigned long long)(clock64() - t0);
+            if (PROF) t_e3 += (unsigned long long)(clock64() - t0);
         };
         for (long long it = 0; it < my_tiles; ++it) {
             const int b = p.dbuf ? (int)(it & 1) : 0;
             const uint32_t use = p.dbuf ? (uint32_t)(it >> 1) : (uint32_t)it;
             // ---- E2: acc2 -> bias, ReLU, bf16 hi/lo -> TMEM operand A2[b] of layer 3 ----
-            mbar_wait_timed(acc2_full, (uint32_t)(it & 1), p.prof, w_acc2f);
-            mbar_wait_timed(&a2_empty[b], (use & 1) ^ 1, p.prof, w_a2e);
-            const long long t0 = p.prof ? clock64() : 0;
+            mbar_wait_timed<PROF>(acc2_full, (uint32_t)(it & 1), w_acc2f);
+            mbar_wait_timed<PROF>(&a2_empty[b], (use & 1) ^ 1, w_a2e);
+            const long long t0 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t t_acc2 = lane_addr + col_acc2;
             const uint32_t t_hi = lane_addr + col_a2 + (uint32_t)b * p.n2, t_lo = t_hi + (uint32_t)(p.n2 >> 1);
-            for (int c0 = half * 16; c0 < p.n2; c0 += 32) {
-                uint32_t v[16];
-                tmem_ld16(t_acc2 + c0, v);
-                tmem_ld_wait();
+            // two 16-column chunks per step: both TMEM loads in flight before the single wait
+            auto convert = [&](const uint32_t (&v)[16], int c0) {
                 uint32_t hi[8], lo[8];
                 const float4 *b4 = reinterpret_cast<const float4 *>(bias2 + c0);
 #pragma unroll
@@ -291,11 +300,29 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
                     const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
                     const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
                     const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-                    split2(x0, x1, hi[2 * j4], lo[2 * j4]);
-                    split2(x2, x3, hi[2 * j4 + 1], lo[2 * j4 + 1]);
+                    uint2 h2, l2;
+                    split4(make_float4(x0, x1, x2, x3), h2, l2);
+                    hi[2 * j4] = h2.x; hi[2 * j4 + 1] = h2.y;
+                    lo[2 * j4] = l2.x; lo[2 * j4 + 1] = l2.y;
                 }
                 tmem_st8(t_hi + (c0 >> 1), hi);
                 tmem_st8(t_lo + (c0 >> 1), lo);
+            };
+            const int n2e = (p.dbg & 2) ? 0 : p.n2;
+            int c0 = half * 16;
+            for (; c0 + 32 < n2e; c0 += 64) {
+                uint32_t va[16], vb[16];
+                tmem_ld16(t_acc2 + c0, va);
+                tmem_ld16(t_acc2 + c0 + 32, vb);
+                tmem_ld_wait();
+                convert(va, c0);
+                convert(vb, c0 + 32);
+            }
+            if (c0 < n2e) {
+                uint32_t va[16];
+                tmem_ld16(t_acc2 + c0, va);
+                tmem_ld_wait();
+                convert(va, c0);
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -304,11 +331,11 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
                 mbar_arrive(&a2_full[b]);
                 mbar_arrive(acc2_empty);
             }
-            if (p.prof) t_e2 += (unsigned long long)(clock64() - t0);
+            if (PROF) t_e2 += (unsigned long long)(clock64() - t0);
             if (it > 0) e3(it - 1);
         }
         if (my_tiles > 0) e3(my_tiles - 1);
-        if (p.prof && ew == 0 && lane == 0) {
+        if (PROF && ew == 0 && lane == 0) {
             unsigned long long *o = p.prof + (size_t)blockIdx.x * 32;
             o[8] = w_acc2f; o[9] = w_a2e; o[10] = w_acc3f; o[11] = w_bar; o[12] = t_e2; o[13] = t_e3;
         }
@@ -323,11 +350,14 @@ __global__ void __maxnreg__(72) sa_fused_tc_kernel(const SaParams p) {
 }
 
 unsigned long long *g_prof = nullptr;
+int g_dbg = 0;
 
 }  // namespace
 
 // stopwatch buffer for tools/prof_tc.py: 32 u64 per CTA (device memory) or NULL to disable
 PN2_API void pn2_sa_fused_tc_set_profile(void *buf) { g_prof = static_cast<unsigned long long *>(buf); }
+// profiling experiments only (tools/prof_tc.py): switch off parts of the epilogue to see what the rest costs
+PN2_API void pn2_sa_fused_tc_set_debug(int bits) { g_dbg = bits; }
 
 // One SA scale, layers 1(pair-wise half) + 2 + 3 + max over nsample, fully on chip.
 //   h (clouds*n, ldh): per-point half of layer 1 (bias / BN folded in), c1 channels
@@ -361,6 +391,7 @@ PN2_API int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, con
     p.b2 = b2; p.b3 = b3; p.c2 = c2; p.c3 = c3; p.y = y; p.ldy = ldy;
     p.dbuf = (3 * n2 + n3 <= 512) ? 1 : 0;
     p.prof = g_prof;
+    p.dbg = g_dbg;
     if (p.rows == 0) return PN2_OK;
     int stages = kMaxStages;
     SmemLayout L = make_layout(p, stages);
@@ -372,13 +403,26 @@ PN2_API int pn2_sa_fused_tc_f32(const float *h, int ldh, const int32_t *idx, con
     p.stages = stages;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(sa_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    sa_fused_tc_kernel<<<(unsigned)tc::persistent_grid(p.tiles, sms), kThreads, L.total + 1024, stream>>>(p);
+    const unsigned grid = (unsigned)tc::persistent_grid(p.tiles, sms);
+    const int vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
+    const bool fast = tc::producer_fast(vec_ok, c1);
+    const size_t smem_bytes = L.total + 1024;
+    if (p.prof) {   // stopwatch instantiations: tools/prof_tc.py only
+        if (fast) sa_fused_tc_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_tc_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    } else {
+        if (fast) sa_fused_tc_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_tc_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    }
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -38,6 +38,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = pn2_smem_u32(bar);
     uint32_t done = 0;
+    // NOT unrolled: ptxas otherwise replicates the try_wait / NANOSLEEP body 64x at every call site (13 k of the
+    // fused SA kernel's 15 k instructions were unrolled polls) and every role pays instruction-cache misses
+    // ("no_inst" stalls after each wait) for code that never runs.
+#pragma unroll 1
     for (uint32_t spin = 0; spin < 4096u; ++spin) {
         asm volatile(
             "{\n"
@@ -53,10 +57,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     __trap();
 }
 // Optional in-kernel stopwatch (tools/prof_tc.py): cycles a role spends blocked on a barrier.
-// `prof` is a device buffer of 32 u64 per CTA or nullptr (the default).
-__device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, const unsigned long long *prof,
-                                                unsigned long long &acc) {
-    if (prof == nullptr) {
+// PROF is a KERNEL template parameter: the product instantiation carries no stopwatch code at all.
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_timed(uint64_t *bar, uint32_t parity, unsigned long long &acc) {
+    if (!PROF) {
         mbar_wait(bar, parity);
         return;
     }
@@ -147,6 +151,24 @@ __device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint
         : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The MMA warp runs its tile / K-block loops with all 32
+// lanes so that every address, descriptor and phase bit is warp-uniform and lives in uniform
+// registers; only the tcgen05.mma / commit instructions sit under this predicate.  Wrapping the
+// whole loop in `if (lane == 0)` instead makes the compiler treat all of it as divergent, and it then
+// feeds every UTCHMMA through an ELECT + 4x R2UR.BROADCAST + BRA.U.ANY loop (11 instructions and a
+// vector->uniform round trip per MMA, ~1000 instructions per 48-MMA tile).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ MMA issue (one thread)
 // D[tmem] (+)= A[smem] . B[smem]^T   (both operands K-major)
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -203,6 +225,24 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Four values at once for the producers (the SM is instruction-issue bound in the fused kernels, so
+// the split is written for instruction count): one F2FP per pair for hi, the bf16 -> fp32 expansion
+// as one shift / one mask instead of PRMT + shift per element, x - hi on the packed fp32 pipe
+// (FADD2, both halves IEEE round-to-nearest, i.e. the same bits as the scalar subtraction), one
+// F2FP per pair for lo.  10 instructions per float4 instead of 16; identical results to split2().
+__device__ __forceinline__ void split4(const float4 &v, uint2 &hi, uint2 &lo) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    hi.x = *reinterpret_cast<const uint32_t *>(&h01);
+    hi.y = *reinterpret_cast<const uint32_t *>(&h23);
+    const float2 n01 = make_float2(-__uint_as_float(hi.x << 16), -__uint_as_float(hi.x & 0xffff0000u));
+    const float2 n23 = make_float2(-__uint_as_float(hi.y << 16), -__uint_as_float(hi.y & 0xffff0000u));
+    const float2 l01 = __fadd2_rn(make_float2(v.x, v.y), n01);
+    const float2 l23 = __fadd2_rn(make_float2(v.z, v.w), n23);
+    const __nv_bfloat162 q01 = __floats2bfloat162_rn(l01.x, l01.y), q23 = __floats2bfloat162_rn(l23.x, l23.y);
+    lo.x = *reinterpret_cast<const uint32_t *>(&q01);
+    lo.y = *reinterpret_cast<const uint32_t *>(&q23);
 }
 
 }  // namespace tc

@@ -53,13 +53,14 @@ __device__ __forceinline__ void lds128(const float *p, float4 &v) {
 // issued together, the idx loads of the NEXT tile are issued before this tile's coordinates are
 // consumed, and rows past the end are clamped (not branched around) so nothing serialises the loads.
 // Row -> (centre, cloud) uses one 64-bit division per TILE (uniform) and 32-bit ones per row.
+template <bool PROF>
 __device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
     const long long first = blockIdx.x, stride = gridDim.x;
     const uint32_t ns = (uint32_t)a.ns, m = (uint32_t)a.m;
     const long long last_row = a.rows - 1;
     constexpr int Q = kBM / 32;
     unsigned long long w_slot = 0;
-    const long long t_begin = a.prof ? clock64() : 0;
+    const long long t_begin = PROF ? clock64() : 0;
     int jn[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) jn[q] = 0;
@@ -99,7 +100,7 @@ __device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) jn[q] = __ldg(a.idx + min(nrow0 + q * 32 + lane, last_row));
         }
-        mbar_wait_timed(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1, a.prof, w_slot);
+        mbar_wait_timed<PROF>(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1, w_slot);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             RowMeta mt;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void meta_run(const ProducerArgs &a, int lane) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&a.meta_full[slot]);
     }
-    if (a.prof && lane == 0) {
+    if (PROF && lane == 0) {
         unsigned long long *o = a.prof + (size_t)blockIdx.x * 32;
         o[17] = w_slot;
         o[18] = (unsigned long long)(clock64() - t_begin);
@@ -134,7 +135,7 @@ constexpr int kGroupWarps = kProdWarps / kGroups;          // 8
 constexpr int kRowsPerPass = 2 * kGroupWarps;               // 16
 constexpr int kPasses = kBM / kRowsPerPass;                 // 8 float4 per thread per K-block
 
-template <bool GATHER, bool FAST, class StageHook>
+template <bool GATHER, bool FAST, bool PROF, class StageHook>
 __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, StageHook hook) {
     const int lane = ptid & 31, pw = ptid >> 5;
     const int group = pw % kGroups, wg = pw / kGroups;
@@ -145,19 +146,21 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     const uint32_t toff = (uint32_t)(((rsub >> 3) << 10) + ((rsub & 7) << 7)) +
                           ((((uint32_t)((lane & 15) >> 1) ^ (uint32_t)(rsub & 7)) << 4) | ((uint32_t)(lane & 1) << 3));
     const long long first = blockIdx.x, stride = gridDim.x;
-    const long long my_items = first < a.items ? (a.items - first + stride - 1) / stride : 0;
-    const long long total_steps = my_items * a.nkb;
+    // per-CTA counts fit 32 bits (a CTA walks at most items / gridDim.x tiles): 64-bit bookkeeping in this
+    // loop was a measurable share of the producers' instructions
+    const int my_items = first < a.items ? (int)((a.items - first + stride - 1) / stride) : 0;
+    const int total_steps = my_items * a.nkb;
 
     // position of the step whose loads are issued next (l_*) and of the step stored next (s_*)
-    long long l_t = group, s_t = group;
-    long long l_it = group / a.nkb, s_it = l_it;
+    int l_t = group, s_t = group;
+    int l_it = group / a.nkb, s_it = l_it;
     int l_kb = group % a.nkb, s_kb = l_kb;
-    long long meta_seen = -1, meta_freed = 0;   // tiles whose meta this warp has waited for / released
+    int meta_seen = -1, meta_freed = 0;   // tiles whose meta this warp has waited for / released
     int stage = group % a.stages;
     uint32_t phase = (uint32_t)((group / a.stages) & 1);
 
     unsigned long long w_meta = 0, w_stage = 0;   // stopwatch (a.prof): cycles blocked on row metadata / on a free stage
-    const long long t_begin = a.prof ? clock64() : 0;
+    const long long t_begin = PROF ? clock64() : 0;
     float4 areg[kPasses];
     auto issue_loads = [&]() {
         const int k = l_kb * kBK + kq;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
         long long row0 = 0;
         if (GATHER) {
             if (l_it != meta_seen) {
-                mbar_wait_timed(&a.meta_full[l_it % kMetaDepth], (uint32_t)((l_it / kMetaDepth) & 1), a.prof, w_meta);
+                mbar_wait_timed<PROF>(&a.meta_full[l_it % kMetaDepth], (uint32_t)((l_it / kMetaDepth) & 1), w_meta);
                 meta_seen = l_it;
             }
         } else {
@@ -215,7 +218,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     if (l_t < total_steps) issue_loads();
     while (s_t < total_steps) {
         uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
-        mbar_wait_timed(&a.empty[stage], phase ^ 1, a.prof, w_stage);
+        mbar_wait_timed<PROF>(&a.empty[stage], phase ^ 1, w_stage);
         if (wg == 0 && lane == 0) hook(first + s_it * stride, s_kb, stage);
         const int k = s_kb * kBK + kq;
         const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM + rsub;
@@ -231,10 +234,18 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
             if (GATHER) {
                 // layer-1 output of this (centre, neighbour) pair: relu(H_j + W1x . (x_j - centre))
                 const float4 q = *reinterpret_cast<const float4 *>(mt + ps * kRowsPerPass);   // (src bits, dx, dy, dz)
-                v.x = fmaxf(fmaf(w2.x, q.w, fmaf(w1.x, q.z, fmaf(w0.x, q.y, v.x))), 0.f);
-                v.y = fmaxf(fmaf(w2.y, q.w, fmaf(w1.y, q.z, fmaf(w0.y, q.y, v.y))), 0.f);
-                v.z = fmaxf(fmaf(w2.z, q.w, fmaf(w1.z, q.z, fmaf(w0.z, q.y, v.z))), 0.f);
-                v.w = fmaxf(fmaf(w2.w, q.w, fmaf(w1.w, q.z, fmaf(w0.w, q.y, v.w))), 0.f);
+                // packed fp32 FMAs (two channels per instruction; each half rounds like fmaf)
+                const float2 qy = make_float2(q.y, q.y), qz = make_float2(q.z, q.z), qw = make_float2(q.w, q.w);
+                float2 t01 = __ffma2_rn(make_float2(w0.x, w0.y), qy, make_float2(v.x, v.y));
+                float2 t23 = __ffma2_rn(make_float2(w0.z, w0.w), qy, make_float2(v.z, v.w));
+                t01 = __ffma2_rn(make_float2(w1.x, w1.y), qz, t01);
+                t23 = __ffma2_rn(make_float2(w1.z, w1.w), qz, t23);
+                t01 = __ffma2_rn(make_float2(w2.x, w2.y), qw, t01);
+                t23 = __ffma2_rn(make_float2(w2.z, w2.w), qw, t23);
+                v.x = fmaxf(t01.x, 0.f);
+                v.y = fmaxf(t01.y, 0.f);
+                v.z = fmaxf(t23.x, 0.f);
+                v.w = fmaxf(t23.y, 0.f);
                 if (!FAST && k + 3 >= a.cin) {     // keep the K padding at zero
                     if (k + 0 >= a.cin) v.x = 0.f;
                     if (k + 1 >= a.cin) v.y = 0.f;
@@ -243,8 +254,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
                 }
             }
             uint2 hi, lo;
-            split2(v.x, v.y, hi.x, lo.x);
-            split2(v.z, v.w, hi.y, lo.y);
+            split4(v, hi, lo);
             *reinterpret_cast<uint2 *>(sbase + ps * 2048) = hi;
             *reinterpret_cast<uint2 *>(sbase + kTileBytes + ps * 2048) = lo;
         }
@@ -256,14 +266,14 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
         s_kb += kGroups;
         while (s_kb >= a.nkb) { s_kb -= a.nkb; ++s_it; }
         if (GATHER && lane == 0) {
-            const long long upto = s_t < total_steps ? s_it : my_items;
+            const int upto = s_t < total_steps ? s_it : my_items;
             for (; meta_freed < upto; ++meta_freed) mbar_arrive(&a.meta_empty[meta_freed % kMetaDepth]);
         }
         stage += kGroups;
         while (stage >= a.stages) { stage -= a.stages; phase ^= 1; }
         if (l_t < total_steps) issue_loads();
     }
-    if (a.prof && ptid == 0) {
+    if (PROF && ptid == 0) {
         unsigned long long *o = a.prof + (size_t)blockIdx.x * 32;
         o[14] = w_meta;
         o[15] = w_stage;
@@ -271,11 +281,14 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     }
 }
 
-// FAST: 16-byte aligned rows and K a multiple of 64 -- no per-element bounds in the inner loops
-template <bool GATHER, class StageHook>
+// FAST: 16-byte aligned rows and K a multiple of 64 -- no per-element bounds in the inner loops.  The
+// choice is a KERNEL template parameter (made on the host by producer_fast()): with both bodies in one
+// kernel the producers' code doubles and the roles evict each other from the instruction cache.
+inline bool producer_fast(int vec_ok, int cin) { return vec_ok && (cin & (kBK - 1)) == 0; }
+
+template <bool GATHER, bool FAST, bool PROF, class StageHook>
 __device__ __forceinline__ void producer_run(const ProducerArgs &a, int ptid, StageHook hook) {
-    if (a.vec_ok && (a.cin & (kBK - 1)) == 0) producer_body<GATHER, true>(a, ptid, hook);
-    else producer_body<GATHER, false>(a, ptid, hook);
+    producer_body<GATHER, FAST, PROF>(a, ptid, hook);
 }
 
 }  // namespace tc

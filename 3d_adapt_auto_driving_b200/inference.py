@@ -26,7 +26,7 @@ class Detector:
     so it is captured once per input shape into a CUDA graph and replayed; `detect_device` then
     returns views of the graph's static output buffers (valid until the next call)."""
 
-    def __init__(self, model, device=None, use_graph=True, depth=2):
+    def __init__(self, model, device=None, use_graph=True, depth=3):
         self.model = model.eval()
         self.device = device if device is not None else next(model.parameters()).device
         self.mean_size = torch.from_numpy(cfg.CLS_MEAN_SIZE[0]).to(self.device)

@@ -177,6 +177,9 @@ int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int 
 
 /* tuning hook: per-CTA stopwatch buffer (32 u64 per CTA, device memory) for the fused SA kernel, NULL = off */
 void pn2_sa_fused_tc_set_profile(void *buf);
+/* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
+ * (results become garbage); 0 restores the product behaviour. */
+void pn2_sa_fused_tc_set_debug(int bits);
 
 #ifdef __cplusplus
 }

@@ -46,20 +46,25 @@ for i in range(iters):
 import ctypes
 cabi = importlib.import_module(PKG + ".cabi")
 NCTA = 148 * 4    # persistent_grid() launches up to 4 CTAs per SM
-prof = torch.zeros((NCTA * 32,), dtype=torch.int64, device="cuda")
-cabi.lib().pn2_sa_fused_tc_set_profile(ctypes.c_void_p(prof.data_ptr()))
-L2, L3 = fz.PackedLayer(l2w, l2.b, True), fz.PackedLayer(l3w, l3.b, True)
-fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
-torch.cuda.synchronize()
-cabi.lib().pn2_sa_fused_tc_set_profile(ctypes.c_void_p(0))
-pr = prof.view(NCTA, 32).double().cpu()
-pr = pr[pr[:, 5] > 0]
-tiles = pr[:, 5].clamp_min(1)
-print("CTAs that ran: %d, tiles per CTA %.1f" % (pr.shape[0], float(tiles.mean())))
 names = {0: "MMA thread total", 1: "MMA wait operand ring", 2: "MMA wait acc2 empty (E2)", 3: "MMA wait A2 full (E2)",
          4: "MMA wait acc3 empty (E3)", 6: "MMA issue layer 2 (24 MMAs)", 7: "MMA issue layer 3 (24 MMAs)", 8: "EPI wait acc2 full (M2)", 9: "EPI wait A2 empty (M3)", 10: "EPI wait acc3 full (M3)",
-         11: "EPI barrier+combine", 12: "EPI E2 work", 13: "EPI E3 work", 14: "PROD wait row metadata", 15: "PROD wait free stage",
+         12: "EPI E2 work", 13: "EPI E3 work", 14: "PROD wait row metadata", 15: "PROD wait free stage",
          16: "PROD total", 17: "META wait free slot", 18: "META total"}
-print("fused SA kernel, cycles per tile (mean over CTAs):")
+L2, L3 = fz.PackedLayer(l2w, l2.b, True), fz.PackedLayer(l3w, l3.b, True)
+cols = {}
+for dbg in (0, 1, 2, 3):      # bit0: E3 without its TMEM loads / pooling, bit1: E2 without its TMEM ld/st
+    prof = torch.zeros((NCTA * 32,), dtype=torch.int64, device="cuda")
+    cabi.lib().pn2_sa_fused_tc_set_debug(dbg)
+    cabi.lib().pn2_sa_fused_tc_set_profile(ctypes.c_void_p(prof.data_ptr()))
+    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
+    torch.cuda.synchronize()
+    cabi.lib().pn2_sa_fused_tc_set_profile(ctypes.c_void_p(0))
+    cabi.lib().pn2_sa_fused_tc_set_debug(0)
+    pr = prof.view(NCTA, 32).double().cpu()
+    pr = pr[pr[:, 5] > 0]
+    tiles = pr[:, 5].clamp_min(1)
+    cols[dbg] = {k: float((pr[:, k] / tiles).mean()) for k in names}
+print("fused SA kernel, cycles per tile (mean over %d CTAs, %.1f tiles each); columns: product | no E3 | no E2 | neither" % (
+    pr.shape[0], float(tiles.mean())))
 for k, n in names.items():
-    print("  %-28s %9.0f" % (n, float((pr[:, k] / tiles).mean())))
+    print("  %-28s %9.0f %9.0f %9.0f %9.0f" % (n, cols[0][k], cols[1][k], cols[2][k], cols[3][k]))
