@@ -1,0 +1,426 @@
+// sa_fused_t_tc.cu -- the fused set-abstraction MLP (sa_fused_tc.cu) with a TRANSPOSED last layer.
+//
+// Same contract as pn2_sa_fused_tc_f32: QueryAndGroup (pointnet2_utils.py:241-264) + SharedMLP layers
+// 1-3 (pytorch_utils.py:5-101) + F.max_pool2d over nsample (pointnet2_modules.py:42) for one (SA module,
+// scale), given the per-point half H of layer 1 -- for the shapes whose last layer has exactly 128
+// output channels (RCNN SA1 [128,128,128], RPN SA2 [64,64,128] / [64,96,128]: 80 % of the fused work).
+//
+// Why a second kernel.  In sa_fused_tc.cu the layer-3 accumulator has one ROW of the tile per TMEM lane,
+// so the max over the nsample rows of a centre is a cross-lane reduction: a 5-level shuffle butterfly
+// per 16-column chunk, ~85 issued instructions per chunk and a dependent SHFL chain that the two
+// epilogue warps of a scheduler cannot hide.  The in-kernel stopwatch (tools/prof_tc.py) showed that
+// pooling epilogue (3.4 k cycles per tile) plus the single-buffered layer-3 accumulator it drains
+// serialised against the layer-3 MMAs: 6.6 k cycles per tile against 3.7 k of tensor-pipe work.
+// Here layer 3 is computed as  acc3^T (channels x rows) = W3 (A operand, resident in TENSOR MEMORY)
+// x A2^T (B operand, the layer-2 activation tile in shared memory):
+//   * a TMEM lane now holds one output CHANNEL and the 128 columns are the tile's rows, so the max over
+//     nsample consecutive rows is a plain in-thread FMNMX chain over the registers of a tcgen05.ld --
+//     no shuffles, no atomics, no zero-fill of the output, and the pooled row is written as one coalesced
+//     128-byte store per warp (lanes = consecutive channels);
+//   * W3 leaves shared memory (it is loaded into TMEM once per CTA), which pays for the activation tile
+//     A2 (bf16 hi/lo, 64 KB) that the layer-2 epilogue now writes to shared memory instead of TMEM;
+//   * TMEM: acc2[0] | acc2[1] | W3.hi | W3.lo | acc3  =  2 n2 + c2 + 128 <= 512 columns: the LAYER-2
+//     accumulator is double-buffered, so layer 2 of tile i+2 runs on the tensor pipe while the epilogue
+//     converts tile i+1, and the (now ~10x cheaper) pooling epilogue never holds up layer 3.
+// Roles and the operand producers are those of sa_fused_tc.cu (tc_producer.cuh).
+#include "tc_producer.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int BM = kBM;
+constexpr int BK = kBK;
+constexpr int kEpiW = 8;
+constexpr int kFirstEpiWarp = kProdWarps;                 // producers: warps 0 .. 15
+constexpr int kMetaWarp = kProdWarps + kEpiW;             // 24
+constexpr int kMmaWarp = kMetaWarp + 1;                   // 25 (highest id: first pick of its scheduler)
+constexpr int kThreads = (kProdWarps + kEpiW + 2) * 32;   // 26 warps
+constexpr int kMaxStages = 4;
+constexpr int kABytes = kTileBytes;
+constexpr int kC3 = 128;                                  // output channels = UMMA M of the transposed layer 3
+
+struct SatParams {
+    const float *h; int ldh; int c1;
+    const int32_t *idx; const float *xyz; const float *centres; const float *wxyz;
+    int n, m, ns;
+    long long rows, tiles;
+    const uint8_t *w2blob; int n2, nkb1;          // layer 2: N = n2 = c2, K-blocks of c1 (fused.pack_tc image)
+    const uint32_t *w3hi; const uint32_t *w3lo;   // layer 3: (128, c2 / 2) bf16 pairs, row = output channel
+    const float *b2; const float *b3; int c2, nkb2;
+    float *y; int ldy;
+    int stages;
+};
+
+struct SmemLayout {
+    uint32_t off_w2, off_a2, off_ring, off_meta, off_wx, off_bias, off_bars, off_tmem, total;
+};
+__host__ __device__ inline SmemLayout make_layout(const SatParams &p, int stages) {
+    SmemLayout L;
+    uint32_t o = 0;
+    L.off_w2 = o;   o += (uint32_t)p.nkb1 * 2u * p.n2 * 128u;
+    L.off_a2 = o;   o += (uint32_t)p.nkb2 * 2u * kABytes;        // per K-block: hi tile | lo tile
+    L.off_ring = o; o += (uint32_t)stages * 2u * kABytes;
+    L.off_meta = o; o += kMetaDepth * BM * sizeof(RowMeta);
+    L.off_wx = o;   o += 3u * p.nkb1 * BK * 4u;
+    L.off_bias = o; o += 2 * 128 * 4;
+    L.off_bars = o; o += (2 * kMaxStages + 12 + 2 * kMetaDepth) * 8;
+    L.off_tmem = o; o += 16;
+    L.total = o;
+    return L;
+}
+
+template <bool FAST>
+__global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kpad = p.nkb1 * BK;
+    const SmemLayout L = make_layout(p, p.stages);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+    uint64_t *empty = full + kMaxStages;
+    uint64_t *acc2_full = empty + kMaxStages;   // [2]
+    uint64_t *acc2_empty = acc2_full + 2;       // [2]
+    uint64_t *a2_full = acc2_empty + 2;
+    uint64_t *a2_empty = a2_full + 1;
+    uint64_t *acc3_full = a2_empty + 1;
+    uint64_t *acc3_empty = acc3_full + 1;
+    uint64_t *w_full = acc3_empty + 1;          // W2 in shared memory (bulk copy)
+    uint64_t *w3_full = w_full + 1;             // W3 in tensor memory (epilogue warps)
+    uint64_t *meta_full = w3_full + 1;
+    uint64_t *meta_empty = meta_full + kMetaDepth;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_tmem);
+
+    const uint32_t w2_bytes = (uint32_t)p.nkb1 * 2u * p.n2 * 128u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], kGroupWarps);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc2_full[a], 1);
+            mbar_init(&acc2_empty[a], kEpiW);
+        }
+        mbar_init(a2_full, kEpiW);
+        mbar_init(a2_empty, 1);
+        mbar_init(acc3_full, 1);
+        mbar_init(acc3_empty, kEpiW);
+        mbar_init(w_full, 1);
+        mbar_init(w3_full, kEpiW);
+        for (int q = 0; q < kMetaDepth; ++q) {
+            mbar_init(&meta_full[q], 1);
+            mbar_init(&meta_empty[q], kProdWarps);
+        }
+        fence_barrier_init();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(w_full)), "r"(w2_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pn2_smem_u32(smem + L.off_w2)),
+                     "l"(p.w2blob), "r"(w2_bytes), "r"(pn2_smem_u32(w_full))
+                     : "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+    {
+        float *wxs = reinterpret_cast<float *>(smem + L.off_wx);
+        for (int i = threadIdx.x; i < 3 * kpad; i += kThreads) {
+            const int c = i / kpad, k = i % kpad;
+            wxs[i] = k < p.c1 ? __ldg(p.wxyz + c * p.c1 + k) : 0.f;
+        }
+        float *bias_s = reinterpret_cast<float *>(smem + L.off_bias);
+        for (int i = threadIdx.x; i < 256; i += kThreads) {
+            const int c = i & 127;
+            bias_s[i] = i < 128 ? (c < p.c2 ? __ldg(p.b2 + c) : 0.f) : __ldg(p.b3 + c);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t col_acc2 = 0;                                   // buffer b at b * n2
+    const uint32_t col_w3 = 2u * (uint32_t)p.n2;                   // hi, lo c2 / 2 columns after it
+    const uint32_t col_acc3 = col_w3 + (uint32_t)p.c2;
+    const int half_c2 = p.c2 >> 1;
+
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const int my_tiles = first < p.tiles ? (int)((p.tiles - first + stride - 1) / stride) : 0;
+
+    ProducerArgs pa;
+    pa.x = p.h; pa.ldx = p.ldh; pa.cin = p.c1; pa.rows = p.rows;
+    pa.x2 = nullptr; pa.ldx2 = 0; pa.kb_split = 0x7fffffff;
+    pa.vec_ok = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.h) & 15) == 0);
+    pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
+    pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = p.tiles;
+    pa.ring = smem + L.off_ring; pa.stage_bytes = 2 * kABytes; pa.full = full; pa.empty = empty;
+    pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = nullptr;
+
+    if (warp < kProdWarps) {
+        // =============================== producers (tc_producer.cuh) ===============================
+        producer_run<true, FAST, false>(pa, (int)threadIdx.x, [](long long, int, int) {});
+    } else if (warp == kMetaWarp) {
+        meta_run<false>(pa, lane);
+    } else if (warp == kMmaWarp) {
+        // =============================== MMA issuer ===============================
+        // All 32 lanes run the loops (uniform operands, tc::elect_one()); one elected lane issues.
+        // Tensor-pipe order  M2(0) | M2(1) M3(0) | M2(2) M3(1) | ...
+        if (my_tiles > 0) {
+            const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
+            const uint32_t idesc3 = make_idesc_bf16(kC3, BM);       // M = channels, N = the tile's 128 rows
+            const uint32_t w2a = pn2_smem_u32(smem + L.off_w2), a2a = pn2_smem_u32(smem + L.off_a2);
+            int stage = 0;
+            uint32_t phase = 0;
+            mbar_wait(w_full, 0);
+            mbar_wait(w3_full, 0);
+            tc_fence_after_sync();
+            auto issue_m2 = [&](int it) {
+                const int buf = it & 1;
+                mbar_wait(&acc2_empty[buf], (uint32_t)((it >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d = tmem_base + col_acc2 + (uint32_t)(buf * p.n2);
+                for (int kb = 0; kb < p.nkb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t sa = pn2_smem_u32(smem + L.off_ring + (size_t)stage * 2 * kABytes);
+                    const uint32_t a_hi = desc_lo(sa), a_lo = desc_lo(sa + kABytes);
+                    const uint32_t wb = w2a + (uint32_t)kb * 2u * p.n2 * 128u;
+                    const uint32_t b_hi = desc_lo(wb), b_lo = desc_lo(wb + p.n2 * 128u);
+                    const int krem = p.c1 - kb * BK;
+                    const int ksteps = krem >= BK ? 4 : (krem + 15) >> 4;
+                    if (elect_one()) {
+                        if (ksteps == 4 && kb > 0) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                mma_ss_lo(d, a_hi + ks * 2, b_hi + ks * 2, idesc2, (kb | ks) ? 1u : 0u);
+                                mma_ss_lo(d, a_hi + ks * 2, b_lo + ks * 2, idesc2, 1u);
+                                mma_ss_lo(d, a_lo + ks * 2, b_hi + ks * 2, idesc2, 1u);
+                            }
+                        }
+                        mma_commit(&empty[stage]);
+                        if (kb == p.nkb1 - 1) mma_commit(&acc2_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            };
+            issue_m2(0);
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) issue_m2(it + 1);
+                // layer 3 (transposed): acc3^T = W3 (TMEM) x A2^T (shared memory, written by the epilogue)
+                mbar_wait(a2_full, (uint32_t)(it & 1));
+                mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d3 = tmem_base + col_acc3;
+                const uint32_t w3h = tmem_base + col_w3, w3l = w3h + (uint32_t)half_c2;
+                const int ksteps3 = p.c2 >> 4;
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps3; ++ks) {
+                        const uint32_t tb = a2a + (uint32_t)(ks >> 2) * 2u * kABytes;
+                        const uint32_t b_hi = desc_lo(tb) + (uint32_t)((ks & 3) * 2);
+                        const uint32_t b_lo = desc_lo(tb + kABytes) + (uint32_t)((ks & 3) * 2);
+                        mma_ts_lo(d3, w3h + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
+                        mma_ts_lo(d3, w3h + ks * 8, b_lo, idesc3, 1u);
+                        mma_ts_lo(d3, w3l + ks * 8, b_hi, idesc3, 1u);
+                    }
+                    mma_commit(acc3_full);
+                    mma_commit(a2_empty);
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue ===============================
+        // order  W3 -> TMEM | E2(0) | E2(1) E3(0) | E2(2) E3(1) | ... | E3(last)
+        const float *bias2 = reinterpret_cast<const float *>(smem + L.off_bias);
+        const float *bias3 = bias2 + 128;
+        const int ew = warp - kFirstEpiWarp;
+        const int q = ew & 3, half = ew >> 2;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int r = q * 32 + lane;                 // tile row (E2) / output channel (W3 load, E3) of this thread
+        {
+            // W3 -> tensor memory: warps with half 0 load the hi words of their 32 channels, half 1 the lo words
+            const uint32_t *src = (half ? p.w3lo : p.w3hi) + (size_t)r * half_c2;
+            const uint32_t dst = lane_addr + col_w3 + (uint32_t)(half * half_c2);
+            for (int j0 = 0; j0 < half_c2; j0 += 8) {
+                const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+                const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(src + j0 + 4));
+                const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                tmem_st8(dst + j0, w);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(w3_full);
+        }
+        uint8_t *a2s = smem + L.off_a2;
+        auto e3 = [&](int it) {
+            // acc3^T: lane = channel, columns = tile rows -> in-thread max over the nsample rows of each centre
+            const long long tile = first + (long long)it * stride;
+            mbar_wait(acc3_full, (uint32_t)(it & 1));
+            tc_fence_after_sync();
+            const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
+            float cm[4];
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t va[16], vb[16];
+                tmem_ld16(t3 + jp * 32, va);
+                tmem_ld16(t3 + jp * 32 + 16, vb);
+                tmem_ld_wait();
+                float ma = __uint_as_float(va[0]), mb = __uint_as_float(vb[0]);
+#pragma unroll
+                for (int j = 1; j < 16; ++j) {
+                    ma = fmaxf(ma, __uint_as_float(va[j]));
+                    mb = fmaxf(mb, __uint_as_float(vb[j]));
+                }
+                cm[2 * jp] = ma;
+                cm[2 * jp + 1] = mb;
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc3_empty);      // the accumulator is in registers: layer 3 of the next tile may start
+            const float b = bias3[r];
+            const long long row_base = tile * BM + half * 64;       // first tile row covered by this warp
+            auto emit = [&](float mval, long long first_row, bool atomic) {
+                if (first_row < p.rows) {
+                    const float o = fmaxf(mval + b, 0.f);
+                    float *dst = p.y + (first_row / p.ns) * p.ldy + r;
+                    if (atomic) atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(o));
+                    else *dst = o;
+                }
+            };
+            if (p.ns == 16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) emit(cm[j], row_base + j * 16, false);
+            } else if (p.ns == 32) {
+                emit(fmaxf(cm[0], cm[1]), row_base, false);
+                emit(fmaxf(cm[2], cm[3]), row_base + 32, false);
+            } else {
+                const float m4 = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                emit(m4, p.ns == 64 ? row_base : tile * BM, p.ns != 64);   // nsample 128: two warps share a centre
+            }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            // ---- E2: acc2[buf] -> bias, ReLU, bf16 hi/lo -> shared-memory operand A2 of layer 3 ----
+            mbar_wait(&acc2_full[buf], (uint32_t)((it >> 1) & 1));
+            mbar_wait(a2_empty, (uint32_t)(it & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t t_acc2 = lane_addr + col_acc2 + (uint32_t)(buf * p.n2);
+            auto convert = [&](const uint32_t (&v)[16], int c0) {
+                // 16 consecutive k of row r: two 16-byte chunks of the row's 128-byte line in K-block c0 / 64
+                uint4 hi[2], lo[2];
+                const float4 *b4 = reinterpret_cast<const float4 *>(bias2 + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 bb = b4[j4];
+                    const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+                    const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+                    const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+                    const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+                    uint2 h2, l2;
+                    split4(make_float4(x0, x1, x2, x3), h2, l2);
+                    if (j4 & 1) { hi[j4 >> 1].z = h2.x; hi[j4 >> 1].w = h2.y; lo[j4 >> 1].z = l2.x; lo[j4 >> 1].w = l2.y; }
+                    else        { hi[j4 >> 1].x = h2.x; hi[j4 >> 1].y = h2.y; lo[j4 >> 1].x = l2.x; lo[j4 >> 1].y = l2.y; }
+                }
+                uint8_t *tile_hi = a2s + (size_t)(c0 >> 6) * 2 * kABytes;
+                const int ci = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4 *>(tile_hi + sw128_offset(r, ci)) = hi[0];
+                *reinterpret_cast<uint4 *>(tile_hi + sw128_offset(r, ci + 1)) = hi[1];
+                *reinterpret_cast<uint4 *>(tile_hi + kABytes + sw128_offset(r, ci)) = lo[0];
+                *reinterpret_cast<uint4 *>(tile_hi + kABytes + sw128_offset(r, ci + 1)) = lo[1];
+            };
+            int c0 = half * 16;
+            for (; c0 + 32 < p.n2; c0 += 64) {
+                uint32_t va[16], vb[16];
+                tmem_ld16(t_acc2 + c0, va);
+                tmem_ld16(t_acc2 + c0 + 32, vb);
+                tmem_ld_wait();
+                convert(va, c0);
+                convert(vb, c0 + 32);
+            }
+            if (c0 < p.n2) {
+                uint32_t va[16];
+                tmem_ld16(t_acc2 + c0, va);
+                tmem_ld_wait();
+                convert(va, c0);
+            }
+            fence_proxy_async_smem();      // generic-proxy stores -> visible to the MMA's async-proxy operand reads
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(a2_full);
+                mbar_arrive(&acc2_empty[buf]);
+            }
+            if (it > 0) e3(it - 1);
+        }
+        if (my_tiles > 0) e3(my_tiles - 1);
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+// pn2_sa_fused_tc_f32 with the last layer transposed (see the header of this file).
+//   w3hi / w3lo: (128, c2 / 2) uint32 each, W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
+//   with the even k in the low half (fused.pack_w3t).
+// Supported: c3 == 128, c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
+// the two halves of a centre with atomicMax, so y must be zero-filled for it (not for 16 / 32 / 64).
+PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                                  const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2,
+                                  const void *w3hi, const void *w3lo, const float *b3, float *y, int ldy, int clouds,
+                                  int n, int m, int ns, int c1, int c2, int c3, cudaStream_t stream) {
+    if (!h || !idx || !xyz || !centres || !wxyz || !w2blob || !w3hi || !w3lo || !b2 || !b3 || !y || clouds < 0 ||
+        n <= 0 || m < 0 || c1 <= 0 || c2 <= 0 || ldh < c1 || ldy < c3 || (long long)clouds * n > 2147483647LL) {
+        pn2_set_last_error("pn2_sa_fused_t_tc_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (c3 != kC3 || !(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || c2 > 128 || n2 != c2 ||
+        nkb1 * BK < c1 || 2 * n2 + c2 + BM > 512 || ((reinterpret_cast<uintptr_t>(w3hi) | reinterpret_cast<uintptr_t>(w3lo)) & 15)) {
+        pn2_set_last_error("pn2_sa_fused_t_tc_f32: unsupported shape");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    SatParams p = {};
+    p.h = h; p.ldh = ldh; p.c1 = c1; p.idx = idx; p.xyz = xyz; p.centres = centres; p.wxyz = wxyz;
+    p.n = n; p.m = m; p.ns = ns;
+    p.rows = (long long)clouds * m * ns;
+    p.tiles = (p.rows + BM - 1) / BM;
+    p.w2blob = static_cast<const uint8_t *>(w2blob); p.n2 = n2; p.nkb1 = nkb1;
+    p.w3hi = static_cast<const uint32_t *>(w3hi); p.w3lo = static_cast<const uint32_t *>(w3lo);
+    p.b2 = b2; p.b3 = b3; p.c2 = c2; p.nkb2 = (c2 + BK - 1) / BK; p.y = y; p.ldy = ldy;
+    if (p.rows == 0) return PN2_OK;
+    int stages = kMaxStages;
+    SmemLayout L = make_layout(p, stages);
+    while (stages > 2 && L.total + 1024 > 227 * 1024) L = make_layout(p, --stages);
+    if (L.total + 1024 > 227 * 1024) {
+        pn2_set_last_error("pn2_sa_fused_t_tc_f32: does not fit in shared memory");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    p.stages = stages;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)tc::persistent_grid(p.tiles, sms);
+    const int vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
+    const size_t smem_bytes = L.total + 1024;
+    if (tc::producer_fast(vec_ok, c1)) sa_fused_t_tc_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    else sa_fused_t_tc_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

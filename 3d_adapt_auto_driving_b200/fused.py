@@ -56,6 +56,15 @@ class PackedLayer:
         wp[:, :cin] = w
         self.w, self.b, self.relu, self.cin, self.cout, self.ldw = wp, b.contiguous(), bool(relu), cin, cout, kpad
         self._tc = None
+        self._w3t = None
+
+    @property
+    def w3t(self):
+        """(hi, lo) int32 tensors (cout, cin / 2): the layer as the tensor-memory A operand of the transposed
+        last SA layer (csrc/sa_fused_t_tc.cu): bf16 pairs (k even in the low half), row = output channel."""
+        if self._w3t is None:
+            self._w3t = pack_w3t(self.w[:, :self.cin])
+        return self._w3t
 
     @property
     def tc(self):
@@ -189,6 +198,14 @@ def pack_tc(w):
     return blob.view(torch.uint8).reshape(-1), ntile, nchunks, nkb
 
 
+def pack_w3t(w):
+    """w (cout, cin) f32, cin even -> (hi, lo) int32 (cout, cin / 2): bf16 split x = hi + lo, two k per word."""
+    w = w.contiguous()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi.contiguous().view(torch.int32), lo.contiguous().view(torch.int32)
+
+
 class PackedLayerTC:
     def __init__(self, w, b, relu):
         self.cout, self.cin = w.shape
@@ -274,6 +291,21 @@ def sa_fused_supported(l2, l3, ns):
     return smem <= 227 * 1024
 
 
+SA_TRANSPOSED = os.environ.get("PN2_SA_TRANSPOSED", "1") != "0"
+
+
+def sa_fused_t_supported(l2, l3, ns):
+    """shape test mirroring pn2_sa_fused_t_tc_f32 (csrc/sa_fused_t_tc.cu): last layer of exactly 128 channels."""
+    if not SA_TRANSPOSED or MLP_ENGINE != "tc" or ns not in (16, 32, 64, 128) or not (l2.relu and l3.relu):
+        return False
+    t2 = l2.tc
+    if l3.cout != 128 or l2.cout % 16 or l2.cout > 128 or t2.nchunks != 1 or t2.ntile != l2.cout:
+        return False
+    nkb2 = (l2.cout + 63) // 64
+    smem = (t2.nkb * 2 * t2.ntile * 128 + nkb2 * 32768 + 2 * 32768 + 4 * 128 * 16 + 3 * t2.nkb * 64 * 4 + 1024 + 512 + 1024)
+    return smem <= 227 * 1024
+
+
 def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
     """gather + pair-wise half of layer 1 + layer 2 + layer 3 + max over nsample in one kernel."""
     B, M, ns = idx.shape
@@ -284,6 +316,15 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
     assert orows == B * M and oc == l3.cout
     t2, t3 = l2.tc, l3.tc
     rows = B * M * ns
+    if sa_fused_t_supported(l2, l3, ns):
+        w3hi, w3lo = l3.w3t
+        if ns >= 128:
+            o2.zero_()
+        cabi.call("pn2_sa_fused_t_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
+                  i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(w3hi), ptr(w3lo), ptr(l3.b), ptr(o2), i32(ldy), i32(B),
+                  i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout),
+                  work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
+        return out
     if ns >= 64:
         o2.zero_()
     cabi.call("pn2_sa_fused_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),

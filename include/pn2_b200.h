@@ -176,6 +176,13 @@ int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int 
                             void *stream);
 
 /* tuning hook: per-CTA stopwatch buffer (32 u64 per CTA, device memory) for the fused SA kernel, NULL = off */
+/* pn2_sa_fused_tc_f32 with the last layer computed transposed (W3 resident in tensor memory, rows of the
+ * tile as accumulator columns, so the max over nsample is an in-thread reduction): the shapes with exactly
+ * 128 output channels.  w3hi / w3lo: (128, c2 / 2) uint32, bf16 hi / lo pairs of W3.  csrc/sa_fused_t_tc.cu. */
+int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
+                          const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3hi,
+                          const void *w3lo, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
+                          int c2, int c3, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
  * (results become garbage); 0 restores the product behaviour. */

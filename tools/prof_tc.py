@@ -31,16 +31,26 @@ for i in range(iters):
     fz.linear_tc(mid, l3, out=out, pool=ns)
     e2.record()
     torch.cuda.synchronize()
-    e3 = torch.cuda.Event(enable_timing=True)
+    e3, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     L2, L3 = fz.PackedLayer(l2w, l2.b, True), fz.PackedLayer(l3w, l3.b, True)
+    fz.SA_TRANSPOSED = False
     fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
     e2.record()
     fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out2)
     e3.record()
+    fz.SA_TRANSPOSED = True
+    out3 = torch.full_like(out2, -7.0)
+    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out3)
+    e3b = torch.cuda.Event(enable_timing=True)
+    e3b.record()
+    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, L2, L3, out3)
+    e4.record()
     torch.cuda.synchronize()
-    print("gather layer %.3f ms   pooled layer %.3f ms   fused SA %.3f ms  (rows %d)  fused==layered: %.2e" % (
-        s.elapsed_time(e), e.elapsed_time(e2), e2.elapsed_time(e3), R * M * ns,
-        float((out - out2).abs().max() / out.abs().max())))
+    print("gather layer %.3f ms   pooled layer %.3f ms   fused SA %.3f ms   fused SA (transposed L3) %.3f ms  (rows %d)  "
+          "fused==layered: %.2e  transposed==fused: %.2e" % (
+        s.elapsed_time(e), e.elapsed_time(e2), e2.elapsed_time(e3), e3b.elapsed_time(e4), R * M * ns,
+        float((out - out2).abs().max() / out.abs().max()), float((out3 - out2).abs().max() / out2.abs().max())))
+fz.SA_TRANSPOSED = False
 
 # ---- in-kernel stopwatch of the fused SA kernel (cycles per role blocked on each barrier) ----
 import ctypes
