@@ -2,8 +2,9 @@
 //
 // Same contract as pn2_sa_fused_tc_f32: QueryAndGroup (pointnet2_utils.py:241-264) + SharedMLP layers
 // 1-3 (pytorch_utils.py:5-101) + F.max_pool2d over nsample (pointnet2_modules.py:42) for one (SA module,
-// scale), given the per-point half H of layer 1 -- for the shapes whose last layer has exactly 128
-// output channels (RCNN SA1 [128,128,128], RPN SA2 [64,64,128] / [64,96,128]: 80 % of the fused work).
+// scale), given the per-point half H of layer 1 -- for the shapes whose last layer has 128 output
+// channels (RCNN SA1 [128,128,128], RPN SA2 [64,64,128] / [64,96,128]) or 256 (RCNN SA2 [128,128,256], which
+// does not fit the row-major kernel at all and used to run layer by layer through a 1.6 GB intermediate).
 //
 // Why a second kernel.  In sa_fused_tc.cu the layer-3 accumulator has one ROW of the tile per TMEM lane,
 // so the max over the nsample rows of a centre is a cross-lane reduction: a 5-level shuffle butterfly
@@ -22,6 +23,8 @@
 //   * TMEM: acc2[0] | acc2[1] | W3.hi | W3.lo | acc3  =  2 n2 + c2 + 128 <= 512 columns: the LAYER-2
 //     accumulator is double-buffered, so layer 2 of tile i+2 runs on the tensor pipe while the epilogue
 //     converts tile i+1, and the (now ~10x cheaper) pooling epilogue never holds up layer 3.
+//     With 256 output channels layer 3 runs as two passes of 128 over the same A2 tile (W3 takes 2 c2 columns,
+//     acc2 falls back to one buffer; layer 2 of the next tile is issued between the two passes).
 // Roles and the operand producers are those of sa_fused_tc.cu (tc_producer.cuh).
 #include "tc_producer.cuh"
 
@@ -37,7 +40,7 @@ constexpr int kMmaWarp = kMetaWarp + 1;                   // 25 (highest id: fir
 constexpr int kThreads = (kProdWarps + kEpiW + 2) * 32;   // 26 warps
 constexpr int kMaxStages = 4;
 constexpr int kABytes = kTileBytes;
-constexpr int kC3 = 128;                                  // output channels = UMMA M of the transposed layer 3
+constexpr int kC3 = 128;                                  // output channels per layer-3 pass = UMMA M
 
 struct SatParams {
     const float *h; int ldh; int c1;
@@ -47,6 +50,8 @@ struct SatParams {
     const uint8_t *w2blob; int n2, nkb1;          // layer 2: N = n2 = c2, K-blocks of c1 (fused.pack_tc image)
     const uint32_t *w3hi; const uint32_t *w3lo;   // layer 3: (128, c2 / 2) bf16 pairs, row = output channel
     const float *b2; const float *b3; int c2, nkb2;
+    int c3, nm3;                                  // output channels, passes of 128 channels (1 or 2)
+    int nb2;                                      // layer-2 accumulator buffers (2 when TMEM has room)
     float *y; int ldy;
     int stages;
 };
@@ -62,7 +67,7 @@ __host__ __device__ inline SmemLayout make_layout(const SatParams &p, int stages
     L.off_ring = o; o += (uint32_t)stages * 2u * kABytes;
     L.off_meta = o; o += kMetaDepth * BM * sizeof(RowMeta);
     L.off_wx = o;   o += 3u * p.nkb1 * BK * 4u;
-    L.off_bias = o; o += 2 * 128 * 4;
+    L.off_bias = o; o += (128 + 256) * 4;
     L.off_bars = o; o += (2 * kMaxStages + 12 + 2 * kMetaDepth) * 8;
     L.off_tmem = o; o += 16;
     L.total = o;
@@ -126,18 +131,16 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             wxs[i] = k < p.c1 ? __ldg(p.wxyz + c * p.c1 + k) : 0.f;
         }
         float *bias_s = reinterpret_cast<float *>(smem + L.off_bias);
-        for (int i = threadIdx.x; i < 256; i += kThreads) {
-            const int c = i & 127;
-            bias_s[i] = i < 128 ? (c < p.c2 ? __ldg(p.b2 + c) : 0.f) : __ldg(p.b3 + c);
-        }
+        for (int i = threadIdx.x; i < 128 + p.c3; i += kThreads)
+            bias_s[i] = i < 128 ? (i < p.c2 ? __ldg(p.b2 + i) : 0.f) : __ldg(p.b3 + (i - 128));
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t col_acc2 = 0;                                   // buffer b at b * n2
-    const uint32_t col_w3 = 2u * (uint32_t)p.n2;                   // hi, lo c2 / 2 columns after it
-    const uint32_t col_acc3 = col_w3 + (uint32_t)p.c2;
+    const uint32_t col_w3 = (uint32_t)(p.nb2 * p.n2);              // pass j: hi at + j * c2, lo c2 / 2 columns after it
+    const uint32_t col_acc3 = col_w3 + (uint32_t)(p.nm3 * p.c2);
     const int half_c2 = p.c2 >> 1;
 
     const long long first = blockIdx.x, stride = gridDim.x;
@@ -172,8 +175,9 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             mbar_wait(w3_full, 0);
             tc_fence_after_sync();
             auto issue_m2 = [&](int it) {
-                const int buf = it & 1;
-                mbar_wait(&acc2_empty[buf], (uint32_t)((it >> 1) & 1) ^ 1);
+                const int buf = p.nb2 == 2 ? (it & 1) : 0;
+                const int use = p.nb2 == 2 ? (it >> 1) : it;
+                mbar_wait(&acc2_empty[buf], (uint32_t)(use & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d = tmem_base + col_acc2 + (uint32_t)(buf * p.n2);
                 for (int kb = 0; kb < p.nkb1; ++kb) {
@@ -207,15 +211,14 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             };
-            issue_m2(0);
-            for (int it = 0; it < my_tiles; ++it) {
-                if (it + 1 < my_tiles) issue_m2(it + 1);
-                // layer 3 (transposed): acc3^T = W3 (TMEM) x A2^T (shared memory, written by the epilogue)
-                mbar_wait(a2_full, (uint32_t)(it & 1));
-                mbar_wait(acc3_empty, (uint32_t)(it & 1) ^ 1);
+            // one pass of layer 3 (transposed): acc3^T = W3[pass] (TMEM) x A2^T (shared memory, written by the epilogue)
+            auto issue_m3 = [&](int it, int j) {
+                const int cnt = it * p.nm3 + j;
+                if (j == 0) mbar_wait(a2_full, (uint32_t)(it & 1));
+                mbar_wait(acc3_empty, (uint32_t)(cnt & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d3 = tmem_base + col_acc3;
-                const uint32_t w3h = tmem_base + col_w3, w3l = w3h + (uint32_t)half_c2;
+                const uint32_t w3h = tmem_base + col_w3 + (uint32_t)(j * p.c2), w3l = w3h + (uint32_t)half_c2;
                 const int ksteps3 = p.c2 >> 4;
                 if (elect_one()) {
                     for (int ks = 0; ks < ksteps3; ++ks) {
@@ -227,9 +230,23 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                         mma_ts_lo(d3, w3l + ks * 8, b_hi, idesc3, 1u);
                     }
                     mma_commit(acc3_full);
-                    mma_commit(a2_empty);
+                    if (j == p.nm3 - 1) mma_commit(a2_empty);
                 }
                 __syncwarp();
+            };
+            issue_m2(0);
+            for (int it = 0; it < my_tiles; ++it) {
+                if (p.nb2 == 2) {
+                    // double-buffered acc2: layer 2 of the next tile first, it overlaps this tile's conversion epilogue
+                    if (it + 1 < my_tiles) issue_m2(it + 1);
+                    for (int j = 0; j < p.nm3; ++j) issue_m3(it, j);
+                } else {
+                    // single acc2 (it is free once this tile's conversion is done, which pass 0 waits for anyway):
+                    // layer 2 of the next tile sits between the passes and covers the pooling of pass 0
+                    issue_m3(it, 0);
+                    if (it + 1 < my_tiles) issue_m2(it + 1);
+                    for (int j = 1; j < p.nm3; ++j) issue_m3(it, j);
+                }
             }
         }
         __syncwarp();
@@ -244,13 +261,15 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
         const int r = q * 32 + lane;                 // tile row (E2) / output channel (W3 load, E3) of this thread
         {
             // W3 -> tensor memory: warps with half 0 load the hi words of their 32 channels, half 1 the lo words
-            const uint32_t *src = (half ? p.w3lo : p.w3hi) + (size_t)r * half_c2;
-            const uint32_t dst = lane_addr + col_w3 + (uint32_t)(half * half_c2);
-            for (int j0 = 0; j0 < half_c2; j0 += 8) {
-                const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(src + j0));
-                const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(src + j0 + 4));
-                const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                tmem_st8(dst + j0, w);
+            for (int j = 0; j < p.nm3; ++j) {
+                const uint32_t *src = (half ? p.w3lo : p.w3hi) + (size_t)(j * kC3 + r) * half_c2;
+                const uint32_t dst = lane_addr + col_w3 + (uint32_t)(j * p.c2 + half * half_c2);
+                for (int j0 = 0; j0 < half_c2; j0 += 8) {
+                    const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+                    const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(src + j0 + 4));
+                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    tmem_st8(dst + j0, w);
+                }
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -258,10 +277,10 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             if (lane == 0) mbar_arrive(w3_full);
         }
         uint8_t *a2s = smem + L.off_a2;
-        auto e3 = [&](int it) {
+        auto e3 = [&](int it, int j) {
             // acc3^T: lane = channel, columns = tile rows -> in-thread max over the nsample rows of each centre
             const long long tile = first + (long long)it * stride;
-            mbar_wait(acc3_full, (uint32_t)(it & 1));
+            mbar_wait(acc3_full, (uint32_t)((it * p.nm3 + j) & 1));
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
             float cm[4];
@@ -283,12 +302,13 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc3_empty);      // the accumulator is in registers: layer 3 of the next tile may start
-            const float b = bias3[r];
+            const int ch = j * kC3 + r;
+            const float b = bias3[ch];
             const long long row_base = tile * BM + half * 64;       // first tile row covered by this warp
             auto emit = [&](float mval, long long first_row, bool atomic) {
                 if (first_row < p.rows) {
                     const float o = fmaxf(mval + b, 0.f);
-                    float *dst = p.y + (first_row / p.ns) * p.ldy + r;
+                    float *dst = p.y + (first_row / p.ns) * p.ldy + ch;
                     if (atomic) atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(o));
                     else *dst = o;
                 }
@@ -304,10 +324,12 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 emit(m4, p.ns == 64 ? row_base : tile * BM, p.ns != 64);   // nsample 128: two warps share a centre
             }
         };
+        const bool pipelined = p.nb2 == 2;     // pooling of tile i-1 after the conversion of tile i (see the MMA order)
         for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
+            const int buf = pipelined ? (it & 1) : 0;
+            const int use = pipelined ? (it >> 1) : it;
             // ---- E2: acc2[buf] -> bias, ReLU, bf16 hi/lo -> shared-memory operand A2 of layer 3 ----
-            mbar_wait(&acc2_full[buf], (uint32_t)((it >> 1) & 1));
+            mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
             mbar_wait(a2_empty, (uint32_t)(it & 1) ^ 1);
             tc_fence_after_sync();
             const uint32_t t_acc2 = lane_addr + col_acc2 + (uint32_t)(buf * p.n2);
@@ -356,9 +378,14 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 mbar_arrive(a2_full);
                 mbar_arrive(&acc2_empty[buf]);
             }
-            if (it > 0) e3(it - 1);
+            if (!pipelined) {
+                for (int j = 0; j < p.nm3; ++j) e3(it, j);
+            } else if (it > 0) {
+                for (int j = 0; j < p.nm3; ++j) e3(it - 1, j);
+            }
         }
-        if (my_tiles > 0) e3(my_tiles - 1);
+        if (pipelined && my_tiles > 0)
+            for (int j = 0; j < p.nm3; ++j) e3(my_tiles - 1, j);
     }
 
     tc_fence_before_sync();
@@ -372,9 +399,10 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
 }  // namespace
 
 // pn2_sa_fused_tc_f32 with the last layer transposed (see the header of this file).
-//   w3hi / w3lo: (128, c2 / 2) uint32 each, W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
+//   w3hi / w3lo: (c3, c2 / 2) uint32 each, W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
 //   with the even k in the low half (fused.pack_w3t).
-// Supported: c3 == 128, c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
+// Supported: c3 == 128 or 256 (256 = two passes of layer 3 over the same activation tile; the layer-2 accumulator
+// is then single-buffered), c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
 // the two halves of a centre with atomicMax, so y must be zero-filled for it (not for 16 / 32 / 64).
 PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                                   const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2,
@@ -385,8 +413,10 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: bad argument");
         return PN2_ERR_INVALID;
     }
-    if (c3 != kC3 || !(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || c2 > 128 || n2 != c2 ||
-        nkb1 * BK < c1 || 2 * n2 + c2 + BM > 512 || ((reinterpret_cast<uintptr_t>(w3hi) | reinterpret_cast<uintptr_t>(w3lo)) & 15)) {
+    const int nm3 = c3 / kC3;
+    const int nb2 = (2 * n2 + nm3 * c2 + BM <= 512) ? 2 : 1;
+    if ((c3 != kC3 && c3 != 2 * kC3) || !(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || c2 > 128 || n2 != c2 ||
+        nkb1 * BK < c1 || nb2 * n2 + nm3 * c2 + BM > 512 || ((reinterpret_cast<uintptr_t>(w3hi) | reinterpret_cast<uintptr_t>(w3lo)) & 15)) {
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: unsupported shape");
         return PN2_ERR_UNSUPPORTED;
     }
@@ -398,6 +428,7 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     p.w2blob = static_cast<const uint8_t *>(w2blob); p.n2 = n2; p.nkb1 = nkb1;
     p.w3hi = static_cast<const uint32_t *>(w3hi); p.w3lo = static_cast<const uint32_t *>(w3lo);
     p.b2 = b2; p.b3 = b3; p.c2 = c2; p.nkb2 = (c2 + BK - 1) / BK; p.y = y; p.ldy = ldy;
+    p.c3 = c3; p.nm3 = nm3; p.nb2 = nb2;
     if (p.rows == 0) return PN2_OK;
     int stages = kMaxStages;
     SmemLayout L = make_layout(p, stages);

@@ -295,11 +295,14 @@ SA_TRANSPOSED = os.environ.get("PN2_SA_TRANSPOSED", "1") != "0"
 
 
 def sa_fused_t_supported(l2, l3, ns):
-    """shape test mirroring pn2_sa_fused_t_tc_f32 (csrc/sa_fused_t_tc.cu): last layer of exactly 128 channels."""
+    """shape test mirroring pn2_sa_fused_t_tc_f32 (csrc/sa_fused_t_tc.cu): last layer of 128 or 256 channels."""
     if not SA_TRANSPOSED or MLP_ENGINE != "tc" or ns not in (16, 32, 64, 128) or not (l2.relu and l3.relu):
         return False
     t2 = l2.tc
-    if l3.cout != 128 or l2.cout % 16 or l2.cout > 128 or t2.nchunks != 1 or t2.ntile != l2.cout:
+    if l3.cout not in (128, 256) or l2.cout % 16 or l2.cout > 128 or t2.nchunks != 1 or t2.ntile != l2.cout:
+        return False
+    nm3 = l3.cout // 128
+    if l2.cout + nm3 * l2.cout + 128 > 512:          # TMEM: acc2 (x2 when there is room) | W3 | acc3
         return False
     nkb2 = (l2.cout + 63) // 64
     smem = (t2.nkb * 2 * t2.ntile * 128 + nkb2 * 32768 + 2 * 32768 + 4 * 128 * 16 + 3 * t2.nkb * 64 * 4 + 1024 + 512 + 1024)
@@ -314,7 +317,7 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
     assert hrows == B * N and c1 == l2.cin and l3.cin == l2.cout
     o2, orows, ldy, oc = _rows2d(out)
     assert orows == B * M and oc == l3.cout
-    t2, t3 = l2.tc, l3.tc
+    t2 = l2.tc
     rows = B * M * ns
     if sa_fused_t_supported(l2, l3, ns):
         w3hi, w3lo = l3.w3t
@@ -325,6 +328,7 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
                   i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout),
                   work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
         return out
+    t3 = l3.tc
     if ns >= 64:
         o2.zero_()
     cabi.call("pn2_sa_fused_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),

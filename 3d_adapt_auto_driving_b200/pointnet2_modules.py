@@ -112,7 +112,8 @@ class _PointnetSAModuleBase(nn.Module):
                 h = entry["b1"].unsqueeze(0).expand(B * N, c1).contiguous()
             cout = layers[-1].cout
             dst = out2[:, col:col + cout]
-            if len(layers) == 3 and fz.sa_fused_supported(layers[1], layers[2], g.nsample):
+            if len(layers) == 3 and (fz.sa_fused_t_supported(layers[1], layers[2], g.nsample)
+                                     or fz.sa_fused_supported(layers[1], layers[2], g.nsample)):
                 fz.sa_fused_tc(h, idx, xyz, new_xyz, entry["wxyz"], layers[1], layers[2], dst)
             elif len(layers) == 2:
                 fz.sa_group_linear(h, idx, xyz, new_xyz, entry["wxyz"], layers[1], out=dst, pool=g.nsample)

@@ -112,12 +112,7 @@ def test_sa_group_linear_tc_vs_fp64(cuda, c1, cout, ns, pool):
     assert rel_err(y, ref) < 3e-5
 
 
-@pytest.mark.parametrize("c1,c2,c3,ns,B,N,M", [(128, 128, 128, 64, 5, 512, 128), (16, 16, 32, 16, 2, 4096, 1024),
-                                                (32, 32, 64, 32, 2, 4096, 1000), (64, 96, 128, 32, 3, 1024, 250),
-                                                (128, 128, 128, 64, 300, 512, 128)])
-def test_sa_fused_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
-    """whole SA scale on chip (csrc/sa_fused_tc.cu): gather + layer-1 xyz half + layers 2, 3 + max."""
-    fz = load("fused")
+def _sa_fused_case(cuda, fz, c1, c2, c3, ns, B, N, M):
     g = torch.Generator(device="cpu").manual_seed(c1 + c3 + B)
     xyz = torch.rand((B, N, 3), generator=g).cuda()
     centres = xyz[:, :M].contiguous()
@@ -127,20 +122,62 @@ def test_sa_fused_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
     w2 = (torch.randn((c2, c1), generator=g) / c1 ** 0.5).cuda(); b2 = torch.randn((c2,), generator=g).cuda()
     w3 = (torch.randn((c3, c2), generator=g) / c2 ** 0.5).cuda(); b3 = torch.randn((c3,), generator=g).cuda()
     l2, l3 = fz.PackedLayer(w2, b2, True), fz.PackedLayer(w3, b3, True)
-    assert fz.sa_fused_supported(l2, l3, ns)
     out = torch.full((B * M, c3 + 8), -1.0, device=cuda)
-    fz.sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out[:, 4:4 + c3])
-    # fp64 reference in chunks of clouds (the grouped tensor is big)
-    for b0 in range(0, B, 20):
-        sl = slice(b0, min(B, b0 + 20)); nb = sl.stop - sl.start
-        j = idx[sl].long()
-        ar = torch.arange(nb, device=cuda).view(nb, 1, 1)
-        hj = h.view(B, N, c1)[sl].double()[ar, j]
-        d = xyz[sl].double()[ar, j] - centres[sl].double().unsqueeze(2)
-        a1 = torch.relu(hj + d @ wxyz.double())
-        a2 = torch.relu(a1 @ w2.double().t() + b2.double())
-        a3 = torch.relu(a2 @ w3.double().t() + b3.double())
-        ref = a3.max(dim=2)[0].view(nb * M, c3)
-        got = out[b0 * M:(b0 + nb) * M, 4:4 + c3]
-        assert rel_err(got, ref) < 5e-5, (b0, rel_err(got, ref))
-    assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0   # neighbours untouched
+
+    def check():
+        # fp64 reference in chunks of clouds (the grouped tensor is big)
+        for b0 in range(0, B, 20):
+            sl = slice(b0, min(B, b0 + 20)); nb = sl.stop - sl.start
+            j = idx[sl].long()
+            ar = torch.arange(nb, device=cuda).view(nb, 1, 1)
+            hj = h.view(B, N, c1)[sl].double()[ar, j]
+            d = xyz[sl].double()[ar, j] - centres[sl].double().unsqueeze(2)
+            a1 = torch.relu(hj + d @ wxyz.double())
+            a2 = torch.relu(a1 @ w2.double().t() + b2.double())
+            a3 = torch.relu(a2 @ w3.double().t() + b3.double())
+            ref = a3.max(dim=2)[0].view(nb * M, c3)
+            got = out[b0 * M:(b0 + nb) * M, 4:4 + c3]
+            assert rel_err(got, ref) < 5e-5, (b0, rel_err(got, ref))
+        assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0   # neighbours untouched
+    return l2, l3, (h, idx, xyz, centres, wxyz), out, check
+
+
+@pytest.mark.parametrize("c1,c2,c3,ns,B,N,M", [(128, 128, 128, 64, 5, 512, 128), (16, 16, 32, 16, 2, 4096, 1024),
+                                                (32, 32, 64, 32, 2, 4096, 1000), (64, 96, 128, 32, 3, 1024, 250),
+                                                (128, 128, 128, 64, 300, 512, 128)])
+def test_sa_fused_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
+    """whole SA scale on chip, row-major last layer (csrc/sa_fused_tc.cu): gather + layer-1 xyz half + layers
+    2, 3 + max (shuffle-butterfly pooling)."""
+    fz = load("fused")
+    l2, l3, args, out, check = _sa_fused_case(cuda, fz, c1, c2, c3, ns, B, N, M)
+    assert fz.sa_fused_supported(l2, l3, ns)
+    saved, fz.SA_TRANSPOSED = fz.SA_TRANSPOSED, False
+    try:
+        fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+    finally:
+        fz.SA_TRANSPOSED = saved
+    check()
+
+
+@pytest.mark.parametrize("c1,c2,c3,ns,B,N,M", [(128, 128, 128, 64, 5, 512, 128), (64, 96, 128, 32, 3, 1024, 250),
+                                                (64, 64, 128, 16, 2, 1024, 999), (128, 128, 256, 64, 7, 128, 32),
+                                                (128, 128, 256, 16, 3, 512, 50), (128, 128, 128, 128, 3, 512, 33),
+                                                (128, 128, 256, 128, 2, 512, 17), (32, 16, 128, 32, 2, 256, 77),
+                                                (128, 128, 256, 64, 400, 128, 32)])
+def test_sa_fused_t_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
+    """whole SA scale on chip, TRANSPOSED last layer (csrc/sa_fused_t_tc.cu): W3 in tensor memory, in-thread
+    max-pool; 128 output channels (double-buffered layer-2 accumulator) and 256 (two passes), every nsample,
+    ragged last tiles."""
+    fz = load("fused")
+    l2, l3, args, out, check = _sa_fused_case(cuda, fz, c1, c2, c3, ns, B, N, M)
+    assert fz.SA_TRANSPOSED and fz.sa_fused_t_supported(l2, l3, ns)
+    fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+    check()
+    if c3 == 128 and fz.sa_fused_supported(l2, l3, ns):      # the two kernels agree to rounding of the accumulation order
+        out_t = out.clone()
+        saved, fz.SA_TRANSPOSED = fz.SA_TRANSPOSED, False
+        try:
+            fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+        finally:
+            fz.SA_TRANSPOSED = saved
+        assert rel_err(out_t[:, 4:4 + c3], out[:, 4:4 + c3].double()) < 1e-6
