@@ -207,8 +207,8 @@ def run_b200(args):
     breakdown = cabi.profile_stop()
     step_kernel_ms = sum(v["ms"] for v in breakdown.values())
     top = max(breakdown, key=lambda k: breakdown[k]["ms"])
-    mlp_names = {"pn2_linear_f32", "pn2_sa_group_linear_f32", "pn2_linear_tc_f32", "pn2_sa_group_linear_tc_f32",
-                 "pn2_sa_fused_tc_f32"}
+    mlp_names = {"pn2_linear_f32", "pn2_sa_group_linear_f32", "pn2_linear_tc_f32", "pn2_linear_tc2_f32",
+                 "pn2_sa_group_linear_tc_f32", "pn2_sa_fused_tc_f32", "pn2_sa_fused_t_tc_f32"}
     # the shared-MLP kernels are one family (same contraction, three fusion levels): judged together
     mlp_ms = sum(v["ms"] for k, v in breakdown.items() if k in mlp_names)
     if mlp_ms >= breakdown[top]["ms"]:
