@@ -68,7 +68,7 @@ def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     # large levels take the spatially culled scan (same outputs); it needs b*n int32 of scratch
     order = torch.empty((b, n), dtype=torch.int32, device=unknown.device) if (n >= 1024 and m >= 512) else None
     cabi.call("pn2_three_nn_culled_f32", ptr(unknown), ptr(known), ptr(dist2), ptr(idx), ptr(order), i32(b), i32(n),
-              i32(m), work=9.0 * b * n * m)
+              i32(m), work=12.0 * b * n * m)      # scan bytes: 12 B per unknown-known pair
 
 
 def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):

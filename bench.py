@@ -337,6 +337,14 @@ def run_b200(args):
         "roofline": roof,
         "kernel_breakdown_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
         "kernel_ms_per_step_sum": round(step_kernel_ms, 3),
+        # the scan kernels against the HBM roofline (north_star: FPS + ball_query), all launches of one eager step:
+        # scan bytes are SURVEY 8(d)'s (16 B per point and FPS round, 12 B per centre-point pair), not DRAM traffic --
+        # both kernels run on chip, so the figure may exceed 1
+        "scan_roofline": {k: {"ms": round(v["ms"], 4), "scan_GBps": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1),
+                              "frac_of_hbm_peak": round(v["work"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
+                          for k, v in breakdown.items()
+                          if k in ("pn2_fps_f32", "pn2_ball_query_culled_f32", "pn2_ball_query_f32", "pn2_ball_query_dual_f32",
+                                   "pn2_three_nn_culled_f32", "pn2_three_nn_f32") and v["ms"] > 0},
         "mlp_tflops_effective": FLOPS_PER_SCENE * scenes / (ms_total * 1e-3) / 1e12,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
