@@ -1,0 +1,167 @@
+// mt_select.cu -- HOST code: the np.random draws of KittiRCNNDataset._sample_indices
+// (pointrcnn/lib/datasets/kitti_rcnn_dataset.py:291-320) replayed on an MT19937 state, bit for bit what numpy's
+// legacy RandomState does (numpy/random/mtrand.pyx: choice -> permutation -> shuffle -> random_interval;
+// randint -> masked rejection), without the interpreter.
+//
+// Why native: which points a scene keeps is DEFINED by that generator stream, so the draws cannot move to the
+// GPU, and in Python they cost 1.8-2.3 ms per scene (a 50 k-element permutation through numpy's generic
+// byte-wise swap loop + a 16384-element shuffle) -- more than the whole GPU forward pass of the scene (0.57 ms).
+// The generator state is handed over explicitly (key[624], pos = np.random.get_state()[1:3]), so the global
+// np.random stream of the reference stays intact across calls, and because ctypes releases the GIL scenes with
+// their own seed are drawn on several host threads (datasets/gpu_loader.py).
+//
+// Checked against numpy itself (tests/test_gpu_loader_cpu.py): selections and final generator state equal.
+#include "common.cuh"
+#include <stdint.h>
+#include <string.h>
+
+namespace {
+
+struct MT {
+    uint32_t *key;   // 624 words, caller-owned
+    int pos;
+};
+
+inline void mt_gen(MT &s) {
+    const uint32_t N = 624, M = 397, MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+    uint32_t *mt = s.key;
+    uint32_t y;
+    uint32_t kk = 0;
+    for (; kk < N - M; ++kk) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + M] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+    }
+    for (; kk < N - 1; ++kk) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+    }
+    y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+    mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+    s.pos = 0;
+}
+
+inline uint32_t mt_next32(MT &s) {
+    if (s.pos == 624) mt_gen(s);
+    uint32_t y = s.key[s.pos++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+inline uint64_t mt_next64(MT &s) {   // numpy: (uint64_t)mt19937_next(state) << 32 | mt19937_next(state)
+    const uint64_t hi = mt_next32(s);
+    return (hi << 32) | mt_next32(s);
+}
+
+// numpy/random/src/distributions/distributions.c: random_interval (legacy masked rejection)
+inline uint64_t interval(MT &s, uint64_t max) {
+    if (max == 0) return 0;
+    uint64_t mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+    uint64_t value;
+    if (max <= 0xffffffffull) {
+        while ((value = (mt_next32(s) & mask)) > max) {}
+    } else {
+        while ((value = (mt_next64(s) & mask)) > max) {}
+    }
+    return value;
+}
+
+// RandomState.shuffle on a 1-D array: for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j])
+template <class T>
+inline void shuffle(MT &s, T *x, long long n) {
+    for (long long i = n - 1; i > 0; --i) {
+        const long long j = (long long)interval(s, (uint64_t)i);
+        const T t = x[i]; x[i] = x[j]; x[j] = t;
+    }
+}
+
+// RandomState.choice(n, size, replace=False) = permutation(n)[:size]: the whole permutation is drawn
+inline void choice_no_replace(MT &s, long long n, long long *scratch) {
+    for (long long i = 0; i < n; ++i) scratch[i] = i;
+    shuffle(s, scratch, n);
+}
+
+// RandomState.choice(n, size, replace=True) = randint(0, n, size): legacy masked rejection on [0, n-1]
+inline void choice_replace(MT &s, long long n, long long size, long long *out) {
+    const uint64_t rng = (uint64_t)(n - 1);
+    for (long long i = 0; i < size; ++i) out[i] = rng == 0 ? 0 : (long long)interval(s, rng);
+}
+
+}  // namespace
+
+// RandomState(seed) / np.random.seed(seed) for an integer seed: init_genrand, pos = 624.
+PN2_API void pn2_mt_seed(uint32_t seed, uint32_t *key, int32_t *pos) {
+    key[0] = seed;
+    for (uint32_t i = 1; i < 624; ++i) key[i] = 1812433253u * (key[i - 1] ^ (key[i - 1] >> 30)) + i;
+    *pos = 624;
+}
+
+// The draws of _sample_indices for one scene, from the counts of pn2_scene_filter_f32, encoded for
+// pn2_scene_gather_f32 ([0, 2^30) near_list index, [2^30, 2^31) far_list index, negative = -(valid index) - 1).
+// key (624) / pos: MT19937 state, updated in place.  scratch: max(n_valid, npoints) + npoints int64.
+// Returns PN2_OK, or PN2_ERR_INVALID for an empty population that would have to be sampled (numpy raises there).
+PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, int n_far, int npoints,
+                                  int npoints_faraway, int with_replace, int32_t *sel, long long *scratch) {
+    if (!key || !pos || !sel || !scratch || n_valid < 0 || n_near < 0 || n_far < 0 || npoints <= 0 || n_near + n_far != n_valid) {
+        pn2_set_last_error("pn2_mt_draw_selection: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    MT s = {key, *pos};
+    const long long pop = n_valid > npoints ? n_valid : npoints;
+    long long *choice = scratch + pop;          // npoints entries: the selection before the final shuffle
+    const long long FAR_BASE = 1ll << 30;
+    long long len = 0;
+    if (npoints < n_valid) {
+        // far points: all of them, or npoints_faraway of a permutation
+        long long n_far_sel = n_far;
+        const bool far_sub = n_far > npoints_faraway;
+        if (far_sub) {
+            choice_no_replace(s, n_far, scratch);
+            n_far_sel = npoints_faraway;
+        }
+        const long long need = npoints - n_far_sel;
+        // the far selection is parked at the END of `choice` while the near draw uses the scratch
+        for (long long i = 0; i < n_far_sel; ++i) choice[need + i] = (far_sub ? scratch[i] : i) + FAR_BASE;
+        if (need > 0) {
+            if (n_near == 0) {
+                pn2_set_last_error("pn2_mt_draw_selection: no near point to draw from");
+                return PN2_ERR_INVALID;
+            }
+            if (n_near < need || with_replace) {
+                choice_replace(s, n_near, need, choice);
+            } else {
+                choice_no_replace(s, n_near, scratch);
+                memcpy(choice, scratch, (size_t)need * sizeof(long long));
+            }
+        }
+        len = npoints;      // near (need) followed by far (n_far_sel): np.concatenate((near, far)); need <= 0 cannot happen (npoints_faraway < npoints)
+        if (need < 0) {
+            pn2_set_last_error("pn2_mt_draw_selection: npoints_faraway exceeds npoints");
+            return PN2_ERR_INVALID;
+        }
+    } else {
+        for (long long i = 0; i < n_valid; ++i) choice[i] = -i - 1;
+        len = n_valid;
+        if (npoints > n_valid) {
+            const long long missing = npoints - n_valid;
+            if (n_valid == 0) {
+                pn2_set_last_error("pn2_mt_draw_selection: empty scene");
+                return PN2_ERR_INVALID;
+            }
+            if (n_valid < missing) {
+                choice_replace(s, n_valid, missing, scratch);
+            } else {
+                choice_no_replace(s, n_valid, scratch);
+            }
+            for (long long i = 0; i < missing; ++i) choice[n_valid + i] = -scratch[i] - 1;
+            len = npoints;
+        }
+    }
+    shuffle(s, choice, len);                    // np.random.shuffle(choice)
+    for (long long i = 0; i < len; ++i) sel[i] = (int32_t)choice[i];
+    *pos = s.pos;
+    return PN2_OK;
+}

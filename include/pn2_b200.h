@@ -177,8 +177,8 @@ int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int 
 
 /* tuning hook: per-CTA stopwatch buffer (32 u64 per CTA, device memory) for the fused SA kernel, NULL = off */
 /* pn2_sa_fused_tc_f32 with the last layer computed transposed (W3 resident in tensor memory, rows of the
- * tile as accumulator columns, so the max over nsample is an in-thread reduction): the shapes with exactly
- * 128 output channels.  w3hi / w3lo: (128, c2 / 2) uint32, bf16 hi / lo pairs of W3.  csrc/sa_fused_t_tc.cu. */
+ * tile as accumulator columns, so the max over nsample is an in-thread reduction): the shapes with 128 or
+ * 256 output channels.  w3hi / w3lo: (c3, c2 / 2) uint32, bf16 hi / lo pairs of W3.  csrc/sa_fused_t_tc.cu. */
 int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                           const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3hi,
                           const void *w3lo, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
@@ -187,6 +187,29 @@ void pn2_sa_fused_tc_set_profile(void *buf);
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
  * (results become garbage); 0 restores the product behaviour. */
 void pn2_sa_fused_tc_set_debug(int bits);
+
+/* ---- GPU data path of KittiRCNNDataset.get_rpn_sample (csrc/scene_prepare.cu) ----
+ * pn2_scene_filter_f32: per scene lidar -> rect (lib/utils/calibration.py:51-58), projection into the image
+ * (:60-71), the image / PC_AREA_SCOPE filter (lib/datasets/kitti_rcnn_dataset.py:201-222) and the ordered
+ * near / far index lists (:291-296), numpy's float32 arithmetic reproduced bit for bit.
+ *   raw (total, 4) f32 = the .bin clouds of the batch concatenated, offsets (b + 1) int64, calib (b, 32) f32 =
+ *   {np.dot(V2C.T, R0.T) (4,3), P2.T (4,3), image width, height, pad}; x0 .. z1 = PC_AREA_SCOPE;
+ *   valid (b, cap, 4) f32 rect x, y, z, intensity of the kept points in input order; near_list / far_list (b, cap)
+ *   int32 positions in `valid`; counts (b, 4) int32 = {valid, near, far, 0}.  One CTA per scene.
+ * pn2_scene_gather_f32: pts (b, npoints, 3) [and feat (b, npoints) = intensity - 0.5, or NULL] of the selection
+ *   sel (b, npoints) int32 drawn on the host from the counts (datasets/gpu_loader.py: draw_selection). */
+int pn2_scene_filter_f32(const float *raw, const long long *offsets, const float *calib, double x0, double x1, double y0,
+                         double y1, double z0, double z1, int reduce_by_range, float near_z, float *valid,
+                         int32_t *near_list, int32_t *far_list, int32_t *counts, int b, long long cap, void *stream);
+int pn2_scene_gather_f32(const float *valid, const int32_t *near_list, const int32_t *far_list, const int32_t *sel,
+                         float *pts, float *feat, int b, int npoints, long long cap, void *stream);
+
+/* HOST functions (no device work): the np.random draws of KittiRCNNDataset._sample_indices
+ * (lib/datasets/kitti_rcnn_dataset.py:291-320) on an explicit MT19937 state, bit for bit numpy's legacy
+ * RandomState.choice / shuffle / randint.  key (624) + pos as in np.random.get_state().  csrc/mt_select.cu. */
+void pn2_mt_seed(uint32_t seed, uint32_t *key, int32_t *pos);
+int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, int n_far, int npoints,
+                          int npoints_faraway, int with_replace, int32_t *sel, long long *scratch);
 
 #ifdef __cplusplus
 }
