@@ -119,6 +119,10 @@ class GpuSceneLoader:
         # the MT19937 draws of a batch (1.8 ms per scene for a 50 k-point permutation + the 16384 shuffle; mtrand runs
         # them without the GIL).  With the reference's single global stream the draws stay serial by definition.
         self._io = concurrent.futures.ThreadPoolExecutor(max_workers=2)
+        # one more thread runs prepare() itself a batch ahead, on the loader's own CUDA stream: the (serial, by the
+        # reference's definition) global-stream draws then overlap the consumer's Python work instead of adding to it
+        self._prep = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        self._stream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None
         self._rng_pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)))
 
     def __len__(self):
@@ -203,7 +207,7 @@ class GpuSceneLoader:
                   i32(1 if cfg.PC_REDUCE_BY_RANGE else 0), ctypes.c_float(40.0), ptr(buf["valid"]), ptr(buf["near"]),
                   ptr(buf["far"]), ptr(buf["counts"]), i32(b), ctypes.c_longlong(cap), work=16.0 * raw.shape[0])
         buf["counts_h"].copy_(buf["counts"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()                          # the draws need the counts
+        torch.cuda.current_stream().synchronize()                          # the draws need the counts (loader stream only)
         counts = buf["counts_h"].numpy()
         sel = buf["sel_h"].numpy()
         def scratch_for(k):
@@ -241,15 +245,31 @@ class GpuSceneLoader:
             out["gt_boxes3d"] = gt
         return out
 
+    def _prepare_on_stream(self, host):
+        with torch.cuda.stream(self._stream):
+            batch = self.prepare(None, host=host)
+            batch["ready"] = torch.cuda.Event()
+            batch["ready"].record(self._stream)
+        return batch
+
     def __iter__(self):
+        """Batches in dataset order.  Files are read two batches ahead and prepare() runs one batch ahead on the loader's
+        stream; the consumer's current stream is made to wait for the batch before it is yielded."""
         n = len(self.ds)
         starts = list(range(0, n, self.batch_size))
-        ahead = []                                   # load_raw futures, at most 2 in flight (the staging ring has 4 slots)
+        raw_ahead, prep_ahead = [], []               # load_raw futures (<= 2: the staging ring has 4 slots), prepare futures (<= 2)
         nxt = 0
-        for start in starts:
-            while nxt < len(starts) and len(ahead) < 2:
+        for _ in starts:
+            while nxt < len(starts) and len(raw_ahead) + len(prep_ahead) < 3:
                 rng_ = range(starts[nxt], min(n, starts[nxt] + self.batch_size))
-                ahead.append(self._io.submit(self.load_raw, rng_))
+                raw_ahead.append(self._io.submit(self.load_raw, rng_))
                 nxt += 1
-            host = ahead.pop(0).result()
-            yield self.prepare(None, host=host)
+            while raw_ahead and len(prep_ahead) < 2:
+                prep_ahead.append(self._prep.submit(self._prepare_on_stream, raw_ahead.pop(0).result()))
+            batch = prep_ahead.pop(0).result()
+            cur = torch.cuda.current_stream()
+            cur.wait_event(batch.pop("ready"))
+            for key in ("pts_input", "pts_rect", "pts_features"):
+                if key in batch:
+                    batch[key].record_stream(cur)    # allocated on the loader's stream, consumed on the caller's
+            yield batch

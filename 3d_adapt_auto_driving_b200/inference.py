@@ -164,6 +164,8 @@ class Detector:
                 shape = tuple(pts.shape)
                 graph, static_in, rec, num = slot["graphs"].get(shape) or self._slot_capture(slot, shape)
                 static_in.copy_(pts, non_blocking=True)
+                if pts.is_cuda:
+                    pts.record_stream(st)           # produced on another stream (e.g. the GPU data loader's)
                 graph.replay()
             else:
                 rec, num = self._step(pts.to(self.device, non_blocking=True).float())
