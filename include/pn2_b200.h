@@ -211,6 +211,30 @@ void pn2_mt_seed(uint32_t seed, uint32_t *key, int32_t *pos);
 int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, int n_far, int npoints,
                           int npoints_faraway, int with_replace, int32_t *sel, long long *scratch);
 
+/* ---- KITTI AP evaluator around rotate_iou (evaluate/eval2.py; csrc/kitti_eval.cu) ----
+ * pn2_d3_overlap_f64 (DEVICE): d3_box_overlap_kernel (eval2.py:136-162): camera boxes (., 7) float64 and the rotated
+ *   BEV intersection areas rinc (n, k) float32 (pn2_rotate_iou_eval_f32, criterion 2) -> out (n, k) float64.
+ * Host functions (float64 / int64 arrays, no device work):
+ *   pn2_eval_image_box_overlap   image_box_overlap (:104-127)
+ *   pn2_eval_collect_thresholds  compute_statistics_jit(thresh 0, compute_fp False) over the images of one dataset
+ *                                part (:506-520): scores of the true positives
+ *   pn2_eval_fused_statistics    fused_compute_statistics (:311-358): pr (n_thresholds, 4) += [tp, fp, fn, similarity]
+ *   overlaps: (total_dt, total_gt) of the part; gt_datas (., 5), dt_datas (., 6), dontcares (., 4). */
+int pn2_d3_overlap_f64(const double *boxes, long long n, const double *qboxes, long long k, const float *rinc,
+                       int criterion, double *out, void *stream);
+int pn2_eval_image_box_overlap(const double *boxes, long long n, const double *qboxes, long long k, int criterion,
+                               double *out);
+int pn2_eval_collect_thresholds(const double *overlaps, long long total_dt, long long total_gt, const long long *gt_nums,
+                                const long long *dt_nums, const long long *dc_nums, long long n_img,
+                                const double *gt_datas, const double *dt_datas, const double *dontcares,
+                                const long long *ignored_gts, const long long *ignored_dets, int metric,
+                                double min_overlap, double *thresholds_out, long long *n_out);
+int pn2_eval_fused_statistics(const double *overlaps, long long total_dt, long long total_gt, double *pr,
+                              const long long *gt_nums, const long long *dt_nums, const long long *dc_nums,
+                              long long n_img, const double *gt_datas, const double *dt_datas, const double *dontcares,
+                              const long long *ignored_gts, const long long *ignored_dets, int metric, double min_overlap,
+                              const double *thresholds, long long n_thresholds, int compute_aos);
+
 #ifdef __cplusplus
 }
 #endif
