@@ -235,6 +235,15 @@ int pn2_eval_fused_statistics(const double *overlaps, long long total_dt, long l
                               const long long *ignored_gts, const long long *ignored_dets, int metric, double min_overlap,
                               const double *thresholds, long long n_thresholds, int compute_aos);
 
+/* ---- Statistical Normalization point rescale on the GPU (stat_norm/norm.py:186-244, 42-45;
+ * csrc/stat_norm.cu), default options (avoid_conflict = align_front = False): float64 arithmetic in numpy's dgemm
+ * order, output = the float32 rows of the rescaled .bin, bit-identical to rescale_ptc + format_lidar_data.
+ * mats (b, 42) f64 = {V2C^T (4,3), R0 (3,3), inv(R0) (3,3), C2V^T (4,3)}; boxes (nboxes, 18) f64 =
+ * {t[3], R[9], l/2, h, w/2, scale[3]} of the rescaled-class objects in label order, box_offsets (b + 1). */
+int pn2_stat_rescale_f64(const float *raw, const long long *offsets, const double *mats, const double *boxes,
+                         const int32_t *box_offsets, double *rect, unsigned char *untouched, float *out,
+                         int32_t *out_counts, int32_t *box_counts, int b, long long cap, long long cap_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
