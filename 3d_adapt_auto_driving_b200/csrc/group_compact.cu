@@ -1,0 +1,81 @@
+// group_compact.cu -- the UNIQUE rows of ball-query groups, for the duplicate-skipping SA kernels.
+//
+// ball_query pads a group that found cnt < nsample neighbours with copies of its first hit
+// (pointnet2/src/ball_query_gpu.cu:35-39: the first hit fills every slot, later hits overwrite slots 1..cnt-1), and the
+// reference then pushes all nsample rows through the shared MLP and max-pools them (pointnet2_modules.py:38-44).  The
+// padded rows are bit-for-bit copies of row 0, so they cannot change the maximum: only the first cnt rows of a group
+// carry information.  On the benchmark clouds 44-92 % of all grouped rows are such copies (tools/bq_fill_stats.py).
+// Since the hits of a group are distinct point indices, cnt = 1 + #{k >= 1 : idx[k] != idx[0]} and the unique rows are
+// exactly slots 0..cnt-1.  (A group without any hit keeps its zero-initialised row: cnt = 1, neighbour 0, like the
+// reference, which gathers point 0 sixty-four times.)
+//   pn2_group_unique_count_i32: cnt (G) from idx (G, ns)
+//   pn2_group_compact_i32     : with the exclusive prefix sum of cnt, the compact row list
+//                               cmap[u] = group (centre) of unique row u, jmap[u] = its neighbour index.
+// Both enqueue on the stream and never synchronise; the total U = sum(cnt) stays on the device (the SA kernel reads it).
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) unique_count_kernel(const int32_t *__restrict__ idx, long long g, int ns,
+                                                          int32_t *__restrict__ cnt) {
+    const long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (grp >= g) return;
+    const int32_t *row = idx + grp * ns;
+    const int32_t first = __ldg(row);
+    int c = 0;
+    for (int k = lane; k < ns; k += 32) c += (k == 0 || __ldg(row + k) != first) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[grp] = c;
+}
+
+__global__ void __launch_bounds__(256) compact_kernel(const int32_t *__restrict__ idx, long long g, int ns,
+                                                     const int32_t *__restrict__ cnt, const long long *__restrict__ offs,
+                                                     int32_t *__restrict__ cmap, int32_t *__restrict__ jmap) {
+    const long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (grp >= g) return;
+    const long long o = offs[grp];
+    const int32_t *row = idx + grp * ns;
+    const int32_t first = __ldg(row);
+    int base = 0;
+    for (int k0 = 0; k0 < ns; k0 += 32) {         // ordered: slot 0 and every slot that differs from it (for ball_query
+        const int k = k0 + lane;                  // output these are the leading cnt slots; any idx tensor is handled)
+        const int32_t v = k < ns ? __ldg(row + k) : first;
+        const bool keep = k < ns && (k == 0 || v != first);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const long long pos = o + base + __popc(bal & ((1u << lane) - 1u));
+            cmap[pos] = (int32_t)grp;
+            jmap[pos] = v;
+        }
+        base += __popc(bal);
+    }
+}
+
+}  // namespace
+
+PN2_API int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int32_t *cnt, cudaStream_t stream) {
+    if (g < 0 || ns <= 0 || (g > 0 && (!idx || !cnt))) {
+        pn2_set_last_error("pn2_group_unique_count_i32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (g == 0) return PN2_OK;
+    unique_count_kernel<<<(unsigned)((g + 7) / 8), 256, 0, stream>>>(idx, g, ns, cnt);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// offs (G) int64: EXCLUSIVE prefix sum of cnt; cmap / jmap: capacity >= sum(cnt)
+PN2_API int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
+                                  int32_t *cmap, int32_t *jmap, cudaStream_t stream) {
+    if (g < 0 || ns <= 0 || (g > 0 && (!idx || !cnt || !offs || !cmap || !jmap)) || g > 2147483647LL) {
+        pn2_set_last_error("pn2_group_compact_i32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (g == 0) return PN2_OK;
+    compact_kernel<<<(unsigned)((g + 7) / 8), 256, 0, stream>>>(idx, g, ns, cnt, offs, cmap, jmap);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

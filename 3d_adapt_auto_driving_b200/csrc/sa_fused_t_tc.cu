@@ -54,10 +54,13 @@ struct SatParams {
     int nb2;                                      // layer-2 accumulator buffers (2 when TMEM has room)
     float *y; int ldy;
     int stages;
+    // duplicate-skipping mode (group_compact.cu): only the unique rows of every group are pushed through the MLP.
+    // cmap[u] = centre of compact row u, jmap[u] = its neighbour index, *rows_dev = number of compact rows (device).
+    const int32_t *cmap; const int32_t *jmap; const long long *rows_dev;
 };
 
 struct SmemLayout {
-    uint32_t off_w2, off_a2, off_ring, off_meta, off_wx, off_bias, off_bars, off_tmem, total;
+    uint32_t off_w2, off_a2, off_ring, off_meta, off_wx, off_bias, off_cid, off_bars, off_tmem, total;
 };
 __host__ __device__ inline SmemLayout make_layout(const SatParams &p, int stages) {
     SmemLayout L;
@@ -68,13 +71,79 @@ __host__ __device__ inline SmemLayout make_layout(const SatParams &p, int stages
     L.off_meta = o; o += kMetaDepth * BM * sizeof(RowMeta);
     L.off_wx = o;   o += 3u * p.nkb1 * BK * 4u;
     L.off_bias = o; o += (128 + 256) * 4;
+    L.off_cid = o;  o += kEpiW * 64 * 4;                          // compact mode: centre ids of each epilogue warp's 64 columns
     L.off_bars = o; o += (2 * kMaxStages + 12 + 2 * kMetaDepth) * 8;
     L.off_tmem = o; o += 16;
     L.total = o;
     return L;
 }
 
-template <bool FAST>
+// Row metadata in compact mode: row u of the compact list is (centre cmap[u], neighbour jmap[u]); same software
+// pipelining as tc::meta_run (the list entries of the NEXT tile are in flight while this tile's coordinates arrive).
+__device__ __forceinline__ void meta_run_compact(const ProducerArgs &a, int lane, const int32_t *__restrict__ cmap,
+                                                 const int32_t *__restrict__ jmap) {
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const uint32_t m = (uint32_t)a.m;
+    const long long last_row = a.rows - 1;
+    constexpr int Q = kBM / 32;
+    int cn[Q], jn[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { cn[q] = 0; jn[q] = 0; }
+    if (first < a.items) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const long long u = min(first * kBM + q * 32 + lane, last_row);
+            cn[q] = __ldg(cmap + u);
+            jn[q] = __ldg(jmap + u);
+        }
+    }
+    long long it = 0;
+    for (long long item = first; item < a.items; item += stride, ++it) {
+        const int slot = (int)(it % kMetaDepth);
+        const long long row0 = item * kBM;
+        int src[Q];
+        float pj[Q][3], pc[Q][3];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const bool live = row0 + q * 32 + lane <= last_row;
+            const uint32_t centre = (uint32_t)cn[q];
+            const long long s = (long long)(centre / m) * a.n + jn[q];
+            src[q] = live ? (int)s : 0;
+            const float *gj = a.xyz + s * 3, *gc = a.centres + (long long)centre * 3;
+            pj[q][0] = __ldg(gj); pj[q][1] = __ldg(gj + 1); pj[q][2] = __ldg(gj + 2);
+            pc[q][0] = __ldg(gc); pc[q][1] = __ldg(gc + 1); pc[q][2] = __ldg(gc + 2);
+            if (!live) { pj[q][0] = pc[q][0]; pj[q][1] = pc[q][1]; pj[q][2] = pc[q][2]; }
+        }
+        if (item + stride < a.items) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const long long u = min((item + stride) * kBM + q * 32 + lane, last_row);
+                cn[q] = __ldg(cmap + u);
+                jn[q] = __ldg(jmap + u);
+            }
+        }
+        mbar_wait(&a.meta_empty[slot], (uint32_t)((it / kMetaDepth) & 1) ^ 1);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            RowMeta mt;
+            mt.src = src[q];
+            mt.dx = pj[q][0] - pc[q][0];
+            mt.dy = pj[q][1] - pc[q][1];
+            mt.dz = pj[q][2] - pc[q][2];
+            a.meta[slot * kBM + q * 32 + lane] = mt;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a.meta_full[slot]);
+    }
+}
+
+// one run of equal centre ids ends: combine its maximum into the pooled output (rare: out of line, one copy of the code)
+__device__ __noinline__ void flush_run(float *dst, float v) {
+    atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(v));
+}
+
+// COMPACT (duplicate-skipping rows) is a kernel template parameter: the dense instantiation carries none of its code
+template <bool FAST, bool COMPACT>
 __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -143,15 +212,19 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     const uint32_t col_acc3 = col_w3 + (uint32_t)(p.nm3 * p.c2);
     const int half_c2 = p.c2 >> 1;
 
+    // compact mode: the row count is data dependent and lives on the device (no host synchronisation anywhere)
+    constexpr bool compact = COMPACT;
+    const long long n_rows = compact ? *p.rows_dev : p.rows;
+    const long long n_tiles = compact ? (n_rows + BM - 1) / BM : p.tiles;
     const long long first = blockIdx.x, stride = gridDim.x;
-    const int my_tiles = first < p.tiles ? (int)((p.tiles - first + stride - 1) / stride) : 0;
+    const int my_tiles = first < n_tiles ? (int)((n_tiles - first + stride - 1) / stride) : 0;
 
     ProducerArgs pa;
-    pa.x = p.h; pa.ldx = p.ldh; pa.cin = p.c1; pa.rows = p.rows;
+    pa.x = p.h; pa.ldx = p.ldh; pa.cin = p.c1; pa.rows = n_rows;
     pa.x2 = nullptr; pa.ldx2 = 0; pa.kb_split = 0x7fffffff;
     pa.vec_ok = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.h) & 15) == 0);
     pa.idx = p.idx; pa.xyz = p.xyz; pa.centres = p.centres; pa.n = p.n; pa.m = p.m; pa.ns = p.ns;
-    pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = p.tiles;
+    pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = n_tiles;
     pa.ring = smem + L.off_ring; pa.stage_bytes = 2 * kABytes; pa.full = full; pa.empty = empty;
     pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
     pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = nullptr;
@@ -160,20 +233,23 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
         // =============================== producers (tc_producer.cuh) ===============================
         producer_run<true, FAST, false>(pa, (int)threadIdx.x, [](long long, int, int) {});
     } else if (warp == kMetaWarp) {
-        meta_run<false>(pa, lane);
+        if (compact) meta_run_compact(pa, lane, p.cmap, p.jmap);
+        else meta_run<false>(pa, lane);
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
         // All 32 lanes run the loops (uniform operands, tc::elect_one()); one elected lane issues.
         // Tensor-pipe order  M2(0) | M2(1) M3(0) | M2(2) M3(1) | ...
+        // (a CTA without a tile -- possible in compact mode, where the grid is sized for the upper bound -- still has
+        // to see its weight copies land before it may exit)
+        mbar_wait(w_full, 0);
+        mbar_wait(w3_full, 0);
+        tc_fence_after_sync();
         if (my_tiles > 0) {
             const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
             const uint32_t idesc3 = make_idesc_bf16(kC3, BM);       // M = channels, N = the tile's 128 rows
             const uint32_t w2a = pn2_smem_u32(smem + L.off_w2), a2a = pn2_smem_u32(smem + L.off_a2);
             int stage = 0;
             uint32_t phase = 0;
-            mbar_wait(w_full, 0);
-            mbar_wait(w3_full, 0);
-            tc_fence_after_sync();
             auto issue_m2 = [&](int it) {
                 const int buf = p.nb2 == 2 ? (it & 1) : 0;
                 const int use = p.nb2 == 2 ? (it >> 1) : it;
@@ -280,9 +356,64 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
         auto e3 = [&](int it, int j) {
             // acc3^T: lane = channel, columns = tile rows -> in-thread max over the nsample rows of each centre
             const long long tile = first + (long long)it * stride;
+            int *cid_s = reinterpret_cast<int *>(smem + L.off_cid) + ew * 64;
+            if (compact && j == 0) {
+                // centre ids of this warp's 64 columns -> shared memory BEFORE waiting for the accumulator: the global
+                // (L2) latency of the list stays off the section during which acc3 is held; -1 marks columns past the end
+                const long long u0 = tile * BM + half * 64;
+                const long long left = n_rows - u0;
+                const int ncols = left >= 64 ? 64 : (left > 0 ? (int)left : 0);
+                __syncwarp();
+                int2 t = make_int2(-1, -1);
+                if (2 * lane < ncols) t = __ldg(reinterpret_cast<const int2 *>(p.cmap + u0) + lane);
+                if (2 * lane + 1 >= ncols) t.y = -1;
+                reinterpret_cast<int2 *>(cid_s)[lane] = t;
+                __syncwarp();
+            }
             mbar_wait(acc3_full, (uint32_t)((it * p.nm3 + j) & 1));
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
+            if (compact) {
+                // compact rows: the columns of a centre are a run of equal ids (warp-uniform), of any length and possibly
+                // continued in the next warp / tile -> running max, one atomicMax per run and channel (y is zeroed)
+                const int ch = j * kC3 + r;
+                const float b = bias3[ch];
+                float *ych = p.y + ch;
+                int cur = -1;
+                float run = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t va[16], vb[16];
+                    tmem_ld16(t3 + c0, va);
+                    tmem_ld16(t3 + c0 + 16, vb);
+                    tmem_ld_wait();
+                    if (c0 == 32) {        // the last loads are done: the accumulator may be overwritten
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc3_empty);
+                    }
+                    const int4 *c4 = reinterpret_cast<const int4 *>(cid_s + c0);
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const int4 q = c4[k4];                                   // broadcast LDS.128: four warp-uniform ids
+                        const int cs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = 4 * k4 + e;
+                            const float x = __uint_as_float(k < 16 ? va[k] : vb[k - 16]);
+                            if (cs[e] != cur) {
+                                if (cur >= 0) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                                cur = cs[e];
+                                run = x;
+                            } else {
+                                run = fmaxf(run, x);
+                            }
+                        }
+                    }
+                }
+                if (cur >= 0) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                return;
+            }
             float cm[4];
 #pragma unroll
             for (int jp = 0; jp < 2; ++jp) {
@@ -404,10 +535,18 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
 // Supported: c3 == 128 or 256 (256 = two passes of layer 3 over the same activation tile; the layer-2 accumulator
 // is then single-buffered), c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
 // the two halves of a centre with atomicMax, so y must be zero-filled for it (not for 16 / 32 / 64).
+// Duplicate-skipping mode: cmap / jmap / rows_dev from pn2_group_compact_i32 (all three or none).  y must then be
+// zero-filled (runs of a centre are combined with atomicMax); without them every nsample-row group is processed.
 PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                                   const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2,
                                   const void *w3hi, const void *w3lo, const float *b3, float *y, int ldy, int clouds,
-                                  int n, int m, int ns, int c1, int c2, int c3, cudaStream_t stream) {
+                                  int n, int m, int ns, int c1, int c2, int c3, const int32_t *cmap, const int32_t *jmap,
+                                  const long long *rows_dev, cudaStream_t stream) {
+    if ((cmap != nullptr) != (jmap != nullptr) || (cmap != nullptr) != (rows_dev != nullptr) ||
+        (cmap && (reinterpret_cast<uintptr_t>(cmap) & 15))) {
+        pn2_set_last_error("pn2_sa_fused_t_tc_f32: cmap / jmap / rows_dev go together (cmap 16-byte aligned)");
+        return PN2_ERR_INVALID;
+    }
     if (!h || !idx || !xyz || !centres || !wxyz || !w2blob || !w3hi || !w3lo || !b2 || !b3 || !y || clouds < 0 ||
         n <= 0 || m < 0 || c1 <= 0 || c2 <= 0 || ldh < c1 || ldy < c3 || (long long)clouds * n > 2147483647LL) {
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: bad argument");
@@ -429,6 +568,7 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     p.w3hi = static_cast<const uint32_t *>(w3hi); p.w3lo = static_cast<const uint32_t *>(w3lo);
     p.b2 = b2; p.b3 = b3; p.c2 = c2; p.nkb2 = (c2 + BK - 1) / BK; p.y = y; p.ldy = ldy;
     p.c3 = c3; p.nm3 = nm3; p.nb2 = nb2;
+    p.cmap = cmap; p.jmap = jmap; p.rows_dev = rows_dev;
     if (p.rows == 0) return PN2_OK;
     int stages = kMaxStages;
     SmemLayout L = make_layout(p, stages);
@@ -440,8 +580,10 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     p.stages = stages;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
     int dev = 0, sms = 148;
@@ -450,8 +592,14 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     const unsigned grid = (unsigned)tc::persistent_grid(p.tiles, sms);
     const int vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const size_t smem_bytes = L.total + 1024;
-    if (tc::producer_fast(vec_ok, c1)) sa_fused_t_tc_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(p);
-    else sa_fused_t_tc_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    const bool fast = tc::producer_fast(vec_ok, c1);
+    if (cmap) {
+        if (fast) sa_fused_t_tc_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_t_tc_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    } else {
+        if (fast) sa_fused_t_tc_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_t_tc_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    }
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

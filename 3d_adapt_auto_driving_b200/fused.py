@@ -292,6 +292,25 @@ def sa_fused_supported(l2, l3, ns):
 
 
 SA_TRANSPOSED = os.environ.get("PN2_SA_TRANSPOSED", "1") != "0"
+# Push only the UNIQUE rows of every ball-query group through the SA MLP (csrc/group_compact.cu): a group that found
+# cnt < nsample neighbours is padded with copies of its first hit, which cannot change the max-pool.
+SA_SKIP_DUPLICATES = os.environ.get("PN2_SA_SKIP_DUPLICATES", "1") != "0"
+SA_SKIP_MIN_ROWS = 1 << 20      # below ~1 M grouped rows the two compaction launches + the zero-fill cost more than they save
+
+
+def group_compact(idx):
+    """idx (B, M, ns) int32 from ball_query -> (cmap, jmap int32 lists of the unique rows, device int64 row count);
+    no host synchronisation (the count stays on the device)."""
+    B, M, ns = idx.shape
+    G = B * M
+    cnt = torch.empty((G,), dtype=torch.int32, device=idx.device)
+    cabi.call("pn2_group_unique_count_i32", ptr(idx), _i64(G), i32(ns), ptr(cnt))
+    incl = torch.cumsum(cnt, dim=0, dtype=torch.int64)
+    offs = incl - cnt
+    cmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
+    jmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
+    cabi.call("pn2_group_compact_i32", ptr(idx), _i64(G), i32(ns), ptr(cnt), ptr(offs), ptr(cmap), ptr(jmap))
+    return cmap, jmap, incl[G - 1:G]
 
 
 def sa_fused_t_supported(l2, l3, ns):
@@ -305,7 +324,7 @@ def sa_fused_t_supported(l2, l3, ns):
     if l2.cout + nm3 * l2.cout + 128 > 512:          # TMEM: acc2 (x2 when there is room) | W3 | acc3
         return False
     nkb2 = (l2.cout + 63) // 64
-    smem = (t2.nkb * 2 * t2.ntile * 128 + nkb2 * 32768 + 2 * 32768 + 4 * 128 * 16 + 3 * t2.nkb * 64 * 4 + 1024 + 512 + 1024)
+    smem = (t2.nkb * 2 * t2.ntile * 128 + nkb2 * 32768 + 2 * 32768 + 4 * 128 * 16 + 3 * t2.nkb * 64 * 4 + 1536 + 2048 + 512 + 1024)
     return smem <= 227 * 1024
 
 
@@ -321,11 +340,14 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
     rows = B * M * ns
     if sa_fused_t_supported(l2, l3, ns):
         w3hi, w3lo = l3.w3t
-        if ns >= 128:
+        cmap = jmap = nrows = None
+        if SA_SKIP_DUPLICATES and rows >= SA_SKIP_MIN_ROWS:
+            cmap, jmap, nrows = group_compact(idx)
+        if ns >= 128 or cmap is not None:
             o2.zero_()
         cabi.call("pn2_sa_fused_t_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
                   i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(w3hi), ptr(w3lo), ptr(l3.b), ptr(o2), i32(ldy), i32(B),
-                  i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout),
+                  i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout), ptr(cmap), ptr(jmap), ptr(nrows),
                   work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
         return out
     t3 = l3.tc

@@ -182,7 +182,14 @@ int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int 
 int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                           const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3hi,
                           const void *w3lo, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
-                          int c2, int c3, void *stream);
+                          int c2, int c3, const int32_t *cmap, const int32_t *jmap, const long long *rows_dev, void *stream);
+/* The unique rows of ball-query groups (a group with cnt < nsample hits is padded with copies of its first hit, which
+ * cannot change the max-pool): cnt (G) from idx (G, ns); with the exclusive prefix sum offs (G) int64 of cnt, the compact
+ * row list cmap[u] = group, jmap[u] = neighbour index (u < sum cnt).  Passed to pn2_sa_fused_t_tc_f32 (cmap, jmap and
+ * the device-resident row count) the SA kernel processes only those rows.  csrc/group_compact.cu. */
+int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int32_t *cnt, void *stream);
+int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
+                          int32_t *cmap, int32_t *jmap, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
  * (results become garbage); 0 restores the product behaviour. */

@@ -181,3 +181,41 @@ def test_sa_fused_t_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
         finally:
             fz.SA_TRANSPOSED = saved
         assert rel_err(out_t[:, 4:4 + c3], out[:, 4:4 + c3].double()) < 1e-6
+
+
+@pytest.mark.parametrize("c1,c2,c3,ns,B,N,M", [(128, 128, 128, 64, 40, 512, 128), (128, 128, 256, 64, 30, 128, 32),
+                                                (64, 96, 128, 32, 3, 1024, 250), (64, 64, 128, 16, 2, 1024, 999)])
+def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, M):
+    """Duplicate-skipping mode (csrc/group_compact.cu + compact rows in sa_fused_t_tc.cu) on ball_query-shaped groups
+    (cnt real neighbours, then copies of the first hit; some groups full, some with a single hit): the pooled output
+    EQUALS the dense kernel's bit for bit (a max over a multiset does not see duplicates), and the fp64 reference."""
+    fz = load("fused")
+    l2, l3, args, out, check = _sa_fused_case(cuda, fz, c1, c2, c3, ns, B, N, M)
+    h, idx, xyz, centres, wxyz = args
+    g = torch.Generator(device="cpu").manual_seed(7)
+    cnt = torch.randint(1, ns + 1, (B, M, 1), generator=g)
+    cnt[0, :5] = ns
+    cnt[-1, -5:] = 1
+    k = torch.arange(ns).view(1, 1, ns)
+    idx_cpu = idx.cpu()
+    # distinct neighbours per group like ball_query: a random permutation prefix, padded with the first hit
+    perm = torch.argsort(torch.rand((B, M, N), generator=g), dim=2)[:, :, :ns].to(torch.int32)
+    idx_pad = torch.where(k < cnt, perm, perm[:, :, :1]).contiguous().to(cuda)
+    args = (h, idx_pad, xyz, centres, wxyz)
+    cm, jm, nrows = fz.group_compact(idx_pad)
+    assert int(nrows.item()) == int(cnt.sum())
+    u = int(nrows.item())
+    assert torch.equal(cm[:u].cpu(), torch.repeat_interleave(torch.arange(B * M, dtype=torch.int32), cnt.view(-1)))
+    assert torch.equal(jm[:u].cpu(), idx_pad.cpu()[k.expand(B, M, ns) < cnt])
+    saved, saved_min = fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS
+    try:
+        fz.SA_SKIP_MIN_ROWS = 0
+        fz.SA_SKIP_DUPLICATES = False
+        dense = torch.full((B * M, c3), -3.0, device=cuda)
+        fz.sa_fused_tc(*args, l2, l3, dense)
+        fz.SA_SKIP_DUPLICATES = True
+        fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+    finally:
+        fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS = saved, saved_min
+    assert torch.equal(out[:, 4:4 + c3], dense)
+    assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0
