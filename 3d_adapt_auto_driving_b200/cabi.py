@@ -70,6 +70,10 @@ def profile_start(names=None):
     _profile = {"names": set(names) if names else None, "records": []}
 
 
+def profiling():
+    return _profile is not None
+
+
 def profile_stop():
     """-> {name: {"launches", "ms", "work"}} ; synchronises."""
     global _profile

@@ -200,8 +200,8 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             wxs[i] = k < p.c1 ? __ldg(p.wxyz + c * p.c1 + k) : 0.f;
         }
         float *bias_s = reinterpret_cast<float *>(smem + L.off_bias);
-        for (int i = threadIdx.x; i < 128 + p.c3; i += kThreads)
-            bias_s[i] = i < 128 ? (i < p.c2 ? __ldg(p.b2 + i) : 0.f) : __ldg(p.b3 + (i - 128));
+        for (int i = threadIdx.x; i < 128 + p.nm3 * kC3; i += kThreads)
+            bias_s[i] = i < 128 ? (i < p.c2 ? __ldg(p.b2 + i) : 0.f) : (i - 128 < p.c3 ? __ldg(p.b3 + (i - 128)) : 0.f);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -402,7 +402,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                             const int k = 4 * k4 + e;
                             const float x = __uint_as_float(k < 16 ? va[k] : vb[k - 16]);
                             if (cs[e] != cur) {
-                                if (cur >= 0) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                                if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
                                 cur = cs[e];
                                 run = x;
                             } else {
@@ -411,7 +411,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                         }
                     }
                 }
-                if (cur >= 0) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
                 return;
             }
             float cm[4];
@@ -437,7 +437,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             const float b = bias3[ch];
             const long long row_base = tile * BM + half * 64;       // first tile row covered by this warp
             auto emit = [&](float mval, long long first_row, bool atomic) {
-                if (first_row < p.rows) {
+                if (first_row < p.rows && ch < p.c3) {
                     const float o = fmaxf(mval + b, 0.f);
                     float *dst = p.y + (first_row / p.ns) * p.ldy + ch;
                     if (atomic) atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(o));
@@ -530,9 +530,9 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
 }  // namespace
 
 // pn2_sa_fused_tc_f32 with the last layer transposed (see the header of this file).
-//   w3hi / w3lo: (c3, c2 / 2) uint32 each, W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
+//   w3hi / w3lo: (ceil(c3 / 128) * 128, c2 / 2) uint32 each (rows past c3 zero), W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
 //   with the even k in the low half (fused.pack_w3t).
-// Supported: c3 == 128 or 256 (256 = two passes of layer 3 over the same activation tile; the layer-2 accumulator
+// Supported: c3 <= 128 (the accumulator is padded to 128 channel lanes, only c3 are stored) or 256 (two passes of layer 3 over the same activation tile; the layer-2 accumulator
 // is then single-buffered), c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
 // the two halves of a centre with atomicMax, so y must be zero-filled for it (not for 16 / 32 / 64).
 // Duplicate-skipping mode: cmap / jmap / rows_dev from pn2_group_compact_i32 (all three or none).  y must then be
@@ -552,9 +552,9 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: bad argument");
         return PN2_ERR_INVALID;
     }
-    const int nm3 = c3 / kC3;
+    const int nm3 = (c3 + kC3 - 1) / kC3;
     const int nb2 = (2 * n2 + nm3 * c2 + BM <= 512) ? 2 : 1;
-    if ((c3 != kC3 && c3 != 2 * kC3) || !(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || c2 > 128 || n2 != c2 ||
+    if (c3 <= 0 || (c3 > kC3 && c3 != 2 * kC3) || !(ns == 16 || ns == 32 || ns == 64 || ns == 128) || (c2 & 15) || c2 > 128 || n2 != c2 ||
         nkb1 * BK < c1 || nb2 * n2 + nm3 * c2 + BM > 512 || ((reinterpret_cast<uintptr_t>(w3hi) | reinterpret_cast<uintptr_t>(w3lo)) & 15)) {
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: unsupported shape");
         return PN2_ERR_UNSUPPORTED;

@@ -199,7 +199,12 @@ def pack_tc(w):
 
 
 def pack_w3t(w):
-    """w (cout, cin) f32, cin even -> (hi, lo) int32 (cout, cin / 2): bf16 split x = hi + lo, two k per word."""
+    """w (cout, cin) f32, cin even -> (hi, lo) int32 (cout padded to a multiple of 128 with zero rows, cin / 2):
+    bf16 split x = hi + lo, two k per word."""
+    cout, cin = w.shape
+    pad = (cout + 127) // 128 * 128
+    if pad != cout:
+        w = torch.cat((w, torch.zeros((pad - cout, cin), dtype=w.dtype, device=w.device)), dim=0)
     w = w.contiguous()
     hi = w.to(torch.bfloat16)
     lo = (w - hi.float()).to(torch.bfloat16)
@@ -295,6 +300,10 @@ SA_TRANSPOSED = os.environ.get("PN2_SA_TRANSPOSED", "1") != "0"
 # Push only the UNIQUE rows of every ball-query group through the SA MLP (csrc/group_compact.cu): a group that found
 # cnt < nsample neighbours is padded with copies of its first hit, which cannot change the max-pool.
 SA_SKIP_DUPLICATES = os.environ.get("PN2_SA_SKIP_DUPLICATES", "1") != "0"
+# The transposed kernel also handles last layers of fewer than 128 channels (accumulator padded to 128 lanes), but for
+# the two RPN SA1 scales (32 / 64 channels, 16 / 32-channel hidden layers) it measured no faster than the row-major
+# kernel (0.39 vs 0.43 ms per step: those launches are prologue- and producer-bound, not pooling-bound): not routed.
+SA_TRANSPOSED_SMALL = os.environ.get("PN2_SA_TRANSPOSED_SMALL", "0") == "1"
 SA_SKIP_MIN_ROWS = 1 << 20      # below ~1 M grouped rows the two compaction launches + the zero-fill cost more than they save
 
 
@@ -314,13 +323,15 @@ def group_compact(idx):
 
 
 def sa_fused_t_supported(l2, l3, ns):
-    """shape test mirroring pn2_sa_fused_t_tc_f32 (csrc/sa_fused_t_tc.cu): last layer of 128 or 256 channels."""
+    """shape test mirroring pn2_sa_fused_t_tc_f32 (csrc/sa_fused_t_tc.cu): last layer of up to 128 channels, or 256."""
     if not SA_TRANSPOSED or MLP_ENGINE != "tc" or ns not in (16, 32, 64, 128) or not (l2.relu and l3.relu):
         return False
     t2 = l2.tc
-    if l3.cout not in (128, 256) or l2.cout % 16 or l2.cout > 128 or t2.nchunks != 1 or t2.ntile != l2.cout:
+    if (l3.cout > 128 and l3.cout != 256) or l2.cout % 16 or l2.cout > 128 or t2.nchunks != 1 or t2.ntile != l2.cout:
         return False
-    nm3 = l3.cout // 128
+    if l3.cout < 128 and not SA_TRANSPOSED_SMALL:
+        return False
+    nm3 = (l3.cout + 127) // 128
     if l2.cout + nm3 * l2.cout + 128 > 512:          # TMEM: acc2 (x2 when there is room) | W3 | acc3
         return False
     nkb2 = (l2.cout + 63) // 64
@@ -345,6 +356,8 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
             cmap, jmap, nrows = group_compact(idx)
         if ns >= 128 or cmap is not None:
             o2.zero_()
+        if cmap is not None and cabi.profiling():
+            rows = int(nrows.item())       # bench.py's per-kernel accounting counts the rows really processed (syncs; profiling only)
         cabi.call("pn2_sa_fused_t_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
                   i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(w3hi), ptr(w3lo), ptr(l3.b), ptr(o2), i32(ldy), i32(B),
                   i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout), ptr(cmap), ptr(jmap), ptr(nrows),

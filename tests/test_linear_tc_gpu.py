@@ -163,6 +163,7 @@ def test_sa_fused_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
                                                 (64, 64, 128, 16, 2, 1024, 999), (128, 128, 256, 64, 7, 128, 32),
                                                 (128, 128, 256, 16, 3, 512, 50), (128, 128, 128, 128, 3, 512, 33),
                                                 (128, 128, 256, 128, 2, 512, 17), (32, 16, 128, 32, 2, 256, 77),
+                                                (16, 16, 32, 16, 2, 4096, 1024), (32, 32, 64, 32, 2, 4096, 1000),
                                                 (128, 128, 256, 64, 400, 128, 32)])
 def test_sa_fused_t_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
     """whole SA scale on chip, TRANSPOSED last layer (csrc/sa_fused_t_tc.cu): W3 in tensor memory, in-thread
@@ -170,8 +171,12 @@ def test_sa_fused_t_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
     ragged last tiles."""
     fz = load("fused")
     l2, l3, args, out, check = _sa_fused_case(cuda, fz, c1, c2, c3, ns, B, N, M)
-    assert fz.SA_TRANSPOSED and fz.sa_fused_t_supported(l2, l3, ns)
-    fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+    saved_small, fz.SA_TRANSPOSED_SMALL = fz.SA_TRANSPOSED_SMALL, True       # < 128 channels: supported, not routed by default
+    try:
+        assert fz.SA_TRANSPOSED and fz.sa_fused_t_supported(l2, l3, ns)
+        fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+    finally:
+        fz.SA_TRANSPOSED_SMALL = saved_small
     check()
     if c3 == 128 and fz.sa_fused_supported(l2, l3, ns):      # the two kernels agree to rounding of the accumulation order
         out_t = out.clone()
@@ -184,7 +189,8 @@ def test_sa_fused_t_tc_vs_fp64(cuda, c1, c2, c3, ns, B, N, M):
 
 
 @pytest.mark.parametrize("c1,c2,c3,ns,B,N,M", [(128, 128, 128, 64, 40, 512, 128), (128, 128, 256, 64, 30, 128, 32),
-                                                (64, 96, 128, 32, 3, 1024, 250), (64, 64, 128, 16, 2, 1024, 999)])
+                                                (64, 96, 128, 32, 3, 1024, 250), (64, 64, 128, 16, 2, 1024, 999),
+                                                (16, 16, 32, 16, 2, 2048, 777), (32, 32, 64, 32, 2, 2048, 512)])
 def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, M):
     """Duplicate-skipping mode (csrc/group_compact.cu + compact rows in sa_fused_t_tc.cu) on ball_query-shaped groups
     (cnt real neighbours, then copies of the first hit; some groups full, some with a single hit): the pooled output
@@ -207,15 +213,16 @@ def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, 
     u = int(nrows.item())
     assert torch.equal(cm[:u].cpu(), torch.repeat_interleave(torch.arange(B * M, dtype=torch.int32), cnt.view(-1)))
     assert torch.equal(jm[:u].cpu(), idx_pad.cpu()[k.expand(B, M, ns) < cnt])
-    saved, saved_min = fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS
+    saved, saved_min, saved_small = fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL
     try:
         fz.SA_SKIP_MIN_ROWS = 0
+        fz.SA_TRANSPOSED_SMALL = True
         fz.SA_SKIP_DUPLICATES = False
         dense = torch.full((B * M, c3), -3.0, device=cuda)
         fz.sa_fused_tc(*args, l2, l3, dense)
         fz.SA_SKIP_DUPLICATES = True
         fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
     finally:
-        fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS = saved, saved_min
+        fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL = saved, saved_min, saved_small
     assert torch.equal(out[:, 4:4 + c3], dense)
     assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0
