@@ -52,18 +52,20 @@ struct TcParams {
     int ntile, nchunks, nkb, stages;
     long long items;        // tiles * nchunks
     int vec_ok;             // rows of x are 16-byte aligned (ldx % 4 == 0, base aligned)
+    int cpre;               // MODE 2: input channels of the on-the-fly first layer (wxyz = its (cpre + 1, cin) weights + bias)
 };
+constexpr int kPre = 5;     // the instantiated first-layer width (RCNN xyz_up_layer: x, y, z, mask, depth)
 
 // shared memory carve-up (dynamic, 1024-aligned base)
 struct SmemLayout {
     uint32_t stage_bytes, off_meta, off_wx, off_bias, off_stg, off_part, off_bars, off_tmem, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int ntile, int stages, int kpad, bool gather) {
+__host__ __device__ inline SmemLayout make_layout(int ntile, int stages, int kpad, bool gather, int nwx = 3) {
     SmemLayout L;
     L.stage_bytes = 2 * kABytes + 2 * ntile * 128;
     uint32_t o = L.stage_bytes * stages;
     L.off_meta = o; o += gather ? kMetaDepth * BM * sizeof(RowMeta) : 0;
-    L.off_wx = o;   o += gather ? 3 * kpad * 4 : 0;
+    L.off_wx = o;   o += (gather || nwx != 3) ? nwx * kpad * 4 : 0;
     L.off_bias = o; o += 256 * 4;
     L.off_stg = o;  L.off_part = o;   // staging (un-pooled store) and partial maxima (pooled) share space
     o += (kEpiWarps * 32 * kStgLd * 4 > 8 * 256 * 4) ? kEpiWarps * 32 * kStgLd * 4 : 8 * 256 * 4;
@@ -73,14 +75,17 @@ __host__ __device__ inline SmemLayout make_layout(int ntile, int stages, int kpa
     return L;
 }
 
-template <bool GATHER, bool FAST>
+// MODE 0: plain rows, 1: gathered rows + xyz half of the previous layer (SA), 2: on-the-fly first layer (producer_pre)
+template <int MODE, bool FAST>
 __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
+    constexpr bool GATHER = MODE == 1;
+    constexpr bool PRE = MODE == 2;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled operand tiles need 1 KB alignment in the shared window (1 KB of slack is allocated)
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpad = p.nkb * BK;
-    const SmemLayout L = make_layout(p.ntile, p.stages, kpad, GATHER);
+    const SmemLayout L = make_layout(p.ntile, p.stages, kpad, GATHER, PRE ? kPre + 1 : 3);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.off_bars);
     uint64_t *empty = full + kMaxStages;
     uint64_t *acc_full = empty + kMaxStages;
@@ -105,9 +110,9 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
-    if (GATHER) {
+    if (GATHER || PRE) {
         float *wxs = reinterpret_cast<float *>(smem + L.off_wx);
-        for (int i = threadIdx.x; i < 3 * kpad; i += kThreads) {
+        for (int i = threadIdx.x; i < (PRE ? kPre + 1 : 3) * kpad; i += kThreads) {
             const int c = i / kpad, k = i % kpad;
             wxs[i] = k < p.cin ? __ldg(p.wxyz + c * p.cin + k) : 0.f;
         }
@@ -129,7 +134,7 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
         const uint32_t bbytes = 2u * p.ntile * 128u;
-        producer_run<GATHER, FAST, false>(pa, (int)threadIdx.x, [&](long long item, int kb, int stage) {
+        auto weight_hook = [&](long long item, int kb, int stage) {
             // weight K-block: one bulk copy (TMA), completes on the same barrier as the A rows
             const uint8_t *src = p.wblob + ((size_t)(item % p.nchunks) * p.nkb + kb) * bbytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(&full[stage])),
@@ -139,7 +144,9 @@ __global__ void __maxnreg__(72) linear_tc_kernel(const TcParams p) {
                              pn2_smem_u32(smem + (size_t)stage * L.stage_bytes + 2 * kABytes)),
                          "l"(src), "r"(bbytes), "r"(pn2_smem_u32(&full[stage]))
                          : "memory");
-        });
+        };
+        if (PRE) producer_pre<kPre>(pa, (int)threadIdx.x, weight_hook);
+        else producer_run<GATHER, FAST, false>(pa, (int)threadIdx.x, weight_hook);
     } else if (warp == kMetaWarp) {
         if (GATHER) meta_run<false>(pa, lane);
     } else if (warp == kMmaWarp) {
@@ -295,27 +302,29 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <bool GATHER>
+template <int MODE>
 int launch_tc(TcParams &p, cudaStream_t stream) {
+    constexpr bool GATHER = MODE == 1;
+    const int nwx = MODE == 2 ? kPre + 1 : 3;
     const int kpad = p.nkb * BK;
     int stages = kMaxStages;
-    SmemLayout L = make_layout(p.ntile, stages, kpad, GATHER);
-    while (stages > 2 && L.total + 1024 > 227 * 1024) L = make_layout(p.ntile, --stages, kpad, GATHER);
+    SmemLayout L = make_layout(p.ntile, stages, kpad, GATHER, nwx);
+    while (stages > 2 && L.total + 1024 > 227 * 1024) L = make_layout(p.ntile, --stages, kpad, GATHER, nwx);
     if (L.total + 1024 > 227 * 1024) {
         pn2_set_last_error("linear_tc: shared memory budget exceeded");
         return PN2_ERR_UNSUPPORTED;
     }
     p.stages = stages;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[GATHER]) {
-        cudaFuncSetAttribute(linear_tc_kernel<GATHER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(linear_tc_kernel<GATHER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done[GATHER] = true;
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[MODE]) {
+        cudaFuncSetAttribute(linear_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(linear_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done[MODE] = true;
     }
     const unsigned grid = (unsigned)tc::persistent_grid(p.items, sm_count());
     // the second-source (concatenated input) path exists only in the FAST producer; pn2_linear_tc2_f32 guarantees it
-    if (tc::producer_fast(p.vec_ok, p.cin)) linear_tc_kernel<GATHER, true><<<grid, kThreads, L.total + 1024, stream>>>(p);
-    else linear_tc_kernel<GATHER, false><<<grid, kThreads, L.total + 1024, stream>>>(p);
+    if (MODE == 2 || tc::producer_fast(p.vec_ok, p.cin)) linear_tc_kernel<MODE, true><<<grid, kThreads, L.total + 1024, stream>>>(p);
+    else linear_tc_kernel<MODE, false><<<grid, kThreads, L.total + 1024, stream>>>(p);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
@@ -366,7 +375,7 @@ PN2_API int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int nt
     }
     p.x = x; p.ldx = ldx;
     p.vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    return launch_tc<false>(p, stream);
+    return launch_tc<0>(p, stream);
 }
 
 // pn2_linear_tc_f32 on a column-wise concatenation [x | x2] that is never materialised: the first
@@ -396,7 +405,7 @@ PN2_API int pn2_linear_tc2_f32(const float *x, int ldx, int c_a, const float *x2
     }
     p.x = x; p.ldx = ldx; p.vec_ok = 1;
     p.x2 = x2; p.ldx2 = ldx2; p.kb_split = c_a / BK;
-    return launch_tc<false>(p, stream);
+    return launch_tc<0>(p, stream);
 }
 
 // Tensor-core version of pn2_sa_group_linear_f32 (gather + xyz half of layer 1 + ReLU fused into
@@ -418,5 +427,33 @@ PN2_API int pn2_sa_group_linear_tc_f32(const float *h, int ldh, const int32_t *i
     p.x = h; p.ldx = ldh;
     p.idx = idx; p.xyz = xyz; p.centres = centres; p.wxyz = wxyz; p.n = n; p.m = m; p.ns = ns;
     p.vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
-    return launch_tc<true>(p, stream);
+    return launch_tc<1>(p, stream);
+}
+
+// Two layers in one launch when the first one is tiny:  Y = act(relu(x[:, :cpre] . Wpre^T + bpre) . W^T + b) [max over pool].
+// x (rows, ldx): only its first cpre columns are read (ldx >= 8, rows 16-byte aligned); wpre (cpre + 1, c1): the cpre
+// weight rows of the first layer (input-major) followed by its bias row; the second layer as in pn2_linear_tc_f32 with
+// cin = c1.  The first layer runs in exact fp32 inside the operand producers, its output is never written.
+// Instantiated for cpre = 5 (RCNN xyz_up_layer, rcnn_net.py:41-47).
+PN2_API int pn2_linear_pre_tc_f32(const float *x, int ldx, int cpre, const float *wpre, const void *wblob, int ntile,
+                                  int nchunks, int nkb, const float *bias, float *y, int ldy, long long rows, int c1,
+                                  int cout, int relu, int pool, cudaStream_t stream) {
+    TcParams p = {};
+    if (!x || !wpre || ldx < 8 || (ldx & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) {
+        pn2_set_last_error("pn2_linear_pre_tc_f32: bad argument (rows of x must be 16-byte aligned, ldx >= 8)");
+        return PN2_ERR_INVALID;
+    }
+    if (cpre != kPre || nchunks != 1) {
+        pn2_set_last_error("pn2_linear_pre_tc_f32: instantiated for a 5-channel first layer and cout <= 256");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    const int rc = fill_common(p, wblob, ntile, nchunks, nkb, bias, nullptr, 0, y, ldy, rows, c1, cout, relu, pool);
+    if (rc) return rc;
+    if (rows == 0) return PN2_OK;
+    if (rows > 2147483647LL) {
+        pn2_set_last_error("pn2_linear_pre_tc_f32: too many rows");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    p.x = x; p.ldx = ldx; p.vec_ok = 1; p.wxyz = wpre; p.cpre = cpre;
+    return launch_tc<2>(p, stream);
 }

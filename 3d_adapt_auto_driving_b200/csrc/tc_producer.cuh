@@ -281,6 +281,81 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     }
 }
 
+// ---- producers of a layer whose INPUT is itself a tiny first layer computed on the fly:
+//        A[row][k] = relu(bpre[k] + sum_{c < CPRE} Wpre[c][k] * x[row][c])          (fp32 FMAs, packed)
+//      e.g. RCNN xyz_up_layer (rcnn_net.py:41-47: SharedMLP [5 -> 128 -> 128]): the 128-channel output of its first
+//      layer (0.42 GB written and read back per step) never exists; the producers read 5 floats per row instead of 128.
+//      a.wxs holds (CPRE + 1, kpad) floats: the CPRE weight rows, then the bias row.  Plain consecutive rows, nchunks = 1,
+//      rows of x 16-byte aligned.  No global prefetch structure is needed: the inputs are 20 bytes per row.
+template <int CPRE, class StageHook>
+__device__ __forceinline__ void producer_pre(const ProducerArgs &a, int ptid, StageHook hook) {
+    static_assert(CPRE >= 1 && CPRE <= 8, "first layer of up to 8 input channels");
+    const int lane = ptid & 31, pw = ptid >> 5;
+    const int group = pw % kGroups, wg = pw / kGroups;
+    const int rsub = wg * 2 + (lane >> 4);
+    const int kq = (lane & 15) * 4;
+    const uint32_t toff = (uint32_t)(((rsub >> 3) << 10) + ((rsub & 7) << 7)) +
+                          ((((uint32_t)((lane & 15) >> 1) ^ (uint32_t)(rsub & 7)) << 4) | ((uint32_t)(lane & 1) << 3));
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const int my_items = first < a.items ? (int)((a.items - first + stride - 1) / stride) : 0;
+    const int total_steps = my_items * a.nkb;
+    int s_t = group, s_it = group / a.nkb, s_kb = group % a.nkb;
+    int stage = group % a.stages;
+    uint32_t phase = (uint32_t)((group / a.stages) & 1);
+    while (s_t < total_steps) {
+        uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
+        mbar_wait(&a.empty[stage], phase ^ 1);
+        if (wg == 0 && lane == 0) hook(first + (long long)s_it * stride, s_kb, stage);
+        const int k = s_kb * kBK + kq;
+        float2 w01[CPRE + 1], w23[CPRE + 1];               // weights of this thread's 4 channels; row CPRE = bias
+#pragma unroll
+        for (int c = 0; c <= CPRE; ++c) {
+            const float4 w = *reinterpret_cast<const float4 *>(a.wxs + c * a.kpad + k);
+            w01[c] = make_float2(w.x, w.y);
+            w23[c] = make_float2(w.z, w.w);
+        }
+        const long long row0 = (first + (long long)s_it * stride) * kBM + rsub;
+#pragma unroll
+        for (int ps = 0; ps < kPasses; ++ps) {
+            const long long row = min(row0 + ps * kRowsPerPass, a.rows - 1);
+            const float *xr = a.x + row * a.ldx;
+            float in[8];
+            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(xr));
+            in[0] = q0.x; in[1] = q0.y; in[2] = q0.z; in[3] = q0.w;
+            if (CPRE > 4) {
+                const float4 q1 = __ldg(reinterpret_cast<const float4 *>(xr + 4));   // the row has >= 8 floats (checked on the host)
+                in[4] = q1.x; in[5] = q1.y; in[6] = q1.z; in[7] = q1.w;
+            }
+            float2 t01 = w01[CPRE], t23 = w23[CPRE];
+#pragma unroll
+            for (int c = 0; c < CPRE; ++c) {
+                const float2 xc = make_float2(in[c], in[c]);
+                t01 = __ffma2_rn(w01[c], xc, t01);
+                t23 = __ffma2_rn(w23[c], xc, t23);
+            }
+            float4 v = make_float4(fmaxf(t01.x, 0.f), fmaxf(t01.y, 0.f), fmaxf(t23.x, 0.f), fmaxf(t23.y, 0.f));
+            if (k + 3 >= a.cin) {                          // keep the K padding at zero
+                if (k + 0 >= a.cin) v.x = 0.f;
+                if (k + 1 >= a.cin) v.y = 0.f;
+                if (k + 2 >= a.cin) v.z = 0.f;
+                if (k + 3 >= a.cin) v.w = 0.f;
+            }
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            *reinterpret_cast<uint2 *>(sbase + ps * 2048) = hi;
+            *reinterpret_cast<uint2 *>(sbase + kTileBytes + ps * 2048) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a.full[stage]);
+        s_t += kGroups;
+        s_kb += kGroups;
+        while (s_kb >= a.nkb) { s_kb -= a.nkb; ++s_it; }
+        stage += kGroups;
+        while (stage >= a.stages) { stage -= a.stages; phase ^= 1; }
+    }
+}
+
 // FAST: 16-byte aligned rows and K a multiple of 64 -- no per-element bounds in the inner loops.  The
 // choice is a KERNEL template parameter (made on the host by producer_fast()): with both bodies in one
 // kernel the producers' code doubles and the roles evict each other from the instruction cache.

@@ -243,6 +243,27 @@ def linear_tc(x, layer, out=None, pool=1, res=None, relu=None):
     return out
 
 
+def linear_pre(x, cpre, l1, l2, out=None):
+    """y = act2(relu(x[:, :cpre] @ W1^T + b1) @ W2^T + b2) in ONE launch (pn2_linear_pre_tc_f32): the tiny first layer
+    runs in fp32 inside the operand producers of the second and its output is never materialised.  x (rows, C >= 8) with
+    16-byte aligned rows.  Returns None when the shape is not the instantiated one (callers then run the two layers)."""
+    x2, rows, ldx, cx = _rows2d(x)
+    if (MLP_ENGINE != "tc" or cpre != 5 or l1.cin != cpre or not l1.relu or l2.cin != l1.cout or l2.tc.nchunks != 1
+            or cx < 8 or ldx % 4 or x2.data_ptr() % 16):
+        return None
+    if getattr(l1, "_wpre", None) is None:
+        l1._wpre = torch.cat((l1.w[:, :cpre].t().contiguous(), l1.b.view(1, -1)), dim=0).contiguous()    # (cpre + 1, c1)
+    tc = l2.tc
+    if out is None:
+        out = torch.empty((rows, l2.cout), dtype=torch.float32, device=x.device)
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == rows and oc == l2.cout
+    cabi.call("pn2_linear_pre_tc_f32", ptr(x2), i32(ldx), i32(cpre), ptr(l1._wpre), ptr(tc.blob), i32(tc.ntile),
+              i32(tc.nchunks), i32(tc.nkb), ptr(tc.b), ptr(o2), i32(ldy), _i64(rows), i32(l2.cin), i32(l2.cout),
+              i32(1 if l2.relu else 0), i32(1), work=2.0 * rows * (cpre * l1.cout + l2.cin * l2.cout))
+    return out
+
+
 def linear_cat(xa, xb, layer, out=None):
     """y = act(cat[xa, xb] @ W^T + b) without materialising the concatenation on the tensor-core engine
     (pn2_linear_tc2_f32); the exact-fp32 engine concatenates and calls linear()."""

@@ -183,9 +183,13 @@ class RCNNNet(nn.Module):
         nin = self.rcnn_input_channel
         rows = pts_input.view(R * S, C)
         xyz = pts_input[..., 0:3].contiguous()
-        cur = rows[:, 0:nin]
-        for layer in pk["up"]:
-            cur = fz.linear(cur, layer)
+        cur = None
+        if len(pk["up"]) == 2:
+            cur = fz.linear_pre(rows, nin, pk["up"][0], pk["up"][1])   # [5 -> 128 -> 128] in one launch, layer 1 on the fly
+        if cur is None:
+            cur = rows[:, 0:nin]
+            for layer in pk["up"]:
+                cur = fz.linear(cur, layer)
         rpn_feat = rows[:, feat_off:]
         if fz.MLP_ENGINE == "tc" and feat_off % 4 == 0 and C % 4 == 0 and rpn_feat.shape[1] % 64 == 0:
             merged = fz.linear_cat(cur, rpn_feat, pk["merge"])            # one GEMM over the virtual concatenation

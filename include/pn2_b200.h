@@ -155,6 +155,12 @@ int pn2_linear_tc_f32(const float *x, int ldx, const void *wblob, int ntile, int
 int pn2_linear_tc2_f32(const float *x, int ldx, int c_a, const float *x2, int ldx2, const void *wblob, int ntile,
                        int nchunks, int nkb, const float *bias, const float *res, int ldr, float *y, int ldy,
                        long long rows, int cin, int cout, int relu, int pool, void *stream);
+/* Two layers in one launch when the first one is tiny (RCNN xyz_up_layer [5 -> 128 -> 128], rcnn_net.py:41-47):
+ * y = act(relu(x[:, :cpre] . Wpre^T + bpre) . W^T + b); wpre (cpre + 1, c1) = the first layer's weight rows
+ * (input-major) then its bias row.  cpre = 5. */
+int pn2_linear_pre_tc_f32(const float *x, int ldx, int cpre, const float *wpre, const void *wblob, int ntile, int nchunks,
+                          int nkb, const float *bias, float *y, int ldy, long long rows, int c1, int cout, int relu,
+                          int pool, void *stream);
 int pn2_sa_group_linear_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                                const float *wxyz, const void *wblob, int ntile, int nchunks, int nkb, const float *bias,
                                float *y, int ldy, int clouds, int n, int m, int ns, int c1, int cout, int relu, int pool,

@@ -226,3 +226,26 @@ def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, 
         fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL = saved, saved_min, saved_small
     assert torch.equal(out[:, 4:4 + c3], dense)
     assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0
+
+
+def test_linear_pre_two_layers_in_one_launch(cuda):
+    """pn2_linear_pre_tc_f32: relu(relu(x[:, :5] W1^T + b1) W2^T + b2) with the 5-channel layer computed inside the
+    producers, against fp64 and against the two separate launches; strided input rows (the pooled ROI tensor), ragged
+    row counts."""
+    fz = load("fused")
+    g = torch.Generator(device="cpu").manual_seed(11)
+    w1 = (torch.randn((128, 5), generator=g) / 5 ** 0.5).cuda(); b1 = torch.randn((128,), generator=g).cuda()
+    w2 = (torch.randn((128, 128), generator=g) / 128 ** 0.5).cuda(); b2 = torch.randn((128,), generator=g).cuda()
+    l1, l2 = fz.PackedLayer(w1, b1, True), fz.PackedLayer(w2, b2, True)
+    for rows in (128 * 40, 1000, 77):
+        wide = torch.randn((rows, 136), generator=g).cuda()             # rows of the padded pooled tensor
+        got = fz.linear_pre(wide, 5, l1, l2)
+        assert got is not None and got.shape == (rows, 128)
+        x = wide[:, :5].double()
+        ref = torch.relu(torch.relu(x @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double())
+        assert rel_err(got, ref) < 3e-5
+        two = fz.linear(fz.linear(wide[:, :5], l1), l2)
+        assert rel_err(got, two.double()) < 3e-5
+    # not the instantiated shape -> None (the caller runs the layers one by one)
+    l1b = fz.PackedLayer((torch.randn((128, 6), generator=g)).cuda(), b1, True)
+    assert fz.linear_pre(wide, 6, l1b, l2) is None
