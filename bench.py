@@ -197,7 +197,7 @@ def run_b200(args):
         e.record()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print(json.dumps({"minimal": True, "ms_per_step": s.elapsed_time(e) / K, "steps": K}), flush=True)
+        emit({"minimal": True, "ms_per_step": s.elapsed_time(e) / K, "steps": K})
         return
 
     # which C-ABI kernel dominates a step (one profiled step, untimed)
@@ -350,7 +350,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_sample(torch, 1024)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -371,7 +371,7 @@ def run_reference(args):
         base.update({"value": cpu["value"], "ms_per_step": 1e3 * B / cpu["value"], "cpu_baseline": cpu,
                      "config": {"workload": "CPU port (oracle/) of the same workload; legacy-CUDA library unavailable"},
                      "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base), flush=True)
+        emit(base)
         return
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -434,10 +434,37 @@ def run_reference(args):
                                        "CUDA path on the same B200, this is the CPU port on the host cores"),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
-    print(json.dumps(base), flush=True)
+    emit(base)
+
+
+class QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first
+    collective), so file descriptor 1 points at stderr while the benchmark runs and is restored for the result line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def emit(line):
+    """print the result line on the REAL stdout (see QuietStdout)."""
+    sys.stdout.flush()
+    os.write(QUIET.saved if QUIET is not None else 1, (json.dumps(line) + "\n").encode())
+
+
+QUIET = None
 
 
 def main():
+    global QUIET
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -453,10 +480,15 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    with QuietStdout() as q:
+        QUIET = q
+        try:
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_b200(args)
+        finally:
+            QUIET = None
 
 
 if __name__ == "__main__":
