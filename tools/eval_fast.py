@@ -10,8 +10,11 @@ final_result/data output of `eval_rcnn.py --eval_mode rcnn` (pointrcnn/tools/eva
 
 With --per_scene_seed (or a sharded run) the files are byte-identical to the unmodified eval_rcnn.py run with
 PN2_PER_SCENE_SEED=1 (tests/test_gpu_loader_gpu.py); without it the np.random stream is consumed in scene order
-exactly like eval_rcnn.py with --workers 0.  Under torchrun every rank takes sample_id_list[rank::world] and the
-detection records are merged with one all_gather (parallel.py)."""
+exactly like eval_rcnn.py with --workers 0.  Under torchrun (one process per GPU) every rank evaluates
+sample_id_list[rank::world] with per-scene seeds (the dataset shards itself, datasets/kitti_rcnn_dataset.py), writes
+the result files of its own scenes into the shared output directory, and the ranks meet in ONE all_gather of their
+(scenes, detections) counts before rank 0 adds the empty files: the directory is byte-identical to a single-GPU
+--per_scene_seed run."""
 import argparse
 import concurrent.futures
 import importlib
@@ -34,6 +37,14 @@ def load(sub):
 def run(data_root, output_dir, batch_size=16, depth=3, ckpt=None, per_scene_seed=False, seed=666, gpu_loader=True,
         split=None, writers=4, log=print):
     import torch
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        os.environ["PN2_SHARD_RANK"], os.environ["PN2_SHARD_WORLD"] = str(rank), str(world)   # the dataset keeps its shard
     cfgm = load("config")
     cfgm.use_default_yaml("rcnn")
     cfg = cfgm.cfg
@@ -94,10 +105,21 @@ def run(data_root, output_dir, batch_size=16, depth=3, ckpt=None, per_scene_seed
         j.result()
     dt = time.perf_counter() - t0
     split_file = os.path.abspath(os.path.join(dataset.imageset_dir, '..', '..', 'ImageSets', dataset.split + '.txt'))
-    empty = ko.dump_empty_files(final_dir, [x.strip() for x in open(split_file).readlines()]) if not dataset.per_scene_seed \
-        or int(os.environ.get("PN2_SHARD_WORLD", "1")) == 1 else 0
-    log("eval_fast: %d scenes, %d detections, %d empty files, %.2f s = %.1f scenes/s (%s data path, %d batches in flight)"
-        % (n_scenes, n_det[0], empty, dt, n_scenes / dt, "GPU" if gpu_loader else "CPU", depth))
+    if dist is not None:
+        # the single collective: every rank's (scenes, detections); it is also the point after which all result files exist
+        mine = torch.tensor([n_scenes, n_det[0]], dtype=torch.int64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        n_scenes, n_det[0] = int(sum(int(t[0]) for t in every)), int(sum(int(t[1]) for t in every))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    empty = 0
+    if rank == 0:
+        empty = ko.dump_empty_files(final_dir, [x.strip() for x in open(split_file).readlines()])
+    if rank == 0:
+        log("eval_fast: %d scenes, %d detections, %d empty files, %.2f s = %.1f scenes/s (%s data path, %d batches in flight, "
+            "%d GPU%s)" % (n_scenes, n_det[0], empty, dt, n_scenes / dt, "GPU" if gpu_loader else "CPU", depth, world,
+                           "s" if world > 1 else ""))
     return {"scenes": n_scenes, "detections": n_det[0], "seconds": dt, "scenes_per_s": n_scenes / dt, "final_dir": final_dir}
 
 
@@ -115,7 +137,11 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     res = run(args.data_root, args.output_dir, args.batch_size, args.depth, args.ckpt, args.per_scene_seed,
               gpu_loader=not args.cpu_loader)
-    print(json.dumps({k: v for k, v in res.items()}))
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({k: v for k, v in res.items()}))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
