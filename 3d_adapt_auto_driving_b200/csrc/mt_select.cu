@@ -50,44 +50,59 @@ inline uint32_t mt_next32(MT &s) {
     return y;
 }
 
-inline uint64_t mt_next64(MT &s) {   // numpy: (uint64_t)mt19937_next(state) << 32 | mt19937_next(state)
-    const uint64_t hi = mt_next32(s);
-    return (hi << 32) | mt_next32(s);
-}
 
-// numpy/random/src/distributions/distributions.c: random_interval (legacy masked rejection)
-inline uint64_t interval(MT &s, uint64_t max) {
+// numpy/random/src/distributions/distributions.c: random_interval (legacy masked rejection): the smallest bit mask
+// covering max, then draws until one falls into [0, max].  (All populations here are < 2^31: the 32-bit branch.)
+inline uint32_t mask_of(uint32_t max) {
+    uint32_t mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    return mask;
+}
+inline uint32_t interval(MT &s, uint32_t max) {
     if (max == 0) return 0;
-    uint64_t mask = max;
-    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
-    uint64_t value;
-    if (max <= 0xffffffffull) {
-        while ((value = (mt_next32(s) & mask)) > max) {}
-    } else {
-        while ((value = (mt_next64(s) & mask)) > max) {}
-    }
+    const uint32_t mask = mask_of(max);
+    uint32_t value;
+    while ((value = (mt_next32(s) & mask)) > max) {}
     return value;
 }
 
-// RandomState.shuffle on a 1-D array: for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j])
-template <class T>
-inline void shuffle(MT &s, T *x, long long n) {
+// RandomState.shuffle on a 1-D array: for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]).
+// The mask only changes when i crosses a power of two, so it is carried instead of rebuilt every step; the generator
+// position lives in a local and the state words are read through a restrict pointer (x and key are both 32-bit integer
+// arrays: without it every swap forces the compiler to reload the generator state).
+inline void shuffle(MT &s, int32_t *__restrict__ x, long long n) {
+    if (n < 2) return;
+    uint32_t *__restrict__ key = s.key;
+    int pos = s.pos;
+    uint32_t mask = mask_of((uint32_t)(n - 1));
     for (long long i = n - 1; i > 0; --i) {
-        const long long j = (long long)interval(s, (uint64_t)i);
-        const T t = x[i]; x[i] = x[j]; x[j] = t;
+        const uint32_t max = (uint32_t)i;
+        if (max <= (mask >> 1)) mask >>= 1;
+        uint32_t j;
+        do {
+            if (pos == 624) { s.pos = pos; mt_gen(s); pos = 0; }
+            uint32_t y = key[pos++];
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            j = y & mask;
+        } while (j > max);
+        const int32_t t = x[i]; x[i] = x[j]; x[j] = t;
     }
+    s.pos = pos;
 }
 
 // RandomState.choice(n, size, replace=False) = permutation(n)[:size]: the whole permutation is drawn
-inline void choice_no_replace(MT &s, long long n, long long *scratch) {
-    for (long long i = 0; i < n; ++i) scratch[i] = i;
+inline void choice_no_replace(MT &s, long long n, int32_t *scratch) {
+    for (long long i = 0; i < n; ++i) scratch[i] = (int32_t)i;
     shuffle(s, scratch, n);
 }
 
 // RandomState.choice(n, size, replace=True) = randint(0, n, size): legacy masked rejection on [0, n-1]
-inline void choice_replace(MT &s, long long n, long long size, long long *out) {
-    const uint64_t rng = (uint64_t)(n - 1);
-    for (long long i = 0; i < size; ++i) out[i] = rng == 0 ? 0 : (long long)interval(s, rng);
+inline void choice_replace(MT &s, long long n, long long size, int32_t *out) {
+    const uint32_t rng = (uint32_t)(n - 1);
+    for (long long i = 0; i < size; ++i) out[i] = rng == 0 ? 0 : (int32_t)interval(s, rng);
 }
 
 }  // namespace
@@ -101,18 +116,19 @@ PN2_API void pn2_mt_seed(uint32_t seed, uint32_t *key, int32_t *pos) {
 
 // The draws of _sample_indices for one scene, from the counts of pn2_scene_filter_f32, encoded for
 // pn2_scene_gather_f32 ([0, 2^30) near_list index, [2^30, 2^31) far_list index, negative = -(valid index) - 1).
-// key (624) / pos: MT19937 state, updated in place.  scratch: max(n_valid, npoints) + npoints int64.
+// key (624) / pos: MT19937 state, updated in place.  scratch: max(n_valid, npoints) + npoints int32.
 // Returns PN2_OK, or PN2_ERR_INVALID for an empty population that would have to be sampled (numpy raises there).
 PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, int n_far, int npoints,
-                                  int npoints_faraway, int with_replace, int32_t *sel, long long *scratch) {
-    if (!key || !pos || !sel || !scratch || n_valid < 0 || n_near < 0 || n_far < 0 || npoints <= 0 || n_near + n_far != n_valid) {
+                                  int npoints_faraway, int with_replace, int32_t *sel, int32_t *scratch) {
+    if (!key || !pos || !sel || !scratch || n_valid < 0 || n_near < 0 || n_far < 0 || npoints <= 0 || n_near + n_far != n_valid ||
+        n_valid >= (1 << 30)) {
         pn2_set_last_error("pn2_mt_draw_selection: bad argument");
         return PN2_ERR_INVALID;
     }
     MT s = {key, *pos};
     const long long pop = n_valid > npoints ? n_valid : npoints;
-    long long *choice = scratch + pop;          // npoints entries: the selection before the final shuffle
-    const long long FAR_BASE = 1ll << 30;
+    int32_t *choice = scratch + pop;            // npoints entries: the selection before the final shuffle
+    const int32_t FAR_BASE = 1 << 30;
     long long len = 0;
     if (npoints < n_valid) {
         // far points: all of them, or npoints_faraway of a permutation
@@ -123,8 +139,12 @@ PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int 
             n_far_sel = npoints_faraway;
         }
         const long long need = npoints - n_far_sel;
+        if (need < 0) {
+            pn2_set_last_error("pn2_mt_draw_selection: npoints_faraway exceeds npoints");
+            return PN2_ERR_INVALID;
+        }
         // the far selection is parked at the END of `choice` while the near draw uses the scratch
-        for (long long i = 0; i < n_far_sel; ++i) choice[need + i] = (far_sub ? scratch[i] : i) + FAR_BASE;
+        for (long long i = 0; i < n_far_sel; ++i) choice[need + i] = (far_sub ? scratch[i] : (int32_t)i) + FAR_BASE;
         if (need > 0) {
             if (n_near == 0) {
                 pn2_set_last_error("pn2_mt_draw_selection: no near point to draw from");
@@ -134,16 +154,12 @@ PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int 
                 choice_replace(s, n_near, need, choice);
             } else {
                 choice_no_replace(s, n_near, scratch);
-                memcpy(choice, scratch, (size_t)need * sizeof(long long));
+                memcpy(choice, scratch, (size_t)need * sizeof(int32_t));
             }
         }
-        len = npoints;      // near (need) followed by far (n_far_sel): np.concatenate((near, far)); need <= 0 cannot happen (npoints_faraway < npoints)
-        if (need < 0) {
-            pn2_set_last_error("pn2_mt_draw_selection: npoints_faraway exceeds npoints");
-            return PN2_ERR_INVALID;
-        }
+        len = npoints;      // near (need) followed by far (n_far_sel): np.concatenate((near, far))
     } else {
-        for (long long i = 0; i < n_valid; ++i) choice[i] = -i - 1;
+        for (long long i = 0; i < n_valid; ++i) choice[i] = (int32_t)(-i - 1);
         len = n_valid;
         if (npoints > n_valid) {
             const long long missing = npoints - n_valid;
@@ -161,7 +177,7 @@ PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int 
         }
     }
     shuffle(s, choice, len);                    // np.random.shuffle(choice)
-    for (long long i = 0; i < len; ++i) sel[i] = (int32_t)choice[i];
+    memcpy(sel, choice, (size_t)len * sizeof(int32_t));
     *pos = s.pos;
     return PN2_OK;
 }

@@ -62,7 +62,7 @@ def _mt_lib():
         u32p, i32p, i64p = (ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_longlong))
         lib.pn2_mt_seed.argtypes = [ctypes.c_uint32, u32p, i32p]
         lib.pn2_mt_seed.restype = None
-        lib.pn2_mt_draw_selection.argtypes = [u32p, i32p] + [ctypes.c_int] * 6 + [i32p, i64p]
+        lib.pn2_mt_draw_selection.argtypes = [u32p, i32p] + [ctypes.c_int] * 6 + [i32p, i32p]
         lib.pn2_mt_draw_selection.restype = ctypes.c_int
         lib._pn2_mt_ready = True
     return lib
@@ -95,12 +95,12 @@ class MTState:
 
 def draw_selection_native(state, n_valid, n_near, n_far, npoints, npoints_faraway, with_replace, out, scratch):
     """draw_selection() by csrc/mt_select.cu on an explicit MT19937 state (GIL released during the call): the same
-    selection and the same final generator state as the numpy calls.  out (npoints,) int32, scratch int64."""
+    selection and the same final generator state as the numpy calls.  out (npoints,) int32, scratch int32."""
     lib = _mt_lib()
     rc = lib.pn2_mt_draw_selection(state.key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(state.pos),
                                    int(n_valid), int(n_near), int(n_far), int(npoints), int(npoints_faraway),
                                    1 if with_replace else 0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                                   scratch.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+                                   scratch.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     cabi.check(rc, "pn2_mt_draw_selection")
 
 
@@ -211,7 +211,7 @@ class GpuSceneLoader:
         counts = buf["counts_h"].numpy()
         sel = buf["sel_h"].numpy()
         def scratch_for(k):
-            return np.empty((max(int(counts[k, 0]), npoints) + npoints,), np.int64)
+            return np.empty((max(int(counts[k, 0]), npoints) + npoints,), np.int32)
         if ds.per_scene_seed:
             # every scene has its own generator: draw on several host threads (the native call releases the GIL)
             def draw(k):

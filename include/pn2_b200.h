@@ -222,7 +222,7 @@ int pn2_scene_gather_f32(const float *valid, const int32_t *near_list, const int
  * RandomState.choice / shuffle / randint.  key (624) + pos as in np.random.get_state().  csrc/mt_select.cu. */
 void pn2_mt_seed(uint32_t seed, uint32_t *key, int32_t *pos);
 int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, int n_far, int npoints,
-                          int npoints_faraway, int with_replace, int32_t *sel, long long *scratch);
+                          int npoints_faraway, int with_replace, int32_t *sel, int32_t *scratch);
 
 /* ---- KITTI AP evaluator around rotate_iou (evaluate/eval2.py; csrc/kitti_eval.cu) ----
  * pn2_d3_overlap_f64 (DEVICE): d3_box_overlap_kernel (eval2.py:136-162): camera boxes (., 7) float64 and the rotated

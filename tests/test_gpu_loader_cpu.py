@@ -66,7 +66,7 @@ def test_native_mt19937_draws_equal_numpy(n_valid, n_far, npoints, faraway, with
     for seed in (666, 0, 2 ** 32 - 1):
         np.random.seed(seed)
         np.random.random_sample(5)                      # a stream that is already under way (pos != 624)
-        scratch = np.empty((max(n_valid, npoints) + npoints,), np.int64)
+        scratch = np.empty((max(n_valid, npoints) + npoints,), np.int32)
         for rep in range(3):                            # consecutive scenes on one stream
             st = gl.MTState.from_numpy_global()
             want = gl.draw_selection(n_valid, n_near, n_far, npoints, faraway, with_replace)
