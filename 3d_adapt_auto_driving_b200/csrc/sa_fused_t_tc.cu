@@ -373,7 +373,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             mbar_wait(acc3_full, (uint32_t)((it * p.nm3 + j) & 1));
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
-            if (compact) {
+            if constexpr (COMPACT) {
                 // compact rows: the columns of a centre are a run of equal ids (warp-uniform), of any length and possibly
                 // continued in the next warp / tile -> running max, one atomicMax per run and channel (y is zeroed)
                 const int ch = j * kC3 + r;
@@ -412,8 +412,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                     }
                 }
                 if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
-                return;
-            }
+            } else {
             float cm[4];
 #pragma unroll
             for (int jp = 0; jp < 2; ++jp) {
@@ -454,6 +453,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 const float m4 = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
                 emit(m4, p.ns == 64 ? row_base : tile * BM, p.ns != 64);   // nsample 128: two warps share a centre
             }
+            }   // dense rows
         };
         const bool pipelined = p.nb2 == 2;     // pooling of tile i-1 after the conversion of tile i (see the MMA order)
         for (int it = 0; it < my_tiles; ++it) {
