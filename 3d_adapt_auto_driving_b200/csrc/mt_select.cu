@@ -145,17 +145,16 @@ PN2_API int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int 
         }
         // the far selection is parked at the END of `choice` while the near draw uses the scratch
         for (long long i = 0; i < n_far_sel; ++i) choice[need + i] = (far_sub ? scratch[i] : (int32_t)i) + FAR_BASE;
-        if (need > 0) {
-            if (n_near == 0) {
-                pn2_set_last_error("pn2_mt_draw_selection: no near point to draw from");
-                return PN2_ERR_INVALID;
-            }
-            if (n_near < need || with_replace) {
-                choice_replace(s, n_near, need, choice);
-            } else {
-                choice_no_replace(s, n_near, scratch);
-                memcpy(choice, scratch, (size_t)need * sizeof(int32_t));
-            }
+        if (need > 0 && n_near == 0) {
+            pn2_set_last_error("pn2_mt_draw_selection: no near point to draw from");
+            return PN2_ERR_INVALID;
+        }
+        if (n_near < need || with_replace) {
+            choice_replace(s, n_near, need, choice);
+        } else {
+            // also for need == 0: choice(n, 0, replace=False) is permutation(n)[:0] -- the generator still advances
+            choice_no_replace(s, n_near, scratch);
+            memcpy(choice, scratch, (size_t)need * sizeof(int32_t));
         }
         len = npoints;      // near (need) followed by far (n_far_sel): np.concatenate((near, far))
     } else {

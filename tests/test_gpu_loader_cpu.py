@@ -90,3 +90,39 @@ def test_native_mt19937_draws_equal_numpy(n_valid, n_far, npoints, faraway, with
     np.random.seed(3)
     gl.draw_selection(n_valid, n_near, n_far, npoints, faraway, with_replace)
     assert np.array_equal(a, np.random.random_sample(4))
+
+
+def test_native_mt19937_draws_fuzz_small_cases():
+    """Random small (n_valid, n_far, npoints, npoints_faraway, with_replace) against numpy, INCLUDING the corners the
+    reference configuration never reaches (npoints_faraway >= npoints, so no near point is needed: numpy's
+    choice(n, 0, replace=False) still draws the whole permutation and the stream must advance the same way) and the
+    cases where numpy raises (nothing to draw from): there the native call must fail too, never invent a selection."""
+    gl = load("datasets.gpu_loader")
+    rs = np.random.RandomState(0)
+    n_ok = n_err = 0
+    for _ in range(4000):
+        n_valid = int(rs.randint(0, 120))
+        n_far = int(rs.randint(0, n_valid + 1))
+        npoints = int(rs.randint(1, 100))
+        faraway = int(rs.randint(0, npoints + 3))
+        with_replace = bool(rs.randint(2))
+        seed = int(rs.randint(0, 2 ** 31))
+        case = (n_valid, n_far, npoints, faraway, with_replace, seed)
+        ref = np.random.RandomState(seed)
+        try:
+            want = gl.draw_selection(n_valid, n_valid - n_far, n_far, npoints, faraway, with_replace, rng=ref)
+        except ValueError:
+            want = None
+        st = gl.MTState.seeded(seed)
+        got = np.empty((npoints,), np.int32)
+        scratch = np.empty((max(n_valid, npoints) + npoints,), np.int32)
+        if want is None:
+            with pytest.raises(Exception):
+                gl.draw_selection_native(st, n_valid, n_valid - n_far, n_far, npoints, faraway, with_replace, got, scratch)
+            n_err += 1
+            continue
+        gl.draw_selection_native(st, n_valid, n_valid - n_far, n_far, npoints, faraway, with_replace, got, scratch)
+        assert np.array_equal(got, want), case
+        assert np.array_equal(st.key, ref.get_state()[1]) and int(st.pos.value) == ref.get_state()[2], case
+        n_ok += 1
+    assert n_ok > 3000 and n_err > 10          # both kinds of case were actually exercised
