@@ -268,3 +268,30 @@ PN2_API int pn2_eval_collect_thresholds(const double *overlaps, long long total_
     *n_out = n;
     return PN2_OK;
 }
+
+// compute_statistics_jit itself (eval2.py:172-298) for ONE image, every mode: out4 = {tp, fp, fn, similarity} with the
+// reference's conventions (similarity 0 unless compute_fp && compute_aos, -1 when there is neither a tp nor a fp),
+// thresholds_out (capacity gt_size) = scores of the true positives, *n_thresholds = tp.  overlaps is (det, gt) with
+// row stride ldo.
+PN2_API int pn2_eval_image_statistics(const double *overlaps, long long ldo, const double *gt_datas, long long gt_size,
+                                      const double *dt_datas, long long det_size, const long long *ignored_gt,
+                                      const long long *ignored_det, const double *dc_bboxes, long long n_dc, int metric,
+                                      double min_overlap, double thresh, int compute_fp, int compute_aos, double *out4,
+                                      double *thresholds_out, long long *n_thresholds) {
+    if (gt_size < 0 || det_size < 0 || n_dc < 0 || !out4 || !n_thresholds || ldo < gt_size ||
+        (gt_size > 0 && (!gt_datas || !ignored_gt || !thresholds_out)) || (det_size > 0 && (!dt_datas || !ignored_det)) ||
+        (gt_size * det_size > 0 && !overlaps) || (n_dc > 0 && !dc_bboxes)) {
+        pn2_set_last_error("pn2_eval_image_statistics: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    std::vector<char> assigned, ign_thr;
+    std::vector<double> delta, work;
+    const Stats s = compute_statistics(overlaps, ldo, gt_datas, gt_size, dt_datas, det_size, ignored_gt, ignored_det,
+                                       dc_bboxes, n_dc, metric, min_overlap, thresh, compute_fp != 0, compute_aos != 0,
+                                       thresholds_out, n_thresholds, assigned, ign_thr, delta, work);
+    out4[0] = (double)s.tp;
+    out4[1] = (double)s.fp;
+    out4[2] = (double)s.fn;
+    out4[3] = s.similarity;
+    return PN2_OK;
+}

@@ -42,6 +42,8 @@ def _lib():
                                                   _i64p, i, dbl, _f64p, ll, i]
         lib.pn2_eval_collect_thresholds.argtypes = [_f64p, ll, ll, _i64p, _i64p, _i64p, ll, _f64p, _f64p, _f64p, _i64p, _i64p,
                                                     i, dbl, _f64p, _i64p]
+        lib.pn2_eval_image_statistics.argtypes = [_f64p, ll, _f64p, ll, _f64p, ll, _i64p, _i64p, _f64p, ll, i, dbl, dbl, i, i,
+                                                  _f64p, _f64p, _i64p]
         lib._pn2_eval_ready = True
     return lib
 
@@ -184,27 +186,20 @@ def get_split_parts(num, num_part):
 
 def compute_statistics_jit(overlaps, gt_datas, dt_datas, ignored_gt, ignored_det, dc_bboxes, metric, min_overlap,
                            thresh=0, compute_fp=False, compute_aos=False):
-    """eval2.py:172-298 for ONE image -> (tp, fp, fn, similarity, thresholds).  Kept for API compatibility; eval_class
-    drives whole parts per native call instead."""
+    """eval2.py:172-298 for ONE image -> (tp, fp, fn, similarity, thresholds), the reference's values in every mode
+    (similarity -1 where it is undefined).  eval_class drives whole parts per native call instead."""
     ov = _c64(overlaps)
     gt, dt, dc = _c64(gt_datas, 5), _c64(dt_datas, 6), _c64(dc_bboxes, 4)
     ig, idt = np.ascontiguousarray(ignored_gt, np.int64), np.ascontiguousarray(ignored_det, np.int64)
-    one = lambda v: np.array([v], np.int64)
-    if not compute_fp:
-        th = np.zeros((max(gt.shape[0], 1),), np.float64)
-        n = ctypes.c_longlong(0)
-        cabi.check(_lib().pn2_eval_collect_thresholds(_d(ov), dt.shape[0], gt.shape[0], _l(one(gt.shape[0])),
-                                                      _l(one(dt.shape[0])), _l(one(dc.shape[0])), 1, _d(gt), _d(dt), _d(dc),
-                                                      _l(ig), _l(idt), int(metric), float(min_overlap), _d(th),
-                                                      ctypes.byref(n)), "pn2_eval_collect_thresholds")
-        # without compute_fp the reference also counts tp / fn; callers of this mode only use the thresholds
-        return int(n.value), 0, 0, 0, th[:n.value]
-    pr = np.zeros((1, 4), np.float64)
-    cabi.check(_lib().pn2_eval_fused_statistics(_d(ov), dt.shape[0], gt.shape[0], _d(pr), _l(one(gt.shape[0])),
-                                                _l(one(dt.shape[0])), _l(one(dc.shape[0])), 1, _d(gt), _d(dt), _d(dc), _l(ig),
-                                                _l(idt), int(metric), float(min_overlap), _d(np.array([thresh], np.float64)),
-                                                1, 1 if compute_aos else 0), "pn2_eval_fused_statistics")
-    return int(pr[0, 0]), int(pr[0, 1]), int(pr[0, 2]), float(pr[0, 3]), np.zeros((0,))
+    out4 = np.zeros((4,), np.float64)
+    th = np.zeros((max(gt.shape[0], 1),), np.float64)
+    n = np.zeros((1,), np.int64)
+    cabi.check(_lib().pn2_eval_image_statistics(_d(ov), gt.shape[0], _d(gt), gt.shape[0], _d(dt), dt.shape[0], _l(ig),
+                                                _l(idt), _d(dc), dc.shape[0], int(metric), float(min_overlap),
+                                                float(thresh), 1 if compute_fp else 0, 1 if compute_aos else 0, _d(out4),
+                                                _d(th), _l(n)), "pn2_eval_image_statistics")
+    sim = out4[3] if (compute_fp and compute_aos) else 0
+    return int(out4[0]), int(out4[1]), int(out4[2]), (float(sim) if sim != -1 else -1), th[:int(n[0])]
 
 
 def fused_compute_statistics(overlaps, pr, gt_nums, dt_nums, dc_nums, gt_datas, dt_datas, dontcares, ignored_gts,

@@ -232,6 +232,8 @@ int pn2_mt_draw_selection(uint32_t *key, int32_t *pos, int n_valid, int n_near, 
  *   pn2_eval_collect_thresholds  compute_statistics_jit(thresh 0, compute_fp False) over the images of one dataset
  *                                part (:506-520): scores of the true positives
  *   pn2_eval_fused_statistics    fused_compute_statistics (:311-358): pr (n_thresholds, 4) += [tp, fp, fn, similarity]
+ *   pn2_eval_image_statistics    compute_statistics_jit (:172-298) for one image, every mode: out4 = {tp, fp, fn,
+ *                                similarity (-1 = undefined)}, thresholds_out (gt_size) / *n_thresholds = tp scores
  *   overlaps: (total_dt, total_gt) of the part; gt_datas (., 5), dt_datas (., 6), dontcares (., 4). */
 int pn2_d3_overlap_f64(const double *boxes, long long n, const double *qboxes, long long k, const float *rinc,
                        int criterion, double *out, void *stream);
@@ -242,6 +244,11 @@ int pn2_eval_collect_thresholds(const double *overlaps, long long total_dt, long
                                 const double *gt_datas, const double *dt_datas, const double *dontcares,
                                 const long long *ignored_gts, const long long *ignored_dets, int metric,
                                 double min_overlap, double *thresholds_out, long long *n_out);
+int pn2_eval_image_statistics(const double *overlaps, long long ldo, const double *gt_datas, long long gt_size,
+                              const double *dt_datas, long long det_size, const long long *ignored_gt,
+                              const long long *ignored_det, const double *dc_bboxes, long long n_dc, int metric,
+                              double min_overlap, double thresh, int compute_fp, int compute_aos, double *out4,
+                              double *thresholds_out, long long *n_thresholds);
 int pn2_eval_fused_statistics(const double *overlaps, long long total_dt, long long total_gt, double *pr,
                               const long long *gt_nums, const long long *dt_nums, const long long *dc_nums,
                               long long n_img, const double *gt_datas, const double *dt_datas, const double *dontcares,

@@ -1,0 +1,106 @@
+"""Differential test of the evaluator mirror against the REFERENCE module itself (evaluate/eval2.py, numba CPU code,
+imported from /root/reference with `rotate_iou` stubbed by the CPU oracle as tools/make_kitti_eval_fixture.py does).
+Only where the reference tree exists (the build container); on the GPU box the committed golden vectors
+(tests/test_kitti_eval_cpu.py, tests/test_kitti_eval_gpu.py) carry the parity.  Random small cases reach the corners a
+single golden data set does not: tied scores and overlaps, ignored / DontCare combinations, empty sides, every mode
+of compute_statistics_jit."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import load, ROOT
+
+REF = "/root/reference/evaluate"
+pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "eval2.py")), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def both():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_kitti_eval_fixture as fx
+    saved = sys.modules.get("rotate_iou")
+    stub = types.ModuleType("rotate_iou")
+    stub.rotate_iou_gpu_eval = fx.oracle_riou
+    sys.modules["rotate_iou"] = stub
+    sys.path.insert(0, REF)
+    try:
+        import eval2 as ref
+    finally:
+        sys.path.remove(REF)
+        if saved is None:
+            sys.modules.pop("rotate_iou", None)
+        else:
+            sys.modules["rotate_iou"] = saved
+    ev = load("evaluate.eval2")
+    old = ev.rotate_iou_gpu_eval
+    ev.rotate_iou_gpu_eval = fx.oracle_riou
+    yield ref, ev, fx
+    ev.rotate_iou_gpu_eval = old
+    sys.modules.pop("eval2", None)
+
+
+def _boxes(rs, n):
+    b = np.round(rs.uniform(0, 10, (n, 4)), 0 if rs.randint(2) else 3)
+    b[:, 2:] = b[:, :2] + np.round(rs.uniform(0, 5, (n, 2)), 0 if rs.randint(2) else 3)      # degenerate sides included
+    return b
+
+
+def test_compute_statistics_every_mode(both):
+    ref, ev, _ = both
+    rs = np.random.RandomState(0)
+    for it in range(400):
+        ng, nd, ndc = int(rs.randint(0, 9)), int(rs.randint(0, 9)), int(rs.randint(0, 3))
+        ov = rs.uniform(0, 1, (nd, ng))
+        ov[rs.uniform(size=ov.shape) < 0.4] = 0.0
+        if rs.randint(2):
+            ov = np.round(ov, 1)                                    # tied overlaps
+        gt = np.concatenate([_boxes(rs, ng), rs.uniform(-3, 3, (ng, 1))], 1)
+        sc = np.round(rs.uniform(0, 1, (nd, 1)), 1 if rs.randint(2) else 6)     # tied scores
+        dt = np.concatenate([_boxes(rs, nd), rs.uniform(-3, 3, (nd, 1)), sc], 1)
+        ig, idt = rs.randint(-1, 2, ng).astype(np.int64), rs.randint(-1, 2, nd).astype(np.int64)
+        dc = _boxes(rs, ndc)
+        metric, mo = int(rs.randint(3)), float(rs.choice([0.25, 0.5, 0.7]))
+        th = float(rs.choice([0.0, 0.3, 0.5, -100.0]))
+        for cfp in (False, True):
+            for aos in (False, True):
+                a = ref.compute_statistics_jit(ov, gt, dt, ig, idt, dc, metric, mo, thresh=th, compute_fp=cfp, compute_aos=aos)
+                b = ev.compute_statistics_jit(ov, gt, dt, ig, idt, dc, metric, mo, th, cfp, aos)
+                assert a[:3] == b[:3], (it, cfp, aos)
+                assert a[3] == b[3] or abs(a[3] - b[3]) < 1e-12, (it, cfp, aos, a[3], b[3])
+                assert np.array_equal(np.asarray(a[4]), b[4]), (it, cfp, aos)
+
+
+def test_image_box_overlap_and_thresholds(both):
+    ref, ev, _ = both
+    rs = np.random.RandomState(5)
+    for _ in range(150):
+        a, b = _boxes(rs, int(rs.randint(1, 6))), _boxes(rs, int(rs.randint(1, 6)))
+        for crit in (-1, 0, 1, 2):
+            assert np.array_equal(ref.image_box_overlap(a, b, crit), ev.image_box_overlap(a, b, crit), equal_nan=True)
+    for _ in range(500):
+        n = int(rs.randint(0, 60))
+        sc = np.round(rs.uniform(0, 1, n), 2 if rs.randint(2) else 8)
+        num_gt, ns = int(rs.randint(max(n, 1), n + 20)), int(rs.choice([11, 41]))
+        assert np.array_equal(np.asarray(ref.get_thresholds(sc.copy(), num_gt, ns)),
+                              np.asarray(ev.get_thresholds(sc.copy(), num_gt, ns)))
+
+
+def test_clean_data_and_official_result_other_seeds(both, capsys):
+    ref, ev, fx = both
+    gts, dts = fx.make_annos(57, seed=7)                  # the reference needs more images than its 50 parts
+    for g, d in zip(gts[:20], dts[:20]):
+        for diff in (0, 1, 2):
+            for cls in (0, 1, 2):
+                r, m = ref.clean_data(g, d, cls, "kitti", diff), ev.clean_data(g, d, cls, "kitti", diff)
+                assert r[0] == m[0] and list(r[1]) == list(m[1]) and list(r[2]) == list(m[2])
+                assert np.array_equal(np.asarray(r[3], np.float64).reshape(-1, 4), np.asarray(m[3], np.float64).reshape(-1, 4))
+    for cls in (0, [0, 1, 2]):
+        r_txt, r_ret = ref.get_official_eval_result(gts, dts, cls, "kitti")
+        m_txt, m_ret = ev.get_official_eval_result(gts, dts, cls, "kitti")
+        assert r_txt == m_txt
+        for k in r_ret:
+            if k != "result":
+                assert np.array_equal(np.float64(r_ret[k]), np.float64(m_ret[k]), equal_nan=True), k
