@@ -43,16 +43,27 @@ _CORNER_TOP = np.array([0, 0, 0, 0, 1, 1, 1, 1], np.float32)
 
 def boxes3d_to_corners3d(boxes3d, rotate=True):
     """numpy (N,7) [x,y,z,h,w,l,ry] -> (N,8,3) corners in rect-camera coordinates
-    (kitti_utils.py:66-98; y points down, the box origin is the bottom-face centre)."""
+    (kitti_utils.py:66-98; y points down, the box origin is the bottom-face centre).
+    Bit-identical to the reference, whose rotation is a batched np.matmul of the float32 (N,8,3) offsets with a
+    TRANSPOSED VIEW of a (3,3,N) rotation stack: the corners end up in the %.4f text of eval_rcnn.py:76-101 through
+    the image projection, so the same numpy routine is applied to operands of the same dtype and memory layout
+    (one rounding per product-sum differs between matmul's accumulation and x*c + z*s written out)."""
     b = np.asarray(boxes3d)
-    h, w, l, ry = b[:, 3:4], b[:, 4:5], b[:, 5:6], b[:, 6]
-    xc = (l / 2.0).astype(np.float32) * _CORNER_SX          # (N,8)
-    zc = (w / 2.0).astype(np.float32) * _CORNER_SZ
-    yc = (-h).astype(np.float32) * _CORNER_TOP
+    n = b.shape[0]
+    h, w, l = b[:, 3:4], b[:, 4:5], b[:, 5:6]
+    off = np.empty((n, 8, 3), np.float32)                    # (x, y, z) offsets of the corners before rotation
+    off[:, :, 0] = (l / 2.0) * _CORNER_SX
+    off[:, :, 1] = (-h) * _CORNER_TOP
+    off[:, :, 2] = (w / 2.0) * _CORNER_SZ
     if rotate:
-        c, s = np.cos(ry)[:, None], np.sin(ry)[:, None]
-        xc, zc = xc * c + zc * s, -xc * s + zc * c
-    out = np.stack((b[:, 0:1] + xc, b[:, 1:2] + yc, b[:, 2:3] + zc), axis=2)
+        ry = b[:, 6]
+        c, s = np.cos(ry), np.sin(ry)
+        rot = np.zeros((3, 3, ry.size), np.result_type(c.dtype, np.float32))
+        rot[0, 0], rot[0, 2] = c, -s
+        rot[1, 1] = 1
+        rot[2, 0], rot[2, 2] = s, c
+        off = np.matmul(off, rot.transpose(2, 0, 1))         # (N,8,3) @ (N,3,3): rows [x y z] times R
+    out = np.stack((b[:, 0:1] + off[:, :, 0], b[:, 1:2] + off[:, :, 1], b[:, 2:3] + off[:, :, 2]), axis=2)
     return out.astype(np.float32)
 
 
