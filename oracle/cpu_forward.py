@@ -167,10 +167,13 @@ def rcnn_forward(pkg, rcnn, info):
     pooled[:, :, :, 0:3] -= rois[:, :, 0:3].unsqueeze(2)
     flat = pooled.view(B * M, pooled.shape[2], pooled.shape[3])
     ry = rois.reshape(-1, 7)[:, 6]
-    cosa, sina = torch.cos(ry).view(-1, 1, 1), torch.sin(ry).view(-1, 1, 1)
-    x, z = flat[:, :, 0:1].clone(), flat[:, :, 2:3].clone()
-    flat[:, :, 0:1] = x * cosa - z * sina
-    flat[:, :, 2:3] = x * sina + z * cosa
+    # kitti_utils.py:45-63: [x', z'] = [x, z] @ [[cos, -sin], [sin, cos]]^T as a batched matmul (its accumulation,
+    # not x*cos - z*sin written out: the two differ in the last bit)
+    cosa, sina = torch.cos(ry).view(-1, 1), torch.sin(ry).view(-1, 1)
+    rot = torch.stack((torch.cat((cosa, -sina), dim=1), torch.cat((sina, cosa), dim=1)), dim=1)      # (B*M, 2, 2)
+    xz = torch.matmul(torch.stack((flat[:, :, 0], flat[:, :, 2]), dim=2), rot.permute(0, 2, 1))
+    flat[:, :, 0] = xz[:, :, 0]
+    flat[:, :, 2] = xz[:, :, 1]
     nin = rcnn.rcnn_input_channel
     pxyz = flat[..., 0:3].contiguous()
     xyz_feature = rcnn.xyz_up_layer(flat[..., 0:nin].transpose(1, 2).unsqueeze(3))
