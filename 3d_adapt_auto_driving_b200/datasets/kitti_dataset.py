@@ -1,5 +1,10 @@
-"""Mirror of pointrcnn/lib/datasets/kitti_dataset.py: per-sample file access of a KITTI-format tree
-<root>/KITTI/{ImageSets/<split>.txt, object/training/{velodyne,calib,label_2,image_2}} (:12-69)."""
+"""File access of a KITTI-format tree, with the interface of pointrcnn/lib/datasets/kitti_dataset.py:12-69:
+
+    <root>/KITTI/ImageSets/<split>.txt                      one six-digit sample id per line
+    <root>/KITTI/object/{training|testing}/velodyne/######.bin   float32 (x, y, z, intensity)
+                                          /calib/######.txt, /label_2/######.txt, /image_2/######.png, /planes/
+
+Attribute and method names are the ones KittiRCNNDataset and eval_rcnn.py use."""
 import os
 
 import numpy as np
@@ -9,43 +14,43 @@ from PIL import Image
 from .. import calibration
 from .. import object3d
 
+_SUBDIRS = {'image_dir': 'image_2', 'lidar_dir': 'velodyne', 'calib_dir': 'calib', 'label_dir': 'label_2',
+            'plane_dir': 'planes'}
+
 
 class KittiDataset(torch_data.Dataset):
     def __init__(self, root_dir, split='train', subsample=-1, shuffle_subsample=None):
         self.split = split
-        is_test = self.split == 'test'
-        self.imageset_dir = os.path.join(root_dir, 'KITTI', 'object', 'testing' if is_test else 'training')
-        split_dir = os.path.join(root_dir, 'KITTI', 'ImageSets', split + '.txt')
-        self.image_idx_list = [x.strip() for x in open(split_dir).readlines()]
-        if subsample > 0 and split == 'train':
-            self.image_idx_list = self.image_idx_list[:subsample]
-        self.num_sample = len(self.image_idx_list)
-        self.image_dir = os.path.join(self.imageset_dir, 'image_2')
-        self.lidar_dir = os.path.join(self.imageset_dir, 'velodyne')
-        self.calib_dir = os.path.join(self.imageset_dir, 'calib')
-        self.label_dir = os.path.join(self.imageset_dir, 'label_2')
-        self.plane_dir = os.path.join(self.imageset_dir, 'planes')
+        kitti = os.path.join(root_dir, 'KITTI')
+        self.imageset_dir = os.path.join(kitti, 'object', 'testing' if split == 'test' else 'training')
+        for attr, sub in _SUBDIRS.items():
+            setattr(self, attr, os.path.join(self.imageset_dir, sub))
+        with open(os.path.join(kitti, 'ImageSets', split + '.txt')) as f:
+            ids = [line.strip() for line in f.readlines()]
+        if split == 'train' and subsample > 0:
+            ids = ids[:subsample]
+        self.image_idx_list = ids
+        self.num_sample = len(ids)
+
+    @staticmethod
+    def _existing(directory, idx, ext):
+        path = os.path.join(directory, '%06d%s' % (idx, ext))
+        assert os.path.exists(path), path
+        return path
 
     def get_image_shape(self, idx):
-        img_file = os.path.join(self.image_dir, '%06d.png' % idx)
-        assert os.path.exists(img_file)
-        width, height = Image.open(img_file).size
+        with Image.open(self._existing(self.image_dir, idx, '.png')) as img:
+            width, height = img.size
         return height, width, 3
 
     def get_lidar(self, idx):
-        lidar_file = os.path.join(self.lidar_dir, '%06d.bin' % idx)
-        assert os.path.exists(lidar_file)
-        return np.fromfile(lidar_file, dtype=np.float32).reshape(-1, 4)
+        return np.fromfile(self._existing(self.lidar_dir, idx, '.bin'), dtype=np.float32).reshape(-1, 4)
 
     def get_calib(self, idx):
-        calib_file = os.path.join(self.calib_dir, '%06d.txt' % idx)
-        assert os.path.exists(calib_file)
-        return calibration.Calibration(calib_file)
+        return calibration.Calibration(self._existing(self.calib_dir, idx, '.txt'))
 
     def get_label(self, idx):
-        label_file = os.path.join(self.label_dir, '%06d.txt' % idx)
-        assert os.path.exists(label_file)
-        return object3d.get_objects_from_label(label_file)
+        return object3d.get_objects_from_label(self._existing(self.label_dir, idx, '.txt'))
 
     def __len__(self):
         raise NotImplementedError

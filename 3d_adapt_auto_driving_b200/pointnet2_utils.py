@@ -1,14 +1,20 @@
-"""Host-side mirror of pointrcnn/pointnet2_lib/pointnet2/pointnet2_utils.py.
+"""Python front of the point-set ops, with the public names and tensor layouts of
+pointrcnn/pointnet2_lib/pointnet2/pointnet2_utils.py so that modules written against it keep working:
 
-Same public names, argument meaning and return layouts:
-    furthest_point_sample, gather_operation, three_nn, three_interpolate,
-    grouping_operation, ball_query, QueryAndGroup, GroupAll.
-Outputs are allocated with torch.empty/zeros on the input's device (the reference uses the
-legacy torch.cuda.*Tensor constructors, pointnet2_utils.py:25-26) and the work is done by the
-sm_100a kernels behind `pointnet2_cuda`.
+    furthest_point_sample(xyz (B,N,3), npoint)            -> idx (B,npoint) int32, idx[:, 0] == 0        (:10-36)
+    gather_operation(features (B,C,N), idx (B,M))         -> (B,C,M), differentiable in features        (:39-73)
+    three_nn(unknown (B,n,3), known (B,m,3))              -> (dist (B,n,3) = sqrt(d2), idx int32)       (:76-105)
+    three_interpolate(features (B,C,m), idx, weight)      -> (B,C,n), differentiable in features        (:108-153)
+    grouping_operation(features (B,C,N), idx (B,M,S))     -> (B,C,M,S), differentiable in features      (:156-197)
+    ball_query(radius, nsample, xyz, new_xyz)             -> idx (B,M,S) int32, zero rows where empty   (:200-228)
+    QueryAndGroup, GroupAll                               grouping modules                              (:231-290)
+
+Design: the index-producing ops (sampling, ball query, 3-NN) have no gradient, so they are plain functions; only the
+three feature-moving ops are autograd Functions (forward kernel, backward kernel, what backward needs).  Outputs are allocated on the input's device -- the reference's torch.cuda.*Tensor
+constructors pin everything to the current CUDA device -- and the work is done by the sm_100a kernels behind
+`pointnet2_cuda` (C-ABI).  The inference modules do not come through here when `fused` is on (fused.py reads the
+indices straight into the tensor-core SA kernels); this is the op-by-op path and the parity reference for it.
 """
-from typing import Tuple
-
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -16,187 +22,156 @@ from torch.autograd import Function
 from . import pointnet2_cuda as pointnet2
 
 
-class FurthestPointSampling(Function):
-    """pointnet2_utils.py:10-36.  xyz (B,N,3) -> (B,npoint) int32; idx[:,0] == 0."""
-
-    @staticmethod
-    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
-        assert xyz.is_contiguous()
-        B, N, _ = xyz.size()
-        output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-        pointnet2.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, output)
-        ctx.mark_non_differentiable(output)
-        return output
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None
+def _require_contiguous(**tensors):
+    for name, t in tensors.items():
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
 
 
-furthest_point_sample = FurthestPointSampling.apply
+def _new(like, shape, dtype, fill=None):
+    if fill is None:
+        return torch.empty(shape, dtype=dtype, device=like.device)
+    return torch.full(shape, fill, dtype=dtype, device=like.device)
 
 
+# ---- index-producing ops: no gradient flows through them -------------------------------------------------------
+@torch.no_grad()
+def furthest_point_sample(xyz, npoint):
+    _require_contiguous(xyz=xyz)
+    b, n = xyz.shape[0], xyz.shape[1]
+    idx = _new(xyz, (b, npoint), torch.int32)
+    running_min = _new(xyz, (b, n), torch.float32, fill=1e10)       # squared distance to the selected set so far
+    pointnet2.furthest_point_sampling_wrapper(b, n, npoint, xyz, running_min, idx)
+    return idx
+
+
+@torch.no_grad()
+def ball_query(radius, nsample, xyz, new_xyz):
+    _require_contiguous(xyz=xyz, new_xyz=new_xyz)
+    b, n, m = xyz.shape[0], xyz.shape[1], new_xyz.shape[1]
+    idx = _new(xyz, (b, m, nsample), torch.int32, fill=0)           # centres without a neighbour keep the zero row
+    pointnet2.ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx)
+    return idx
+
+
+@torch.no_grad()
+def three_nn(unknown, known):
+    _require_contiguous(unknown=unknown, known=known)
+    b, n, m = unknown.shape[0], unknown.shape[1], known.shape[1]
+    dist2 = _new(unknown, (b, n, 3), torch.float32)
+    idx = _new(unknown, (b, n, 3), torch.int32)
+    pointnet2.three_nn_wrapper(b, n, m, unknown, known, dist2, idx)
+    return torch.sqrt(dist2), idx                                   # callers get distances, the kernel squared ones
+
+
+# ---- feature-moving ops: gradient w.r.t. the features only -----------------------------------------------------
 class GatherOperation(Function):
-    """pointnet2_utils.py:39-73.  features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
-
     @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        B, npoint = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-        pointnet2.gather_points_wrapper(B, C, N, npoint, features, idx, output)
-        ctx.for_backwards = (idx, C, N)
-        return output
+    def forward(ctx, features, idx):
+        _require_contiguous(features=features, idx=idx)
+        b, c, n = features.shape
+        m = idx.shape[1]
+        out = _new(features, (b, c, m), torch.float32)
+        pointnet2.gather_points_wrapper(b, c, n, m, features, idx, out)
+        ctx.saved = (idx, n)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, C, N = ctx.for_backwards
-        B, npoint = idx.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
-        return grad_features, None
-
-
-gather_operation = GatherOperation.apply
-
-
-class ThreeNN(Function):
-    """pointnet2_utils.py:76-105.  Returns (sqrt(dist2), idx) like the reference (:98)."""
-
-    @staticmethod
-    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        assert unknown.is_contiguous()
-        assert known.is_contiguous()
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
-        dist = torch.sqrt(dist2)
-        ctx.mark_non_differentiable(dist, idx)
-        return dist, idx
-
-    @staticmethod
-    def backward(ctx, a=None, b=None):
-        return None, None
-
-
-three_nn = ThreeNN.apply
-
-
-class ThreeInterpolate(Function):
-    """pointnet2_utils.py:108-153.  features (B,C,m), idx/weight (B,n,3) -> (B,C,n)."""
-
-    @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        assert weight.is_contiguous()
-        B, c, m = features.size()
-        n = idx.size(1)
-        ctx.three_interpolate_for_backward = (idx, weight, m)
-        output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-        pointnet2.three_interpolate_wrapper(B, c, m, n, features, idx, weight, output)
-        return output
-
-    @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
-        idx, weight, m = ctx.three_interpolate_for_backward
-        B, c, n = grad_out.size()
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-        pointnet2.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
-        return grad_features, None, None
-
-
-three_interpolate = ThreeInterpolate.apply
+        idx, n = ctx.saved
+        b, c, m = grad_out.shape
+        grad = _new(grad_out, (b, c, n), torch.float32, fill=0)
+        pointnet2.gather_points_grad_wrapper(b, c, n, m, grad_out.contiguous(), idx, grad)
+        return grad, None
 
 
 class GroupingOperation(Function):
-    """pointnet2_utils.py:156-197.  features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample)."""
+    @staticmethod
+    def forward(ctx, features, idx):
+        _require_contiguous(features=features, idx=idx)
+        b, c, n = features.shape
+        m, s = idx.shape[1], idx.shape[2]
+        out = _new(features, (b, c, m, s), torch.float32)
+        pointnet2.group_points_wrapper(b, c, n, m, s, features, idx, out)
+        ctx.saved = (idx, n)
+        return out
 
     @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        B, nfeatures, nsample = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-        pointnet2.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, output)
-        ctx.for_backwards = (idx, N)
-        return output
+    def backward(ctx, grad_out):
+        idx, n = ctx.saved
+        b, c, m, s = grad_out.shape
+        grad = _new(grad_out, (b, c, n), torch.float32, fill=0)
+        pointnet2.group_points_grad_wrapper(b, c, n, m, s, grad_out.contiguous(), idx, grad)
+        return grad, None
+
+
+class ThreeInterpolate(Function):
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        _require_contiguous(features=features, idx=idx, weight=weight)
+        b, c, m = features.shape
+        n = idx.shape[1]
+        out = _new(features, (b, c, n), torch.float32)
+        pointnet2.three_interpolate_wrapper(b, c, m, n, features, idx, weight, out)
+        ctx.saved = (idx, weight, m)
+        return out
 
     @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
-        idx, N = ctx.for_backwards
-        B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
-        return grad_features, None
+    def backward(ctx, grad_out):
+        idx, weight, m = ctx.saved
+        b, c, n = grad_out.shape
+        grad = _new(grad_out, (b, c, m), torch.float32, fill=0)
+        pointnet2.three_interpolate_grad_wrapper(b, c, n, m, grad_out.contiguous(), idx, weight, grad)
+        return grad, None, None
 
 
+gather_operation = GatherOperation.apply
 grouping_operation = GroupingOperation.apply
+three_interpolate = ThreeInterpolate.apply
 
 
-class BallQuery(Function):
-    """pointnet2_utils.py:200-228.  idx is zero-initialised here (:218): rows of centres
-    without any neighbour stay 0, exactly as in the reference."""
+class _ApplyAlias:
+    """`FurthestPointSampling.apply(...)`-style access for code written against the reference's Function classes."""
 
-    @staticmethod
-    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-        assert new_xyz.is_contiguous()
-        assert xyz.is_contiguous()
-        B, N, _ = xyz.size()
-        npoint = new_xyz.size(1)
-        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
-        ctx.mark_non_differentiable(idx)
-        return idx
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None, None, None
+    def __init__(self, fn):
+        self.apply = fn
 
 
-ball_query = BallQuery.apply
+FurthestPointSampling, BallQuery, ThreeNN = _ApplyAlias(furthest_point_sample), _ApplyAlias(ball_query), _ApplyAlias(three_nn)
+
+
+# ---- grouping modules ----------------------------------------------------------------------------------------------
+def _with_xyz(grouped_xyz, grouped_features, use_xyz):
+    """Channel layout of a group: [relative xyz (3), features (C)] on dim 1, or one of the two alone."""
+    if grouped_features is None:
+        if not use_xyz:
+            raise ValueError("a group needs features or use_xyz=True")
+        return grouped_xyz
+    return torch.cat([grouped_xyz, grouped_features], dim=1) if use_xyz else grouped_features
 
 
 class QueryAndGroup(nn.Module):
-    """pointnet2_utils.py:231-264: ball_query -> group xyz -> subtract centre -> group
-    features -> cat [xyz, features] on dim 1."""
+    """Ball query around each centre, neighbours' coordinates made relative to it, features gathered alongside."""
 
-    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+    def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+    def forward(self, xyz, new_xyz, features=None):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            if self.use_xyz:
-                return torch.cat([grouped_xyz, grouped_features], dim=1)
-            return grouped_features
-        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-        return grouped_xyz
+        rel = grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
+        return _with_xyz(rel, None if features is None else grouping_operation(features, idx), self.use_xyz)   # (B,3+C,M,S)
 
 
 class GroupAll(nn.Module):
-    """pointnet2_utils.py:267-290: one group holding every point, xyz NOT centred."""
+    """One group holding every point; coordinates stay absolute (there is no centre)."""
 
-    def __init__(self, use_xyz: bool = True):
+    def __init__(self, use_xyz=True):
         super().__init__()
         self.use_xyz = use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            if self.use_xyz:
-                return torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, 3 + C, 1, N)
-            return grouped_features
-        return grouped_xyz
+    def forward(self, xyz, new_xyz, features=None):
+        everything = xyz.transpose(1, 2).unsqueeze(2)                                                          # (B,3,1,N)
+        if features is None:
+            return everything
+        return _with_xyz(everything, features.unsqueeze(2), self.use_xyz)

@@ -104,3 +104,48 @@ def test_clean_data_and_official_result_other_seeds(both, capsys):
         for k in r_ret:
             if k != "result":
                 assert np.array_equal(np.float64(r_ret[k]), np.float64(m_ret[k]), equal_nan=True), k
+
+
+def test_label_readers_equal_reference(tmp_path):
+    """evaluate/kitti_common.py readers: the reference module (its unused `skimage` import stubbed) and the mirror on
+    label files with / without the score column, an empty file, extra non-result files in the folder."""
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.io", "kitti_common")}
+    sk = types.ModuleType("skimage")
+    sk.io = types.ModuleType("skimage.io")
+    sys.modules["skimage"], sys.modules["skimage.io"] = sk, sk.io
+    sys.path.insert(0, REF)
+    try:
+        sys.modules.pop("kitti_common", None)
+        import kitti_common as rkc
+    finally:
+        sys.path.remove(REF)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    kc = load("evaluate.kitti_common")
+    rs = np.random.RandomState(2)
+    names = ["Car", "Pedestrian", "Cyclist", "Van", "DontCare", "Person_sitting"]
+    for d, with_score in (("gt", False), ("dt", True)):
+        os.makedirs(tmp_path / d)
+        for i in (0, 3, 4, 11, 250):
+            n = 0 if i == 4 else int(rs.randint(1, 9))
+            lines = []
+            for _ in range(n):
+                v = rs.uniform(-50, 80, 12)
+                line = "%s %.2f %d %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f" % (
+                    names[rs.randint(len(names))], rs.uniform(0, 1), rs.randint(-1, 4), *v)
+                lines.append(line + (" %.4f" % rs.uniform(-3, 3) if with_score else ""))
+            (tmp_path / d / ("%06d.txt" % i)).write_text("\n".join(lines) + ("\n" if n and rs.randint(2) else ""))
+        (tmp_path / d / "notes.txt").write_text("not a result file\n")
+        (tmp_path / d / "1234567.txt").write_text("seven digits\n")
+        for ids in (None, [3, 11], [4]):
+            a, b = rkc.get_label_annos(str(tmp_path / d), ids), kc.get_label_annos(str(tmp_path / d), ids)
+            assert len(a) == len(b) == (5 if ids is None else len(ids))
+            for x, y in zip(a, b):
+                assert set(x) == set(y)
+                for k in x:
+                    assert x[k].shape == y[k].shape and np.array_equal(x[k], y[k]), (d, ids, k)
+                    assert x[k].dtype == y[k].dtype or x[k].size == 0, (d, ids, k, x[k].dtype, y[k].dtype)
+    assert rkc.get_image_index_str(7) == kc.get_image_index_str(7) == "000007"
