@@ -185,3 +185,68 @@ def reference_forward(model, pts_input):
     with cpu_cuda(), torch.no_grad():
         out = model({"pts_input": pts_input})
     return {k: v for k, v in out.items() if isinstance(v, torch.Tensor)}
+
+
+# ---- the reference's eval_rcnn.py itself, end to end on the CPU ---------------------------------------------------------
+_TENSORBOARDX = "class SummaryWriter(object):\n    def __init__(self, *a, **k): pass\n    def add_scalar(self, *a, **k): pass\n"
+
+
+def stage_reference_tree(dest):
+    """<dest>/pointrcnn with `lib`, `pointnet2_lib`, `tools/train_utils`, `tools/cfgs` SYMLINKED to /root/reference and
+    tools/{eval_rcnn.py,_init_path.py} copied there at run time (the script derives its data root from its own
+    realpath, eval_rcnn.py:854, and the reference tree is read-only) -> the tools directory to run in."""
+    import shutil
+    root = os.path.join(dest, "pointrcnn")
+    tools = os.path.join(root, "tools")
+    os.makedirs(tools)
+    for name in ("lib", "pointnet2_lib"):
+        os.symlink(os.path.join(REF, name), os.path.join(root, name))
+    for name in ("train_utils", "cfgs"):
+        os.symlink(os.path.join(REF, "tools", name), os.path.join(tools, name))
+    for name in ("eval_rcnn.py", "_init_path.py"):
+        shutil.copyfile(os.path.join(REF, "tools", name), os.path.join(tools, name))
+    os.makedirs(os.path.join(tools, "tensorboardX"))
+    with open(os.path.join(tools, "tensorboardX", "__init__.py"), "w") as f:
+        f.write(_TENSORBOARDX)
+    return tools
+
+
+def run_reference_eval(tools_dir, argv, timeout=1800):
+    """`python eval_rcnn.py <argv>` in tools_dir, on the CPU: this file is the interpreter's entry point, installs the
+    stubs and then executes the script as __main__."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--run", "eval_rcnn.py"] + list(argv)
+    return subprocess.run(cmd, cwd=tools_dir, capture_output=True, text=True, timeout=timeout)
+
+
+def _main_run(script, argv):
+    import runpy
+    ed = types.ModuleType("easydict")
+    ed.EasyDict = _AttrDict
+    sys.modules.update(dict(_extension_stubs(), easydict=ed))
+    old_load = yaml.load
+    yaml.load = lambda f, *a, **k: old_load(f, Loader=yaml.SafeLoader)
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    sys.argv = [script] + argv
+    sys.path.insert(0, os.getcwd())
+    import _init_path  # noqa: F401  (the script's own path set-up, executed a little earlier)
+    # The one accommodation: eval_rcnn.py:862 passes far_points= to a constructor whose parameter is called
+    # npoints_faraway (kitti_rcnn_dataset.py:13-16) -- a TypeError of the reference against itself (SURVEY.md 8b).
+    import lib.datasets.kitti_rcnn_dataset as ds_mod
+    ref_init = ds_mod.KittiRCNNDataset.__init__
+
+    def init_accepting_far_points(self, *a, far_points=None, **k):
+        if far_points is not None:
+            k["npoints_faraway"] = far_points
+        ref_init(self, *a, **k)
+
+    ds_mod.KittiRCNNDataset.__init__ = init_accepting_far_points
+    with cpu_cuda():
+        runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--run":
+        _main_run(sys.argv[2], sys.argv[3:])
+    else:
+        raise SystemExit("usage: refnet_cpu.py --run <script.py> [script args]")
