@@ -23,8 +23,9 @@ def load(sub):
     return importlib.import_module(PKG + "." + sub)
 
 
-def per_call_ms(fn, n):
-    fn(0)
+def per_call_ms(fn, n, warmup=1):
+    for i in range(warmup):
+        fn(i)
     t0 = time.perf_counter()
     for i in range(n):
         fn(i)
@@ -63,7 +64,8 @@ def main():
         res["mt19937_draws_numpy"] = per_call_ms(
             lambda i: gl.draw_selection(n_valid, n_valid - n_far, n_far, 16384, 4000, False, rng=rs), 30)
         np.random.seed(0)
-        res["reference_numpy_data_path_dataset_getitem"] = per_call_ms(lambda i: ds[i % 16], 32)
+        # the first passes are 3-5x slower (allocator growth for the ~20 MB of temporaries per scene): warm up over them
+        res["reference_numpy_data_path_dataset_getitem"] = per_call_ms(lambda i: ds[i % 16], 48, warmup=48)
     res = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()}
     text = json.dumps(res, indent=1)
     print(text)
