@@ -29,3 +29,23 @@ def test_ops_refuse_cpu_tensors():
     x = torch.zeros(1, 8, 3)
     with pytest.raises(cabi.Pn2Error):
         p2.furthest_point_sampling_wrapper(1, 8, 2, x, torch.zeros(1, 8), torch.zeros(1, 2, dtype=torch.int32))
+
+
+def test_product_path_has_no_cpu_fallback():
+    """Without a CUDA device the product fails loudly instead of computing on the CPU: the model's forward raises at
+    its first kernel call and bench.py exits non-zero with a message (the CPU port under oracle/ is never reached)."""
+    import subprocess
+    import sys
+    import pytest
+    import torch
+    from conftest import ROOT
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cabi = load("cabi")
+    model = load("inference").build_model(seed=0, device="cpu")
+    with pytest.raises(cabi.Pn2Error):
+        model({"pts_input": torch.zeros(1, 16384, 3)})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode != 0 and "CUDA device" in (r.stderr + r.stdout)
+    assert '"metric"' not in r.stdout                       # no bench line was printed
