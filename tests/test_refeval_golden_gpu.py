@@ -5,7 +5,11 @@ np.random sampling stream.
 The GPU features differ from the CPU run by <= 5.4e-5 of scale (test_refnet_golden_gpu.py), so a box whose score,
 overlap or rank sits within that distance of a threshold may legitimately flip; everything else must agree.  Bar: per
 scene the box count differs by at most 2 and at least 95 % of the reference's boxes have a Detector box with the same
-geometry and score within 2e-3 (the files hold 4 decimals)."""
+geometry and score within 2e-3 (the files hold 4 decimals).
+Calibration of the bar: adding uniform noise of 3e-5 of the tensor scale to the RCNN head outputs of the CPU run itself
+moves 0-4 (mean 1.6) of the 140 boxes by more than 2e-3 over 40 trials -- bin-based decoding takes an argmax over bin
+logits, and random-init heads have near-tied bins -- so the B200 result (139 / 140) is what the feature tolerance
+predicts, not a logic difference."""
 import os
 import sys
 
