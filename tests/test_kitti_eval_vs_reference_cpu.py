@@ -149,3 +149,50 @@ def test_label_readers_equal_reference(tmp_path):
                     assert x[k].shape == y[k].shape and np.array_equal(x[k], y[k]), (d, ids, k)
                     assert x[k].dtype == y[k].dtype or x[k].size == 0, (d, ids, k, x[k].dtype, y[k].dtype)
     assert rkc.get_image_index_str(7) == kc.get_image_index_str(7) == "000007"
+
+
+def test_evaluate_from_directories_equals_reference_evaluate_py(both, tmp_path, capsys):
+    """evaluate/evaluate.py::evaluate (label / result directories + split file -> AP text and dict), the reference's
+    driver imported live, against tools/kitti_ap.py::evaluate_dirs on the same files."""
+    ref, ev, fx = both
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import kitti_ap
+    gts, dts = fx.make_annos(57, seed=11)
+    for d, annos, with_score in (("label_2", gts, False), ("data", dts, True)):
+        os.makedirs(tmp_path / d)
+        for i, a in enumerate(annos):
+            lines = []
+            for k in range(len(a["name"])):
+                l, h, w = a["dimensions"][k]
+                line = "%s %.2f %d %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f" % (
+                    a["name"][k], a["truncated"][k], a["occluded"][k], a["alpha"][k], *a["bbox"][k], h, w, l,
+                    *a["location"][k], a["rotation_y"][k])
+                lines.append(line + (" %.4f" % a["score"][k] if with_score else ""))
+            (tmp_path / d / ("%06d.txt" % i)).write_text("\n".join(lines))
+    (tmp_path / "val.txt").write_text("\n".join(str(i) for i in range(57)) + "\n")
+    # the reference driver: its kitti_common (skimage stubbed) and eval2 (rotate_iou stubbed with the CPU oracle)
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.io", "kitti_common", "evaluate", "eval2", "rotate_iou")}
+    sk = types.ModuleType("skimage")
+    sk.io = types.ModuleType("skimage.io")
+    stub = types.ModuleType("rotate_iou")
+    stub.rotate_iou_gpu_eval = fx.oracle_riou
+    sys.modules.update({"skimage": sk, "skimage.io": sk.io, "rotate_iou": stub, "eval2": ref})
+    sys.modules.pop("kitti_common", None)
+    sys.modules.pop("evaluate", None)
+    sys.path.insert(0, REF)
+    try:
+        import evaluate as ref_driver
+        want_txt, want = ref_driver.evaluate(str(tmp_path / "data"), label_split_file=str(tmp_path / "val.txt"),
+                                             label_path=str(tmp_path / "label_2"), dataset="kitti", current_class=0)
+    finally:
+        sys.path.remove(REF)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    got_txt, got, _, _ = kitti_ap.evaluate_dirs(str(tmp_path / "label_2"), str(tmp_path / "data"), list(range(57)), "kitti", 0)
+    assert got_txt == want_txt
+    for k in want:
+        if k != "result":
+            assert np.array_equal(np.float64(want[k]), np.float64(got[k]), equal_nan=True), k
