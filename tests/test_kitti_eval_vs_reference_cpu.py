@@ -199,16 +199,20 @@ def test_evaluate_from_directories_equals_reference_evaluate_py(both, tmp_path, 
 
 
 def test_other_datasets_difficulty_rules(both):
-    """clean_data's per-dataset rules (kitti / argo / nusc / lyft / waymo) for all six difficulties and five classes,
-    and the official result for two non-KITTI data sets."""
+    """clean_data's per-dataset rules (kitti / argo / nusc / lyft / waymo) for all six difficulties and the three classes
+    it knows (a class index beyond them is an IndexError on both sides), and the official result for two non-KITTI
+    data sets."""
     ref, ev, fx = both
     gts, dts = fx.make_annos(57, seed=21)
     for dataset in ("kitti", "argo", "nusc", "lyft", "waymo"):
         for i in range(0, 57, 4):
             for diff in range(6):
-                for cls in range(5):
+                for cls in range(3):
                     r, m = ref.clean_data(gts[i], dts[i], cls, dataset, diff), ev.clean_data(gts[i], dts[i], cls, dataset, diff)
                     assert r[0] == m[0] and list(r[1]) == list(m[1]) and list(r[2]) == list(m[2]), (dataset, i, diff, cls)
+    for mod in (ref, ev):
+        with pytest.raises(IndexError):
+            mod.clean_data(gts[0], dts[0], 3, "kitti", 0)
     for dataset in ("argo", "waymo"):
         r_txt, r_ret = ref.get_official_eval_result(gts, dts, 0, dataset)
         m_txt, m_ret = ev.get_official_eval_result(gts, dts, 0, dataset)
