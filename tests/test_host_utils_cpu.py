@@ -49,3 +49,27 @@ def test_mirrors_equal_live_reference_other_seeds(tmp_path):
     # float64 boxes (eval_rcnn.py hands float32; the dtype promotion must still be the reference's)
     b64 = fx.inputs(4)[0].astype(np.float64)
     assert np.array_equal(ku.boxes3d_to_corners3d(b64), rku.boxes3d_to_corners3d(b64))
+
+
+@pytest.mark.skipif(not os.path.isdir(fx.REF), reason="reference tree not present")
+def test_calibration_corners_of_the_interface(tmp_path):
+    """the parts of Calibration the fixture does not exercise: attributes, img_to_rect, float64 inputs, zero depth"""
+    _, rcal, _ = fx.reference_modules()
+    cal = load("calibration")
+    path = fx.calib_file(str(tmp_path))
+    a, b = rcal.Calibration(path), cal.Calibration(path)
+    for k in ("P2", "R0", "V2C", "cu", "cv", "fu", "fv", "tx", "ty"):
+        x, y = np.asarray(getattr(a, k)), np.asarray(getattr(b, k))
+        assert x.dtype == y.dtype and np.array_equal(x, y), k
+    raw_a, raw_b = rcal.get_calib_from_file(path), cal.get_calib_from_file(path)
+    assert set(raw_a) == set(raw_b) and all(np.array_equal(raw_a[k], raw_b[k]) for k in raw_a)
+    rs = np.random.RandomState(0)
+    u, v, d = (rs.uniform(0, s, 100).astype(np.float32) for s in (1242, 375, 70))
+    assert np.array_equal(a.img_to_rect(u, v, d), b.img_to_rect(u, v, d))
+    p64 = rs.uniform(-40, 70, (1000, 3))
+    assert a.lidar_to_rect(p64).dtype == b.lidar_to_rect(p64).dtype and np.array_equal(a.lidar_to_rect(p64), b.lidar_to_rect(p64))
+    pz = rs.uniform(-40, 70, (50, 3)).astype(np.float32)
+    pz[::5, 2] = 0                                                   # z == 0 divides by 1e-9
+    (ia, da), (ib, db) = a.rect_to_img(pz.copy()), b.rect_to_img(pz.copy())
+    assert np.array_equal(ia, ib, equal_nan=True) and np.array_equal(da, db)
+    assert np.array_equal(a.cart_to_hom(pz), b.cart_to_hom(pz))
