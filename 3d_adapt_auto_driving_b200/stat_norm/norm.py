@@ -149,48 +149,60 @@ def scale_labels(objs, mapping, ratios, calib, w0, h0, align_front=False, rescal
     return regenerate_labels(new_obj, calib, w0, h0)
 
 
+def _box_frame(obj):
+    """rotation whose columns are the box axes in rect-camera coordinates: (p - t) @ R = box-frame coordinates
+    (x along the length, y negative upwards from the bottom face, z along the width)"""
+    c, s = np.cos(obj.ry), np.sin(obj.ry)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _between(v, lo, hi):
+    return (v > lo) & (v < hi)
+
+
+def _largest_safe_ratio(mapping, obj, local, inside, ground_clear_count):
+    """avoid_conflict (norm.py:205-216): take the full change (ratio 1) and back off in steps of 0.1 until the scaled
+    patch's bounding volume, ignoring the lowest 0.5 m, holds fewer than 10 points more than the original box did"""
+    for ratio in np.arange(1, -0.1, -0.1):
+        scaled = local[inside] * mapping(obj, ratio)
+        lo, hi = np.min(scaled, axis=0), np.max(scaled, axis=0)
+        swallowed = _between(local[:, 0], lo[0], hi[0]) & _between(local[:, 1], lo[1], -0.5) & _between(local[:, 2], lo[2], hi[2])
+        if np.sum(swallowed) - ground_clear_count < 10:
+            break
+    return ratio, scaled
+
+
 def rescale_ptc(mapping, velo, labels, calib, avoid_conflict=False, align_front=False, rescaled_classes=("Car", "Van")):
     """velo (N,4) float32, labels [Object3d], calib -> ((N,3) float64 velodyne coordinates, ratios).
     Points strictly inside a Car / Van box are scaled about the box's bottom-face centre along its
     own axes; output order is [patch of box 0, patch of box 1, ..., untouched points] (norm.py:186-244)."""
     ptc = calib.project_velo_to_rect(velo[:, :3])
-    new_ptc = []
-    mask = np.ones(ptc.shape[0]).astype(bool)
-    ratios = []
-    for obj in labels:
-        if obj.cls_type not in rescaled_classes:
-            continue
-        c, s = np.cos(obj.ry), np.sin(obj.ry)
-        R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
-        _ptc = np.dot(ptc - obj.t, R)                                  # box frame: x along l, y up is negative, z along w
-        in_x = (_ptc[:, 0] > -obj.l / 2.0) & (_ptc[:, 0] < obj.l / 2.0)
-        in_z = (_ptc[:, 2] > -obj.w / 2.0) & (_ptc[:, 2] < obj.w / 2.0)
-        _mask = in_x & (_ptc[:, 1] > -obj.h) & (_ptc[:, 1] < 0) & in_z
+    untouched = np.ones(ptc.shape[0]).astype(bool)
+    patches, ratios = [], []
+    for obj in (o for o in labels if o.cls_type in rescaled_classes):
+        R = _box_frame(obj)
+        local = np.dot(ptc - obj.t, R)
+        in_footprint = _between(local[:, 0], -obj.l / 2.0, obj.l / 2.0), _between(local[:, 2], -obj.w / 2.0, obj.w / 2.0)
+        above_floor = local[:, 1] > -obj.h
+        inside = in_footprint[0] & above_floor & (local[:, 1] < 0) & in_footprint[1]
         ratio = 0
-        _env_mask0 = in_x & (_ptc[:, 1] > -obj.h) & (_ptc[:, 1] < -0.5) & in_z
-        if np.sum(_mask) > 0:
-            mask[_mask] = False
+        if np.sum(inside) > 0:
+            untouched[inside] = False
             if avoid_conflict:
-                # shrink the change until the grown box swallows fewer than 10 extra neighbouring points
-                for ratio in np.arange(1, -0.1, -0.1):
-                    tmp_ptc = _ptc[_mask] * mapping(obj, ratio)
-                    _env_mask = (_ptc[:, 0] > np.min(tmp_ptc[:, 0])) & (_ptc[:, 0] < np.max(tmp_ptc[:, 0])) & \
-                                (_ptc[:, 1] > np.min(tmp_ptc[:, 1])) & (_ptc[:, 1] < -0.5) & \
-                                (_ptc[:, 2] > np.min(tmp_ptc[:, 2])) & (_ptc[:, 2] < np.max(tmp_ptc[:, 2]))
-                    if np.sum(_env_mask) - np.sum(_env_mask0) < 10:
-                        break
+                ground_clear = in_footprint[0] & above_floor & (local[:, 1] < -0.5) & in_footprint[1]
+                ratio, scaled = _largest_safe_ratio(mapping, obj, local, inside, np.sum(ground_clear))
             else:
                 ratio = 1
-                tmp_ptc = _ptc[_mask] * mapping(obj, ratio)
-            ptc_patch = np.dot(tmp_ptc, R.T) + obj.t
+                scaled = local[inside] * mapping(obj, ratio)
+            patch = np.dot(scaled, R.T) + obj.t
             if align_front:
                 l, h, w = (np.array([obj.l, obj.h, obj.w]) * mapping(obj, ratio).reshape(-1)).tolist()
                 for shift, angle in _front_alignment_shifts(obj, l, w):
-                    ptc_patch[:, 0] += shift * np.cos(angle)
-                    ptc_patch[:, 2] += shift * np.sin(angle)
-            new_ptc.append(ptc_patch)
+                    patch[:, 0] += shift * np.cos(angle)
+                    patch[:, 2] += shift * np.sin(angle)
+            patches.append(patch)
         ratios.append(ratio)
-    return calib.project_rect_to_velo(np.concatenate(new_ptc + [ptc[mask]], axis=0)), ratios
+    return calib.project_rect_to_velo(np.concatenate(patches + [ptc[untouched]], axis=0)), ratios
 
 
 def get_image_size(path):
