@@ -16,6 +16,7 @@ is bit-identical to collate_batch over dataset[i] (tests/test_gpu_loader_gpu.py)
 """
 import concurrent.futures
 import ctypes
+import threading
 import os
 
 import numpy as np
@@ -119,6 +120,9 @@ class GpuSceneLoader:
         # the MT19937 draws of a batch (1.8 ms per scene for a 50 k-point permutation + the 16384 shuffle; mtrand runs
         # them without the GIL).  With the reference's single global stream the draws stay serial by definition.
         self._io = concurrent.futures.ThreadPoolExecutor(max_workers=2)
+        # pinned staging ring for load_raw: one slot per job that can be in flight (3 submitted + 1 being consumed) + 1
+        self._ring = {"slots": [None] * 6, "next": 0}
+        self._ring_lock = threading.Lock()
         # one more thread runs prepare() itself a batch ahead, on the loader's own CUDA stream: the (serial, by the
         # reference's definition) global-stream draws then overlap the consumer's Python work instead of adding to it
         self._prep = concurrent.futures.ThreadPoolExecutor(max_workers=1)
@@ -146,9 +150,10 @@ class GpuSceneLoader:
         """pinned host staging (raw points, offsets, calibration), a small ring so that the H2D copies of one batch
         may still be in flight while the next batch is read; allocated once and grown on demand -- a fresh
         cudaHostAlloc per batch costs more than reading the files."""
-        ring = self.__dict__.setdefault("_ring", {"slots": [None] * 4, "next": 0})
-        k = ring["next"]
-        ring["next"] = (k + 1) % len(ring["slots"])
+        with self._ring_lock:            # load_raw runs on the two _io workers concurrently: slot choice must be atomic
+            ring = self._ring
+            k = ring["next"]
+            ring["next"] = (k + 1) % len(ring["slots"])
         slot = ring["slots"][k]
         if slot is None or slot["raw"].shape[0] < nbytes_points or slot["calib"].shape[0] < b:
             pin = torch.cuda.is_available()

@@ -170,7 +170,9 @@ def d3_box_overlap_kernel(boxes, qboxes, rinc, criterion=-1):
 def d3_box_overlap(boxes, qboxes, criterion=-1):
     """eval2.py:165-169."""
     rinc = rotate_iou_gpu_eval(boxes[:, [0, 2, 3, 5, 6]], qboxes[:, [0, 2, 3, 5, 6]], 2)
-    rinc = np.ascontiguousarray(rinc, dtype=np.float64)
+    # float32 like the reference's: its in-place numba loop rounds every inc / ua to rinc's dtype before the match
+    # thresholds see it
+    rinc = np.ascontiguousarray(rinc, dtype=np.float32)
     d3_box_overlap_kernel(boxes, qboxes, rinc, criterion)
     return rinc
 

@@ -88,7 +88,8 @@ class Detector:
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         l0 = cabi.launch_count
-        with torch.cuda.graph(graph):
+        # thread_local: loader threads (datasets/gpu_loader.py) may allocate device / pinned memory while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             rec, num = self._step(static_in)
         self.launches_per_step = cabi.launch_count - l0
         self._graphs[shape] = (graph, static_in, rec, num)
@@ -141,7 +142,7 @@ class Detector:
         graph = torch.cuda.CUDAGraph()
         from . import cabi
         l0 = cabi.launch_count
-        with torch.cuda.graph(graph, stream=st):
+        with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
             rec, num = self._step(static_in)
         self.launches_per_step = cabi.launch_count - l0
         slot["graphs"][shape] = (graph, static_in, rec, num)

@@ -14,7 +14,7 @@ from .. import roipool3d_utils
 from ..config import cfg
 
 
-class RCNNNet(nn.Module):
+class RCNNNet(pt_utils.PackedCacheMixin, nn.Module):
     def __init__(self, num_classes, input_channels=0, use_xyz=True):
         super().__init__()
         self.SA_modules = nn.ModuleList()
@@ -65,14 +65,11 @@ class RCNNNet(nn.Module):
                     nn.init.constant_(m.bias, 0)
         nn.init.normal_(self.reg_layer[-1].conv.weight, mean=0, std=0.001)
 
-    def train(self, mode=True):
-        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
-            self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
+    def _source_modules(self):
+        mods = [self.cls_layer, self.reg_layer]
+        if cfg.RCNN.USE_RPN_FEATURES:
+            mods += [self.xyz_up_layer, self.merge_down_layer]
+        return mods
 
     @staticmethod
     def _break_up_pc(pc):
@@ -166,18 +163,18 @@ class RCNNNet(nn.Module):
     def _forward_fused(self, pts_input, feat_off):
         """pts_input (R, S, ld) point-major rows, R = B * rois: columns [0, rcnn_input_channel) are
         xyz + extras, the rpn features start at column feat_off."""
-        if self._packed is None:
+        if not self._packed_valid():
             up = fz.pack_sequential(self.xyz_up_layer)
             merge = fz.pack_sequential(self.merge_down_layer)[0]
             c = up[-1].cout
             wm = merge.w[:, :merge.cin]
-            self._packed = {
+            self._store_packed({
                 "up": up, "merge": merge,
                 # merge_down on cat[xyz_feature, rpn_feature] = W_a xyz_feature + (W_b rpn_feature + b)
                 "merge_a": fz.PackedLayer(wm[:, :c], torch.zeros_like(merge.b), merge.relu),
                 "merge_b": fz.PackedLayer(wm[:, c:], merge.b, False),
                 "cls": fz.pack_sequential(self.cls_layer), "reg": fz.pack_sequential(self.reg_layer),
-            }
+            })
         pk = self._packed
         R, S, C = pts_input.shape
         nin = self.rcnn_input_channel

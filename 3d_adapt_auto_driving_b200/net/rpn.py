@@ -14,7 +14,7 @@ from ..config import cfg
 from ..proposal_layer import ProposalLayer
 
 
-class RPN(nn.Module):
+class RPN(pt_utils.PackedCacheMixin, nn.Module):
     def __init__(self, use_xyz=True, mode='TRAIN'):
         super().__init__()
         self.training_mode = (mode == 'TRAIN')
@@ -47,21 +47,15 @@ class RPN(nn.Module):
             nn.init.constant_(self.rpn_cls_layer[2].conv.bias, -np.log((1 - pi) / pi))
         nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
 
-    def train(self, mode=True):
-        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
-            self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
+    def _source_modules(self):
+        return (self.rpn_cls_layer, self.rpn_reg_layer)
 
     def forward(self, input_data):
         pts_input = input_data['pts_input']
         if self.backbone_net.can_fuse(pts_input):
             backbone_xyz, feats_pm = self.backbone_net.forward_pm(pts_input)          # (B,N,3), (B,N,C)
-            if self._packed is None:
-                self._packed = (fz.pack_sequential(self.rpn_cls_layer), fz.pack_sequential(self.rpn_reg_layer))
+            if not self._packed_valid():
+                self._store_packed((fz.pack_sequential(self.rpn_cls_layer), fz.pack_sequential(self.rpn_reg_layer)))
             B, N, _ = feats_pm.shape
             outs = []
             for layers in self._packed:

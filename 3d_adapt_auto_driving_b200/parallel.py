@@ -6,7 +6,7 @@ Scenes are independent, so rank r of W evaluates sample_id_list[r::W] (the datas
 PN2_SHARD_RANK / PN2_SHARD_WORLD, datasets/kitti_rcnn_dataset.py) with the unmodified eval_rcnn.py
 writing into a per-rank output directory -- its "dump empty files" loop (eval_rcnn.py:638-649) would
 otherwise create empty results for scenes a rank does not own.  Afterwards every rank packs the
-KITTI result lines of its own scenes into a fixed-width float64 tensor, a single all_gather
+KITTI result lines of its own scenes into ONE fixed-width float64 row, a single all_gather_into_tensor
 (NCCL over NVLink on GPUs, gloo in the CPU tests) moves them, and rank 0 writes the merged
 result directory.  Payload: scenes x 100 x 13 doubles, a few MB for the 7481-scene KITTI val set."""
 import os
@@ -51,24 +51,31 @@ def write_result_dir(out_dir, sample_ids, records, counts, cls_name="Car"):
                 print(("%s -1 -1" % cls_name) + "".join(" %.4f" % v for v in rec[i, k]), file=f)
 
 
-def gather_results(records, counts, device=None):
-    """THE collective: all ranks contribute (n_r, max_det, FIELDS) / (n_r,), padded to the largest
-    shard, one all_gather each for the records and the counts -> per-rank lists on every rank."""
+def gather_results(records, counts, n_max, device=None):
+    """THE collective.  Every rank contributes (n_r, max_det, FIELDS) records and (n_r,) counts, n_r <= n_max (n_max is
+    the largest shard: ceil(len(all_ids) / world) for shard_ids, known without communication).  Shard size, counts and
+    records are packed into ONE float64 row [n_r | counts padded to n_max | records padded to n_max] and moved by a
+    single all_gather_into_tensor -> per-rank (records, counts) on every rank."""
     world = dist.get_world_size()
     device = device or records.device
-    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    n_max = int(max(int(s.item()) for s in sizes))
-    pad_rec = torch.zeros((n_max,) + tuple(records.shape[1:]), dtype=records.dtype, device=device)
-    pad_cnt = torch.zeros((n_max,), dtype=counts.dtype, device=device)
-    pad_rec[:records.shape[0]] = records.to(device)
-    pad_cnt[:counts.shape[0]] = counts.to(device)
-    all_rec = [torch.empty_like(pad_rec) for _ in range(world)]
-    all_cnt = [torch.empty_like(pad_cnt) for _ in range(world)]
-    dist.all_gather(all_rec, pad_rec)
-    dist.all_gather(all_cnt, pad_cnt)
-    return [(all_rec[r][:int(sizes[r].item())], all_cnt[r][:int(sizes[r].item())]) for r in range(world)]
+    n = records.shape[0]
+    if n > n_max or counts.shape[0] != n:
+        raise ValueError("shard of %d scenes exceeds n_max=%d" % (n, n_max))
+    per = int(np.prod(records.shape[1:]))
+    row = torch.zeros((1 + n_max + n_max * per,), dtype=torch.float64, device=device)
+    row[0] = n
+    row[1:1 + n] = counts.to(device=device, dtype=torch.float64)
+    row[1 + n_max:1 + n_max + n * per] = records.to(device=device, dtype=torch.float64).reshape(-1)
+    flat = torch.empty((world * row.numel(),), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(flat, row)
+    out = flat.view(world, row.numel())
+    res = []
+    for r in range(world):
+        nr = int(out[r, 0].item())
+        cnt = out[r, 1:1 + nr].to(counts.dtype)
+        rec = out[r, 1 + n_max:1 + n_max + nr * per].reshape((nr,) + tuple(records.shape[1:])).to(records.dtype)
+        res.append((rec, cnt))
+    return res
 
 
 def merge_sharded_results(all_ids, rank_final_dir, merged_dir, cls_name="Car", device=None):
@@ -76,7 +83,7 @@ def merge_sharded_results(all_ids, rank_final_dir, merged_dir, cls_name="Car", d
     rank, world = dist.get_rank(), dist.get_world_size()
     mine = shard_ids(all_ids, rank, world)
     rec, cnt = pack_result_dir(rank_final_dir, mine)
-    gathered = gather_results(rec, cnt, device=device)
+    gathered = gather_results(rec, cnt, n_max=(len(all_ids) + world - 1) // world, device=device)
     total = 0
     if rank == 0:
         for r, (rrec, rcnt) in enumerate(gathered):

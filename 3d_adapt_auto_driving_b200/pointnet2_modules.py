@@ -24,7 +24,7 @@ from . import pytorch_utils as pt_utils
 from . import fused as fz
 
 
-class _PointnetSAModuleBase(nn.Module):
+class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
     def __init__(self):
         super().__init__()
         self.npoint = None
@@ -34,18 +34,9 @@ class _PointnetSAModuleBase(nn.Module):
         self.fused = True
         self._packed = None
 
-    # ---- cache of folded weights for the fused path ----
-    def train(self, mode=True):
-        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
-            self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
+    # ---- cache of folded weights for the fused path (pt_utils.PackedCacheMixin) ----
     def _pack(self):
-        if self._packed is None:
+        if not self._packed_valid():
             packed = []
             for mlp in self.mlps:
                 layers = fz.pack_sequential(mlp)
@@ -57,7 +48,7 @@ class _PointnetSAModuleBase(nn.Module):
                     entry["first_f"] = fz.PackedLayer(w1[:, 3:], first.b, False) if first.cin > 3 else None
                     entry["b1"] = first.b
                 packed.append(entry)
-            self._packed = packed
+            self._store_packed(packed)
         return self._packed
 
     def _can_fuse(self, xyz):
@@ -65,11 +56,13 @@ class _PointnetSAModuleBase(nn.Module):
             return False
         if any(not getattr(g, "use_xyz", True) for g in self.groupers):
             return False
-        if any(len(list(m.children())) < 2 for m in self.mlps):
+        if any(len(list(m.children())) < 2 or not pt_utils.foldable(m) for m in self.mlps):
             return False
         for g in self.groupers:
             if isinstance(g, pointnet2_utils.QueryAndGroup) and (128 % g.nsample or g.nsample % 4):
                 return False
+            if isinstance(g, pointnet2_utils.GroupAll) and (128 % xyz.shape[1] or xyz.shape[1] % 4):
+                return False      # the pooled-linear kernel needs the group size to divide its 128-row tile
         return True
 
     def forward_pm(self, xyz, feats_pm=None, new_xyz=None):
@@ -182,7 +175,7 @@ class PointnetSAModule(PointnetSAModuleMSG):
                          pool_method=pool_method, instance_norm=instance_norm)
 
 
-class PointnetFPModule(nn.Module):
+class PointnetFPModule(pt_utils.PackedCacheMixin, nn.Module):
     """Feature propagation (pointnet2_modules.py:116-156)."""
 
     def __init__(self, *, mlp: List[int], bn: bool = True):
@@ -191,19 +184,10 @@ class PointnetFPModule(nn.Module):
         self.fused = True
         self._packed = None
 
-    def train(self, mode=True):
-        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
-            self._packed = None
-        return super().train(mode)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward_pm(self, unknown, known, unknow_feats_pm, known_feats_pm):
         """point-major variant: unknow_feats_pm (B,n,C1) or None, known_feats_pm (B,m,C2) -> (B,n,mlp[-1])."""
-        if self._packed is None:
-            self._packed = fz.pack_sequential(self.mlp)
+        if not self._packed_valid():
+            self._store_packed(fz.pack_sequential(self.mlp))
         B, n, _ = unknown.shape
         c2 = known_feats_pm.shape[2]
         c1 = unknow_feats_pm.shape[2] if unknow_feats_pm is not None else 0
@@ -223,7 +207,7 @@ class PointnetFPModule(nn.Module):
 
     def forward(self, unknown, known, unknow_feats, known_feats):
         """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m) -> (B,mlp[-1],n)."""
-        if self.fused and not self.training and unknown.is_cuda and known is not None:
+        if self.fused and not self.training and unknown.is_cuda and known is not None and pt_utils.foldable(self.mlp):
             out = self.forward_pm(unknown, known,
                                   unknow_feats.transpose(1, 2).contiguous() if unknow_feats is not None else None,
                                   known_feats.transpose(1, 2).contiguous())

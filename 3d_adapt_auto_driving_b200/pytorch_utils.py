@@ -113,6 +113,57 @@ class FC(nn.Sequential):
             add_norm_act(out_size)
 
 
+class PackedCacheMixin:
+    """Folded (conv + eval BatchNorm) and tensor-core-packed weights are DERIVED data kept in `self._packed`.  They are
+    dropped on a train()/eval() mode switch, on load_state_dict, on any Module._apply (.to / .cuda / .half / .float move
+    or retype the sources) and whenever a source parameter / buffer was replaced or written in place since packing
+    (optimizer step, `p.copy_()` under no_grad, BatchNorm statistics update: torch bumps `_version`).  Not detectable:
+    writes through `.data` (they bypass the version counter) -- call invalidate_packed() after those.  A captured CUDA
+    graph (inference.Detector) bakes the packed buffers in: re-create the Detector after changing weights."""
+
+    def invalidate_packed(self):
+        self._packed = None
+        self._packed_key = None
+
+    def _source_modules(self):
+        """modules whose parameters / buffers the cache is derived from (default: the whole module)."""
+        return (self,)
+
+    def _source_key(self):
+        key = []
+        for m in self._source_modules():
+            key.extend((id(t), t._version, t.device) for t in m.parameters())
+            key.extend((id(t), t._version, t.device) for t in m.buffers())
+        return tuple(key)
+
+    def _packed_valid(self):
+        """True when `self._packed` exists and still describes the current parameters (call before using it)."""
+        if getattr(self, "_packed", None) is None:
+            return False
+        if getattr(self, "_packed_key", None) != self._source_key():
+            self.invalidate_packed()
+            return False
+        return True
+
+    def _store_packed(self, packed):
+        self._packed = packed
+        self._packed_key = self._source_key()
+        return packed
+
+    def train(self, mode=True):
+        if bool(mode) != self.training:   # eval() on an eval-mode module (point_rcnn.py:34 does it every forward) keeps the cache
+            self.invalidate_packed()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        return super()._apply(fn, *a, **k)
+
+
 # ---------------------------------------------------------------------------------------------
 # inference-time view of a conv block: (W (cout, cin) f32, b (cout) f32, relu: bool) with the
 # eval-mode BatchNorm folded in:  y = gamma * (Wx + b0 - mean) / sqrt(var + eps) + beta
@@ -133,5 +184,22 @@ def fold_layer(block):
         scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
         w = w * scale[:, None]
         b = (b - bn.running_mean.detach()) * scale + bn.bias.detach()
-    relu = any(isinstance(getattr(block, n), nn.ReLU) for n in names if n.endswith("activation"))
-    return w.contiguous(), b.contiguous(), relu
+    acts = [getattr(block, n) for n in names if n.endswith("activation")]
+    if any(not isinstance(a, nn.ReLU) for a in acts):
+        raise NotImplementedError("only ReLU (or no activation) folds into the fused kernels")
+    return w.contiguous(), b.contiguous(), bool(acts)
+
+
+def foldable(seq):
+    """every conv block of an nn.Sequential (SharedMLP / head) is post-activation conv [+ BN] [+ ReLU]: what the fused
+    kernels implement; anything else takes the reference-structured path."""
+    for m in seq.children():
+        if isinstance(m, nn.Dropout):
+            continue
+        names = [n for n, _ in m.named_children()]
+        convs = [n for n in names if n.endswith("conv")]
+        if len(convs) != 1 or names.index(convs[0]) != 0 or any(n.endswith("in") for n in names):
+            return False
+        if any(not isinstance(getattr(m, n), nn.ReLU) for n in names if n.endswith("activation")):
+            return False
+    return True

@@ -39,7 +39,9 @@ us_car_stats = load_json(os.path.join(car_sales_path, "us.json"))
 germany_car_stats = load_json(os.path.join(car_sales_path, "germany.json"))
 car_stats_external = {"kitti": germany_car_stats, "argo_new": us_car_stats, "nusc": us_car_stats,
                       "lyft": us_car_stats, "waymo": us_car_stats}
-datasets = tuple(car_stats_external)
+# config_path.py:24-40: the experiment datasets; "argo" has no car-sales table (norm.py:34-39 names it "argo_new"),
+# so convert("argo", ..., use_car_sales_stats=True) raises KeyError exactly like the reference
+datasets = ("kitti", "argo", "nusc", "lyft", "waymo")
 
 
 def format_lidar_data(x, dst):

@@ -11,11 +11,12 @@ host buffers with the detections copied back for `e2e`).  Scenes shard across ra
 scaling); the only collective is one all_gather of the detection records at the end of the e2e
 region.  One JSON line on stdout (rank 0).
 
---impl reference runs the REFERENCE implementation of the same path: its own CUDA kernels
-(oracle/_ref/libpn2_legacy.so = the reference .cu files compiled unchanged) under the
-reference's op-by-op Python composition and per-scene host-greedy NMS, on the same GPU, and
-next to it the CPU port (oracle/cpu_forward.py) on a bounded sample.  The reference has no CPU
-implementation of this path; see DESIGN.md "Reference arm".
+--impl reference runs the STOCK REFERENCE: its own, unmodified Python (lib/net/point_rcnn.py, pointnet2_lib/pointnet2/*.py,
+lib/rpn/proposal_layer.py, the eval loop body of tools/eval_rcnn.py:497-627; oracle/refnet_gpu.py imports them from
+baseline/_ref/pointrcnn) over its own CUDA kernels (oracle/_ref/libpn2_legacy.so = the reference .cu files compiled
+unchanged), on every rank's GPU, same weights, same batches, same JSON keys.  `--impl mirror` is round 1's arm (the package's
+module mirrors with fused=False on the legacy kernels), kept as a cross-check.  The CPU port (oracle/cpu_forward.py) is timed
+next to it on a bounded sample: the reference has no CPU implementation of this path; see DESIGN.md "Reference arm".
 """
 import argparse
 import importlib
@@ -133,17 +134,54 @@ def cpu_port_sample(torch, batch_seed, max_scenes=4, budget_s=12.0):
     pkg = {"cfg": load("config").cfg, "decode_bbox_target": load("bbox_transform").decode_bbox_target}
     pts = torch.from_numpy(syn.make_clouds("lidar", max_scenes, NPOINTS, seed=batch_seed))
     t0 = time.perf_counter()
-    done = 0
+    done, dets = 0, []
     for i in range(max_scenes):
         out = cf.pointrcnn_forward(pkg, model, pts[i:i + 1])
-        cf.postprocess(pkg, out, 1)
+        dets.append(cf.postprocess(pkg, out, 1)[0])
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d scene(s) of batch 0 (16384 pts, 100 ROIs each), %.1f s; C restatement of the reference "
-                      "kernels single-threaded + torch CPU fp32 convs on %d threads" % (done, dt, torch.get_num_threads())}
+                      "kernels single-threaded + torch CPU fp32 convs on %d threads" % (done, dt, torch.get_num_threads()),
+            "_detections": dets}
+
+
+def match_detections(ref, got, tol=2e-3):
+    """per scene lists of (boxes (k,7), scores (k,)) -> {"matched", "total", "extra", "max_abs_err"}: a reference box is
+    matched when some produced box agrees with it in all seven fields and the raw score within `tol` (a score or an
+    overlap within ~5e-5 of a threshold may legitimately flip a box: tests/test_refeval_golden_gpu.py)."""
+    import numpy as np
+    matched = total = extra = 0
+    worst = 0.0
+    for (rb, rs), (gb, gs) in zip(ref, got):
+        total += len(rb)
+        used = np.zeros(len(gb), bool)
+        r = np.concatenate([np.asarray(rb, np.float64).reshape(-1, 7), np.asarray(rs, np.float64).reshape(-1, 1)], axis=1)
+        g = np.concatenate([np.asarray(gb, np.float64).reshape(-1, 7), np.asarray(gs, np.float64).reshape(-1, 1)], axis=1)
+        for row in r:
+            if not len(g):
+                break
+            err = np.abs(g - row).max(axis=1)
+            err[used] = np.inf
+            j = int(err.argmin())
+            if err[j] <= tol:
+                used[j] = True
+                matched += 1
+                worst = max(worst, float(err[j]))
+        extra += int((~used).sum())
+    return {"matched": matched, "total": total, "extra": extra, "max_abs_err": worst, "tol": tol}
+
+
+def workload_config(B, world):
+    """the `config` both arms print (identical by construction)."""
+    return {"workload": "BASELINE.json configs[3]: full PointRCNN RPN+RCNN forward (default.yaml, random-init weights "
+                        "seed 0) + eval_rcnn.py decode/score/rotated-NMS, batch=16 synthetic KITTI-shaped clouds of "
+                        "16384 points per GPU",
+            "batch_per_gpu": B, "npoints": NPOINTS, "rois_per_scene": 100, "parallelism": "scene-shard x%d" % world,
+            "l2": "per-step working set (pooled ROI tensor 0.44 GB + SA activations) >> 126 MB L2; inputs rotate over "
+                  "4 batches"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -188,6 +226,15 @@ def run_b200(args):
 
     run_steps(max(W, 2 * args.depth))
     torch.cuda.synchronize()
+    if args.min_seconds > 0:
+        # sustained figure: size K so that the timed region lasts at least --min-seconds (probe: 10 steps)
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); run_steps(10); e0.record(); torch.cuda.synchronize()
+        K = max(K, int(args.min_seconds * 1e3 / (s0.elapsed_time(e0) / 10)) + 1)
+        if dist is not None:
+            t = torch.tensor([K], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            K = int(t.item())
 
     if args.minimal:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,6 +299,9 @@ def run_b200(args):
     for i in range(2):
         det.detect(host[i % 4], out_rec, out_cnt)
     keep_rec = torch.empty((K, B, 100, 8), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, K, B, 100, 8), dtype=torch.float32, device=dev) if dist is not None else None
+    if dist is not None:
+        dist.all_gather_into_tensor(gathered, keep_rec)      # untimed: NCCL channel set-up for this size
     checksum = 0.0
     barrier()
     t0 = time.perf_counter()
@@ -278,8 +328,7 @@ def run_b200(args):
             checksum += float(h_num.sum())
         det.drain()
     if dist is not None:
-        gathered = [torch.empty_like(keep_rec) for _ in range(world)]
-        dist.all_gather(gathered, keep_rec)                 # the single collective: detection boxes
+        dist.all_gather_into_tensor(gathered, keep_rec)     # the single collective: detection boxes
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()
@@ -318,15 +367,14 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[3]: full PointRCNN RPN+RCNN forward (default.yaml, random-init "
-                               "weights seed 0) + eval_rcnn.py decode/score/rotated-NMS, batch=16 synthetic KITTI-shaped "
-                               "clouds of 16384 points per GPU",
-                   "batch_per_gpu": B, "npoints": NPOINTS, "rois_per_scene": 100, "parallelism": "scene-shard x%d" % world,
-                   "launch": ("one CUDA graph replay per step" if det.use_graph else "eager")
-                             + (", %d steps in flight on %d streams" % (args.depth, args.depth) if args.depth > 1 else ""),
-                   "batches_in_flight": args.depth,
-                   "eager_ms_per_step": eager_ms / K,
-                   "l2": "per-step working set (pooled ROI tensor 0.44 GB + SA activations) >> 126 MB L2; inputs rotate over 4 batches"},
+        "config": workload_config(B, world),
+        "execution": {"launch": ("one CUDA graph replay per step" if det.use_graph else "eager")
+                                + (", %d steps in flight on %d streams" % (args.depth, args.depth) if args.depth > 1 else ""),
+                      "batches_in_flight": args.depth, "eager_ms_per_step": eager_ms / K,
+                      "timed_region_s": ms_total * 1e-3,
+                      "sampling": "bench batches are fixed synthetic clouds; dataset-level runs (tools/eval_sharded.py, "
+                                  "tools/eval_fast.py) seed np.random per scene when sharded, a documented deviation from "
+                                  "the reference's single global stream (DESIGN.md 6)"},
         "e2e": {"value": scenes / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * NPOINTS * 3 * 4,
                 "d2h_bytes_per_step": B * 100 * 8 * 4 + B * 4,
                 "collective": "one all_gather of (K,B,100,8) f32 detection records" if world > 1 else None,
@@ -348,7 +396,16 @@ def run_b200(args):
         "mlp_tflops_effective": FLOPS_PER_SCENE * scenes / (ms_total * 1e-3) / 1e12,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_port_sample(torch, 1024)
+        cpu = cpu_port_sample(torch, 1024)
+        ref_dets = cpu.pop("_detections")
+        # parity inside the bench: the CPU port's detections for the first scenes of batch 0 against what the timed
+        # configuration (B=16 x 16384, CUDA graph, batches in flight) produces for the same batch
+        h_rec, h_cnt = det.detect(host[0], out_rec, out_cnt)
+        got = inf.records_to_lists(h_rec, h_cnt)[:len(ref_dets)]
+        line["parity_in_bench"] = dict(match_detections(ref_dets, got), scenes=len(ref_dets),
+                                       against="oracle/cpu_forward.py (CPU port, pinned bit-for-bit to the reference's "
+                                               "own network code: tests/test_refnet_vs_port_cpu.py)")
+        line["cpu_baseline"] = cpu
     if rank == 0:
         emit(line)
     if dist is not None:
@@ -357,6 +414,85 @@ def run_b200(args):
 
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The stock reference (oracle/refnet_gpu.py: its unmodified Python over its unmodified kernels) on every rank."""
+    import torch
+    from oracle import refnet_gpu
+    B, K, W = args.batch, args.steps, args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, world)}
+    if not refnet_gpu.available("legacy"):
+        # no GPU / no legacy library / no staged reference tree: the CPU port on rank 0 is all there is
+        if rank != 0:
+            return
+        cpu = cpu_port_sample(torch, 1024)
+        cpu.pop("_detections")
+        base.update({"n_gpus": 1, "value": cpu["value"], "ms_per_step": 1e3 * B / cpu["value"], "cpu_baseline": cpu,
+                     "execution": {"arm": "CPU port (oracle/) of the same workload; stock reference unavailable here"},
+                     "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        emit(base)
+        return
+    dist, world, rank, local = dist_setup(torch, args.gpus)
+    dev = torch.device("cuda", local)
+    syn, inf = load("synthetic"), load("inference")
+    state = inf.build_model(seed=0, device="cpu").state_dict()         # the b200 arm's weights
+    ref = refnet_gpu.Reference(state, dev, backend="legacy")
+    host = make_batches(torch, syn, B, 4, seed=1024 + 1000 * rank)      # the b200 arm's batches
+    sampler = ClockSampler(physical_gpu_index(local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        dets = ref.eval_batch(host[i % 4])
+    sampler.start()
+    barrier()
+    copies = refnet_gpu.COPIED
+    copies["h2d"] = copies["d2h"] = 0
+    t0 = time.perf_counter()
+    ndet = 0
+    for i in range(K):
+        dets = ref.eval_batch(host[i % 4])
+        ndet += sum(len(d[1]) for d in dets)
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    clocks = sampler.stop()
+    value = B * K * world / dt
+    base.update({
+        "value": value, "ms_per_step": 1e3 * dt / K,
+        "execution": {"arm": "stock reference: unmodified lib/net/*.py, pointnet2_lib/pointnet2/*.py, lib/rpn/proposal_layer.py, "
+                             "lib/utils/* and the eval-loop body of tools/eval_rcnn.py:497-627 (baseline/_ref/pointrcnn) over "
+                             "oracle/_ref/libpn2_legacy.so (reference .cu compiled unchanged for sm_100a); cuDNN 1x1 convs at "
+                             "torch defaults (cudnn.allow_tf32=%s); per-scene NMS with the blocking mask copy and host "
+                             "greedy pass; one batch at a time on the default stream" % torch.backends.cudnn.allow_tf32,
+                      "batches_in_flight": 1, "timed_region_s": dt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": copies["h2d"] // K, "d2h_bytes_per_step": copies["d2h"] // K,
+                "detections_read_on_host": float(ndet)},
+        "clocks": clocks,
+    })
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_sample(torch, 1024)
+        ref_dets = cpu.pop("_detections")
+        got = ref.eval_batch(host[0])[:len(ref_dets)]
+        base["parity_in_bench"] = dict(match_detections(ref_dets, got), scenes=len(ref_dets),
+                                       against="oracle/cpu_forward.py (CPU port)")
+        base["cpu_baseline"] = dict(cpu, note="the reference has no CPU implementation of this path; `value` above is its "
+                                              "CUDA path on the same B200, this is the CPU port on the host cores")
+    if rank == 0:
+        emit(base)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_mirror(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,7 +501,8 @@ def run_reference(args):
     from oracle import legacy
     have_gpu = torch.cuda.is_available() and legacy.available()
     cpu = cpu_port_sample(torch, 1024)
-    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+    cpu.pop("_detections")
+    base = {"impl": "mirror", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if not have_gpu:
         base.update({"value": cpu["value"], "ms_per_step": 1e3 * B / cpu["value"], "cpu_baseline": cpu,
@@ -470,11 +607,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "mirror"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=3,
                     help="batches in flight (Detector.submit/collect); 1 = one batch at a time on one stream")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--min-seconds", type=float, default=0.0,
+                    help="grow --steps until the timed region lasts this long (sustained figure; default: exactly --steps)")
     ap.add_argument("--minimal", action="store_true",
                     help="warm-up + timed steps only (no profiled step, e2e or CPU legs): the command ncu wraps")
     args = ap.parse_args()
@@ -485,6 +624,8 @@ def main():
         try:
             if args.impl == "reference":
                 run_reference(args)
+            elif args.impl == "mirror":
+                run_mirror(args)
             else:
                 run_b200(args)
         finally:

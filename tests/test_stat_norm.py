@@ -83,8 +83,8 @@ def test_convert_writes_a_rescaled_dataset(scene, tmp_path):
     (src / "training" / "label_2" / "000000.txt").write_text(str(g["labels"]) + "\nDontCare -1 -1 -10 0 0 1 1 -1 -1 -1 -1000 -1000 -1000 -10")
     Image.new("RGB", (1242, 375)).save(str(src / "training" / "image_2" / "000000.png"))
     out = tmp_path / "out"
-    norm.convert("kitti", "argo_new", spath=str(src), dpath=str(out), use_car_sales_stats=True)
-    root = out / "kitti_scaledto_argo_new" / "training"
+    norm.convert("kitti", "nusc", spath=str(src), dpath=str(out), use_car_sales_stats=True)
+    root = out / "kitti_scaledto_nusc" / "training"
     raw = np.fromfile(str(root / "velodyne" / "000000.bin"), np.uint8)
     assert np.array_equal(sha(raw), g["ac0_af0_bin_sha"])
     assert (root / "label_2" / "000000.txt").read_text() == str(g["ac0_af0_labels"])

@@ -91,12 +91,12 @@ def test_convert_gpu_writes_the_same_dataset_as_convert(cuda, tmp_path):
             "\n".join(o.to_kitti_format() for o in labels) + ("\n" if labels else "") +
             "DontCare -1 -1 -10 0 0 1 1 -1 -1 -1 -1000 -1000 -1000 -10")
         Image.new("RGB", (1242, 375)).save(str(src / "training" / "image_2" / (name + ".png")))
-    norm.convert("kitti", "argo_new", spath=str(src), dpath=str(tmp_path / "cpu"), use_car_sales_stats=True)
-    gr.convert_gpu("kitti", "argo_new", spath=str(src), dpath=str(tmp_path / "gpu"), use_car_sales_stats=True, batch_size=2,
+    norm.convert("kitti", "nusc", spath=str(src), dpath=str(tmp_path / "cpu"), use_car_sales_stats=True)
+    gr.convert_gpu("kitti", "nusc", spath=str(src), dpath=str(tmp_path / "gpu"), use_car_sales_stats=True, batch_size=2,
                    device=cuda)
     for sub in ("velodyne", "label_2"):
-        a = tmp_path / "cpu" / "kitti_scaledto_argo_new" / "training" / sub
-        b = tmp_path / "gpu" / "kitti_scaledto_argo_new" / "training" / sub
+        a = tmp_path / "cpu" / "kitti_scaledto_nusc" / "training" / sub
+        b = tmp_path / "gpu" / "kitti_scaledto_nusc" / "training" / sub
         assert sorted(os.listdir(str(a))) == sorted(os.listdir(str(b))) and len(os.listdir(str(a))) == 5
         for f in os.listdir(str(a)):
             assert open(str(a / f), "rb").read() == open(str(b / f), "rb").read(), (sub, f)

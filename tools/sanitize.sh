@@ -1,0 +1,28 @@
+#!/bin/bash
+# compute-sanitizer (memcheck / racecheck / synccheck) over a reduced -m gpu subset that covers the hand-rolled
+# synchronisation: fps_kernel<*,{1,2,4,8}> (st.async into peer CTAs, mbarrier phases), the tcgen05 kernels in compact and
+# dense mode (mbarrier pipelines, tcgen05 commit / wait, atomicMax pooling), nms_kernel, roipool3d_kernel, ball query.
+# Logs -> gpurun_out/sanitizer_<tool>.log (copied to profiles/ by hand).   usage: tools/sanitize.sh [per-tool timeout s]
+T=${1:-420}
+mkdir -p gpurun_out
+SUBSET="tests/test_pn2_ops_gpu.py::test_fps_every_cluster_size_and_temp_writeback tests/test_pn2_ops_gpu.py::test_fps_vs_oracle tests/test_pn2_ops_gpu.py::test_ball_query_vs_oracle tests/test_linear_tc_gpu.py tests/test_iou3d_roipool_gpu.py"
+for tool in memcheck synccheck racecheck; do
+    extra=""
+    [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
+    start=$(date +%s)
+    PN2_SANITIZER=1 timeout $T compute-sanitizer --tool $tool $extra --print-limit 40 --log-file gpurun_out/sanitizer_$tool.raw \
+        python -m pytest $SUBSET -x -q -m gpu -p no:cacheprovider > gpurun_out/sanitizer_$tool.pytest 2>&1
+    rc=$?
+    {
+        echo "# compute-sanitizer --tool $tool $extra ; python -m pytest $SUBSET -x -q -m gpu"
+        echo "# exit code $rc (124 = the $T s budget ran out before the subset finished), $(( $(date +%s) - start )) s"
+        echo "# ---- pytest tail ----"
+        tail -5 gpurun_out/sanitizer_$tool.pytest
+        echo "# ---- sanitizer report (head) ----"
+        head -120 gpurun_out/sanitizer_$tool.raw 2>/dev/null
+        echo "# ---- sanitizer report (tail) ----"
+        tail -8 gpurun_out/sanitizer_$tool.raw 2>/dev/null
+    } > gpurun_out/sanitizer_$tool.log
+    rm -f gpurun_out/sanitizer_$tool.raw gpurun_out/sanitizer_$tool.pytest
+    echo "sanitizer $tool rc=$rc"
+done
