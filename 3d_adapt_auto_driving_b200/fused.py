@@ -155,12 +155,25 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
     return i0, i1
 
 
-def fps_gather(xyz, npoint):
-    """FPS indices (B,npoint) int32 and the sampled centres (B,npoint,3)."""
+# SA levels that sample an already FPS-ordered cloud (every backbone level after the first) first run the exact
+# parallel prefix test (csrc/fps.cu: pn2_fps_prefix_check_f32); clouds that pass get arange(npoint) without the round loop.
+FPS_PREFIX_CHECK = os.environ.get("PN2_FPS_PREFIX_CHECK", "1") != "0"
+
+
+def fps_gather(xyz, npoint, fps_ordered=False):
+    """FPS indices (B,npoint) int32 and the sampled centres (B,npoint,3).  fps_ordered: the caller knows that xyz is
+    the output of a previous furthest point sampling (a hint, never trusted: the prefix test decides per cloud)."""
     B, N, _ = xyz.shape
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-    cabi.call("pn2_fps_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint),
-              work=16.0 * B * max(npoint - 1, 0) * N)
+    if fps_ordered and FPS_PREFIX_CHECK and 1 < npoint <= min(N, 4096):
+        viol = torch.zeros((B,), dtype=torch.int32, device=xyz.device)
+        dmin = torch.empty((B, npoint), dtype=torch.float32, device=xyz.device)
+        cabi.call("pn2_fps_prefix_check_f32", ptr(xyz), ptr(dmin), ptr(viol), i32(B), i32(N), i32(npoint),
+                  work=12.0 * B * npoint * N)
+        cabi.call("pn2_fps_guarded_f32", ptr(xyz), ptr(idx), ptr(viol), i32(B), i32(N), i32(npoint), work=0.0)
+    else:
+        cabi.call("pn2_fps_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint),
+                  work=16.0 * B * max(npoint - 1, 0) * N)
     new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     return idx, new_xyz
 

@@ -47,8 +47,9 @@ class Pointnet2MSG(nn.Module):
         xyz = pointcloud[..., 0:3].contiguous()
         feats = pointcloud[..., 3:].contiguous() if pointcloud.size(-1) > 3 else None
         l_xyz, l_feats = [xyz], [feats]
-        for sa in self.SA_modules:
-            nx, nf = sa.forward_pm(l_xyz[-1], l_feats[-1])
+        for level, sa in enumerate(self.SA_modules):
+            # from the second level on the cloud being sampled is the previous level's centre list: FPS-ordered
+            nx, nf = sa.forward_pm(l_xyz[-1], l_feats[-1], fps_ordered=level > 0)
             l_xyz.append(nx)
             l_feats.append(nf)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):

@@ -194,8 +194,8 @@ class RCNNNet(pt_utils.PackedCacheMixin, nn.Module):
             side = fz.linear(rpn_feat, pk["merge_b"])                     # W_b rpn_feature + b
             merged = fz.linear(cur, pk["merge_a"], res=side)              # relu(W_a xyz_feature + side)
         l_xyz, l_feats = xyz, merged.view(R, S, -1)
-        for sa in self.SA_modules:
-            l_xyz, l_feats = sa.forward_pm(l_xyz, l_feats)
+        for level, sa in enumerate(self.SA_modules):
+            l_xyz, l_feats = sa.forward_pm(l_xyz, l_feats, fps_ordered=level > 0)
         feat = l_feats.reshape(R, -1)
         outs = []
         for layers in (pk["cls"], pk["reg"]):

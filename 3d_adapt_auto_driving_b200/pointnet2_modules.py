@@ -65,9 +65,9 @@ class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
                 return False      # the pooled-linear kernel needs the group size to divide its 128-row tile
         return True
 
-    def forward_pm(self, xyz, feats_pm=None, new_xyz=None):
+    def forward_pm(self, xyz, feats_pm=None, new_xyz=None, fps_ordered=False):
         """xyz (B,N,3), feats_pm (B,N,C) point-major or None -> (new_xyz (B,M,3) or None,
-        out (B,M,sum C_out) point-major)."""
+        out (B,M,sum C_out) point-major).  fps_ordered: xyz is itself the centre list of a previous FPS (fused.fps_gather)."""
         B, N, _ = xyz.shape
         packed = self._pack()
         group_all = isinstance(self.groupers[0], pointnet2_utils.GroupAll)
@@ -85,7 +85,7 @@ class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
             return None, (outs[0] if len(outs) == 1 else torch.cat(outs, dim=2))
 
         if new_xyz is None:
-            _, new_xyz = fz.fps_gather(xyz, self.npoint)
+            _, new_xyz = fz.fps_gather(xyz, self.npoint, fps_ordered=fps_ordered)
         M = new_xyz.shape[1]
         if len(self.groupers) == 2:
             g0, g1 = self.groupers

@@ -12,7 +12,8 @@
  *   - the return value is a status: 0 ok, 1 invalid argument, 2 launch failure,
  *     3 unsupported size.  pn2_last_error() gives the message.  Nothing ever calls exit()
  *     (the reference does: e.g. sampling_gpu.cu:249-252);
- *   - the library is stateless and re-entrant apart from the thread-local error string.
+ *   - the library is stateless and re-entrant apart from the thread-local error string (and the opt-in stopwatch /
+ *     debug hooks of the profiling tools, pn2_sa_fused_tc_set_profile / _set_debug, never used by the product).
  *
  * Each declaration cites the reference interface it replaces (paths relative to the
  * reference repository root).  INTEGRATION.md shows the binding a maintainer adds.
@@ -42,8 +43,19 @@ int pn2_abi_version(void);
 int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, void *stream);
 /* cuda_utils.h:10-14 opt_n_threads: the reference block size that fixes the tie order. */
 int pn2_fps_ref_block_size(int n);
-/* tuning hook: force the CTAs-per-cloud cluster size (0 = heuristic). */
-void pn2_fps_set_cluster(int c);
+/* pn2_fps_f32 with the CTAs-per-cloud thread-block-cluster size given explicitly (1, 2, 4, 8; 0 = heuristic): tests and
+ * tuning.  Same result for every value; no process-global state. */
+int pn2_fps_cluster_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int cluster_size, void *stream);
+/* Exact parallel test "does furthest_point_sample(xyz, m) return 0, 1, ..., m-1?" (true for every SA level of the
+ * backbone after the first: pointnet2_msg.py:131-137 feeds level l the FPS-ordered centres of level l-1, and FPS of a
+ * prefix of an FPS ordering is that prefix unless two candidates tie at the maximum).  viol (B) int32 ZEROED by the
+ * caller, dmin (B, m) f32 scratch; afterwards viol[c] == 0 iff at every round the due point is the STRICT arg-max of the
+ * running min-distances, computed with the reference's own float expressions (sampling_gpu.cu:129-138), so the answer
+ * does not depend on the reference's tie order.  N * m independent pair evaluations instead of m dependent rounds. */
+int pn2_fps_prefix_check_f32(const float *xyz, float *dmin, int32_t *viol, int b, int n, int m, void *stream);
+/* pn2_fps_f32 (temp = NULL) that writes idx = 0..m-1 for the clouds with viol[c] == 0 and runs the round loop for the
+ * others: bit-exact in both cases. */
+int pn2_fps_guarded_f32(const float *xyz, int32_t *idx, const int32_t *viol, int b, int n, int m, void *stream);
 
 /* gather_points_wrapper(b,c,n,npoints,points,idx,out)  sampling.cpp:11-21, sampling_gpu.cu:8-44.
  * points (B,C,N), idx (B,M) int32 -> out (B,C,M). */

@@ -35,11 +35,8 @@ def test_fps_every_cluster_size_and_temp_writeback(cuda, oracle, cluster):
     xyz = torch.from_numpy(xyz_h).to(cuda)
     temp = torch.full((3, 3000), 1e10, device=cuda)
     idx = torch.empty((3, 200), dtype=torch.int32, device=cuda)
-    cabi.lib().pn2_fps_set_cluster(cluster)
-    try:
-        p2c.furthest_point_sampling_wrapper(3, 3000, 200, xyz, temp, idx)
-    finally:
-        cabi.lib().pn2_fps_set_cluster(0)
+    cabi.call("pn2_fps_cluster_f32", cabi.ptr(xyz), cabi.ptr(temp), cabi.ptr(idx), cabi.i32(3), cabi.i32(3000), cabi.i32(200),
+              cabi.i32(cluster))
     ref, ref_temp = oracle.fps(xyz_h, 200)
     assert np.array_equal(idx.cpu().numpy(), ref)
     assert np.array_equal(temp.cpu().numpy(), ref_temp)  # caller scratch mutated like the reference
@@ -241,3 +238,50 @@ def test_legacy_pins_the_oracle(cuda, legacy, oracle):
         d2, i3 = legacy.three_nn(xyz, new_xyz)
         d2o, i3o = oracle.three_nn(xyz_h, new_xyz.cpu().numpy())
         assert np.array_equal(i3.cpu().numpy(), i3o) and np.array_equal(d2.cpu().numpy(), d2o)
+
+
+@pytest.mark.parametrize("kind,n0,n1,m", [("lidar", 16384, 4096, 1024), ("lidar", 4096, 1024, 256), ("uniform", 1024, 256, 64),
+                                           ("ties", 8192, 2048, 512), ("ties", 600, 300, 150), ("lidar", 512, 128, 32)])
+def test_fps_prefix_check_and_guarded_launch(cuda, oracle, kind, n0, n1, m):
+    """pn2_fps_prefix_check_f32 + pn2_fps_guarded_f32 (the backbone's levels 2-4 and RCNN SA2) against the oracle:
+    the sampled cloud is the FPS-ordered output of a previous level.  Where the test passes the kernel writes arange(m)
+    and the oracle's sequential answer must be exactly that; `ties` clouds (lattice points, exact distance ties) make the
+    test fail for some clouds, which then take the real round loop -- bit-exact either way."""
+    fz = load("fused")
+    B = 4
+    xyz0_h = synthetic.make_clouds(kind, B, n0, seed=n0 + m)
+    xyz0 = torch.from_numpy(xyz0_h).to(cuda)
+    _, xyz1 = fz.fps_gather(xyz0, n1)                               # level l-1 (the real kernel)
+    ref1, _ = oracle.fps(xyz0_h, n1)
+    xyz1_h = xyz1.cpu().numpy()
+    assert np.array_equal(xyz1_h, np.take_along_axis(xyz0_h, ref1[:, :, None].astype(np.int64), axis=1))
+    viol = torch.zeros((B,), dtype=torch.int32, device=cuda)
+    dmin = torch.empty((B, m), dtype=torch.float32, device=cuda)
+    cabi = load("cabi")
+    cabi.call("pn2_fps_prefix_check_f32", cabi.ptr(xyz1), cabi.ptr(dmin), cabi.ptr(viol), cabi.i32(B), cabi.i32(n1), cabi.i32(m))
+    idx, _ = fz.fps_gather(xyz1, m, fps_ordered=True)               # check + guarded launch
+    ref2, _ = oracle.fps(xyz1_h, m)
+    assert np.array_equal(idx.cpu().numpy(), ref2)
+    v = viol.cpu().numpy()
+    for b in range(B):
+        if v[b] == 0:
+            assert np.array_equal(ref2[b], np.arange(m)), "prefix test passed but the reference answer is not arange"
+    print("%s %d->%d->%d: %d of %d clouds skip the round loop" % (kind, n0, n1, m, int((v == 0).sum()), B))
+    if kind == "lidar":
+        assert (v == 0).all()
+
+
+def test_fps_prefix_check_rejects_unordered_and_duplicate_clouds(cuda, oracle):
+    """an arbitrary (not FPS-ordered) cloud and a cloud with duplicated points must fail the test and still sample exactly"""
+    fz = load("fused")
+    xyz_h = synthetic.make_clouds("uniform", 3, 2048, seed=11)
+    xyz_h[1, 7] = xyz_h[1, 3]                                       # duplicate of an early point
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    viol = torch.zeros((3,), dtype=torch.int32, device=cuda)
+    dmin = torch.empty((3, 256), dtype=torch.float32, device=cuda)
+    cabi = load("cabi")
+    cabi.call("pn2_fps_prefix_check_f32", cabi.ptr(xyz), cabi.ptr(dmin), cabi.ptr(viol), cabi.i32(3), cabi.i32(2048), cabi.i32(256))
+    assert (viol.cpu().numpy() > 0).all()
+    idx, _ = fz.fps_gather(xyz, 256, fps_ordered=True)
+    ref, _ = oracle.fps(xyz_h, 256)
+    assert np.array_equal(idx.cpu().numpy(), ref)

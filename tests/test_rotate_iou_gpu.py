@@ -61,7 +61,8 @@ def test_contract_dtype_and_empty(cuda):
     f = load("rotate_iou").rotate_iou_gpu_eval
     a = rotate_iou_inputs(3, 7).astype(np.float64)
     out = f(a, a)
-    assert out.dtype == np.float64 and out.shape == (7, 7)      # returned in the input dtype (rotate_iou.py:329)
+    # float32 whatever the input dtype: rotate_iou.py:312 rebinds `boxes` to its float32 cast before :329 reads boxes.dtype
+    assert out.dtype == np.float32 and out.shape == (7, 7)
     assert f(a[:0], a).shape == (0, 7) and f(a[:0], a).dtype == np.float32   # early return keeps float32 (:315-316)
     assert f(a, a[:0]).shape == (7, 0)
     # properties: symmetric IoU under swapping the roles, inter <= min area

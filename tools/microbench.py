@@ -56,15 +56,17 @@ def main(out_path):
             temp = torch.empty((b, n), device=dev)
             idx = torch.empty((b, m), dtype=torch.int32, device=dev)
 
+            cur = [0]
+
             def run_new():
-                cabi.call("pn2_fps_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(b), cabi.i32(n), cabi.i32(m))
+                cabi.call("pn2_fps_cluster_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(b), cabi.i32(n),
+                          cabi.i32(m), cabi.i32(cur[0]))
             clusters = [0] if n < 2048 else [0, 1, 2, 4, 8]
             for c in clusters:
                 if c and b * c > 148 * 4:
                     continue
-                cabi.lib().pn2_fps_set_cluster(c)
+                cur[0] = c
                 t_new = timeit(run_new)
-                cabi.lib().pn2_fps_set_cluster(0)
                 t_leg = None
                 if have_legacy and c == 0:
                     t_leg = timeit(lambda: (temp.fill_(1e10), legacy.fps(xyz, m, temp)))
