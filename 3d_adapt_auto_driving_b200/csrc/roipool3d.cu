@@ -112,6 +112,125 @@ __global__ void __launch_bounds__(kThreads) roipool3d_kernel(const float *__rest
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The RCNN input stage in ONE launch (rcnn_net.py:126-154 with cfg USE_MASK, USE_DEPTH, no intensity):
+//   enlarge_box3d (kitti_utils.py:150-160) -> point-in-box pooling of 512 points per ROI -> canonical transform
+//   (pooled xyz -= roi centre; rotate_pc_along_y_torch by the roi angle, kitti_utils.py:45-63),
+// with the per-point extras [seg mask = sigmoid(score) > thresh, depth / 70 - 0.5] formed on the fly from the raw RPN
+// score and the point norm, so neither the (B, N, 2 + C) feature concat, nor the zero-fill of the 0.44 GB pooled tensor,
+// nor the read-modify-write passes of the transform exist.  Every row of every ROI is written (an empty ROI gives the
+// transformed zero rows the reference produces); the row layout is pn2_roipool3d_split_f32's
+//   [x y z | mask depth | 0-pad to off2 | feat2 (c2)].
+// Float semantics are torch's: the scalar divisor becomes a multiplication by fl(1/70) (ATen div by a CPU scalar), the
+// K = 2 batched matmul of the rotation rounds as fma(z, r1, fl(x * r0)) for this shape (rot_mode 0; 1 / 2: the other
+// orders, see glue.py) -- pinned against torch on the GPU by tests/test_glue_gpu.py.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rp_dot2(float a0, float b0, float a1, float b1, int mode) {
+    if (mode == 0) return __fmaf_rn(a1, b1, __fmul_rn(a0, b0));
+    if (mode == 1) return __fmaf_rn(a0, b0, __fmul_rn(a1, b1));
+    return __fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+
+__global__ void __launch_bounds__(kThreads) roipool3d_canon_kernel(const float *__restrict__ xyz, const float *__restrict__ rois,
+                                                                  const float *__restrict__ score, const float *__restrict__ depth,
+                                                                  const float *__restrict__ feat2, float *__restrict__ pooled,
+                                                                  int32_t *__restrict__ empty, int n, int m, int c2, int off2,
+                                                                  int row, int sampled, float extra, float extra2, float thresh,
+                                                                  float inv_depth, int rot_mode) {
+    extern __shared__ int32_t list[];
+    __shared__ int warp_cnt[kWarps];
+    const int roi = blockIdx.x, cloud = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *bx = rois + ((size_t)cloud * m + roi) * 7;
+    xyz += (size_t)cloud * n * 3;
+    score += (size_t)cloud * n;
+    depth += (size_t)cloud * n;
+    feat2 += (size_t)cloud * n * c2;
+
+    const float rx = __ldg(bx + 0), ry = __ldg(bx + 1), rz = __ldg(bx + 2), ang = __ldg(bx + 6);
+    BoxTest b;
+    {
+        // enlarge_box3d: h, w, l += 2 * extra; y += extra (float adds of the rounded Python scalars)
+        const float by = __fadd_rn(ry, extra), h = __fadd_rn(__ldg(bx + 3), extra2), w = __fadd_rn(__ldg(bx + 4), extra2),
+                    l = __fadd_rn(__ldg(bx + 5), extra2);
+        b.cx = rx;
+        b.cz = rz;
+        b.hh = (double)h * 0.5;
+        b.hl = (double)l * 0.5;
+        b.hw = (double)w * 0.5;
+        b.cy = (float)((double)by - b.hh);
+        b.cosa = cosf(ang);
+        b.sina = sinf(ang);
+    }
+    __syncthreads();
+
+    int cnt = 0;
+    for (int base = 0; base < n && cnt < sampled; base += kThreads) {
+        const int k = base + tid;
+        bool hit = false;
+        if (k < n) hit = in_box(b, __ldg(xyz + (size_t)k * 3), __ldg(xyz + (size_t)k * 3 + 1), __ldg(xyz + (size_t)k * 3 + 2));
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = cnt;
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) {
+            const int cw = warp_cnt[wv];
+            if (wv < warp) off += cw;
+            cnt += cw;
+        }
+        if (hit) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            if (pos < sampled) list[pos] = k;
+        }
+        __syncthreads();
+    }
+    if (cnt == 0 && tid == 0) empty[(size_t)cloud * m + roi] = 1;
+    const int have = min(cnt, sampled);
+    // rotation of the canonical transform: the same cos / sin of the roi angle (torch.cos / torch.sin of a float tensor)
+    const float cosa = b.cosa, sina = b.sina, nsina = -sina;
+    float *dst_base = pooled + ((size_t)cloud * m + roi) * (size_t)sampled * row;
+    for (int s = warp; s < sampled; s += kWarps) {
+        float *dst = dst_base + (size_t)s * row;
+        float px = 0.f, py = 0.f, pz = 0.f, mk = 0.f, dp = 0.f;
+        int src = -1;
+        if (have > 0) {
+            src = list[s < have ? s : s % have];
+            px = __ldg(xyz + (size_t)src * 3);
+            py = __ldg(xyz + (size_t)src * 3 + 1);
+            pz = __ldg(xyz + (size_t)src * 3 + 2);
+        }
+        if (lane < off2) {
+            float v = 0.f;
+            if (lane < 3) {
+                const float x = __fadd_rn(px, -rx), z = __fadd_rn(pz, -rz);
+                if (lane == 0) v = rp_dot2(x, cosa, z, nsina, rot_mode);
+                else if (lane == 1) v = __fadd_rn(py, -ry);
+                else v = rp_dot2(x, sina, z, cosa, rot_mode);
+            } else if (lane == 3) {
+                if (src >= 0) {
+                    const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__ldg(score + src))));
+                    mk = sg > thresh ? 1.0f : 0.0f;
+                }
+                v = mk;
+            } else if (lane == 4) {
+                if (src >= 0) dp = __fadd_rn(__fmul_rn(__ldg(depth + src), inv_depth), -0.5f);
+                v = dp;
+            }
+            dst[lane] = v;
+        }
+        float4 *d2 = reinterpret_cast<float4 *>(dst + off2);
+        if (src >= 0) {
+            const float4 *f2 = reinterpret_cast<const float4 *>(feat2 + (size_t)src * c2);
+            for (int j = lane; j < (c2 >> 2); j += 32) d2[j] = __ldg(f2 + j);
+        } else {
+            for (int j = lane; j < (c2 >> 2); j += 32) d2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int j = off2 + c2 + lane; j < row; j += 32) dst[j] = 0.f;
+    }
+}
+
 }  // namespace
 
 // xyz (B,N,3), boxes3d (B,M,7) ALREADY enlarged by the caller (roipool3d_utils.py:18),
@@ -154,6 +273,35 @@ PN2_API int pn2_roipool3d_split_f32(const float *xyz, const float *boxes3d, cons
     dim3 grid(m, b);
     roipool3d_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(xyz, boxes3d, feat, feat2, pooled, empty, n,
                                                                            m, c, c2, off2, ld_out, sampled);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// rcnn_net.py:126-154 in one launch (see roipool3d_canon_kernel): rois (B, M, 7) NOT enlarged, score (B, N) raw RPN
+// foreground score, depth (B, N) point norm, feat2 (B, N, c2) point features -> pooled (B, M, sampled, ld_out) rows
+// [canonical x y z | mask | depth / 70 - 0.5 | 0-pad | feat2 at column off2 | 0-pad], empty (B, M) int32 ZEROED by the
+// caller.  `pooled` needs no pre-zeroing.  Needs off2 in [5, 32], c2 % 4 == 0, off2 % 4 == 0, ld_out % 4 == 0.
+PN2_API int pn2_roipool3d_canon_f32(const float *xyz, const float *rois, double extra_width, const float *score,
+                                    double score_thresh, const float *depth, double depth_norm, const float *feat2, int c2,
+                                    float *pooled, int ld_out, int off2, int32_t *empty, int b, int n, int m, int sampled,
+                                    int rot_mode, cudaStream_t stream) {
+    if (!xyz || !rois || !score || !depth || !feat2 || !pooled || !empty || b < 0 || n < 0 || m < 0 || c2 <= 0 ||
+        sampled <= 0 || sampled > 8192 || off2 < 5 || off2 > 32 || ld_out < off2 + c2 || depth_norm == 0.0) {
+        pn2_set_last_error("pn2_roipool3d_canon_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if ((c2 & 3) || (off2 & 3) || (ld_out & 3) || (reinterpret_cast<uintptr_t>(feat2) & 15) ||
+        (reinterpret_cast<uintptr_t>(pooled) & 15)) {
+        pn2_set_last_error("pn2_roipool3d_canon_f32: feat2 block must be 16-byte aligned");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    if (b == 0 || m == 0) return PN2_OK;
+    dim3 grid(m, b);
+    // ATen divides by a CPU scalar as a multiplication by the reciprocal formed in float
+    const float inv = 1.0f / (float)depth_norm;
+    roipool3d_canon_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(
+        xyz, rois, score, depth, feat2, pooled, empty, n, m, c2, off2, ld_out, sampled, (float)extra_width,
+        (float)(extra_width * 2), (float)score_thresh, inv, rot_mode);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -57,6 +57,7 @@ struct SatParams {
     // duplicate-skipping mode (group_compact.cu): only the unique rows of every group are pushed through the MLP.
     // cmap[u] = centre of compact row u, jmap[u] = its neighbour index, *rows_dev = number of compact rows (device).
     const int32_t *cmap; const int32_t *jmap; const long long *rows_dev;
+    unsigned long long *prof;                     // optional stopwatch buffer (32 u64 per CTA, tools/prof_sat.py) or nullptr
 };
 
 struct SmemLayout {
@@ -137,13 +138,28 @@ __device__ __forceinline__ void meta_run_compact(const ProducerArgs &a, int lane
     }
 }
 
+// maximum of sixteen accumulator values in eight 3-input FMNMX3 (sm_100) instead of fifteen FMNMX
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
+    const float a = max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    const float b = max3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    const float c = max3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+    const float d = max3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+    const float e = max3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+    return fmaxf(max3(a, b, c), max3(d, e, __uint_as_float(v[15])));
+}
+
 // one run of equal centre ids ends: combine its maximum into the pooled output (rare: out of line, one copy of the code)
 __device__ __noinline__ void flush_run(float *dst, float v) {
     atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(v));
 }
 
 // COMPACT (duplicate-skipping rows) is a kernel template parameter: the dense instantiation carries none of its code
-template <bool FAST, bool COMPACT>
+template <bool FAST, bool COMPACT, bool PROF>
 __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -227,14 +243,14 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     pa.nkb = p.nkb1; pa.stages = p.stages; pa.nchunks = 1; pa.items = n_tiles;
     pa.ring = smem + L.off_ring; pa.stage_bytes = 2 * kABytes; pa.full = full; pa.empty = empty;
     pa.meta = reinterpret_cast<RowMeta *>(smem + L.off_meta); pa.meta_full = meta_full; pa.meta_empty = meta_empty;
-    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = nullptr;
+    pa.wxs = reinterpret_cast<const float *>(smem + L.off_wx); pa.kpad = kpad; pa.prof = p.prof;
 
     if (warp < kProdWarps) {
         // =============================== producers (tc_producer.cuh) ===============================
-        producer_run<true, FAST, false>(pa, (int)threadIdx.x, [](long long, int, int) {});
+        producer_run<true, FAST, PROF>(pa, (int)threadIdx.x, [](long long, int, int) {});
     } else if (warp == kMetaWarp) {
         if (compact) meta_run_compact(pa, lane, p.cmap, p.jmap);
-        else meta_run<false>(pa, lane);
+        else meta_run<PROF>(pa, lane);
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
         // All 32 lanes run the loops (uniform operands, tc::elect_one()); one elected lane issues.
@@ -250,14 +266,16 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             const uint32_t w2a = pn2_smem_u32(smem + L.off_w2), a2a = pn2_smem_u32(smem + L.off_a2);
             int stage = 0;
             uint32_t phase = 0;
+            unsigned long long w_ring = 0, w_acc2 = 0, w_a2 = 0, w_acc3 = 0;
+            const long long t_begin = PROF ? clock64() : 0;
             auto issue_m2 = [&](int it) {
                 const int buf = p.nb2 == 2 ? (it & 1) : 0;
                 const int use = p.nb2 == 2 ? (it >> 1) : it;
-                mbar_wait(&acc2_empty[buf], (uint32_t)(use & 1) ^ 1);
+                mbar_wait_timed<PROF>(&acc2_empty[buf], (uint32_t)(use & 1) ^ 1, w_acc2);
                 tc_fence_after_sync();
                 const uint32_t d = tmem_base + col_acc2 + (uint32_t)(buf * p.n2);
                 for (int kb = 0; kb < p.nkb1; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_timed<PROF>(&full[stage], phase, w_ring);
                     tc_fence_after_sync();
                     const uint32_t sa = pn2_smem_u32(smem + L.off_ring + (size_t)stage * 2 * kABytes);
                     const uint32_t a_hi = desc_lo(sa), a_lo = desc_lo(sa + kABytes);
@@ -290,8 +308,8 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             // one pass of layer 3 (transposed): acc3^T = W3[pass] (TMEM) x A2^T (shared memory, written by the epilogue)
             auto issue_m3 = [&](int it, int j) {
                 const int cnt = it * p.nm3 + j;
-                if (j == 0) mbar_wait(a2_full, (uint32_t)(it & 1));
-                mbar_wait(acc3_empty, (uint32_t)(cnt & 1) ^ 1);
+                if (j == 0) mbar_wait_timed<PROF>(a2_full, (uint32_t)(it & 1), w_a2);
+                mbar_wait_timed<PROF>(acc3_empty, (uint32_t)(cnt & 1) ^ 1, w_acc3);
                 tc_fence_after_sync();
                 const uint32_t d3 = tmem_base + col_acc3;
                 const uint32_t w3h = tmem_base + col_w3 + (uint32_t)(j * p.c2), w3l = w3h + (uint32_t)half_c2;
@@ -324,6 +342,11 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                     for (int j = 1; j < p.nm3; ++j) issue_m3(it, j);
                 }
             }
+            if (PROF && lane == 0) {
+                unsigned long long *o = p.prof + (size_t)blockIdx.x * 32;
+                o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_ring; o[2] = w_acc2; o[3] = w_a2; o[4] = w_acc3;
+                o[5] = (unsigned long long)my_tiles;
+            }
         }
         __syncwarp();
     } else {
@@ -353,6 +376,10 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             if (lane == 0) mbar_arrive(w3_full);
         }
         uint8_t *a2s = smem + L.off_a2;
+        // compact mode: run-start masks of this warp's 64 columns (bit l of run_e / run_o = column 2l / 2l+1 begins a
+        // new centre), computed once per tile when the centre ids are staged
+        uint32_t run_e = 0, run_o = 0;
+        unsigned long long w_acc2f = 0, w_a2e = 0, w_acc3f = 0, t_e2 = 0, t_e3 = 0;
         auto e3 = [&](int it, int j) {
             // acc3^T: lane = channel, columns = tile rows -> in-thread max over the nsample rows of each centre
             const long long tile = first + (long long)it * stride;
@@ -368,45 +395,66 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 if (2 * lane < ncols) t = __ldg(reinterpret_cast<const int2 *>(p.cmap + u0) + lane);
                 if (2 * lane + 1 >= ncols) t.y = -1;
                 reinterpret_cast<int2 *>(cid_s)[lane] = t;
+                int prev = __shfl_up_sync(0xffffffffu, t.y, 1);
+                if (lane == 0) prev = -2;                       // column 0 always opens a run
+                run_e = __ballot_sync(0xffffffffu, t.x != prev);
+                run_o = __ballot_sync(0xffffffffu, t.y != t.x);
                 __syncwarp();
             }
-            mbar_wait(acc3_full, (uint32_t)((it * p.nm3 + j) & 1));
+            mbar_wait_timed<PROF>(acc3_full, (uint32_t)((it * p.nm3 + j) & 1), w_acc3f);
+            const long long te0 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
             if constexpr (COMPACT) {
                 // compact rows: the columns of a centre are a run of equal ids (warp-uniform), of any length and possibly
-                // continued in the next warp / tile -> running max, one atomicMax per run and channel (y is zeroed)
+                // continued in the next warp / tile -> running max, one atomicMax per run and channel (y is zeroed).
+                // Runs are long (tens of columns), so the columns are taken eight at a time: a group without a run start
+                // is four 3-input maxima; only groups that contain a start walk their columns one by one.
                 const int ch = j * kC3 + r;
                 const float b = bias3[ch];
                 float *ych = p.y + ch;
+                const uint32_t run_any = run_e | run_o;
                 int cur = -1;
                 float run = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t va[16], vb[16];
-                    tmem_ld16(t3 + c0, va);
-                    tmem_ld16(t3 + c0 + 16, vb);
-                    tmem_ld_wait();
+                    uint32_t v[32];
+                    {
+                        uint32_t va[16], vb[16];
+                        tmem_ld16(t3 + c0, va);
+                        tmem_ld16(t3 + c0 + 16, vb);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) { v[k] = va[k]; v[16 + k] = vb[k]; }
+                    }
                     if (c0 == 32) {        // the last loads are done: the accumulator may be overwritten
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(acc3_empty);
                     }
-                    const int4 *c4 = reinterpret_cast<const int4 *>(cid_s + c0);
+                    const uint32_t any16 = (run_any >> (c0 >> 1)) & 0xffffu;     // 16 bit pairs = these 32 columns
+                    const uint32_t e16 = (run_e >> (c0 >> 1)) & 0xffffu, o16 = (run_o >> (c0 >> 1)) & 0xffffu;
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const int4 q = c4[k4];                                   // broadcast LDS.128: four warp-uniform ids
-                        const int cs[4] = {q.x, q.y, q.z, q.w};
+                    for (int g = 0; g < 4; ++g) {
+                        if (((any16 >> (4 * g)) & 0xfu) == 0u) {
+                            float m0, m1, m2;
+                            asm("max.f32 %0, %1, %2, %3;" : "=f"(m0) : "f"(__uint_as_float(v[8 * g])), "f"(__uint_as_float(v[8 * g + 1])), "f"(__uint_as_float(v[8 * g + 2])));
+                            asm("max.f32 %0, %1, %2, %3;" : "=f"(m1) : "f"(__uint_as_float(v[8 * g + 3])), "f"(__uint_as_float(v[8 * g + 4])), "f"(__uint_as_float(v[8 * g + 5])));
+                            asm("max.f32 %0, %1, %2, %3;" : "=f"(m2) : "f"(__uint_as_float(v[8 * g + 6])), "f"(__uint_as_float(v[8 * g + 7])), "f"(run));
+                            asm("max.f32 %0, %1, %2, %3;" : "=f"(run) : "f"(m0), "f"(m1), "f"(m2));
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = 4 * k4 + e;
-                            const float x = __uint_as_float(k < 16 ? va[k] : vb[k - 16]);
-                            if (cs[e] != cur) {
-                                if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
-                                cur = cs[e];
-                                run = x;
-                            } else {
-                                run = fmaxf(run, x);
+                            for (int e = 0; e < 8; ++e) {
+                                const int k = 8 * g + e;
+                                const float x = __uint_as_float(v[k]);
+                                const bool start = (((e & 1) ? o16 : e16) >> (k >> 1)) & 1u;
+                                if (start) {
+                                    if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                                    cur = cid_s[c0 + k];
+                                    run = x;
+                                } else {
+                                    run = fmaxf(run, x);
+                                }
                             }
                         }
                     }
@@ -420,14 +468,8 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 tmem_ld16(t3 + jp * 32, va);
                 tmem_ld16(t3 + jp * 32 + 16, vb);
                 tmem_ld_wait();
-                float ma = __uint_as_float(va[0]), mb = __uint_as_float(vb[0]);
-#pragma unroll
-                for (int j = 1; j < 16; ++j) {
-                    ma = fmaxf(ma, __uint_as_float(va[j]));
-                    mb = fmaxf(mb, __uint_as_float(vb[j]));
-                }
-                cm[2 * jp] = ma;
-                cm[2 * jp + 1] = mb;
+                cm[2 * jp] = max16(va);
+                cm[2 * jp + 1] = max16(vb);
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -454,14 +496,16 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 emit(m4, p.ns == 64 ? row_base : tile * BM, p.ns != 64);   // nsample 128: two warps share a centre
             }
             }   // dense rows
+            if (PROF) t_e3 += (unsigned long long)(clock64() - te0);
         };
         const bool pipelined = p.nb2 == 2;     // pooling of tile i-1 after the conversion of tile i (see the MMA order)
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = pipelined ? (it & 1) : 0;
             const int use = pipelined ? (it >> 1) : it;
             // ---- E2: acc2[buf] -> bias, ReLU, bf16 hi/lo -> shared-memory operand A2 of layer 3 ----
-            mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
-            mbar_wait(a2_empty, (uint32_t)(it & 1) ^ 1);
+            mbar_wait_timed<PROF>(&acc2_full[buf], (uint32_t)(use & 1), w_acc2f);
+            mbar_wait_timed<PROF>(a2_empty, (uint32_t)(it & 1) ^ 1, w_a2e);
+            const long long t20 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t t_acc2 = lane_addr + col_acc2 + (uint32_t)(buf * p.n2);
             auto convert = [&](const uint32_t (&v)[16], int c0) {
@@ -509,6 +553,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 mbar_arrive(a2_full);
                 mbar_arrive(&acc2_empty[buf]);
             }
+            if (PROF) t_e2 += (unsigned long long)(clock64() - t20);
             if (!pipelined) {
                 for (int j = 0; j < p.nm3; ++j) e3(it, j);
             } else if (it > 0) {
@@ -517,6 +562,10 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
         }
         if (pipelined && my_tiles > 0)
             for (int j = 0; j < p.nm3; ++j) e3(my_tiles - 1, j);
+        if (PROF && ew == 0 && lane == 0) {
+            unsigned long long *o = p.prof + (size_t)blockIdx.x * 32;
+            o[8] = w_acc2f; o[9] = w_a2e; o[10] = w_acc3f; o[12] = t_e2; o[13] = t_e3;
+        }
     }
 
     tc_fence_before_sync();
@@ -527,7 +576,12 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     }
 }
 
+unsigned long long *g_prof = nullptr;
+
 }  // namespace
+
+// stopwatch buffer for tools/prof_sat.py: 32 u64 per CTA (device memory) or NULL to disable (never used by the product)
+PN2_API void pn2_sa_fused_t_set_profile(void *buf) { g_prof = static_cast<unsigned long long *>(buf); }
 
 // pn2_sa_fused_tc_f32 with the last layer transposed (see the header of this file).
 //   w3hi / w3lo: (ceil(c3 / 128) * 128, c2 / 2) uint32 each (rows past c3 zero), W3 split into bf16 hi / lo, word j of row o = (W3[o][2j], W3[o][2j+1])
@@ -578,12 +632,15 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
         return PN2_ERR_UNSUPPORTED;
     }
     p.stages = stages;
+    p.prof = g_prof;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
     int dev = 0, sms = 148;
@@ -593,12 +650,15 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     const int vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const size_t smem_bytes = L.total + 1024;
     const bool fast = tc::producer_fast(vec_ok, c1);
-    if (cmap) {
-        if (fast) sa_fused_t_tc_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else sa_fused_t_tc_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    if (p.prof && fast) {        // stopwatch build (tools/prof_sat.py only)
+        if (cmap) sa_fused_t_tc_kernel<true, true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_t_tc_kernel<true, false, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    } else if (cmap) {
+        if (fast) sa_fused_t_tc_kernel<true, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_t_tc_kernel<false, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
     } else {
-        if (fast) sa_fused_t_tc_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else sa_fused_t_tc_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        if (fast) sa_fused_t_tc_kernel<true, false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else sa_fused_t_tc_kernel<false, false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
     }
     PN2_CHECK_LAUNCH();
     return PN2_OK;

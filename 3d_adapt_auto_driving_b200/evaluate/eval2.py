@@ -48,73 +48,74 @@ def _lib():
     return lib
 
 
-def get_thresholds(scores, num_gt, num_sample_pts=41):
-    """eval2.py:7-25."""
-    scores = np.sort(np.asarray(scores, dtype=np.float64))[::-1]
-    current_recall = 0
-    thresholds = []
-    for i, score in enumerate(scores):
-        l_recall = (i + 1) / num_gt
-        if i < (len(scores) - 1):
-            r_recall = (i + 2) / num_gt
-        else:
-            r_recall = l_recall
-        if (((r_recall - current_recall) < (current_recall - l_recall)) and (i < (len(scores) - 1))):
-            continue
-        thresholds.append(score)
-        current_recall += 1 / (num_sample_pts - 1.0)
-    return thresholds
+N_RECALL_SAMPLES = 41
+# one row per "difficulty" of this fork: distance bands in metres (camera z) with KITTI's occlusion / truncation limits
+# (eval2.py:31-41: 0-30 easy, 0-70 moderate, 0-70 hard, then the 0-30 / 30-50 / 50-70 m range splits)
+DIFFICULTY_TABLE = (
+    # (z_low, z_high, max_occlusion, max_truncation)
+    (0, 30, 0, 0.15),
+    (0, 70, 1, 0.3),
+    (0, 70, 2, 0.5),
+    (0, 30, 2, 0.5),
+    (30, 50, 2, 0.5),
+    (50, 70, 2, 0.5),
+)
+EVAL_CLASS_NAMES = ('car', 'pedestrian', 'cyclist')
+# ground-truth classes that are neither a hit nor a miss for a detector of the key class (eval2.py:48-53)
+NEIGHBOUR_CLASS = {'pedestrian': 'person_sitting', 'car': 'van'}
+
+
+def get_thresholds(scores, num_gt, num_sample_pts=N_RECALL_SAMPLES):
+    """eval2.py:7-25: the score thresholds at which recall crosses the num_sample_pts equally spaced sample positions.
+    Same arithmetic (rank / num_gt recalls, a running target advanced by 1 / (num_sample_pts - 1.0))."""
+    ranked = np.sort(np.asarray(scores, dtype=np.float64))[::-1]
+    step = 1 / (num_sample_pts - 1.0)
+    target = 0
+    picked = []
+    final = len(ranked) - 1
+    for pos, score in enumerate(ranked):
+        here = (pos + 1) / num_gt
+        beyond = (pos + 2) / num_gt if pos < final else here
+        if pos < final and (beyond - target) < (target - here):
+            continue                                   # the next detection gets closer to the target recall
+        picked.append(score)
+        target += step
+    return picked
+
+
+def _outside_band(z, difficulty):
+    low, high = DIFFICULTY_TABLE[difficulty][0], DIFFICULTY_TABLE[difficulty][1]
+    return ~((low < z) & (z < high))                   # NaN depths are outside, like the reference's chained compare
 
 
 def clean_data(gt_anno, dt_anno, current_class, dataset, difficulty):
-    """eval2.py:28-101: distance-band "difficulties" (0-30 / 0-70 / 0-70 / 0-30 / 30-50 / 50-70 m) with the KITTI
-    occlusion / truncation limits; the height criterion is commented out in the reference and stays out."""
-    CLASS_NAMES = ['car', 'pedestrian', 'cyclist']
-    MAX_OCCLUSION = [0, 1, 2, 2, 2, 2]
-    MAX_TRUNCATION = [0.15, 0.3, 0.5, 0.5, 0.5, 0.5]
-    dc_bboxes, ignored_gt, ignored_dt = [], [], []
-    current_cls_name = CLASS_NAMES[current_class].lower()
-    num_gt = len(gt_anno["name"])
-    num_dt = len(dt_anno["name"])
-    num_valid_gt = 0
-    dist_boundary = np.array([[0, 0, 0, 0, 30, 50],
-                              [30, 70, 70, 30, 50, 70]])
-    for i in range(num_gt):
-        gt_name = gt_anno["name"][i].lower()
-        if gt_name == current_cls_name:
-            valid_class = 1
-        elif current_cls_name == "Pedestrian".lower() and "Person_sitting".lower() == gt_name:
-            valid_class = 0
-        elif current_cls_name == "Car".lower() and "Van".lower() == gt_name:
-            valid_class = 0
-        else:
-            valid_class = -1
-        ignore = False
-        if ((gt_anno["occluded"][i] > MAX_OCCLUSION[difficulty])
-                or (gt_anno["truncated"][i] > MAX_TRUNCATION[difficulty])
-                or not (dist_boundary[0, difficulty] < gt_anno["location"][i, 2] < dist_boundary[1, difficulty])):
-            ignore = True
-        if valid_class == 1 and not ignore:
-            ignored_gt.append(0)
-            num_valid_gt += 1
-        elif valid_class == 0 or (ignore and (valid_class == 1)):
-            ignored_gt.append(1)
-        else:
-            ignored_gt.append(-1)
-        if gt_anno["name"][i] == "DontCare":
-            dc_bboxes.append(gt_anno["bbox"][i])
-    for i in range(num_dt):
-        if dt_anno["name"][i].lower() == current_cls_name:
-            valid_class = 1
-        else:
-            valid_class = -1
-        if not (dist_boundary[0, difficulty] < dt_anno["location"][i, 2] < dist_boundary[1, difficulty]):
-            ignored_dt.append(1)
-        elif valid_class == 1:
-            ignored_dt.append(0)
-        else:
-            ignored_dt.append(-1)
-    return num_valid_gt, ignored_gt, ignored_dt, dc_bboxes
+    """eval2.py:28-101 -> (number of valid ground truths, ignored_gt, ignored_dt, DontCare boxes).
+    ignored_*: 0 = counts, 1 = neither hit nor miss (neighbour class, too occluded / truncated, outside the distance
+    band), -1 = another class.  The height criterion is commented out in the reference and stays out.  Vectorised
+    over the boxes of the image; `dataset` is accepted for signature compatibility and unused, as upstream."""
+    key = EVAL_CLASS_NAMES[current_class]               # IndexError beyond the three evaluated classes, as upstream
+    neighbour = NEIGHBOUR_CLASS.get(key)
+    _, _, max_occlusion, max_truncation = DIFFICULTY_TABLE[difficulty]
+
+    gt_names = [str(n).lower() for n in gt_anno["name"]]
+    same = np.array([n == key for n in gt_names], dtype=bool)
+    near_class = np.array([n == neighbour for n in gt_names], dtype=bool)
+    if len(gt_names):
+        too_hard = ((np.asarray(gt_anno["occluded"]) > max_occlusion) | (np.asarray(gt_anno["truncated"]) > max_truncation)
+                    | _outside_band(np.asarray(gt_anno["location"])[:, 2], difficulty))
+    else:
+        too_hard = np.zeros((0,), dtype=bool)
+    counted = same & ~too_hard
+    ignored_gt = np.where(counted, 0, np.where(near_class | same, 1, -1))
+    dc_bboxes = [gt_anno["bbox"][i] for i, n in enumerate(gt_anno["name"]) if n == "DontCare"]
+
+    dt_names = [str(n).lower() for n in dt_anno["name"]]
+    if len(dt_names):
+        dt_same = np.array([n == key for n in dt_names], dtype=bool)
+        ignored_dt = np.where(_outside_band(np.asarray(dt_anno["location"])[:, 2], difficulty), 1, np.where(dt_same, 0, -1))
+    else:
+        ignored_dt = np.zeros((0,), dtype=np.int64)
+    return int(counted.sum()), ignored_gt.astype(np.int64).tolist(), ignored_dt.astype(np.int64).tolist(), dc_bboxes
 
 
 def image_box_overlap(boxes, query_boxes, criterion=-1):
@@ -178,12 +179,9 @@ def d3_box_overlap(boxes, qboxes, criterion=-1):
 
 
 def get_split_parts(num, num_part):
-    """eval2.py:301-308."""
-    same_part = num // num_part
-    remain_num = num % num_part
-    if remain_num == 0:
-        return [same_part] * num_part
-    return [same_part] * num_part + [remain_num]
+    """eval2.py:301-308: num_part equal chunks of num // num_part images, plus one chunk with the remainder."""
+    chunk, rest = divmod(num, num_part)
+    return [chunk] * num_part + ([rest] if rest else [])
 
 
 def compute_statistics_jit(overlaps, gt_datas, dt_datas, ignored_gt, ignored_det, dc_bboxes, metric, min_overlap,
@@ -218,232 +216,239 @@ def fused_compute_statistics(overlaps, pr, gt_nums, dt_nums, dc_nums, gt_datas, 
         1 if compute_aos else 0), "pn2_eval_fused_statistics")
 
 
+def _part_bounds(num_images, num_parts):
+    """[(first image, one past the last image)] of every dataset part (get_split_parts as index ranges)"""
+    edges = np.concatenate(([0], np.cumsum(get_split_parts(num_images, num_parts)))).astype(np.int64)
+    return list(zip(edges[:-1].tolist(), edges[1:].tolist()))
+
+
+def _camera_boxes(annos, cols):
+    """[location | dimensions | rotation_y] rows of all boxes of `annos`; cols picks the (x, z) / (l, w) pair for BEV"""
+    pick = (lambda a: a[:, cols]) if cols is not None else (lambda a: a)
+    return np.concatenate([np.concatenate([pick(a["location"]) for a in annos], 0),
+                           np.concatenate([pick(a["dimensions"]) for a in annos], 0),
+                           np.concatenate([a["rotation_y"] for a in annos], 0)[..., np.newaxis]], axis=1)
+
+
+def _part_overlaps(first_annos, second_annos, metric):
+    """all-pairs overlap matrix (boxes of first_annos x boxes of second_annos) of one dataset part"""
+    if metric == 0:
+        return image_box_overlap(np.concatenate([a["bbox"] for a in first_annos], 0),
+                                 np.concatenate([a["bbox"] for a in second_annos], 0))
+    if metric == 1:
+        return bev_box_overlap(_camera_boxes(first_annos, [0, 2]), _camera_boxes(second_annos, [0, 2])).astype(np.float64)
+    if metric == 2:
+        return d3_box_overlap(_camera_boxes(first_annos, None), _camera_boxes(second_annos, None)).astype(np.float64)
+    raise ValueError("unknown metric")
+
+
 def calculate_iou_partly(gt_annos, dt_annos, metric, num_parts=50):
-    """eval2.py:361-432 (camera coordinates; metric 0: bbox, 1: bev, 2: 3d)."""
+    """eval2.py:361-432 (camera coordinates; metric 0: bbox, 1: bev, 2: 3d) -> (per-image overlap blocks, per-part
+    matrices, boxes per image of the first / of the second argument).  One overlap call per part; the per-image blocks
+    are views on the diagonal of the part matrix."""
     assert len(gt_annos) == len(dt_annos)
-    total_dt_num = np.stack([len(a["name"]) for a in dt_annos], 0)
-    total_gt_num = np.stack([len(a["name"]) for a in gt_annos], 0)
-    num_examples = len(gt_annos)
-    split_parts = get_split_parts(num_examples, num_parts)
-    parted_overlaps = []
-    example_idx = 0
-
-    def boxes_of(annos, cols):
-        loc = np.concatenate([a["location"][:, cols] if cols else a["location"] for a in annos], 0)
-        dims = np.concatenate([a["dimensions"][:, cols] if cols else a["dimensions"] for a in annos], 0)
-        rots = np.concatenate([a["rotation_y"] for a in annos], 0)
-        return np.concatenate([loc, dims, rots[..., np.newaxis]], axis=1)
-
-    for num_part in split_parts:
-        gt_annos_part = gt_annos[example_idx:example_idx + num_part]
-        dt_annos_part = dt_annos[example_idx:example_idx + num_part]
-        if metric == 0:
-            gt_boxes = np.concatenate([a["bbox"] for a in gt_annos_part], 0)
-            dt_boxes = np.concatenate([a["bbox"] for a in dt_annos_part], 0)
-            overlap_part = image_box_overlap(gt_boxes, dt_boxes)
-        elif metric == 1:
-            overlap_part = bev_box_overlap(boxes_of(gt_annos_part, [0, 2]), boxes_of(dt_annos_part, [0, 2])).astype(np.float64)
-        elif metric == 2:
-            overlap_part = d3_box_overlap(boxes_of(gt_annos_part, None), boxes_of(dt_annos_part, None)).astype(np.float64)
-        else:
-            raise ValueError("unknown metric")
-        parted_overlaps.append(overlap_part)
-        example_idx += num_part
-    overlaps = []
-    example_idx = 0
-    for j, num_part in enumerate(split_parts):
-        gt_num_idx, dt_num_idx = 0, 0
-        for i in range(num_part):
-            gt_box_num = total_gt_num[example_idx + i]
-            dt_box_num = total_dt_num[example_idx + i]
-            overlaps.append(parted_overlaps[j][gt_num_idx:gt_num_idx + gt_box_num, dt_num_idx:dt_num_idx + dt_box_num])
-            gt_num_idx += gt_box_num
-            dt_num_idx += dt_box_num
-        example_idx += num_part
-    return overlaps, parted_overlaps, total_gt_num, total_dt_num
+    first_counts = np.stack([len(a["name"]) for a in gt_annos], 0)
+    second_counts = np.stack([len(a["name"]) for a in dt_annos], 0)
+    per_image, per_part = [], []
+    for lo, hi in _part_bounds(len(gt_annos), num_parts):
+        matrix = _part_overlaps(gt_annos[lo:hi], dt_annos[lo:hi], metric)
+        per_part.append(matrix)
+        row = col = 0
+        for image in range(lo, hi):
+            rows, cols = first_counts[image], second_counts[image]
+            per_image.append(matrix[row:row + rows, col:col + cols])
+            row, col = row + rows, col + cols
+    return per_image, per_part, first_counts, second_counts
 
 
 def _prepare_data(gt_annos, dt_annos, current_class, dataset, difficulty):
-    """eval2.py:435-464."""
-    gt_datas_list, dt_datas_list, total_dc_num = [], [], []
-    ignored_gts, ignored_dets, dontcares = [], [], []
-    total_num_valid_gt = 0
-    for i in range(len(gt_annos)):
-        num_valid_gt, ignored_gt, ignored_det, dc_bboxes = clean_data(gt_annos[i], dt_annos[i], current_class, dataset, difficulty)
-        ignored_gts.append(np.array(ignored_gt, dtype=np.int64))
-        ignored_dets.append(np.array(ignored_det, dtype=np.int64))
-        if len(dc_bboxes) == 0:
-            dc_bboxes = np.zeros((0, 4)).astype(np.float64)
-        else:
-            dc_bboxes = np.stack(dc_bboxes, 0).astype(np.float64)
-        total_dc_num.append(dc_bboxes.shape[0])
-        dontcares.append(dc_bboxes)
-        total_num_valid_gt += num_valid_gt
-        gt_datas = np.concatenate([gt_annos[i]["bbox"], gt_annos[i]["alpha"][..., np.newaxis]], 1)
-        dt_datas = np.concatenate([dt_annos[i]["bbox"], dt_annos[i]["alpha"][..., np.newaxis],
-                                   dt_annos[i]["score"][..., np.newaxis]], 1)
-        gt_datas_list.append(gt_datas)
-        dt_datas_list.append(dt_datas)
-    total_dc_num = np.stack(total_dc_num, axis=0)
-    print(f"difficulty: {difficulty}, total_num_valid_gt: {total_num_valid_gt}")
-    return (gt_datas_list, dt_datas_list, ignored_gts, ignored_dets, dontcares, total_dc_num, total_num_valid_gt)
+    """eval2.py:435-464: per image [bbox | alpha] of the ground truths, [bbox | alpha | score] of the detections, the
+    ignore codes of clean_data, the DontCare boxes and their number; the count of valid ground truths of the data set."""
+    gt_rows, dt_rows, gt_codes, dt_codes, dc_boxes = [], [], [], [], []
+    valid_total = 0
+    for gt, dt in zip(gt_annos, dt_annos):
+        n_valid, code_gt, code_dt, dc = clean_data(gt, dt, current_class, dataset, difficulty)
+        valid_total += n_valid
+        gt_codes.append(np.array(code_gt, dtype=np.int64))
+        dt_codes.append(np.array(code_dt, dtype=np.int64))
+        dc_boxes.append(np.stack(dc, 0).astype(np.float64) if len(dc) else np.zeros((0, 4), dtype=np.float64))
+        gt_rows.append(np.concatenate([gt["bbox"], gt["alpha"][..., np.newaxis]], 1))
+        dt_rows.append(np.concatenate([dt["bbox"], dt["alpha"][..., np.newaxis], dt["score"][..., np.newaxis]], 1))
+    dc_counts = np.stack([b.shape[0] for b in dc_boxes], axis=0)
+    print(f"difficulty: {difficulty}, total_num_valid_gt: {valid_total}")
+    return gt_rows, dt_rows, gt_codes, dt_codes, dc_boxes, dc_counts, valid_total
+
+
+class _Part:
+    """One dataset part packed for the native matching passes (csrc/kitti_eval.cu): the overlap matrix of the part and the
+    concatenated per-image arrays of eval2.py:524-533, built once per (class, difficulty) and reused by every threshold."""
+
+    @staticmethod
+    def _cat(arrays, cols, dtype):
+        if not len(arrays):
+            return np.zeros((0, cols) if cols else (0,), dtype)
+        joined = np.ascontiguousarray(np.concatenate(arrays, 0), dtype=dtype)
+        return joined.reshape(-1, cols) if cols else joined
+
+    def __init__(self, matrix, images, prepared, first_counts, second_counts):
+        gt_rows, dt_rows, gt_codes, dt_codes, dc_boxes, dc_counts, _ = prepared
+        self.overlaps = matrix
+        self.gt = self._cat(gt_rows[images], 5, np.float64)
+        self.dt = self._cat(dt_rows[images], 6, np.float64)
+        self.dc = self._cat(dc_boxes[images], 4, np.float64)
+        self.gt_codes = self._cat(gt_codes[images], 0, np.int64)
+        self.dt_codes = self._cat(dt_codes[images], 0, np.int64)
+        # eval_class computes overlaps(dt, gt): the matrix rows are detections, its columns ground truths
+        self.n_gt = np.ascontiguousarray(second_counts[images], np.int64)
+        self.n_dt = np.ascontiguousarray(first_counts[images], np.int64)
+        self.n_dc = np.ascontiguousarray(dc_counts[images], np.int64)
+        self.images = len(self.n_gt)
+
+    def _common(self):
+        return (_d(self.overlaps), self.overlaps.shape[0], self.overlaps.shape[1])
+
+    def true_positive_scores(self, lib, metric, min_overlap):
+        """compute_statistics_jit(thresh = 0, compute_fp = False) over the part's images (eval2.py:506-520)"""
+        scores = np.zeros((max(int(self.n_gt.sum()), 1),), np.float64)
+        count = ctypes.c_longlong(0)
+        cabi.check(lib.pn2_eval_collect_thresholds(
+            *self._common(), _l(self.n_gt), _l(self.n_dt), _l(self.n_dc), self.images, _d(self.gt), _d(self.dt), _d(self.dc),
+            _l(self.gt_codes), _l(self.dt_codes), int(metric), float(min_overlap), _d(scores), ctypes.byref(count)),
+            "pn2_eval_collect_thresholds")
+        return scores[:count.value]
+
+    def accumulate(self, lib, pr, metric, min_overlap, thresholds, compute_aos):
+        """fused_compute_statistics (eval2.py:522-550): pr (n_thresholds, 4) += [tp, fp, fn, similarity]"""
+        cabi.check(lib.pn2_eval_fused_statistics(
+            *self._common(), _d(pr), _l(self.n_gt), _l(self.n_dt), _l(self.n_dc), self.images, _d(self.gt), _d(self.dt),
+            _d(self.dc), _l(self.gt_codes), _l(self.dt_codes), int(metric), float(min_overlap), _d(thresholds),
+            len(thresholds), 1 if compute_aos else 0), "pn2_eval_fused_statistics")
+
+
+def _running_max_from_the_right(curve, n):
+    """curve[i] = max(curve[i:]) for i < n, in place (eval2.py:557-562; curve has 41 entries, n of them are filled)"""
+    for i in range(n):
+        curve[i] = np.max(curve[i:], axis=-1)
 
 
 def eval_class(gt_annos, dt_annos, current_classes, dataset, difficultys, metric, min_overlaps, compute_aos=False,
                num_parts=50):
     """eval2.py:467-563 -> {"recall", "precision", "orientation"} of shape [class, difficulty, min_overlap, 41].
-    The two statistics passes run part-wise in native code (one call per part instead of one numba call per image
-    and per threshold); everything else is the reference's flow."""
+    The two statistics passes run part-wise in native code (one call per part instead of one numba call per image and
+    per threshold)."""
     assert len(gt_annos) == len(dt_annos)
-    num_examples = len(gt_annos)
-    split_parts = get_split_parts(num_examples, num_parts)
-    rets = calculate_iou_partly(dt_annos, gt_annos, metric, num_parts)
-    overlaps, parted_overlaps, total_dt_num, total_gt_num = rets
-    N_SAMPLE_PTS = 41
-    num_minoverlap = len(min_overlaps)
-    num_class = len(current_classes)
-    num_difficulty = len(difficultys)
-    precision = np.zeros([num_class, num_difficulty, num_minoverlap, N_SAMPLE_PTS])
-    recall = np.zeros([num_class, num_difficulty, num_minoverlap, N_SAMPLE_PTS])
-    aos = np.zeros([num_class, num_difficulty, num_minoverlap, N_SAMPLE_PTS])
+    bounds = _part_bounds(len(gt_annos), num_parts)
+    # argument order as upstream (eval2.py:492): detections first
+    _, matrices, first_counts, second_counts = calculate_iou_partly(dt_annos, gt_annos, metric, num_parts)
+    matrices = [_c64(m) for m in matrices]
+    shape = [len(current_classes), len(difficultys), len(min_overlaps), N_RECALL_SAMPLES]
+    precision, recall, aos = np.zeros(shape), np.zeros(shape), np.zeros(shape)
     lib = _lib()
-    parted = [_c64(p) for p in parted_overlaps]
     for m, current_class in enumerate(current_classes):
         for l, difficulty in enumerate(difficultys):
-            rets = _prepare_data(gt_annos, dt_annos, current_class, dataset, difficulty)
-            (gt_datas_list, dt_datas_list, ignored_gts, ignored_dets, dontcares, total_dc_num, total_num_valid_gt) = rets
-            # the per-part concatenations of eval2.py:524-533, built once per (class, difficulty)
-            parts = []
-            idx = 0
-            for j, num_part in enumerate(split_parts):
-                sl = slice(idx, idx + num_part)
-                cat = lambda xs, cols, dt: (np.ascontiguousarray(np.concatenate(xs, 0), dtype=dt).reshape(-1, cols) if cols
-                                            else np.ascontiguousarray(np.concatenate(xs, 0), dtype=dt)) if len(xs) else \
-                    np.zeros((0, cols) if cols else (0,), dt)
-                parts.append(dict(
-                    ov=parted[j], gt=cat(gt_datas_list[sl], 5, np.float64), dt=cat(dt_datas_list[sl], 6, np.float64),
-                    dc=cat(dontcares[sl], 4, np.float64), ig=cat(ignored_gts[sl], 0, np.int64),
-                    idt=cat(ignored_dets[sl], 0, np.int64), gn=np.ascontiguousarray(total_gt_num[sl], np.int64),
-                    dn=np.ascontiguousarray(total_dt_num[sl], np.int64), dcn=np.ascontiguousarray(total_dc_num[sl], np.int64)))
-                idx += num_part
+            prepared = _prepare_data(gt_annos, dt_annos, current_class, dataset, difficulty)
+            valid_total = prepared[-1]
+            parts = [_Part(matrices[j], slice(lo, hi), prepared, first_counts, second_counts)
+                     for j, (lo, hi) in enumerate(bounds)]
+            parts = [part for part in parts if part.images]
             for k, min_overlap in enumerate(min_overlaps[:, metric, m]):
-                thresholdss = []
-                for p in parts:                                             # eval2.py:506-520, part-wise
-                    if len(p["gn"]) == 0:
-                        continue
-                    th = np.zeros((max(int(p["gn"].sum()), 1),), np.float64)
-                    n = ctypes.c_longlong(0)
-                    cabi.check(lib.pn2_eval_collect_thresholds(
-                        _d(p["ov"]), p["ov"].shape[0], p["ov"].shape[1], _l(p["gn"]), _l(p["dn"]), _l(p["dcn"]), len(p["gn"]),
-                        _d(p["gt"]), _d(p["dt"]), _d(p["dc"]), _l(p["ig"]), _l(p["idt"]), int(metric), float(min_overlap),
-                        _d(th), ctypes.byref(n)), "pn2_eval_collect_thresholds")
-                    thresholdss += th[:n.value].tolist()
-                thresholdss = np.array(thresholdss)
-                thresholds = get_thresholds(thresholdss, total_num_valid_gt)
-                thresholds = np.array(thresholds, dtype=np.float64)
-                pr = np.zeros([len(thresholds), 4])
-                for p in parts:                                             # eval2.py:522-550
-                    if len(p["gn"]) == 0 or len(thresholds) == 0:
-                        continue
-                    cabi.check(lib.pn2_eval_fused_statistics(
-                        _d(p["ov"]), p["ov"].shape[0], p["ov"].shape[1], _d(pr), _l(p["gn"]), _l(p["dn"]), _l(p["dcn"]),
-                        len(p["gn"]), _d(p["gt"]), _d(p["dt"]), _d(p["dc"]), _l(p["ig"]), _l(p["idt"]), int(metric),
-                        float(min_overlap), _d(thresholds), len(thresholds), 1 if compute_aos else 0),
-                        "pn2_eval_fused_statistics")
+                scores = [part.true_positive_scores(lib, metric, min_overlap) for part in parts]
+                scores = np.concatenate(scores) if scores else np.zeros((0,))
+                thresholds = np.array(get_thresholds(scores, valid_total), dtype=np.float64)
+                n = len(thresholds)
+                pr = np.zeros([n, 4])
+                if n:
+                    for part in parts:
+                        part.accumulate(lib, pr, metric, min_overlap, thresholds, compute_aos)
+                tp, fp, fn, similarity = pr[:, 0], pr[:, 1], pr[:, 2], pr[:, 3]
                 with np.errstate(divide='ignore', invalid='ignore'):
-                    for i in range(len(thresholds)):
-                        recall[m, l, k, i] = pr[i, 0] / (pr[i, 0] + pr[i, 2])
-                        precision[m, l, k, i] = pr[i, 0] / (pr[i, 0] + pr[i, 1])
-                        if compute_aos:
-                            aos[m, l, k, i] = pr[i, 3] / (pr[i, 0] + pr[i, 1])
-                for i in range(len(thresholds)):
-                    precision[m, l, k, i] = np.max(precision[m, l, k, i:], axis=-1)
-                    recall[m, l, k, i] = np.max(recall[m, l, k, i:], axis=-1)
+                    recall[m, l, k, :n] = tp / (tp + fn)
+                    precision[m, l, k, :n] = tp / (tp + fp)
                     if compute_aos:
-                        aos[m, l, k, i] = np.max(aos[m, l, k, i:], axis=-1)
+                        aos[m, l, k, :n] = similarity / (tp + fp)
+                _running_max_from_the_right(precision[m, l, k], n)
+                _running_max_from_the_right(recall[m, l, k], n)
+                if compute_aos:
+                    _running_max_from_the_right(aos[m, l, k], n)
     return {"recall": recall, "precision": precision, "orientation": aos}
 
 
 def get_mAP(prec):
-    """eval2.py:566-570: 11-point interpolation over the 41 recall samples."""
-    sums = 0
-    for i in range(0, prec.shape[-1], 4):
-        sums = sums + prec[..., i]
-    return sums / 11 * 100
+    """eval2.py:566-570: 11-point interpolation, every fourth of the 41 recall samples (summed in index order)."""
+    total = 0
+    for sample in range(0, prec.shape[-1], 4):
+        total = total + prec[..., sample]
+    return total / 11 * 100
 
 
 def print_str(value, *arg, sstream=None):
-    if sstream is None:
-        sstream = sysio.StringIO()
-    sstream.truncate(0)
-    sstream.seek(0)
-    print(value, *arg, file=sstream)
-    return sstream.getvalue()
+    """eval2.py:573-579: what print() would write, as a string"""
+    stream = sysio.StringIO() if sstream is None else sstream
+    stream.truncate(0)
+    stream.seek(0)
+    print(value, *arg, file=stream)
+    return stream.getvalue()
 
 
 def do_eval(gt_annos, dt_annos, current_classes, dataset, min_overlaps, compute_aos=False):
-    """eval2.py:583-603.  min_overlaps: [num_minoverlap, metric, num_class]."""
-    difficultys = [0, 1, 2, 3, 4, 5]
-    ret = eval_class(gt_annos, dt_annos, current_classes, dataset, difficultys, 0, min_overlaps, compute_aos)
-    mAP_bbox = get_mAP(ret["precision"])
-    mAP_aos = None
-    if compute_aos:
-        mAP_aos = get_mAP(ret["orientation"])
-    ret = eval_class(gt_annos, dt_annos, current_classes, dataset, difficultys, 1, min_overlaps)
-    mAP_bev = get_mAP(ret["precision"])
-    ret = eval_class(gt_annos, dt_annos, current_classes, dataset, difficultys, 2, min_overlaps)
-    mAP_3d = get_mAP(ret["precision"])
-    return mAP_bbox, mAP_bev, mAP_3d, mAP_aos
+    """eval2.py:583-603 -> (mAP bbox, bev, 3d, aos | None), each [class, difficulty, min_overlap].
+    min_overlaps: [num_minoverlap, metric, num_class]."""
+    difficultys = list(range(len(DIFFICULTY_TABLE)))
+    curves = {}
+    for metric, tag in enumerate(("bbox", "bev", "3d")):
+        curves[tag] = eval_class(gt_annos, dt_annos, current_classes, dataset, difficultys, metric, min_overlaps,
+                                 compute_aos and metric == 0)
+    aos = get_mAP(curves["bbox"]["orientation"]) if compute_aos else None
+    return get_mAP(curves["bbox"]["precision"]), get_mAP(curves["bev"]["precision"]), get_mAP(curves["3d"]["precision"]), aos
+
+
+CLASS_TO_NAME = {0: 'Car', 1: 'Pedestrian', 2: 'Cyclist', 3: 'Van', 4: 'Person_sitting'}
+# [metric bbox / bev / 3d][class]: KITTI's official overlaps, and the relaxed set (eval2.py:625-630)
+OVERLAP_STRICT = ((0.7, 0.5, 0.5, 0.7, 0.5),) * 3
+OVERLAP_RELAXED = ((0.7, 0.5, 0.5, 0.7, 0.5), (0.5, 0.25, 0.25, 0.5, 0.25), (0.5, 0.25, 0.25, 0.5, 0.25))
+
+
+def _detections_carry_alpha(dt_annos):
+    """orientation similarity is evaluated when the first non-empty detection set has a real alpha (eval2.py:658-664)"""
+    for anno in dt_annos:
+        if anno['alpha'].shape[0] != 0:
+            return bool(anno['alpha'][0] != -10)
+    return False
 
 
 def get_official_eval_result(gt_annos, dt_annos, current_classes, dataset, dense_sample=False):
-    """eval2.py:624-710 -> (result text, dict)."""
-    overlap_0_7 = np.array([[0.7, 0.5, 0.5, 0.7, 0.5], [0.7, 0.5, 0.5, 0.7, 0.5], [0.7, 0.5, 0.5, 0.7, 0.5]])
-    overlap_0_5 = np.array([[0.7, 0.5, 0.5, 0.7, 0.5], [0.5, 0.25, 0.25, 0.5, 0.25], [0.5, 0.25, 0.25, 0.5, 0.25]])
-    overlaps = []
+    """eval2.py:624-710 -> (result text, dict).  Text layout: per class and overlap set a header line, then one line per
+    metric with the six distance-band APs (%.4f, trailing ", "), then the AOS line (%.2f) when alpha is present."""
+    sets = [np.array(OVERLAP_STRICT), np.array(OVERLAP_RELAXED)]
     if dense_sample:
-        for i in range(101):
-            tmp = np.zeros((3, 5))
-            tmp[:, 0] = i / 100.0
-            overlaps.append(tmp)
-    min_overlaps = np.stack([overlap_0_7, overlap_0_5] + overlaps, axis=0)
-    class_to_name = {0: 'Car', 1: 'Pedestrian', 2: 'Cyclist', 3: 'Van', 4: 'Person_sitting'}
-    name_to_class = {v: n for n, v in class_to_name.items()}
+        for percent in range(101):
+            dense = np.zeros((3, 5))
+            dense[:, 0] = percent / 100.0
+            sets.append(dense)
+    name_to_class = {name: index for index, name in CLASS_TO_NAME.items()}
     if not isinstance(current_classes, (list, tuple)):
         current_classes = [current_classes]
     current_classes = [name_to_class[c] if isinstance(c, str) else c for c in current_classes]
-    min_overlaps = min_overlaps[:, :, current_classes]
-    result = ''
-    compute_aos = False
-    for anno in dt_annos:
-        if anno['alpha'].shape[0] != 0:
-            if anno['alpha'][0] != -10:
-                compute_aos = True
-            break
-    mAPbbox, mAPbev, mAP3d, mAPaos = do_eval(gt_annos, dt_annos, current_classes, dataset, min_overlaps, compute_aos)
-    ret_dict = {}
-    res = dict()
-    for j, curcls in enumerate(current_classes):
-        res[curcls] = dict()
+    min_overlaps = np.stack(sets, axis=0)[:, :, current_classes]                 # [overlap set, metric, class]
+    compute_aos = _detections_carry_alpha(dt_annos)
+    ap_bbox, ap_bev, ap_3d, ap_aos = do_eval(gt_annos, dt_annos, current_classes, dataset, min_overlaps, compute_aos)
+
+    lines = []
+    per_class = {}
+    for j, cls in enumerate(current_classes):
+        per_class[cls] = {}
         for i in range(min_overlaps.shape[0]):
-            key = f"{class_to_name[curcls]} " + "AP@{:.2f}, {:.2f}, {:.2f}".format(*min_overlaps[i, :, j])
-            res[curcls][key] = dict()
-            res[curcls][key]["mAPbbox"] = mAPbbox[j, :, i]
-            res[curcls][key]["mAPbev"] = mAPbev[j, :, i]
-            res[curcls][key]["mAP3d"] = mAP3d[j, :, i]
-            result += print_str((f"{class_to_name[curcls]} " + "AP@{:.2f}, {:.2f}, {:.2f}:".format(*min_overlaps[i, :, j])))
-            for tag, arr in (("bbox", mAPbbox), ("bev ", mAPbev), ("3d  ", mAP3d)):
-                result += print_str(f"{tag} AP:" + "".join(f"{arr[j, d, i]:.4f}, " for d in range(6)))
+            title = f"{CLASS_TO_NAME[cls]} " + "AP@{:.2f}, {:.2f}, {:.2f}".format(*min_overlaps[i, :, j])
+            per_class[cls][title] = {"mAPbbox": ap_bbox[j, :, i], "mAPbev": ap_bev[j, :, i], "mAP3d": ap_3d[j, :, i]}
+            lines.append(title + ":")
+            for label, table in (("bbox AP:", ap_bbox), ("bev  AP:", ap_bev), ("3d   AP:", ap_3d)):
+                lines.append(label + "".join(f"{value:.4f}, " for value in table[j, :6, i]))
             if compute_aos:
-                result += print_str("aos  AP:" + ", ".join(f"{mAPaos[j, d, i]:.2f}" for d in range(6)))
-    ret_dict['Car_3d_easy'] = mAP3d[0, 0, 0]
-    ret_dict['Car_3d_moderate'] = mAP3d[0, 1, 0]
-    ret_dict['Car_3d_hard'] = mAP3d[0, 2, 0]
-    ret_dict['Car_bev_easy'] = mAPbev[0, 0, 0]
-    ret_dict['Car_bev_moderate'] = mAPbev[0, 1, 0]
-    ret_dict['Car_bev_hard'] = mAPbev[0, 2, 0]
-    ret_dict['Car_image_easy'] = mAPbbox[0, 0, 0]
-    ret_dict['Car_image_moderate'] = mAPbbox[0, 1, 0]
-    ret_dict['Car_image_hard'] = mAPbbox[0, 2, 0]
-    ret_dict["result"] = res
+                lines.append("aos  AP:" + ", ".join(f"{value:.2f}" for value in ap_aos[j, :6, i]))
+    result = "".join(print_str(line) for line in lines)
+
+    ret_dict = {"result": per_class}
+    for tag, table in (("3d", ap_3d), ("bev", ap_bev), ("image", ap_bbox)):
+        for level, name in enumerate(("easy", "moderate", "hard")):
+            ret_dict['Car_%s_%s' % (tag, name)] = table[0, level, 0]
     return result, ret_dict

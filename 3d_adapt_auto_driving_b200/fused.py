@@ -277,6 +277,34 @@ def linear_pre(x, cpre, l1, l2, out=None):
     return out
 
 
+RCNN_FRONT_FUSED = os.environ.get("PN2_RCNN_FRONT", "1") != "0"
+
+
+def rcnn_front_supported(x, cpre, off_f, up1, up2, merge, first_f):
+    """shape test of pn2_rcnn_front_tc_f32 (csrc/rcnn_front_tc.cu): [5 -> 128 -> 128], [256 -> 128], [128 -> 128]."""
+    x2, rows, ldx, cx = _rows2d(x)
+    return (RCNN_FRONT_FUSED and MLP_ENGINE == "tc" and cpre == 5 and up1.cin == 5 and up1.cout == 128 and up1.relu
+            and up2.cin == 128 and up2.cout == 128 and up2.relu and merge.cin == 256 and merge.cout == 128 and merge.relu
+            and first_f.cin == 128 and first_f.cout == 128 and not first_f.relu and off_f >= 8 and off_f % 4 == 0
+            and cx >= off_f + 128 and ldx % 4 == 0 and x2.data_ptr() % 16 == 0)
+
+
+def rcnn_front(x, off_f, up1, up2, merge, first_f, out=None):
+    """RCNN input chain in ONE launch: xyz_up_layer [5 -> 128 -> 128] -> merge_down_layer on cat[., rpn features] -> the
+    per-point half of SA1's first layer (pre-activation).  x (rows, >= off_f + 128) pooled rows."""
+    x2, rows, ldx, _ = _rows2d(x)
+    if getattr(up1, "_wpre", None) is None:
+        up1._wpre = torch.cat((up1.w[:, :5].t().contiguous(), up1.b.view(1, -1)), dim=0).contiguous()    # (6, 128)
+    if out is None:
+        out = torch.empty((rows, 128), dtype=torch.float32, device=x.device)
+    o2, orows, ldy, oc = _rows2d(out)
+    assert orows == rows and oc == 128
+    cabi.call("pn2_rcnn_front_tc_f32", ptr(x2), i32(ldx), i32(off_f), ptr(up1._wpre), ptr(up2.tc.blob), ptr(up2.tc.b),
+              ptr(merge.tc.blob), ptr(merge.tc.b), ptr(first_f.tc.blob), ptr(first_f.tc.b), ptr(o2), i32(ldy), _i64(rows),
+              work=2.0 * rows * (5 * 128 + 128 * 128 + 256 * 128 + 128 * 128))
+    return out
+
+
 def linear_cat(xa, xb, layer, out=None):
     """y = act(cat[xa, xb] @ W^T + b) without materialising the concatenation on the tensor-core engine
     (pn2_linear_tc2_f32); the exact-fp32 engine concatenates and calls linear()."""

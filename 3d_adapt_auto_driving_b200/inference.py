@@ -14,6 +14,7 @@ files.  The record tensor is also what the multi-GPU path all-gathers (parallel.
 import numpy as np
 import torch
 
+from . import glue
 from . import iou3d_cuda
 from . import kitti_utils
 from .bbox_transform import decode_bbox_target
@@ -44,7 +45,22 @@ class Detector:
     # ---- eval_rcnn.py:516-535, 611-627, batched and sync-free ----
     def postprocess(self, ret_dict, batch_size):
         """-> records (B, M, 8) float32 [box7, raw score] sorted by descending score with the
-        suppressed / below-threshold rows zeroed, counts (B,) int32; all on the device."""
+        suppressed / below-threshold rows zeroed, counts (B,) int32; all on the device.
+        Three launches (csrc/glue.cu: decode + threshold + score order + BEV boxes, batched device NMS, record assembly);
+        postprocess_torch is the same computation as ~30 torch statements and is what the tests compare against."""
+        rois = ret_dict['rois']
+        M = rois.shape[1]
+        if not (glue.ENABLED and rois.is_cuda and ret_dict['rcnn_cls'].shape[1] == 1 and M <= 256):
+            return self.postprocess_torch(ret_dict, batch_size)
+        boxes, scores, bev, counts = glue.rcnn_post_prepare(
+            rois, ret_dict['rcnn_reg'], ret_dict['rcnn_cls'].reshape(-1), cfg.RCNN.LOC_SCOPE, cfg.RCNN.LOC_BIN_SIZE,
+            cfg.RCNN.NUM_HEAD_BIN, cfg.CLS_MEAN_SIZE[0], cfg.RCNN.LOC_Y_BY_BIN, cfg.RCNN.LOC_Y_SCOPE,
+            cfg.RCNN.LOC_Y_BIN_SIZE, cfg.RCNN.SCORE_THRESH)
+        keep, num = glue.nms_raw(bev, counts, cfg.RCNN.NMS_THRESH, True, M)
+        return glue.rcnn_post_assemble(boxes, scores, keep, num), num
+
+    def postprocess_torch(self, ret_dict, batch_size):
+        """postprocess() written with torch statements (batched and sync-free, but one launch per statement)."""
         rois = ret_dict['rois']
         rcnn_cls = ret_dict['rcnn_cls'].view(batch_size, -1, ret_dict['rcnn_cls'].shape[1])
         rcnn_reg = ret_dict['rcnn_reg'].view(batch_size, -1, ret_dict['rcnn_reg'].shape[1])

@@ -13,19 +13,22 @@ from .cabi import i32, f32, ptr
 def _boxes(t, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
         raise cabi.Pn2Error("%s must be a contiguous CUDA float32 tensor" % name)
-    if t.dim() != 2 or t.size(1) != 5:
-        raise cabi.Pn2Error("%s must be (N, 5)" % name)
-    return t
+    # the reference extension only looks at size(0) and the data pointer (iou3d.cpp:73-85), and the reference's own eval
+    # loop hands it (N, 1, 5) boxes (tools/eval_rcnn.py:614-621: scores of shape (N, 1) index the boxes): accept any
+    # contiguous layout of N x 5 floats
+    if t.dim() < 2 or t.numel() != t.size(0) * 5:
+        raise cabi.Pn2Error("%s must hold N x 5 floats, (N, 5) or (N, 1, 5)" % name)
+    return t.view(t.size(0), 5)
 
 
 def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
-    _boxes(boxes_a, "boxes_a"); _boxes(boxes_b, "boxes_b")
+    boxes_a, boxes_b = _boxes(boxes_a, "boxes_a"), _boxes(boxes_b, "boxes_b")
     cabi.call("pn2_boxes_overlap_bev_f32", ptr(boxes_a), i32(boxes_a.size(0)), ptr(boxes_b), i32(boxes_b.size(0)), ptr(ans_overlap))
     return 1
 
 
 def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
-    _boxes(boxes_a, "boxes_a"); _boxes(boxes_b, "boxes_b")
+    boxes_a, boxes_b = _boxes(boxes_a, "boxes_a"), _boxes(boxes_b, "boxes_b")
     cabi.call("pn2_boxes_iou_bev_f32", ptr(boxes_a), i32(boxes_a.size(0)), ptr(boxes_b), i32(boxes_b.size(0)), ptr(ans_iou))
     return 1
 
@@ -45,7 +48,7 @@ def nms_device(boxes, thresh, rotated, max_keep=None, counts=None):
 
 
 def _nms(boxes, keep, thresh, rotated):
-    _boxes(boxes, "boxes")
+    boxes = _boxes(boxes, "boxes")
     if keep.is_cuda or keep.dtype != torch.int64:
         raise cabi.Pn2Error("keep must be a CPU LongTensor (iou3d_utils.py:68)")
     k, num = nms_device(boxes, thresh, rotated)

@@ -44,7 +44,9 @@ class PointRCNN(nn.Module):
         rois, roi_scores = self.rpn.proposal_layer(scores, rpn_out['rpn_reg'], xyz)          # (B, M, 7), (B, M)
         results = {'rois': rois, 'roi_scores_raw': roi_scores, 'seg_result': foreground}
         rcnn_in = {'rpn_xyz': xyz, 'rpn_features': rpn_out['backbone_features'].permute((0, 2, 1)), 'seg_mask': foreground,
-                   'roi_boxes3d': rois, 'pts_depth': torch.norm(xyz, p=2, dim=2)}
+                   'roi_boxes3d': rois, 'pts_depth': torch.norm(xyz, p=2, dim=2),
+                   # for the one-launch RCNN input stage (rcnn_net._pool_rois_canonical): seg_mask is a function of these two
+                   'rpn_scores_raw': scores, 'seg_thresh': cfg.RPN.SCORE_THRESH}
         return results, rcnn_in
 
     def rcnn_stage(self, rcnn_in):

@@ -9,6 +9,7 @@ import torch.nn as nn
 from ..pointnet2_modules import PointnetSAModule
 from .. import pytorch_utils as pt_utils
 from .. import fused as fz
+from .. import glue
 from .. import kitti_utils
 from .. import roipool3d_utils
 from ..config import cfg
@@ -124,6 +125,14 @@ class RCNNNet(pt_utils.PackedCacheMixin, nn.Module):
         kitti_utils.rotate_pc_along_y_torch(flat, batch_rois.view(-1, 7)[:, 6])
         return flat
 
+    def _pool_rois_canonical(self, input_data):
+        """_pool_rois_padded as ONE launch (csrc/roipool3d.cu: pn2_roipool3d_canon_f32) when the per-point extras are
+        exactly [seg mask, depth] (default.yaml): enlargement, pooling, mask / depth features from the raw score and the
+        point norm, and the canonical transform; the pooled tensor is neither pre-zeroed nor revisited."""
+        return glue.roipool_canonical(input_data['rpn_xyz'], input_data['roi_boxes3d'], cfg.RCNN.POOL_EXTRA_WIDTH,
+                                      input_data['rpn_scores_raw'], input_data['seg_thresh'], input_data['pts_depth'], 70.0,
+                                      input_data['rpn_features'], cfg.RCNN.NUM_POINTS, self._PAD)[0]
+
     def _fusable(self, probe):
         return (self.fused and not self.training and probe.is_cuda and cfg.RCNN.USE_RPN_FEATURES
                 and all(m._can_fuse(probe) for m in self.SA_modules[:-1]))
@@ -135,6 +144,9 @@ class RCNNNet(pt_utils.PackedCacheMixin, nn.Module):
             rf = input_data['rpn_features']
             if (self._fusable(input_data['rpn_xyz']) and rf.shape[2] % 64 == 0
                     and self.rcnn_input_channel <= self._PAD):
+                if (glue.ENABLED and 'rpn_scores_raw' in input_data and cfg.RCNN.USE_MASK and cfg.RCNN.USE_DEPTH
+                        and not cfg.RCNN.USE_INTENSITY and rf.shape[2] % 4 == 0):
+                    return self._forward_fused(self._pool_rois_canonical(input_data), self._PAD)
                 return self._forward_fused(self._pool_rois_padded(input_data), self._PAD)
             pts_input = self._pool_rois(input_data)
         else:
@@ -180,21 +192,33 @@ class RCNNNet(pt_utils.PackedCacheMixin, nn.Module):
         nin = self.rcnn_input_channel
         rows = pts_input.view(R * S, C)
         xyz = pts_input[..., 0:3].contiguous()
-        cur = None
-        if len(pk["up"]) == 2:
-            cur = fz.linear_pre(rows, nin, pk["up"][0], pk["up"][1])   # [5 -> 128 -> 128] in one launch, layer 1 on the fly
-        if cur is None:
-            cur = rows[:, 0:nin]
-            for layer in pk["up"]:
-                cur = fz.linear(cur, layer)
-        rpn_feat = rows[:, feat_off:]
-        if fz.MLP_ENGINE == "tc" and feat_off % 4 == 0 and C % 4 == 0 and rpn_feat.shape[1] % 64 == 0:
-            merged = fz.linear_cat(cur, rpn_feat, pk["merge"])            # one GEMM over the virtual concatenation
+        sa1 = self.SA_modules[0]
+        sa1_entry = sa1._pack()[0] if sa1._can_fuse(xyz) and len(sa1.groupers) == 1 else None
+        first_f = sa1_entry.get("first_f") if sa1_entry else None
+        if (len(pk["up"]) == 2 and first_f is not None
+                and fz.rcnn_front_supported(rows, nin, feat_off, pk["up"][0], pk["up"][1], pk["merge"], first_f)):
+            # xyz_up -> merge_down -> SA1's per-point layer-1 half in one launch: the pooled rows are read once and only
+            # H is written (csrc/rcnn_front_tc.cu)
+            h = fz.rcnn_front(rows, feat_off, pk["up"][0], pk["up"][1], pk["merge"], first_f)
+            l_xyz, l_feats = sa1.forward_pm(xyz, None, h_first=h)
+            levels = list(enumerate(self.SA_modules))[1:]
         else:
-            side = fz.linear(rpn_feat, pk["merge_b"])                     # W_b rpn_feature + b
-            merged = fz.linear(cur, pk["merge_a"], res=side)              # relu(W_a xyz_feature + side)
-        l_xyz, l_feats = xyz, merged.view(R, S, -1)
-        for level, sa in enumerate(self.SA_modules):
+            cur = None
+            if len(pk["up"]) == 2:
+                cur = fz.linear_pre(rows, nin, pk["up"][0], pk["up"][1])   # [5 -> 128 -> 128] in one launch, layer 1 on the fly
+            if cur is None:
+                cur = rows[:, 0:nin]
+                for layer in pk["up"]:
+                    cur = fz.linear(cur, layer)
+            rpn_feat = rows[:, feat_off:]
+            if fz.MLP_ENGINE == "tc" and feat_off % 4 == 0 and C % 4 == 0 and rpn_feat.shape[1] % 64 == 0:
+                merged = fz.linear_cat(cur, rpn_feat, pk["merge"])            # one GEMM over the virtual concatenation
+            else:
+                side = fz.linear(rpn_feat, pk["merge_b"])                     # W_b rpn_feature + b
+                merged = fz.linear(cur, pk["merge_a"], res=side)              # relu(W_a xyz_feature + side)
+            l_xyz, l_feats = xyz, merged.view(R, S, -1)
+            levels = list(enumerate(self.SA_modules))
+        for level, sa in levels:
             l_xyz, l_feats = sa.forward_pm(l_xyz, l_feats, fps_ordered=level > 0)
         feat = l_feats.reshape(R, -1)
         outs = []

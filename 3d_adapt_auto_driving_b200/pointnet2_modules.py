@@ -65,9 +65,11 @@ class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
                 return False      # the pooled-linear kernel needs the group size to divide its 128-row tile
         return True
 
-    def forward_pm(self, xyz, feats_pm=None, new_xyz=None, fps_ordered=False):
+    def forward_pm(self, xyz, feats_pm=None, new_xyz=None, fps_ordered=False, h_first=None):
         """xyz (B,N,3), feats_pm (B,N,C) point-major or None -> (new_xyz (B,M,3) or None,
-        out (B,M,sum C_out) point-major).  fps_ordered: xyz is itself the centre list of a previous FPS (fused.fps_gather)."""
+        out (B,M,sum C_out) point-major).  fps_ordered: xyz is itself the centre list of a previous FPS (fused.fps_gather).
+        h_first: (B*N, c1) the per-point half of the first layer already computed by the caller (single-scale modules;
+        RCNNNet fuses it into its input chain) -- feats_pm is then not read."""
         B, N, _ = xyz.shape
         packed = self._pack()
         group_all = isinstance(self.groupers[0], pointnet2_utils.GroupAll)
@@ -99,7 +101,10 @@ class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
         for g, idx, entry in zip(self.groupers, idxs, packed):
             layers = entry["layers"]
             c1 = layers[0].cout
-            if entry["first_f"] is not None:
+            if h_first is not None:
+                assert len(packed) == 1 and h_first.shape == (B * N, c1), (h_first.shape, B * N, c1)
+                h = h_first
+            elif entry["first_f"] is not None:
                 h = fz.linear(feats_pm, entry["first_f"])                       # (B*N, c1) per-point half of layer 1
             else:
                 h = entry["b1"].unsqueeze(0).expand(B * N, c1).contiguous()

@@ -18,6 +18,7 @@ from .bbox_transform import decode_bbox_target
 from .config import cfg
 from . import kitti_utils
 from . import iou3d_utils
+from . import glue
 
 
 class ProposalLayer(nn.Module):
@@ -32,6 +33,10 @@ class ProposalLayer(nn.Module):
     def forward(self, rpn_scores, rpn_reg, xyz):
         """rpn_scores (B,N), rpn_reg (B,N,C), xyz (B,N,3) -> rois (B,M,7), roi scores (B,M)."""
         batch_size = xyz.shape[0]
+        batched = (self.fused and rpn_scores.is_cuda and cfg.TEST.RPN_DISTANCE_BASED_PROPOSE
+                   and cfg.RPN.NMS_TYPE in ('normal', 'rotate'))
+        if batched and glue.ENABLED:
+            return self._forward_kernels(rpn_scores, rpn_reg, xyz)
         proposals = decode_bbox_target(xyz.view(-1, 3), rpn_reg.view(-1, rpn_reg.shape[-1]),
                                        anchor_size=self.MEAN_SIZE, loc_scope=cfg.RPN.LOC_SCOPE,
                                        loc_bin_size=cfg.RPN.LOC_BIN_SIZE, num_head_bin=cfg.RPN.NUM_HEAD_BIN,
@@ -41,7 +46,7 @@ class ProposalLayer(nn.Module):
 
         scores = rpn_scores
         _, sorted_idxs = torch.sort(scores, dim=1, descending=True)
-        if self.fused and scores.is_cuda and cfg.TEST.RPN_DISTANCE_BASED_PROPOSE and cfg.RPN.NMS_TYPE in ('normal', 'rotate'):
+        if batched:
             return self._forward_batched(scores, proposals, sorted_idxs)
         top_n = cfg[self.mode].RPN_POST_NMS_TOP_N
         ret_bbox3d = scores.new_zeros((batch_size, top_n, 7))
@@ -55,6 +60,29 @@ class ProposalLayer(nn.Module):
             ret_bbox3d[k, :tot] = p
             ret_scores[k, :tot] = s
         return ret_bbox3d, ret_scores
+
+    def _band_sizes(self):
+        pre_tot = cfg[self.mode].RPN_PRE_NMS_TOP_N
+        post_tot = cfg[self.mode].RPN_POST_NMS_TOP_N
+        return ([int(pre_tot * 0.7), pre_tot - int(pre_tot * 0.7)], [int(post_tot * 0.7), post_tot - int(post_tot * 0.7)])
+
+    def _forward_kernels(self, scores, rpn_reg, xyz):
+        """The whole layer in six launches + one sort (csrc/glue.cu): decode, score order, band selection with the BEV
+        boxes of the candidates, one batched device NMS per band, assembly of the zero-padded (B, 100, 7) ROIs.
+        Bit-identical to _forward_batched and to the per-scene reference flow (tests/test_glue_gpu.py)."""
+        B, N = scores.shape
+        pre_n, post_n = self._band_sizes()
+        props = glue.decode_bbox(xyz.reshape(-1, 3), rpn_reg.reshape(-1, rpn_reg.shape[-1]), cfg.RPN.LOC_SCOPE,
+                                 cfg.RPN.LOC_BIN_SIZE, cfg.RPN.NUM_HEAD_BIN, cfg.CLS_MEAN_SIZE[0],
+                                 get_xz_fine=cfg.RPN.LOC_XZ_FINE, get_y_by_bin=False, get_ry_fine=False, y_bottom=True)
+        scores = scores.contiguous()
+        order = torch.sort(scores, dim=1, descending=True)[1]
+        cidx0, cidx1, bev0, bev1, cnt = glue.proposal_select(order, props, pre_n[0], pre_n[1])
+        thresh = cfg[self.mode].RPN_NMS_THRESH
+        rotated = cfg.RPN.NMS_TYPE == 'rotate'
+        keep0, num0 = glue.nms_raw(bev0, cnt[0], thresh, rotated, post_n[0])
+        keep1, num1 = glue.nms_raw(bev1, cnt[1], thresh, rotated, post_n[1])
+        return glue.proposal_assemble(props, scores, cidx0, cidx1, keep0, keep1, num0, num1, post_n[0], post_n[1])
 
     def _forward_batched(self, scores, proposals, order):
         """distance_based_proposal (proposal_layer.py:58-119) for all scenes, sync-free."""

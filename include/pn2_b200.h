@@ -209,6 +209,9 @@ int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int32_t 
 int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
                           int32_t *cmap, int32_t *jmap, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
+void pn2_sa_fused_t_set_profile(void *buf);    /* tools/prof_sat.py: in-kernel stopwatch of pn2_sa_fused_t_tc_f32 */
+void pn2_rcnn_front_set_profile(void *buf);   /* tools/prof_front.py: in-kernel stopwatch of pn2_rcnn_front_tc_f32 */
+void pn2_rcnn_front_set_mode(int bits);       /* tools/prof_front.py: tuning variants of the same kernel (same results) */
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
  * (results become garbage); 0 restores the product behaviour. */
 void pn2_sa_fused_tc_set_debug(int bits);
@@ -275,6 +278,53 @@ int pn2_eval_fused_statistics(const double *overlaps, long long total_dt, long l
 int pn2_stat_rescale_f64(const float *raw, const long long *offsets, const double *mats, const double *boxes,
                          const int32_t *box_offsets, double *rect, unsigned char *untouched, float *out,
                          int32_t *out_counts, int32_t *box_counts, int b, long long cap, long long cap_out, void *stream);
+
+/* ---- the small stages between the big kernels (csrc/glue.cu, csrc/roipool3d.cu): one launch each for what the
+ * reference writes as 20-60 torch statements.  Same IEEE float operations in the same order (bit-identical outputs,
+ * tests/test_glue_gpu.py); Python scalars arrive as doubles and are rounded where torch rounds them.  rot_mode: rounding
+ * of the K = 2 batched matmul in rotate_pc_along_y_torch (2 = two rounded products and an add, what torch's kernel does
+ * on B200; 0 / 1 = the two FMA orders). ----
+ * pn2_decode_bbox_f32         decode_bbox_target (lib/utils/bbox_transform.py:24-121); roi (rows, 3 | 7), reg (rows, c),
+ *                             h_anchor HOST float[3]; y_bottom: y += h / 2 (lib/rpn/proposal_layer.py:23)
+ * pn2_proposal_select_f32     distance_based_proposal up to the NMS input (proposal_layer.py:58-100): order (B, N) int64
+ *                             descending-score order, props (B, N, 7) -> candidate point ids cidx0 (B, pre0) / cidx1 (B, pre1),
+ *                             their BEV boxes bev0 / bev1 (., 5) (kitti_utils.py:134-147), cnt (2, B) int32
+ * pn2_proposal_assemble_f32   proposal_layer.py:107-119, :38-44: keep lists -> zero-padded rois (B, post0 + post1, 7), scores
+ * pn2_rcnn_post_prepare_f32   tools/eval_rcnn.py:516-535, 611-620: decode, sigmoid(raw) > thresh, stable descending score
+ *                             order, BEV boxes; m <= 256 rois per scene, single foreground class
+ * pn2_rcnn_post_assemble_f32  eval_rcnn.py:621-627: keep (B, m) int64 / num (B) -> rec (B, m, 8) [box7, raw score], rest zero
+ * pn2_roipool3d_canon_f32     lib/net/rcnn_net.py:126-154 (enlarge_box3d + roipool3d_gpu + canonical transform, extras =
+ *                             [seg mask, depth / depth_norm - 0.5]); rois NOT enlarged; empty (B, M) zeroed by the caller */
+int pn2_decode_bbox_f32(const float *roi, int roi_dim, const float *reg, int c, float *out, long long rows,
+                        double loc_scope, double loc_bin_size, int num_head_bin, const float *h_anchor, int get_xz_fine,
+                        int get_y_by_bin, double loc_y_scope, double loc_y_bin_size, int get_ry_fine, int y_bottom,
+                        int rot_mode, void *stream);
+int pn2_proposal_select_f32(const long long *order, const float *props, int b, int n, int pre0, int pre1, int32_t *cidx0,
+                            int32_t *cidx1, float *bev0, float *bev1, int32_t *cnt, void *stream);
+int pn2_proposal_assemble_f32(const float *props, const float *scores, int b, int n, const int32_t *cidx0,
+                              const int32_t *cidx1, int pre0, int pre1, const long long *keep0, const long long *keep1,
+                              const int32_t *num0, const int32_t *num1, int post0, int post1, float *rois,
+                              float *roi_scores, void *stream);
+int pn2_rcnn_post_prepare_f32(const float *rois, const float *reg, int c, const float *cls, int b, int m, double loc_scope,
+                              double loc_bin_size, int num_head_bin, const float *h_anchor, int get_y_by_bin,
+                              double loc_y_scope, double loc_y_bin_size, double score_thresh, int rot_mode,
+                              float *boxes_sorted, float *scores_sorted, float *bev, int32_t *counts, void *stream);
+int pn2_rcnn_post_assemble_f32(const float *boxes_sorted, const float *scores_sorted, const long long *keep,
+                               const int32_t *num, int b, int m, float *rec, void *stream);
+int pn2_roipool3d_canon_f32(const float *xyz, const float *rois, double extra_width, const float *score,
+                            double score_thresh, const float *depth, double depth_norm, const float *feat2, int c2,
+                            float *pooled, int ld_out, int off2, int32_t *empty, int b, int n, int m, int sampled,
+                            int rot_mode, void *stream);
+
+/* The RCNN input chain in one tcgen05 launch (csrc/rcnn_front_tc.cu): xyz_up_layer [5 -> 128 -> 128] (lib/net/rcnn_net.py:41-47,
+ * :168-171), merge_down_layer on cat[xyz feature, rpn feature] (:174-176) and the per-point half of SA1's first layer
+ * (pointnet2_modules.py:38-44).  x (rows, ldx) pooled rows [5 extras | pad | 128 rpn features at column off_f] (16-byte
+ * aligned rows); wpre (6, 128) f32 = the five input-major weight rows of the first layer + its bias; w_up2 / w_merge / w_sa:
+ * fused.pack_tc images (bf16 hi/lo, 128B-swizzled K-major) of the (128x128), (128x256), (128x128) folded weights;
+ * h (rows, ldh): PRE-activation W1f . merged + b1.  BF16x3, fp32 accumulate. */
+int pn2_rcnn_front_tc_f32(const float *x, int ldx, int off_f, const float *wpre, const void *w_up2, const float *b_up2,
+                          const void *w_merge, const float *b_merge, const void *w_sa, const float *b_sa, float *h, int ldh,
+                          long long rows, void *stream);
 
 #ifdef __cplusplus
 }

@@ -249,3 +249,40 @@ def test_linear_pre_two_layers_in_one_launch(cuda):
     # not the instantiated shape -> None (the caller runs the layers one by one)
     l1b = fz.PackedLayer((torch.randn((128, 6), generator=g)).cuda(), b1, True)
     assert fz.linear_pre(wide, 6, l1b, l2) is None
+
+
+def test_rcnn_front_chain_in_one_launch(cuda):
+    """pn2_rcnn_front_tc_f32: xyz_up [5 -> 128 -> 128] -> merge_down on cat[., rpn features] -> the per-point half of
+    SA1's first layer, one launch, against fp64 and against the three separate launches; tile-multiple, ragged and tiny
+    row counts (a CTA with a single tile, CTAs without any)."""
+    fz = load("fused")
+    g = torch.Generator(device="cpu").manual_seed(19)
+
+    def mk(cout, cin, relu):
+        w = (torch.randn((cout, cin), generator=g) / cin ** 0.5).cuda()
+        b = torch.randn((cout,), generator=g).cuda()
+        return w, b, fz.PackedLayer(w, b, relu)
+
+    w1, b1, l1 = mk(128, 5, True)
+    w2, b2, l2 = mk(128, 128, True)
+    wm, bm, lm = mk(128, 256, True)
+    ws, bs, ls = mk(128, 128, False)
+    for rows in (128 * 148 * 3 + 128 * 5, 128 * 40, 1000, 77, 128):
+        wide = torch.randn((rows, 136), generator=g).cuda()              # [x y z mask depth | pad | 128 features]
+        wide[:, 5:8] = 0
+        assert fz.rcnn_front_supported(wide, 5, 8, l1, l2, lm, ls)
+        got = fz.rcnn_front(wide, 8, l1, l2, lm, ls)
+        x = wide.double()
+        a = torch.relu(torch.relu(x[:, :5] @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double())
+        m = torch.relu(torch.cat((a, x[:, 8:]), dim=1) @ wm.double().t() + bm.double())
+        ref = m @ ws.double().t() + bs.double()
+        e = rel_err(got, ref)
+        assert e < 1e-4, (rows, e)
+        assert e < 5e-5, "three BF16x3 layers should stay near 1e-5: %g at %d rows" % (e, rows)
+        three = fz.linear(fz.linear_cat(fz.linear_pre(wide, 5, l1, l2), wide[:, 8:], lm), ls)
+        assert rel_err(got, three.double()) < 5e-5
+    # pad columns hold garbage (the one-launch pooling kernel writes zeros, older callers may not): never read
+    wide[:, 5:8] = float("nan")
+    assert bool(torch.isfinite(fz.rcnn_front(wide, 8, l1, l2, lm, ls)).all())
+    # not the instantiated shape
+    assert not fz.rcnn_front_supported(wide, 5, 8, l1, l2, lm, fz.PackedLayer(ws, bs, True))
