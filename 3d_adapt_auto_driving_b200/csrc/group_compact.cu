@@ -8,15 +8,19 @@
 // Since the hits of a group are distinct point indices, cnt = 1 + #{k >= 1 : idx[k] != idx[0]} and the unique rows are
 // exactly slots 0..cnt-1.  (A group without any hit keeps its zero-initialised row: cnt = 1, neighbour 0, like the
 // reference, which gathers point 0 sixty-four times.)
-//   pn2_group_unique_count_i32: cnt (G) from idx (G, ns)
+//   pn2_group_unique_count_i32: cnt (G) from idx (G, ns), rounded up to a multiple of `align`
 //   pn2_group_compact_i32     : with the exclusive prefix sum of cnt, the compact row list
 //                               cmap[u] = group (centre) of unique row u, jmap[u] = its neighbour index.
+// align (1, 2, 4, 8 or 16, ns % align == 0): a group's rows are topped up to a multiple of `align` with further copies
+// of its row 0 -- still no influence on the maximum -- so that every aligned run of `align` list rows belongs to ONE
+// group.  The transposed SA kernel pools such a list eight columns at a time without looking at per-column centre ids
+// (csrc/sa_fused_t_tc.cu); the price is (align - 1) / 2 extra rows per group on average.
 // Both enqueue on the stream and never synchronise; the total U = sum(cnt) stays on the device (the SA kernel reads it).
 #include "common.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) unique_count_kernel(const int32_t *__restrict__ idx, long long g, int ns,
+__global__ void __launch_bounds__(256) unique_count_kernel(const int32_t *__restrict__ idx, long long g, int ns, int align,
                                                           int32_t *__restrict__ cnt) {
     const long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -27,7 +31,7 @@ __global__ void __launch_bounds__(256) unique_count_kernel(const int32_t *__rest
     for (int k = lane; k < ns; k += 32) c += (k == 0 || __ldg(row + k) != first) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) cnt[grp] = c;
+    if (lane == 0) cnt[grp] = (c + align - 1) / align * align;
 }
 
 __global__ void __launch_bounds__(256) compact_kernel(const int32_t *__restrict__ idx, long long g, int ns,
@@ -52,22 +56,29 @@ __global__ void __launch_bounds__(256) compact_kernel(const int32_t *__restrict_
         }
         base += __popc(bal);
     }
+    // rows up to the (aligned) count: further copies of row 0
+    for (int k = base + lane; k < __ldg(cnt + grp); k += 32) {
+        cmap[o + k] = (int32_t)grp;
+        jmap[o + k] = first;
+    }
 }
 
 }  // namespace
 
-PN2_API int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int32_t *cnt, cudaStream_t stream) {
-    if (g < 0 || ns <= 0 || (g > 0 && (!idx || !cnt))) {
+PN2_API int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt,
+                                       cudaStream_t stream) {
+    if (g < 0 || ns <= 0 || (g > 0 && (!idx || !cnt)) || align < 1 || align > 16 || (align & (align - 1)) || ns % align) {
         pn2_set_last_error("pn2_group_unique_count_i32: bad argument");
         return PN2_ERR_INVALID;
     }
     if (g == 0) return PN2_OK;
-    unique_count_kernel<<<(unsigned)((g + 7) / 8), 256, 0, stream>>>(idx, g, ns, cnt);
+    unique_count_kernel<<<(unsigned)((g + 7) / 8), 256, 0, stream>>>(idx, g, ns, align, cnt);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
 
-// offs (G) int64: EXCLUSIVE prefix sum of cnt; cmap / jmap: capacity >= sum(cnt)
+// cnt (G): pn2_group_unique_count_i32's output (with its align); offs (G) int64: EXCLUSIVE prefix sum of cnt;
+// cmap / jmap: capacity >= sum(cnt)
 PN2_API int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
                                   int32_t *cmap, int32_t *jmap, cudaStream_t stream) {
     if (g < 0 || ns <= 0 || (g > 0 && (!idx || !cnt || !offs || !cmap || !jmap)) || g > 2147483647LL) {

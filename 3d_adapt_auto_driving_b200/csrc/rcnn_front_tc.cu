@@ -171,7 +171,7 @@ __global__ void __maxnreg__(72) rcnn_front_tc_kernel(const FrontParams p) {
             // ---- computed step: relu(bpre + Wpre . x[0:5]) for channels k .. k + 3 ----
             {
                 uint8_t *sbase = smem + L.off_a + (size_t)stage * kStageBytes + toff;
-                mbar_wait_timed<PROF>(&a_empty[stage], phase ^ 1, w_stage);
+                mbar_wait_lazy_timed<PROF>(&a_empty[stage], phase ^ 1, w_stage);
                 const long long tc0 = PROF ? clock64() : 0;
 #pragma unroll
                 for (int ps = 0; ps < kPasses; ++ps) {
@@ -202,7 +202,7 @@ __global__ void __maxnreg__(72) rcnn_front_tc_kernel(const FrontParams p) {
             // ---- loaded step: the row's rpn features ----
             {
                 uint8_t *sbase = smem + L.off_a + (size_t)stage * kStageBytes + toff;
-                mbar_wait_timed<PROF>(&a_empty[stage], phase ^ 1, w_stage);
+                mbar_wait_lazy_timed<PROF>(&a_empty[stage], phase ^ 1, w_stage);
                 const long long tf0 = PROF ? clock64() : 0;
 #pragma unroll
                 for (int ps = 0; ps < kPasses; ++ps) {
@@ -229,7 +229,7 @@ __global__ void __maxnreg__(72) rcnn_front_tc_kernel(const FrontParams p) {
             int stage = 0;
             uint32_t phase = 0;
             auto push = [&](const uint8_t *src) {
-                mbar_wait(&w_empty[stage], phase ^ 1);
+                mbar_wait_lazy(&w_empty[stage], phase ^ 1);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pn2_smem_u32(&w_full[stage])),
                              "r"((uint32_t)kStageBytes)
                              : "memory");

@@ -57,6 +57,7 @@ struct SatParams {
     // duplicate-skipping mode (group_compact.cu): only the unique rows of every group are pushed through the MLP.
     // cmap[u] = centre of compact row u, jmap[u] = its neighbour index, *rows_dev = number of compact rows (device).
     const int32_t *cmap; const int32_t *jmap; const long long *rows_dev;
+    int cmap_align;                               // 1, or 8: every aligned group of eight list rows has one centre
     unsigned long long *prof;                     // optional stopwatch buffer (32 u64 per CTA, tools/prof_sat.py) or nullptr
 };
 
@@ -158,8 +159,10 @@ __device__ __noinline__ void flush_run(float *dst, float v) {
     atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(v));
 }
 
-// COMPACT (duplicate-skipping rows) is a kernel template parameter: the dense instantiation carries none of its code
-template <bool FAST, bool COMPACT, bool PROF>
+// COMPACT (duplicate-skipping rows) is a kernel template parameter, so the dense instantiation carries none of its code:
+// 0 = dense groups of nsample rows, 1 = compact row list with runs of any length, 8 = compact list whose groups are
+// padded to multiples of eight rows (pn2_group_unique_count_i32 with align 8): pooled eight columns at a time
+template <bool FAST, int COMPACT, bool PROF>
 __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (pn2_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -229,7 +232,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     const int half_c2 = p.c2 >> 1;
 
     // compact mode: the row count is data dependent and lives on the device (no host synchronisation anywhere)
-    constexpr bool compact = COMPACT;
+    constexpr bool compact = COMPACT != 0;
     const long long n_rows = compact ? *p.rows_dev : p.rows;
     const long long n_tiles = compact ? (n_rows + BM - 1) / BM : p.tiles;
     const long long first = blockIdx.x, stride = gridDim.x;
@@ -379,33 +382,82 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
         // compact mode: run-start masks of this warp's 64 columns (bit l of run_e / run_o = column 2l / 2l+1 begins a
         // new centre), computed once per tile when the centre ids are staged
         uint32_t run_e = 0, run_o = 0;
+        // compact mode: centre ids of this warp's 64 columns of tile `it` (-1 marks columns past the end of the row list).
+        // The list lives in global memory (L2): the load is issued a whole tile before its values are needed, the first
+        // version fetched it at the start of e3 and stalled the epilogue for the full latency every tile (1.9 k of 8.4 k
+        // cycles per tile in the stopwatch, tools/prof_sat.py)
+        auto cid_fetch = [&](int it) {
+            const long long u0 = (first + (long long)it * stride) * BM + half * 64;
+            const long long left = n_rows - u0;
+            const int ncols = left >= 64 ? 64 : (left > 0 ? (int)left : 0);
+            int2 t = make_int2(-1, -1);
+            if (2 * lane < ncols) t = __ldg(reinterpret_cast<const int2 *>(p.cmap + u0) + lane);
+            if (2 * lane + 1 >= ncols) t.y = -1;
+            return t;
+        };
+        int2 cid_next = make_int2(-1, -1);
+        if (compact && my_tiles > 0) cid_next = cid_fetch(0);
         unsigned long long w_acc2f = 0, w_a2e = 0, w_acc3f = 0, t_e2 = 0, t_e3 = 0;
         auto e3 = [&](int it, int j) {
             // acc3^T: lane = channel, columns = tile rows -> in-thread max over the nsample rows of each centre
             const long long tile = first + (long long)it * stride;
             int *cid_s = reinterpret_cast<int *>(smem + L.off_cid) + ew * 64;
             if (compact && j == 0) {
-                // centre ids of this warp's 64 columns -> shared memory BEFORE waiting for the accumulator: the global
-                // (L2) latency of the list stays off the section during which acc3 is held; -1 marks columns past the end
-                const long long u0 = tile * BM + half * 64;
-                const long long left = n_rows - u0;
-                const int ncols = left >= 64 ? 64 : (left > 0 ? (int)left : 0);
+                // centre ids of this warp's 64 columns (fetched one tile ahead, see cid_fetch) -> shared memory and the
+                // run-start masks, before the accumulator is awaited
                 __syncwarp();
-                int2 t = make_int2(-1, -1);
-                if (2 * lane < ncols) t = __ldg(reinterpret_cast<const int2 *>(p.cmap + u0) + lane);
-                if (2 * lane + 1 >= ncols) t.y = -1;
+                const int2 t = cid_next;
                 reinterpret_cast<int2 *>(cid_s)[lane] = t;
                 int prev = __shfl_up_sync(0xffffffffu, t.y, 1);
                 if (lane == 0) prev = -2;                       // column 0 always opens a run
                 run_e = __ballot_sync(0xffffffffu, t.x != prev);
                 run_o = __ballot_sync(0xffffffffu, t.y != t.x);
                 __syncwarp();
+                if (it + 1 < my_tiles) cid_next = cid_fetch(it + 1);   // in flight during this tile's pooling and the next E2
             }
             mbar_wait_timed<PROF>(acc3_full, (uint32_t)((it * p.nm3 + j) & 1), w_acc3f);
             const long long te0 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
-            if constexpr (COMPACT) {
+            if constexpr (COMPACT == 8) {
+                // compact rows in groups of eight (group_compact.cu, align 8): an aligned group of eight columns belongs to
+                // one centre, so its maximum is four static 3-input maxima and the run logic (warp-uniform) runs once per
+                // GROUP: bit 4g of run_e says whether column 8g opens a new centre.  Per warp and pass: 8 groups instead
+                // of 64 per-column tests -- the per-column version spent 3.9 k cycles per tile here against 1.1 k for
+                // the dense kernel (tools/prof_sat.py), for ~10 % more rows through the MLP.
+                const int ch = j * kC3 + r;
+                const float b = bias3[ch];
+                float *ych = p.y + ch;
+                int cur = -1;
+                float run = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t va[16], vb[16];
+                    tmem_ld16(t3 + c0, va);
+                    tmem_ld16(t3 + c0 + 16, vb);
+                    tmem_ld_wait();
+                    if (c0 == 32) {        // the last loads are done: the accumulator may be overwritten
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc3_empty);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t *v = g < 2 ? va + 8 * g : vb + 8 * (g - 2);
+                        const float m = max3(max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2])),
+                                             max3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5])),
+                                             fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+                        if ((run_e >> ((c0 >> 1) + 4 * g)) & 1u) {
+                            if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+                            cur = cid_s[c0 + 8 * g];
+                            run = m;
+                        } else {
+                            run = fmaxf(run, m);
+                        }
+                    }
+                }
+                if (cur >= 0 && ch < p.c3) flush_run(ych + (long long)cur * p.ldy, fmaxf(run + b, 0.f));
+            } else if constexpr (COMPACT == 1) {
                 // compact rows: the columns of a centre are a run of equal ids (warp-uniform), of any length and possibly
                 // continued in the next warp / tile -> running max, one atomicMax per run and channel (y is zeroed).
                 // Runs are long (tens of columns), so the columns are taken eight at a time: a group without a run start
@@ -589,16 +641,21 @@ PN2_API void pn2_sa_fused_t_set_profile(void *buf) { g_prof = static_cast<unsign
 // Supported: c3 <= 128 (the accumulator is padded to 128 channel lanes, only c3 are stored) or 256 (two passes of layer 3 over the same activation tile; the layer-2 accumulator
 // is then single-buffered), c2 a multiple of 16 and <= 128 (n2 == c2), ns in {16, 32, 64, 128}; nsample 128 combines
 // the two halves of a centre with atomicMax, so y must be zero-filled for it (not for 16 / 32 / 64).
-// Duplicate-skipping mode: cmap / jmap / rows_dev from pn2_group_compact_i32 (all three or none).  y must then be
-// zero-filled (runs of a centre are combined with atomicMax); without them every nsample-row group is processed.
+// Duplicate-skipping mode: cmap / jmap / rows_dev from pn2_group_compact_i32 (all three or none) and cmap_align = the align
+// that list was built with (1 or 8; 8 selects the group-wise pooling epilogue).  y must then be zero-filled (runs of a
+// centre are combined with atomicMax); without them every nsample-row group is processed.
 PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                                   const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2,
                                   const void *w3hi, const void *w3lo, const float *b3, float *y, int ldy, int clouds,
                                   int n, int m, int ns, int c1, int c2, int c3, const int32_t *cmap, const int32_t *jmap,
-                                  const long long *rows_dev, cudaStream_t stream) {
+                                  const long long *rows_dev, int cmap_align, cudaStream_t stream) {
     if ((cmap != nullptr) != (jmap != nullptr) || (cmap != nullptr) != (rows_dev != nullptr) ||
         (cmap && (reinterpret_cast<uintptr_t>(cmap) & 15))) {
         pn2_set_last_error("pn2_sa_fused_t_tc_f32: cmap / jmap / rows_dev go together (cmap 16-byte aligned)");
+        return PN2_ERR_INVALID;
+    }
+    if (cmap && cmap_align != 1 && cmap_align != 8) {
+        pn2_set_last_error("pn2_sa_fused_t_tc_f32: cmap_align must be 1 or 8 (the align given to pn2_group_unique_count_i32)");
         return PN2_ERR_INVALID;
     }
     if (!h || !idx || !xyz || !centres || !wxyz || !w2blob || !w3hi || !w3lo || !b2 || !b3 || !y || clouds < 0 ||
@@ -622,7 +679,7 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     p.w3hi = static_cast<const uint32_t *>(w3hi); p.w3lo = static_cast<const uint32_t *>(w3lo);
     p.b2 = b2; p.b3 = b3; p.c2 = c2; p.nkb2 = (c2 + BK - 1) / BK; p.y = y; p.ldy = ldy;
     p.c3 = c3; p.nm3 = nm3; p.nb2 = nb2;
-    p.cmap = cmap; p.jmap = jmap; p.rows_dev = rows_dev;
+    p.cmap = cmap; p.jmap = jmap; p.rows_dev = rows_dev; p.cmap_align = cmap_align;
     if (p.rows == 0) return PN2_OK;
     int stages = kMaxStages;
     SmemLayout L = make_layout(p, stages);
@@ -633,16 +690,6 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     }
     p.stages = stages;
     p.prof = g_prof;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(sa_fused_t_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -650,15 +697,24 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     const int vec_ok = ((ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     const size_t smem_bytes = L.total + 1024;
     const bool fast = tc::producer_fast(vec_ok, c1);
+    const int mode = cmap ? cmap_align : 0;
+    auto go = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    };
     if (p.prof && fast) {        // stopwatch build (tools/prof_sat.py only)
-        if (cmap) sa_fused_t_tc_kernel<true, true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else sa_fused_t_tc_kernel<true, false, true><<<grid, kThreads, smem_bytes, stream>>>(p);
-    } else if (cmap) {
-        if (fast) sa_fused_t_tc_kernel<true, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else sa_fused_t_tc_kernel<false, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        if (mode == 8) go(sa_fused_t_tc_kernel<true, 8, true>);
+        else if (mode == 1) go(sa_fused_t_tc_kernel<true, 1, true>);
+        else go(sa_fused_t_tc_kernel<true, 0, true>);
+    } else if (mode == 8) {
+        if (fast) go(sa_fused_t_tc_kernel<true, 8, false>);
+        else go(sa_fused_t_tc_kernel<false, 8, false>);
+    } else if (mode == 1) {
+        if (fast) go(sa_fused_t_tc_kernel<true, 1, false>);
+        else go(sa_fused_t_tc_kernel<false, 1, false>);
     } else {
-        if (fast) sa_fused_t_tc_kernel<true, false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else sa_fused_t_tc_kernel<false, false, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        if (fast) go(sa_fused_t_tc_kernel<true, 0, false>);
+        else go(sa_fused_t_tc_kernel<false, 0, false>);
     }
     PN2_CHECK_LAUNCH();
     return PN2_OK;

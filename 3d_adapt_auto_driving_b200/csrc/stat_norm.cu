@@ -1,7 +1,7 @@
 // stat_norm.cu -- Statistical Normalization point rescale for whole scenes on the GPU, sm_100a.
 //
-// Replaces, for the default options of stat_norm/norm.py:convert (avoid_conflict = align_front = False), the numpy
-// chain of rescale_ptc + format_lidar_data per scene (norm.py:186-244, 42-45; utils/kitti_util.py:141-160):
+// Replaces the numpy chain of rescale_ptc + format_lidar_data per scene (norm.py:186-244, 42-45;
+// utils/kitti_util.py:141-160), with all four combinations of convert's avoid_conflict / align_front options:
 //   velodyne -> reference -> rectified camera | per Car / Van box: into the box frame, strict in-box mask, scale
 //   the in-box points per axis, back to the camera frame | [patch of box 0, patch of box 1, ..., untouched points]
 //   -> rectified -> reference -> velodyne | float32 (x, y, z, 1.0) rows of the output .bin.
@@ -33,6 +33,14 @@ struct BoxParams {      // 18 doubles per rescaled box
     double R[9];        // [[c,0,s],[0,1,0],[-s,0,c]] from np.cos / np.sin (ry)
     double half_l, h, half_w;   // obj.l / 2.0, obj.h, obj.w / 2.0
     double scale[3];    // mapping(obj, 1): factors along l, h, w
+};
+
+constexpr int kRatios = 11;     // np.arange(1, -0.1, -0.1): the candidates of the avoid_conflict search (norm.py:206)
+
+struct BoxOpts {        // 78 doubles per rescaled box, only for avoid_conflict / align_front (norm.py:205-240)
+    double scale[kRatios][3];   // mapping(obj, ratio_r): factors along l, h, w for every candidate ratio
+    double shift[kRatios][4];   // align_front: up to two (dx, dz) pairs added to the patch one after the other
+    double nshift;              // 0, 1 or 2 pairs (does not depend on the ratio)
 };
 
 // sum_k a_k * b[k*ld + j], k-sequential FMA chain, first term a plain multiply (numpy / OpenBLAS dgemm order)
@@ -68,8 +76,11 @@ __global__ void __launch_bounds__(kThreads) stat_rescale_kernel(const float4 *__
                                                                const int32_t *__restrict__ box_offsets,
                                                                double *__restrict__ rect, unsigned char *__restrict__ untouched,
                                                                float4 *__restrict__ out, int32_t *__restrict__ out_counts,
-                                                               int32_t *__restrict__ box_counts, long long cap, long long cap_out) {
+                                                               int32_t *__restrict__ box_counts, long long cap, long long cap_out,
+                                                               const BoxOpts *__restrict__ opts, int avoid_conflict,
+                                                               int32_t *__restrict__ box_ratio) {
     __shared__ int wcnt[kWarps];
+    __shared__ double red_lo[kWarps][3], red_hi[kWarps][3];
     __shared__ long long base;
     __shared__ SceneMats m;
     __shared__ BoxParams bp;
@@ -102,6 +113,94 @@ __global__ void __launch_bounds__(kThreads) stat_rescale_kernel(const float4 *__
         if (tid < (int)(sizeof(BoxParams) / 8)) reinterpret_cast<double *>(&bp)[tid] = reinterpret_cast<const double *>(boxes + bi)[tid];
         __syncthreads();
         const long long box_base = base;
+        // scale factors (and front-alignment shifts) of this box: ratio 1 unless the conflict search backs off
+        double sc0 = bp.scale[0], sc1 = bp.scale[1], sc2 = bp.scale[2];
+        int ridx = 0;
+        if (opts != nullptr && avoid_conflict) {
+            // norm.py:205-216.  scaled = local[inside] * mapping(obj, ratio) and its per-axis min / max: the factors are
+            // positive and IEEE multiplication is monotone, so min(scaled_k) = fl(min(local_k) * s_k) exactly -- one
+            // reduction over the in-box points serves all eleven candidate ratios
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            int n_in = 0, n_clear = 0;
+            for (long long i = tid; i < n; i += kThreads) {
+                const double d0 = __dsub_rn(rect[i * 3 + 0], bp.t[0]), d1 = __dsub_rn(rect[i * 3 + 1], bp.t[1]),
+                             d2 = __dsub_rn(rect[i * 3 + 2], bp.t[2]);
+                const double p0 = chain3(d0, d1, d2, bp.R, 3, 0), p1 = chain3(d0, d1, d2, bp.R, 3, 1), p2 = chain3(d0, d1, d2, bp.R, 3, 2);
+                const bool foot = p0 > -bp.half_l && p0 < bp.half_l && p2 > -bp.half_w && p2 < bp.half_w && p1 > -bp.h;
+                if (foot && p1 < 0.0) {
+                    ++n_in;
+                    lo[0] = fmin(lo[0], p0); hi[0] = fmax(hi[0], p0);
+                    lo[1] = fmin(lo[1], p1); hi[1] = fmax(hi[1], p1);
+                    lo[2] = fmin(lo[2], p2); hi[2] = fmax(hi[2], p2);
+                }
+                n_clear += (foot && p1 < -0.5) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                    hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+                }
+                n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+                n_clear += __shfl_xor_sync(0xffffffffu, n_clear, o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { red_lo[warp][k] = lo[k]; red_hi[warp][k] = hi[k]; }
+                wcnt[warp] = n_in;
+            }
+            __syncthreads();
+            int tot_in = 0;
+            for (int w = 0; w < kWarps; ++w) {
+                tot_in += wcnt[w];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], red_lo[w][k]); hi[k] = fmax(hi[k], red_hi[w][k]); }
+            }
+            __syncthreads();
+            if (lane == 0) wcnt[warp] = n_clear;
+            __syncthreads();
+            int tot_clear = 0;
+            for (int w = 0; w < kWarps; ++w) tot_clear += wcnt[w];
+            __syncthreads();
+            if (tot_in > 0) {
+                const BoxOpts &bo = opts[bi];
+                ridx = kRatios - 1;
+                for (int r = 0; r < kRatios; ++r) {
+                    // bounds of the scaled patch; the lowest 0.5 m are ignored (norm.py:211-213)
+                    const double x_lo = __dmul_rn(lo[0], bo.scale[r][0]), x_hi = __dmul_rn(hi[0], bo.scale[r][0]);
+                    const double y_lo = __dmul_rn(lo[1], bo.scale[r][1]);
+                    const double z_lo = __dmul_rn(lo[2], bo.scale[r][2]), z_hi = __dmul_rn(hi[2], bo.scale[r][2]);
+                    int c = 0;
+                    for (long long i = tid; i < n; i += kThreads) {
+                        const double d0 = __dsub_rn(rect[i * 3 + 0], bp.t[0]), d1 = __dsub_rn(rect[i * 3 + 1], bp.t[1]),
+                                     d2 = __dsub_rn(rect[i * 3 + 2], bp.t[2]);
+                        const double p0 = chain3(d0, d1, d2, bp.R, 3, 0), p1 = chain3(d0, d1, d2, bp.R, 3, 1),
+                                     p2 = chain3(d0, d1, d2, bp.R, 3, 2);
+                        c += (p0 > x_lo && p0 < x_hi && p1 > y_lo && p1 < -0.5 && p2 > z_lo && p2 < z_hi) ? 1 : 0;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (lane == 0) wcnt[warp] = c;
+                    __syncthreads();
+                    int swallowed = 0;
+                    for (int w = 0; w < kWarps; ++w) swallowed += wcnt[w];
+                    __syncthreads();
+                    if (swallowed - tot_clear < 10) { ridx = r; break; }      // uniform: every thread sees the same sums
+                }
+                sc0 = bo.scale[ridx][0]; sc1 = bo.scale[ridx][1]; sc2 = bo.scale[ridx][2];
+            }
+            if (tid == 0 && box_ratio) box_ratio[bi] = ridx;
+        } else if (tid == 0 && box_ratio) {
+            box_ratio[bi] = 0;
+        }
+        double sh[4] = {0.0, 0.0, 0.0, 0.0};
+        int nshift = 0;
+        if (opts != nullptr) {
+            nshift = (int)opts[bi].nshift;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sh[k] = opts[bi].shift[ridx][k];
+        }
         for (long long i0 = 0; i0 < n; i0 += kThreads) {
             const long long i = i0 + tid;
             bool in = false;
@@ -125,12 +224,15 @@ __global__ void __launch_bounds__(kThreads) stat_rescale_kernel(const float4 *__
             }
             if (in) {
                 pos += __popc(bal & lt);
-                const double s0 = __dmul_rn(p0, bp.scale[0]), s1 = __dmul_rn(p1, bp.scale[1]), s2 = __dmul_rn(p2, bp.scale[2]);
+                const double s0 = __dmul_rn(p0, sc0), s1 = __dmul_rn(p1, sc1), s2 = __dmul_rn(p2, sc2);
                 // np.dot(tmp, R.T) + obj.t : (R.T)[k][j] = R[j][k]
                 double q0 = __dmul_rn(s0, bp.R[0]); q0 = __fma_rn(s1, bp.R[1], q0); q0 = __fma_rn(s2, bp.R[2], q0);
                 double q1 = __dmul_rn(s0, bp.R[3]); q1 = __fma_rn(s1, bp.R[4], q1); q1 = __fma_rn(s2, bp.R[5], q1);
                 double q2 = __dmul_rn(s0, bp.R[6]); q2 = __fma_rn(s1, bp.R[7], q2); q2 = __fma_rn(s2, bp.R[8], q2);
                 q0 = __dadd_rn(q0, bp.t[0]); q1 = __dadd_rn(q1, bp.t[1]); q2 = __dadd_rn(q2, bp.t[2]);
+                // align_front (norm.py:219-240): patch[:, 0] += shift * cos(angle); patch[:, 2] += shift * sin(angle), per rule
+                if (nshift > 0) { q0 = __dadd_rn(q0, sh[0]); q2 = __dadd_rn(q2, sh[1]); }
+                if (nshift > 1) { q0 = __dadd_rn(q0, sh[2]); q2 = __dadd_rn(q2, sh[3]); }
                 if (pos < cap_out) out[pos] = rect_to_bin_row(m, q0, q1, q2);
                 else overflow = true;
                 untouched[i] = 0;
@@ -188,7 +290,35 @@ PN2_API int pn2_stat_rescale_f64(const float *raw, const long long *offsets, con
     stat_rescale_kernel<<<b, kThreads, 0, stream>>>(reinterpret_cast<const float4 *>(raw), offsets,
                                                     reinterpret_cast<const SceneMats *>(mats),
                                                     reinterpret_cast<const BoxParams *>(boxes), box_offsets, rect, untouched,
-                                                    reinterpret_cast<float4 *>(out), out_counts, box_counts, cap, cap_out);
+                                                    reinterpret_cast<float4 *>(out), out_counts, box_counts, cap, cap_out,
+                                                    nullptr, 0, nullptr);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// pn2_stat_rescale_f64 with the two options of stat_norm/norm.py:convert (norm.py:205-240):
+//   avoid_conflict  per box, the largest ratio of np.arange(1, -0.1, -0.1) whose scaled patch swallows fewer than ten
+//                   foreign points (the search of norm.py:205-216, on the device: one min / max reduction + one count per
+//                   candidate); box_ratio (nboxes) int32 receives the index of the chosen ratio (0 = ratio 1)
+//   align_front     the patch is shifted so that the face nearest to the sensor stays in place (norm.py:219-240)
+// box_opts (nboxes, 78) f64 per rescaled box: scale[11][3] = mapping(obj, ratio_r) for the eleven candidate ratios,
+// shift[11][4] = up to two (dx, dz) pairs per ratio (zeros without align_front), nshift = how many pairs apply -- all
+// computed on the host by the reference's own numpy expressions, so the kernel only reproduces float64 products and sums.
+PN2_API int pn2_stat_rescale_opts_f64(const float *raw, const long long *offsets, const double *mats, const double *boxes,
+                                      const int32_t *box_offsets, const double *box_opts, int avoid_conflict, double *rect,
+                                      unsigned char *untouched, float *out, int32_t *out_counts, int32_t *box_counts,
+                                      int32_t *box_ratio, int b, long long cap, long long cap_out, cudaStream_t stream) {
+    if (b < 0 || cap < 0 || cap_out < 0 || (b > 0 && (!raw || !offsets || !mats || !box_offsets || !rect || !untouched || !out || !out_counts || !box_opts)) ||
+        (reinterpret_cast<uintptr_t>(raw) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+        pn2_set_last_error("pn2_stat_rescale_opts_f64: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (b == 0) return PN2_OK;
+    stat_rescale_kernel<<<b, kThreads, 0, stream>>>(reinterpret_cast<const float4 *>(raw), offsets,
+                                                    reinterpret_cast<const SceneMats *>(mats),
+                                                    reinterpret_cast<const BoxParams *>(boxes), box_offsets, rect, untouched,
+                                                    reinterpret_cast<float4 *>(out), out_counts, box_counts, cap, cap_out,
+                                                    reinterpret_cast<const BoxOpts *>(box_opts), avoid_conflict, box_ratio);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -56,6 +56,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
     __trap();
 }
+// Wait of a role that runs AHEAD of its consumer (an operand producer or the weight stream waiting for a ring stage to
+// drain): the wait is long by construction and nothing downstream is blocked by a slightly late wake-up.  mbar_wait()'s
+// try_wait parks the warp until ANY mbarrier of the CTA changes state, then re-polls: with ~30 barriers ticking, the
+// sixteen producer warps of the fused SA kernel executed 77 M polls (8 instructions each, 41 % of all issued instructions
+// of the kernel, ncu source page) and competed for issue slots with the epilogue warps that bound the kernel.  Here the
+// barrier is tested once and the warp sleeps a fixed ~100 ns between tests.
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = pn2_smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 25); ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(100);
+    }
+    __trap();
+}
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_lazy_timed(uint64_t *bar, uint32_t parity, unsigned long long &acc) {
+    if (!PROF) {
+        mbar_wait_lazy(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait_lazy(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+
 // Optional in-kernel stopwatch (tools/prof_tc.py): cycles a role spends blocked on a barrier.
 // PROF is a KERNEL template parameter: the product instantiation carries no stopwatch code at all.
 template <bool PROF>

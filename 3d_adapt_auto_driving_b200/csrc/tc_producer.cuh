@@ -218,7 +218,7 @@ __device__ __forceinline__ void producer_body(const ProducerArgs &a, int ptid, S
     if (l_t < total_steps) issue_loads();
     while (s_t < total_steps) {
         uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
-        mbar_wait_timed<PROF>(&a.empty[stage], phase ^ 1, w_stage);
+        mbar_wait_lazy_timed<PROF>(&a.empty[stage], phase ^ 1, w_stage);
         if (wg == 0 && lane == 0) hook(first + s_it * stride, s_kb, stage);
         const int k = s_kb * kBK + kq;
         const RowMeta *mt = a.meta + (s_it % kMetaDepth) * kBM + rsub;
@@ -304,7 +304,7 @@ __device__ __forceinline__ void producer_pre(const ProducerArgs &a, int ptid, St
     uint32_t phase = (uint32_t)((group / a.stages) & 1);
     while (s_t < total_steps) {
         uint8_t *sbase = a.ring + (size_t)stage * a.stage_bytes + toff;
-        mbar_wait(&a.empty[stage], phase ^ 1);
+        mbar_wait_lazy(&a.empty[stage], phase ^ 1);
         if (wg == 0 && lane == 0) hook(first + (long long)s_it * stride, s_kb, stage);
         const int k = s_kb * kBK + kq;
         float2 w01[CPRE + 1], w23[CPRE + 1];               // weights of this thread's 4 channels; row CPRE = bias

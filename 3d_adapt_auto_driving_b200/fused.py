@@ -160,6 +160,13 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
 FPS_PREFIX_CHECK = os.environ.get("PN2_FPS_PREFIX_CHECK", "1") != "0"
 
 
+# Thread-block-cluster size of the FPS kernel for clouds above 4096 points (0 = the kernel's latency heuristic, 4 CTAs per
+# cloud).  With several batches in flight (inference.Detector, depth 3) what counts is SM-time, not latency: 2 CTAs per
+# cloud take 3.43 ms instead of 2.91 ms for 16 x (16384 -> 4096) but hold 32 SMs instead of 64 (110 vs 186 SM-ms,
+# tools/bench_fps_cluster.py), and the other streams' tensor-core kernels get the difference.
+FPS_CLUSTER = int(os.environ.get("PN2_FPS_CLUSTER", "0"))
+
+
 def fps_gather(xyz, npoint, fps_ordered=False):
     """FPS indices (B,npoint) int32 and the sampled centres (B,npoint,3).  fps_ordered: the caller knows that xyz is
     the output of a previous furthest point sampling (a hint, never trusted: the prefix test decides per cloud)."""
@@ -171,6 +178,9 @@ def fps_gather(xyz, npoint, fps_ordered=False):
         cabi.call("pn2_fps_prefix_check_f32", ptr(xyz), ptr(dmin), ptr(viol), i32(B), i32(N), i32(npoint),
                   work=12.0 * B * npoint * N)
         cabi.call("pn2_fps_guarded_f32", ptr(xyz), ptr(idx), ptr(viol), i32(B), i32(N), i32(npoint), work=0.0)
+    elif FPS_CLUSTER and N > 4096:
+        cabi.call("pn2_fps_cluster_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint), i32(FPS_CLUSTER),
+                  work=16.0 * B * max(npoint - 1, 0) * N)
     else:
         cabi.call("pn2_fps_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint),
                   work=16.0 * B * max(npoint - 1, 0) * N)
@@ -369,13 +379,18 @@ SA_TRANSPOSED_SMALL = os.environ.get("PN2_SA_TRANSPOSED_SMALL", "0") == "1"
 SA_SKIP_MIN_ROWS = 1 << 20      # below ~1 M grouped rows the two compaction launches + the zero-fill cost more than they save
 
 
-def group_compact(idx):
+SA_COMPACT_ALIGN = int(os.environ.get("PN2_SA_COMPACT_ALIGN", "8"))
+
+
+def group_compact(idx, align=None):
     """idx (B, M, ns) int32 from ball_query -> (cmap, jmap int32 lists of the unique rows, device int64 row count);
-    no host synchronisation (the count stays on the device)."""
+    no host synchronisation (the count stays on the device).  align: every group is topped up to a multiple of `align`
+    rows with copies of its first row (default 8: the SA kernel then pools eight columns at a time)."""
+    align = SA_COMPACT_ALIGN if align is None else align
     B, M, ns = idx.shape
     G = B * M
     cnt = torch.empty((G,), dtype=torch.int32, device=idx.device)
-    cabi.call("pn2_group_unique_count_i32", ptr(idx), _i64(G), i32(ns), ptr(cnt))
+    cabi.call("pn2_group_unique_count_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(cnt))
     incl = torch.cumsum(cnt, dim=0, dtype=torch.int64)
     offs = incl - cnt
     cmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
@@ -419,11 +434,13 @@ def sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out):
         if ns >= 128 or cmap is not None:
             o2.zero_()
         if cmap is not None and cabi.profiling():
-            rows = int(nrows.item())       # bench.py's per-kernel accounting counts the rows really processed (syncs; profiling only)
+            # bench.py's per-kernel accounting counts the UNIQUE rows (not the copies the 8-row alignment adds back):
+            # the conservative figure for roofline.achieved (syncs; profiling only)
+            rows = int((idx[:, :, 1:] != idx[:, :, :1]).sum().item()) + B * M
         cabi.call("pn2_sa_fused_t_tc_f32", ptr(h2), i32(ldh), ptr(idx), ptr(xyz), ptr(centres), ptr(wxyz), ptr(t2.blob),
                   i32(t2.ntile), i32(t2.nkb), ptr(t2.b), ptr(w3hi), ptr(w3lo), ptr(l3.b), ptr(o2), i32(ldy), i32(B),
                   i32(N), i32(M), i32(ns), i32(c1), i32(l2.cout), i32(l3.cout), ptr(cmap), ptr(jmap), ptr(nrows),
-                  work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
+                  i32(SA_COMPACT_ALIGN if cmap is not None else 1), work=2.0 * rows * (c1 * (l2.cout + 3) + l2.cout * l3.cout))
         return out
     t3 = l3.tc
     if ns >= 64:

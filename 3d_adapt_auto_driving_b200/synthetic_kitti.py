@@ -29,10 +29,18 @@ def _rect_to_velo(pts_rect):
     return (ref - V2C[:, 3]) @ np.linalg.inv(V2C[:, :3]).T
 
 
-def write_scene(train_dir, sample_id, rng, npoints=20000, n_cars=4):
-    """one scene: lidar-like cloud in rect coordinates -> velodyne .bin, calib, labels for the car clusters, PNG."""
+def write_scene(train_dir, sample_id, rng, npoints=20000, n_cars=4, n_invisible=0):
+    """one scene: lidar-like cloud in rect coordinates -> velodyne .bin, calib, labels for the car clusters, PNG.
+    n_invisible: additional returns BEHIND the camera (a real 360-degree sweep has ~120 k points of which ~20 k fall into
+    the image): they cost the data path file reading and the lidar -> camera transform and are then filtered out."""
     from PIL import Image
     pts_rect = synthetic.lidar_cloud(rng, npoints, n_cars=n_cars)
+    if n_invisible:
+        back = synthetic.uniform_cloud(rng, n_invisible)
+        back[:, 2] = -back[:, 2] - 1.0                 # z < 0: behind the image plane
+        pts_rect = np.concatenate([pts_rect, back], axis=0)
+        pts_rect = pts_rect[rng.permutation(len(pts_rect))]
+        npoints = len(pts_rect)
     velo = np.concatenate([_rect_to_velo(pts_rect), rng.random_sample((npoints, 1))], axis=1).astype(np.float32)
     velo.tofile(os.path.join(train_dir, 'velodyne', '%06d.bin' % sample_id))
     with open(os.path.join(train_dir, 'calib', '%06d.txt' % sample_id), 'w') as f:
@@ -49,7 +57,7 @@ def write_scene(train_dir, sample_id, rng, npoints=20000, n_cars=4):
         Image.new("L", IMAGE_SIZE).save(png)       # only the size header is read (kitti_dataset.py:50-55)
 
 
-def make_dataset(root, name="kitti", n_scenes=8, split="val", seed=666, npoints=20000):
+def make_dataset(root, name="kitti", n_scenes=8, split="val", seed=666, npoints=20000, n_invisible=0, alias_to=None):
     """-> the dataset root eval_rcnn.py derives from its own location: <root>/multi_data/<name>"""
     data_root = os.path.join(root, "multi_data", name)
     train_dir = os.path.join(data_root, "KITTI", "object", "training")
@@ -58,7 +66,16 @@ def make_dataset(root, name="kitti", n_scenes=8, split="val", seed=666, npoints=
     os.makedirs(os.path.join(data_root, "KITTI", "ImageSets"), exist_ok=True)
     rng = np.random.RandomState(seed)
     for i in range(n_scenes):
-        write_scene(train_dir, i, rng, npoints=npoints)
+        write_scene(train_dir, i, rng, npoints=npoints, n_invisible=n_invisible)
+    total = n_scenes
+    if alias_to and alias_to > n_scenes:
+        # a large data set from a pool of distinct scenes: ids n_scenes .. alias_to-1 are hard links to id % n_scenes
+        for i in range(n_scenes, alias_to):
+            for sub, ext in (("velodyne", ".bin"), ("calib", ".txt"), ("label_2", ".txt"), ("image_2", ".png")):
+                dst = os.path.join(train_dir, sub, "%06d%s" % (i, ext))
+                if not os.path.exists(dst):
+                    os.link(os.path.join(train_dir, sub, "%06d%s" % (i % n_scenes, ext)), dst)
+        total = alias_to
     with open(os.path.join(data_root, "KITTI", "ImageSets", split + ".txt"), "w") as f:
-        f.write("\n".join("%06d" % i for i in range(n_scenes)) + "\n")
+        f.write("\n".join("%06d" % i for i in range(total)) + "\n")
     return data_root

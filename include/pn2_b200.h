@@ -200,12 +200,15 @@ int pn2_rotate_iou_eval_f32(const float *boxes, int n, const float *qboxes, int 
 int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const float *xyz, const float *centres,
                           const float *wxyz, const void *w2blob, int n2, int nkb1, const float *b2, const void *w3hi,
                           const void *w3lo, const float *b3, float *y, int ldy, int clouds, int n, int m, int ns, int c1,
-                          int c2, int c3, const int32_t *cmap, const int32_t *jmap, const long long *rows_dev, void *stream);
+                          int c2, int c3, const int32_t *cmap, const int32_t *jmap, const long long *rows_dev, int cmap_align,
+                          void *stream);
 /* The unique rows of ball-query groups (a group with cnt < nsample hits is padded with copies of its first hit, which
  * cannot change the max-pool): cnt (G) from idx (G, ns); with the exclusive prefix sum offs (G) int64 of cnt, the compact
  * row list cmap[u] = group, jmap[u] = neighbour index (u < sum cnt).  Passed to pn2_sa_fused_t_tc_f32 (cmap, jmap and
- * the device-resident row count) the SA kernel processes only those rows.  csrc/group_compact.cu. */
-int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int32_t *cnt, void *stream);
+ * the device-resident row count) the SA kernel processes only those rows.  align (1 .. 16, a power of two dividing ns)
+ * tops every group up to a multiple of `align` rows with further copies of its row 0, so that an aligned run of `align` list
+ * rows has ONE centre: pn2_sa_fused_t_tc_f32 pools such a list (cmap_align 8) eight columns at a time.  csrc/group_compact.cu. */
+int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, void *stream);
 int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
                           int32_t *cmap, int32_t *jmap, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
@@ -278,6 +281,15 @@ int pn2_eval_fused_statistics(const double *overlaps, long long total_dt, long l
 int pn2_stat_rescale_f64(const float *raw, const long long *offsets, const double *mats, const double *boxes,
                          const int32_t *box_offsets, double *rect, unsigned char *untouched, float *out,
                          int32_t *out_counts, int32_t *box_counts, int b, long long cap, long long cap_out, void *stream);
+/* The same with convert's options (norm.py:205-240): avoid_conflict = per box the largest ratio of np.arange(1, -0.1, -0.1)
+ * whose scaled patch swallows fewer than ten foreign points, found on the device; align_front = shift of the patch that
+ * keeps the face nearest to the sensor in place.  box_opts (nboxes, 78) f64 = {scale[11][3] = mapping(obj, ratio_r),
+ * shift[11][4] = up to two (dx, dz) pairs per ratio, nshift}, all from the reference's numpy expressions on the host;
+ * box_ratio (nboxes) int32 receives the index of the chosen ratio. */
+int pn2_stat_rescale_opts_f64(const float *raw, const long long *offsets, const double *mats, const double *boxes,
+                              const int32_t *box_offsets, const double *box_opts, int avoid_conflict, double *rect,
+                              unsigned char *untouched, float *out, int32_t *out_counts, int32_t *box_counts,
+                              int32_t *box_ratio, int b, long long cap, long long cap_out, void *stream);
 
 /* ---- the small stages between the big kernels (csrc/glue.cu, csrc/roipool3d.cu): one launch each for what the
  * reference writes as 20-60 torch statements.  Same IEEE float operations in the same order (bit-identical outputs,

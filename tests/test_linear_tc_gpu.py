@@ -208,12 +208,21 @@ def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, 
     perm = torch.argsort(torch.rand((B, M, N), generator=g), dim=2)[:, :, :ns].to(torch.int32)
     idx_pad = torch.where(k < cnt, perm, perm[:, :, :1]).contiguous().to(cuda)
     args = (h, idx_pad, xyz, centres, wxyz)
-    cm, jm, nrows = fz.group_compact(idx_pad)
+    cm, jm, nrows = fz.group_compact(idx_pad, align=1)
     assert int(nrows.item()) == int(cnt.sum())
     u = int(nrows.item())
     assert torch.equal(cm[:u].cpu(), torch.repeat_interleave(torch.arange(B * M, dtype=torch.int32), cnt.view(-1)))
     assert torch.equal(jm[:u].cpu(), idx_pad.cpu()[k.expand(B, M, ns) < cnt])
-    saved, saved_min, saved_small = fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL
+    # align 8: every group topped up to a multiple of eight rows with copies of its first neighbour
+    cm8, jm8, nrows8 = fz.group_compact(idx_pad, align=8)
+    cnt8 = (cnt + 7) // 8 * 8
+    u8 = int(nrows8.item())
+    assert u8 == int(cnt8.sum())
+    assert torch.equal(cm8[:u8].cpu(), torch.repeat_interleave(torch.arange(B * M, dtype=torch.int32), cnt8.view(-1)))
+    k8 = k.expand(B, M, ns)
+    want8 = torch.where(k8 < cnt, idx_pad.cpu(), idx_pad.cpu()[:, :, :1].expand(B, M, ns))[k8 < cnt8]
+    assert torch.equal(jm8[:u8].cpu(), want8)
+    saved = (fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL, fz.SA_COMPACT_ALIGN)
     try:
         fz.SA_SKIP_MIN_ROWS = 0
         fz.SA_TRANSPOSED_SMALL = True
@@ -221,11 +230,14 @@ def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, 
         dense = torch.full((B * M, c3), -3.0, device=cuda)
         fz.sa_fused_tc(*args, l2, l3, dense)
         fz.SA_SKIP_DUPLICATES = True
-        fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+        for align in (8, 1):              # group-wise and run-wise pooling epilogue
+            fz.SA_COMPACT_ALIGN = align
+            out.fill_(-1.0)
+            fz.sa_fused_tc(*args, l2, l3, out[:, 4:4 + c3])
+            assert torch.equal(out[:, 4:4 + c3], dense), "align %d" % align
+            assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0
     finally:
-        fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL = saved, saved_min, saved_small
-    assert torch.equal(out[:, 4:4 + c3], dense)
-    assert float(out[:, :4].max()) == -1.0 and float(out[:, 4 + c3:].max()) == -1.0
+        fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL, fz.SA_COMPACT_ALIGN = saved
 
 
 def test_linear_pre_two_layers_in_one_launch(cuda):

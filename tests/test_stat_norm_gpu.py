@@ -16,8 +16,8 @@ def _objects(o3, rng, n_cars, extra=()):
     labels = []
     for _ in range(n_cars):
         x, z = rng.uniform(-15, 15), rng.uniform(6, 45)
-        labels.append(o3.Object3d("%s 0.00 0 0.00 600.00 150.00 700.00 220.00 %.2f %.2f %.2f %.2f %.2f %.2f %.2f" % (
-            rng.choice(["Car", "Van"]), rng.uniform(1.4, 2.0), rng.uniform(1.5, 1.9), rng.uniform(3.5, 5.0), x,
+        labels.append(o3.Object3d("%s 0.00 0 %.2f 600.00 150.00 700.00 220.00 %.2f %.2f %.2f %.2f %.2f %.2f %.2f" % (
+            rng.choice(["Car", "Van"]), rng.uniform(-3.1, 3.1), rng.uniform(1.4, 2.0), rng.uniform(1.5, 1.9), rng.uniform(3.5, 5.0), x,
             rng.uniform(1.4, 1.8), z, rng.uniform(-3.1, 3.1))))
     for line in extra:
         labels.append(o3.Object3d(line))
@@ -47,7 +47,11 @@ def _calib(tmp_path):
     return ku.Calibration(str(p)), str(g["calib"])
 
 
-def test_rescale_scenes_gpu_equals_numpy_bytes(cuda, tmp_path):
+OPTIONS = [(False, False), (True, False), (False, True), (True, True)]     # (avoid_conflict, align_front), norm.py:205-240
+
+
+@pytest.mark.parametrize("avoid_conflict,align_front", OPTIONS)
+def test_rescale_scenes_gpu_equals_numpy_bytes(cuda, tmp_path, avoid_conflict, align_front):
     norm, gr, o3 = load("stat_norm.norm"), load("stat_norm.gpu_rescale"), load("stat_norm.object_3d")
     calib, _ = _calib(tmp_path)
     mapping = norm.get_scale_map(norm.germany_car_stats, norm.us_car_stats)
@@ -59,20 +63,25 @@ def test_rescale_scenes_gpu_equals_numpy_bytes(cuda, tmp_path):
     for n, cars, extra in ((16384, 4, ()), (50000, 9, twin), (3000, 0, ()), (120000, 6, twin[:2]), (1, 1, ())):
         labels = _objects(o3, rng, cars, extra)
         scenes.append((_scene(calib, labels, rng, n), labels, calib))
-    got = gr.rescale_scenes_gpu(mapping, scenes, cuda)
+    got = gr.rescale_scenes_gpu(mapping, scenes, cuda, avoid_conflict=avoid_conflict, align_front=align_front)
     assert len(got) == len(scenes)
     n_dup = 0
+    seen_ratios = set()
     for (velo, labels, calib_), (rows, ratios) in zip(scenes, got):
-        want_pts, want_ratios = norm.rescale_ptc(mapping, velo, labels, calib_)
+        want_pts, want_ratios = norm.rescale_ptc(mapping, velo, labels, calib_, avoid_conflict=avoid_conflict, align_front=align_front)
+        seen_ratios.update(float(r) for r in want_ratios)
         want = np.concatenate([want_pts, np.ones((want_pts.shape[0], 1), dtype=np.float32)], axis=1).astype(np.float32)   # norm.py:43
         assert ratios == want_ratios
         assert rows.shape == want.shape
         assert np.array_equal(rows.view(np.uint32), want.view(np.uint32))
         n_dup += rows.shape[0] - velo.shape[0]
     assert n_dup > 0                                          # the twin boxes really overlapped
+    if avoid_conflict:
+        assert len(seen_ratios - {0.0, 1.0}) > 0, seen_ratios    # the search really backed off for some box
 
 
-def test_convert_gpu_writes_the_same_dataset_as_convert(cuda, tmp_path):
+@pytest.mark.parametrize("avoid_conflict,align_front", OPTIONS)
+def test_convert_gpu_writes_the_same_dataset_as_convert(cuda, tmp_path, avoid_conflict, align_front):
     from PIL import Image
     norm, gr, o3 = load("stat_norm.norm"), load("stat_norm.gpu_rescale"), load("stat_norm.object_3d")
     calib, calib_txt = _calib(tmp_path)
@@ -91,9 +100,10 @@ def test_convert_gpu_writes_the_same_dataset_as_convert(cuda, tmp_path):
             "\n".join(o.to_kitti_format() for o in labels) + ("\n" if labels else "") +
             "DontCare -1 -1 -10 0 0 1 1 -1 -1 -1 -1000 -1000 -1000 -10")
         Image.new("RGB", (1242, 375)).save(str(src / "training" / "image_2" / (name + ".png")))
-    norm.convert("kitti", "nusc", spath=str(src), dpath=str(tmp_path / "cpu"), use_car_sales_stats=True)
+    norm.convert("kitti", "nusc", spath=str(src), dpath=str(tmp_path / "cpu"), use_car_sales_stats=True,
+                 avoid_conflict=avoid_conflict, align_front=align_front)
     gr.convert_gpu("kitti", "nusc", spath=str(src), dpath=str(tmp_path / "gpu"), use_car_sales_stats=True, batch_size=2,
-                   device=cuda)
+                   device=cuda, avoid_conflict=avoid_conflict, align_front=align_front)
     for sub in ("velodyne", "label_2"):
         a = tmp_path / "cpu" / "kitti_scaledto_nusc" / "training" / sub
         b = tmp_path / "gpu" / "kitti_scaledto_nusc" / "training" / sub

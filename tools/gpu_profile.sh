@@ -6,7 +6,7 @@ mkdir -p gpurun_out /tmp/ncu
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --minimal --no-graph --depth 1 > gpurun_out/bench_ncu.log 2>&1; echo "ncu launches exit $?"
 M='gpu__time_duration.sum|dram__bytes_read.sum|dram__bytes_write.sum|sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active|sm__inst_executed_pipe_tensor|sm__throughput.avg.pct_of_peak_sustained_elapsed|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|launch__registers_per_thread|launch__grid_size|launch__block_size|smsp__inst_executed.sum|sm__warps_active.avg.pct_of_peak_sustained_active|lts__t_bytes.sum|l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum|smsp__warp_issue_stalled.*_per_warp_active.pct|Kernel Name|^"ID"'
-timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"linear_tc_kernel|sa_fused_tc_kernel|sa_fused_t_tc_kernel" --profile-from-start off -f -o /tmp/ncu/prof_mlp \
+timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"linear_tc_kernel|sa_fused_tc_kernel|sa_fused_t_tc_kernel|rcnn_front_tc_kernel" --profile-from-start off -f -o /tmp/ncu/prof_mlp \
     python bench.py --steps 1 --warmup 3 --minimal --no-graph --depth 1 > gpurun_out/bench_ncu2.log 2>&1; echo "ncu mlp exit $?"
 ncu -i /tmp/ncu/prof_mlp.ncu-rep --page raw --csv > /tmp/ncu/prof_mlp_raw.csv 2>/dev/null
 python - <<'PY'
@@ -24,7 +24,7 @@ for name in ("prof_mlp", "prof_scan"):
             w.writerow([r[i] for i in keep if i < len(r)])
     print(name, len(rows) - 2, "launches,", len(keep), "columns")
 PY
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fps_kernel|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise|gather_rows|spatial_order|unique_count_kernel|compact_kernel" --profile-from-start off -f -o /tmp/ncu/prof_scan \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fps_kernel|fps_prefix|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise|gather_rows|spatial_order|unique_count_kernel|compact_kernel|decode_kernel|proposal_select|proposal_assemble|rcnn_post" --profile-from-start off -f -o /tmp/ncu/prof_scan \
     python bench.py --steps 1 --warmup 3 --minimal --no-graph --depth 1 > gpurun_out/bench_ncu3.log 2>&1; echo "ncu scan exit $?"
 ncu -i /tmp/ncu/prof_scan.ncu-rep --page raw --csv > /tmp/ncu/prof_scan_raw.csv 2>/dev/null
 python - <<'PY'

@@ -44,7 +44,7 @@ for mean_fill in (64, 48, 32, 16, 4):
     def kern():
         cabi.call("pn2_sa_fused_t_tc_f32", fz.ptr(h), fz.i32(C), fz.ptr(idx), fz.ptr(xyz), fz.ptr(centres), fz.ptr(wxyz), fz.ptr(t2.blob),
                   fz.i32(t2.ntile), fz.i32(t2.nkb), fz.ptr(t2.b), fz.ptr(w3hi), fz.ptr(w3lo), fz.ptr(L3.b), fz.ptr(out), fz.i32(C), fz.i32(R),
-                  fz.i32(S), fz.i32(M), fz.i32(ns), fz.i32(C), fz.i32(C), fz.i32(C), fz.ptr(cm), fz.ptr(jm), fz.ptr(nr))
+                  fz.i32(S), fz.i32(M), fz.i32(ns), fz.i32(C), fz.i32(C), fz.i32(C), fz.ptr(cm), fz.ptr(jm), fz.ptr(nr), fz.i32(fz.SA_COMPACT_ALIGN))
     kern(); torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()

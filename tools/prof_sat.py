@@ -70,10 +70,13 @@ def main():
         l2 = fz.PackedLayer((torch.randn((C, C), generator=g) / C ** 0.5).cuda(), torch.randn(C, generator=g).cuda(), True)
         l3 = fz.PackedLayer((torch.randn((c3, C), generator=g) / C ** 0.5).cuda(), torch.randn(c3, generator=g).cuda(), True)
         out_t = torch.empty((R * M, c3), device="cuda")
-        for skip in (True, False):
-            fz.SA_SKIP_DUPLICATES = skip
-            run("%s, %s" % (tag, "duplicate-skipping" if skip else "dense"), h, idx, xyz, centres, wxyz, l2, l3, out_t)
-    fz.SA_SKIP_DUPLICATES = True
+        uniq = int((idx[:, :, 1:] != idx[:, :, :1]).sum().item()) + R * M
+        print("%s: %d grouped rows, %d unique (%.1f %%), %d after 8-row alignment" % (
+            tag, R * M * ns, uniq, 100.0 * uniq / (R * M * ns), int(fz.group_compact(idx, align=8)[2].item())))
+        for skip, align in ((True, 8), (True, 1), (False, 8)):
+            fz.SA_SKIP_DUPLICATES, fz.SA_COMPACT_ALIGN = skip, align
+            run("%s, %s" % (tag, ("duplicate-skipping, align %d" % align) if skip else "dense"), h, idx, xyz, centres, wxyz, l2, l3, out_t)
+    fz.SA_SKIP_DUPLICATES, fz.SA_COMPACT_ALIGN = True, 8
 
 
 if __name__ == "__main__":

@@ -1,0 +1,249 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: "eval_rcnn.py end-to-end, 7481 synthetic KITTI-val scenes scene-sharded across 8 x B200
+with NCCL gather of boxes", measured for three arms on N GPUs of one node (N = 1 and 8 are the committed records):
+
+  dropin     the reference's UNMODIFIED tools/eval_rcnn.py (sha256-checked) on this package's drop-in tree, scene-sharded
+             by tools/eval_sharded.py (one process per GPU under torch.distributed.run, per-rank output, one NCCL gather of
+             the detection records, rank 0 writes the merged KITTI files)
+  fast       tools/eval_fast.py: the same evaluation with the GPU-side data path and batches in flight
+  reference  the same unmodified script over the reference's own Python and its own CUDA kernels
+             (oracle/run_reference_script.py); the reference has no multi-GPU mode, so for N > 1 every GPU gets its own
+             split file (--set TEST.SPLIT ...) and an independent process
+
+    python tools/run_config5.py --gpus N [--scenes 7481] [--pool 128] [--arms dropin,fast,reference] --out DIR
+
+scenes/s = scenes / wall seconds of the slowest rank, process start to exit (model build, data loader start-up and file
+writing included); `loop_scenes_per_s` is the same over the script's own epoch log lines only.  Every arm writes KITTI
+result files; the merged directory of an N-GPU run is compared byte for byte with the 1-GPU run of the same arm when
+--compare points at that run's output."""
+import argparse
+import datetime
+import filecmp
+import glob
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "3d_adapt_auto_driving_b200"
+PY = sys.executable
+
+
+def torchrun(n, port, script_args, env):
+    cmd = [PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port)] + script_args
+    return subprocess.run(cmd, env=env, capture_output=True, text=True)
+
+
+def loop_seconds(log_file):
+    """seconds between the script's 'EPOCH ... EVALUATION' line and its 'final average detections' line"""
+    if not os.path.exists(log_file):
+        return None
+    stamp = re.compile(r"^(\d{4}-\d{2}-\d{2} \d{2}:\d{2}:\d{2},\d{3})")
+    t0 = t1 = None
+    for line in open(log_file, errors="replace"):
+        m = stamp.match(line)
+        if not m:
+            continue
+        t = datetime.datetime.strptime(m.group(1), "%Y-%m-%d %H:%M:%S,%f")
+        if "EVALUATION" in line and t0 is None:
+            t0 = t
+        if "final average detections" in line:
+            t1 = t
+    return (t1 - t0).total_seconds() if t0 and t1 else None
+
+
+def same_dirs(a, b):
+    fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+    if fa != fb:
+        return False, "file lists differ (%d vs %d)" % (len(fa), len(fb))
+    _, mismatch, errors = filecmp.cmpfiles(a, b, fa, shallow=False)
+    return (not mismatch and not errors), "%d of %d files differ" % (len(mismatch) + len(errors), len(fa))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--scenes", type=int, default=7481)
+    ap.add_argument("--pool", type=int, default=128, help="distinct synthetic scenes; the other ids are hard links")
+    ap.add_argument("--visible", type=int, default=22000, help="points of a scene inside the camera frustum")
+    ap.add_argument("--invisible", type=int, default=98000, help="points behind the camera (filtered by the data path)")
+    ap.add_argument("--arms", default="dropin,fast,reference")
+    ap.add_argument("--batch_size", type=int, default=16)
+    ap.add_argument("--workers", type=int, default=4, help="DataLoader workers of eval_rcnn.py (its default is 4)")
+    ap.add_argument("--work", default="/tmp/pn2_config5")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--compare", default=None, help="output directory of a previous (1-GPU) run: result files must be identical")
+    args = ap.parse_args()
+    import importlib
+    import torch
+    sk = importlib.import_module(PKG + ".synthetic_kitti")
+    et = importlib.import_module(PKG + ".evaltree")
+    inf = importlib.import_module(PKG + ".inference")
+    tu = importlib.import_module(PKG + ".train_utils")
+    os.makedirs(args.out, exist_ok=True)
+    work = args.work
+    n = args.gpus
+    record = {"config": "BASELINE.json configs[4]", "gpus": n, "scenes": args.scenes, "distinct_scenes": args.pool,
+              "points_per_scene": {"visible": args.visible, "behind_camera": args.invisible}, "batch_size": args.batch_size,
+              "dataloader_workers": args.workers, "host_cpus": os.cpu_count(), "arms": {},
+              "sampling": "dropin and fast arms seed np.random per scene at every N (PN2_PER_SCENE_SEED; sharded runs do so by "
+                          "construction: a documented deviation from the reference's single global stream, DESIGN.md 6), which is what "
+                          "makes the N-GPU result files comparable byte for byte with the 1-GPU ones; the reference arm draws from "
+                          "the script's own stream(s)"}
+
+    # ---- data set, drop-in tree, checkpoint (shared by all arms) ----
+    t0 = time.perf_counter()
+    data_parent = os.path.join(work, "data")
+    marker = os.path.join(data_parent, ".ready_%d_%d_%d_%d" % (args.scenes, args.pool, args.visible, args.invisible))
+    if not os.path.exists(marker):
+        shutil.rmtree(data_parent, ignore_errors=True)
+        sk.make_dataset(data_parent, name="kitti", n_scenes=min(args.pool, args.scenes), split="val", seed=666, npoints=args.visible,
+                        n_invisible=args.invisible, alias_to=args.scenes)
+        open(marker, "w").close()
+    multi_data = os.path.join(data_parent, "multi_data")
+    ref_script = os.path.join(ROOT, "oracle", "_ref", "eval_rcnn.py")
+    tree_parent = os.path.join(work, "tree_dropin")
+    shutil.rmtree(tree_parent, ignore_errors=True)
+    tree = et.make_eval_tree(tree_parent, ref_script)
+    os.symlink(multi_data, os.path.join(tree, "multi_data"))
+    ckpt_dir = os.path.join(work, "ckpt")
+    os.makedirs(ckpt_dir, exist_ok=True)
+    ckpt = os.path.join(ckpt_dir, "checkpoint_epoch_1.pth")
+    if not os.path.exists(ckpt):
+        model = inf.build_model(seed=0, device="cpu")
+        with torch.no_grad():
+            model.rcnn_net.cls_layer[-1].conv.bias.fill_(1.0)     # random-init heads score below the 0.3 threshold otherwise
+        tu.save_checkpoint(tu.checkpoint_state(model, None, 1, 1), filename=ckpt[:-4])
+    record["setup_seconds"] = time.perf_counter() - t0
+    base_env = dict(os.environ)
+    base_env.pop("PN2_SHARD_RANK", None)
+    base_env.pop("PN2_SHARD_WORLD", None)
+    dropin_env = dict(base_env, PN2_PER_SCENE_SEED="1")
+    script_args = ["--cfg_file", "cfgs/default.yaml", "--eval_mode", "rcnn", "--ckpt", ckpt, "--batch_size", str(args.batch_size),
+                   "--workers", str(args.workers)]
+    arms = [a for a in args.arms.split(",") if a]
+
+    if "dropin" in arms:
+        out = os.path.join(args.out, "dropin_n%d" % n)
+        shutil.rmtree(out, ignore_errors=True)
+        t0 = time.perf_counter()
+        if n == 1:
+            r = subprocess.run([PY, "eval_rcnn.py"] + script_args + ["--output_dir", os.path.join(out, "rank0")],
+                               cwd=os.path.join(tree, "tools"), env=dropin_env, capture_output=True, text=True)
+            finals = glob.glob(os.path.join(out, "rank0", "eval", "*", "val", "**", "final_result", "data"), recursive=True)
+        else:
+            r = torchrun(n, 29611, [os.path.join(ROOT, "tools", "eval_sharded.py"), "--tree", tree, "--output_dir", out, "--"]
+                         + script_args, dropin_env)
+            finals = [os.path.join(out, "merged", "final_result", "data")]
+        dt = time.perf_counter() - t0
+        arm = {"seconds": dt, "scenes_per_s": args.scenes / dt, "returncode": r.returncode,
+               "what": "unmodified eval_rcnn.py on the drop-in tree" + (", tools/eval_sharded.py + one NCCL gather" if n > 1 else "")}
+        if r.returncode != 0:
+            arm["stderr_tail"] = r.stderr[-1500:]
+        else:
+            loops = [loop_seconds(f) for f in glob.glob(os.path.join(out, "rank*", "eval", "*", "val", "**", "log_eval_one.txt"), recursive=True)]
+            loops = [x for x in loops if x]
+            if loops:
+                arm["loop_seconds_max_rank"] = max(loops)
+                arm["loop_scenes_per_s"] = args.scenes / max(loops)
+            arm["result_files"] = len(os.listdir(finals[0])) if finals and os.path.isdir(finals[0]) else 0
+            arm["final_dir"] = finals[0] if finals else None
+        record["arms"]["dropin"] = arm
+        print("dropin:", json.dumps({k: v for k, v in arm.items() if k != "stderr_tail"}), flush=True)
+
+    if "fast" in arms:
+        out = os.path.join(args.out, "fast_n%d" % n)
+        shutil.rmtree(out, ignore_errors=True)
+        fast_args = [os.path.join(ROOT, "tools", "eval_fast.py"), "--data_root", os.path.join(multi_data, "kitti"), "--output_dir", out,
+                     "--batch_size", str(args.batch_size), "--ckpt", ckpt, "--per_scene_seed"]
+        t0 = time.perf_counter()
+        if n == 1:
+            r = subprocess.run([PY] + fast_args, env=base_env, capture_output=True, text=True)
+        else:
+            r = torchrun(n, 29612, fast_args, base_env)
+        dt = time.perf_counter() - t0
+        arm = {"seconds": dt, "scenes_per_s": args.scenes / dt, "returncode": r.returncode,
+               "what": "tools/eval_fast.py: GPU-side data path, batches in flight, per-scene seeds"}
+        if r.returncode != 0:
+            arm["stderr_tail"] = r.stderr[-1500:]
+        else:
+            for line in r.stdout.splitlines():
+                if line.startswith("{"):
+                    inner = json.loads(line)
+                    arm["loop_seconds_max_rank"] = inner["seconds"]
+                    arm["loop_scenes_per_s"] = inner["scenes_per_s"]
+                    arm["detections"] = inner["detections"]
+            arm["final_dir"] = os.path.join(out, "final_result", "data")
+            arm["result_files"] = len(os.listdir(arm["final_dir"]))
+        record["arms"]["fast"] = arm
+        print("fast:", json.dumps({k: v for k, v in arm.items() if k != "stderr_tail"}), flush=True)
+
+    if "reference" in arms:
+        out = os.path.join(args.out, "reference_n%d" % n)
+        shutil.rmtree(out, ignore_errors=True)
+        ref_work = os.path.join(work, "tree_reference")
+        shutil.rmtree(ref_work, ignore_errors=True)
+        os.makedirs(os.path.join(ref_work, "pointrcnn"))
+        os.symlink(multi_data, os.path.join(ref_work, "pointrcnn", "multi_data"))
+        sets = os.path.join(multi_data, "kitti", "KITTI", "ImageSets")
+        ids = open(os.path.join(sets, "val.txt")).read().split()
+        procs = []
+        t0 = time.perf_counter()
+        for rank in range(n):
+            split = "val" if n == 1 else "val_r%d_of_%d" % (rank, n)
+            if n > 1:
+                with open(os.path.join(sets, split + ".txt"), "w") as f:
+                    f.write("\n".join(ids[rank::n]) + "\n")
+            env = dict(base_env, CUDA_VISIBLE_DEVICES=str(rank))
+            cmd = [PY, os.path.join(ROOT, "oracle", "run_reference_script.py"), "--work", ref_work, "eval_rcnn.py"] + script_args + \
+                  ["--output_dir", os.path.join(out, "rank%d" % rank)] + (["--set", "TEST.SPLIT", split] if n > 1 else [])
+            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+            if rank == 0 and n > 1:
+                time.sleep(3.0)            # the first process stages the tree; the others find it in place
+        outs = [p.communicate() for p in procs]
+        dt = time.perf_counter() - t0
+        rc = max(p.returncode for p in procs)
+        arm = {"seconds": dt, "scenes_per_s": args.scenes / dt, "returncode": rc,
+               "what": "unmodified eval_rcnn.py over the reference's Python and CUDA kernels (oracle/run_reference_script.py)"
+                       + ("; %d independent processes, one split file per GPU" % n if n > 1 else "")}
+        if rc != 0:
+            arm["stderr_tail"] = [o[1][-1500:] for o in outs if o[1]][:1]
+        else:
+            loops = [loop_seconds(f) for f in glob.glob(os.path.join(out, "rank*", "eval", "*", "*", "**", "log_eval_one.txt"), recursive=True)]
+            loops = [x for x in loops if x]
+            if loops:
+                arm["loop_seconds_max_rank"] = max(loops)
+                arm["loop_scenes_per_s"] = args.scenes / max(loops)
+            finals = glob.glob(os.path.join(out, "rank*", "eval", "*", "*", "**", "final_result", "data"), recursive=True)
+            arm["result_files"] = sum(len([f for f in os.listdir(d) if os.path.getsize(os.path.join(d, f)) > 0 or n == 1]) for d in finals)
+            arm["final_dir"] = finals[0] if n == 1 and finals else None
+        record["arms"]["reference"] = arm
+        print("reference:", json.dumps({k: v for k, v in arm.items() if k != "stderr_tail"}), flush=True)
+
+    if args.compare:
+        prev = json.load(open(os.path.join(args.compare, "record.json")))
+        cmp = {}
+        for name in ("dropin", "fast"):
+            a, b = record["arms"].get(name, {}).get("final_dir"), prev["arms"].get(name, {}).get("final_dir")
+            if a and b and os.path.isdir(a) and os.path.isdir(b):
+                ok, msg = same_dirs(a, b)
+                cmp[name] = {"identical_to_%d_gpu_run" % prev["gpus"]: ok, "detail": msg}
+        record["compare"] = cmp
+        print("compare:", json.dumps(cmp), flush=True)
+    if "dropin" in record["arms"] and "reference" in record["arms"] and record["arms"]["reference"].get("returncode") == 0:
+        record["dropin_over_reference"] = record["arms"]["dropin"]["scenes_per_s"] / record["arms"]["reference"]["scenes_per_s"]
+    if "fast" in record["arms"] and "reference" in record["arms"] and record["arms"]["reference"].get("returncode") == 0:
+        record["fast_over_reference"] = record["arms"]["fast"]["scenes_per_s"] / record["arms"]["reference"]["scenes_per_s"]
+    with open(os.path.join(args.out, "record.json"), "w") as f:
+        json.dump(record, f, indent=1)
+    print(json.dumps({k: v for k, v in record.items() if k != "arms"}))
+
+
+if __name__ == "__main__":
+    main()
