@@ -18,26 +18,21 @@ pytestmark = pytest.mark.gpu
 SCRIPT = os.path.join(ROOT, "oracle", "_ref", "eval_rcnn.py")
 
 
-@pytest.mark.skipif(not os.path.exists(SCRIPT), reason="oracle/_ref/eval_rcnn.py not staged (needs /root/reference at build time)")
-def test_unmodified_eval_rcnn_runs_and_matches_detector(cuda, tmp_path):
+def run_script_and_compare(cuda, tmp_path, model, ckpt_path, n_scenes=6, bs=3):
+    """Stage the shim tree + a synthetic data set, run the unmodified eval_rcnn.py on `ckpt_path` as a subprocess, and
+    compare every KITTI result line with the detections of the package's batched Detector holding `model` (the same
+    weights) on the same sampled clouds.  -> number of boxes compared."""
     et, sk, inf = load("evaltree"), load("synthetic_kitti"), load("inference")
-    tu, cfgm = load("train_utils"), load("config")
+    cfgm = load("config")
     root = et.make_eval_tree(str(tmp_path), SCRIPT)
-    n_scenes, bs = 6, 3
     data_root = sk.make_dataset(root, name="kitti", n_scenes=n_scenes, split="val", seed=666)
-    model = inf.build_model(seed=0, device=cuda)
-    # random-init heads score everything below the 0.3 threshold; bias the RCNN score so that boxes survive
-    with torch.no_grad():
-        model.rcnn_net.cls_layer[-1].conv.bias.fill_(1.0)
-    ckpt_dir = tmp_path / "ckpt"
-    ckpt_dir.mkdir()
-    tu.save_checkpoint(tu.checkpoint_state(model, None, 1, 1), filename=str(ckpt_dir / "checkpoint_epoch_1"))
     out_dir = tmp_path / "out"
+    epoch = os.path.basename(ckpt_path).split("_")[-1].split(".")[0]
     cmd = [sys.executable, "eval_rcnn.py", "--cfg_file", "cfgs/default.yaml", "--eval_mode", "rcnn", "--ckpt",
-           str(ckpt_dir / "checkpoint_epoch_1.pth"), "--batch_size", str(bs), "--workers", "0", "--output_dir", str(out_dir)]
+           str(ckpt_path), "--batch_size", str(bs), "--workers", "0", "--output_dir", str(out_dir)]
     r = subprocess.run(cmd, cwd=os.path.join(root, "tools"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
-    final = out_dir / "eval" / "epoch_1" / "val" / "final_result" / "data"
+    final = out_dir / "eval" / ("epoch_%s" % epoch) / "val" / "final_result" / "data"
     files = sorted(os.listdir(str(final)))
     assert files == ["%06d.txt" % i for i in range(n_scenes)]
 
@@ -48,7 +43,7 @@ def test_unmodified_eval_rcnn_runs_and_matches_detector(cuda, tmp_path):
                                                               classes="Car", far_points=4000)
     np.random.seed(666)
     det = inf.Detector(model, cuda, use_graph=False)
-    calib_mod, ku = load("calibration"), load("kitti_utils")
+    ku = load("kitti_utils")
     total = 0
     for b0 in range(0, n_scenes, bs):
         batch = ds.collate_batch([ds[i] for i in range(b0, b0 + bs)])
@@ -70,4 +65,17 @@ def test_unmodified_eval_rcnn_runs_and_matches_detector(cuda, tmp_path):
                 want = np.array([bx[3], bx[4], bx[5], bx[0], bx[1], bx[2], bx[6], sc])
                 np.testing.assert_allclose(got, want, rtol=0, atol=2e-4)
             total += len(lines)
-    assert total > 0
+    return total
+
+
+@pytest.mark.skipif(not os.path.exists(SCRIPT), reason="oracle/_ref/eval_rcnn.py not staged (needs /root/reference at build time)")
+def test_unmodified_eval_rcnn_runs_and_matches_detector(cuda, tmp_path):
+    inf, tu = load("inference"), load("train_utils")
+    model = inf.build_model(seed=0, device=cuda)
+    # random-init heads score everything below the 0.3 threshold; bias the RCNN score so that boxes survive
+    with torch.no_grad():
+        model.rcnn_net.cls_layer[-1].conv.bias.fill_(1.0)
+    ckpt_dir = tmp_path / "ckpt"
+    ckpt_dir.mkdir()
+    tu.save_checkpoint(tu.checkpoint_state(model, None, 1, 1), filename=str(ckpt_dir / "checkpoint_epoch_1"))
+    assert run_script_and_compare(cuda, tmp_path, model, ckpt_dir / "checkpoint_epoch_1.pth") > 0

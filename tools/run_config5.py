@@ -58,6 +58,17 @@ def loop_seconds(log_file):
     return (t1 - t0).total_seconds() if t0 and t1 else None
 
 
+def dir_digest(path):
+    """sha256 over the sorted (file name, content) pairs of a result directory: equal digests = byte-identical KITTI files"""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(path)):
+        h.update(name.encode())
+        with open(os.path.join(path, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def same_dirs(a, b):
     fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
     if fa != fb:
@@ -154,6 +165,8 @@ def main():
                 arm["loop_scenes_per_s"] = args.scenes / max(loops)
             arm["result_files"] = len(os.listdir(finals[0])) if finals and os.path.isdir(finals[0]) else 0
             arm["final_dir"] = finals[0] if finals else None
+            if arm["result_files"]:
+                arm["result_sha256"] = dir_digest(finals[0])
         record["arms"]["dropin"] = arm
         print("dropin:", json.dumps({k: v for k, v in arm.items() if k != "stderr_tail"}), flush=True)
 
@@ -181,6 +194,7 @@ def main():
                     arm["detections"] = inner["detections"]
             arm["final_dir"] = os.path.join(out, "final_result", "data")
             arm["result_files"] = len(os.listdir(arm["final_dir"]))
+            arm["result_sha256"] = dir_digest(arm["final_dir"])
         record["arms"]["fast"] = arm
         print("fast:", json.dumps({k: v for k, v in arm.items() if k != "stderr_tail"}), flush=True)
 
