@@ -5,13 +5,15 @@
 # Logs -> gpurun_out/sanitizer_<tool>.log (copied to profiles/ by hand).   usage: tools/sanitize.sh [per-tool timeout s]
 T=${1:-420}
 mkdir -p gpurun_out
-SUBSET="tests/test_pn2_ops_gpu.py::test_fps_every_cluster_size_and_temp_writeback tests/test_pn2_ops_gpu.py::test_fps_vs_oracle tests/test_pn2_ops_gpu.py::test_ball_query_vs_oracle tests/test_linear_tc_gpu.py tests/test_iou3d_roipool_gpu.py"
+SUBSET="tests/test_pn2_ops_gpu.py::test_fps_every_cluster_size_and_temp_writeback tests/test_pn2_ops_gpu.py::test_fps_vs_oracle tests/test_pn2_ops_gpu.py::test_ball_query_vs_oracle tests/test_linear_tc_gpu.py tests/test_iou3d_roipool_gpu.py tests/test_glue_gpu.py"
 # racecheck runs twice: "racecheck" over the kernels whose shared-memory traffic it can follow (FPS clusters, ball query,
 # NMS, ROI pooling), "racecheck_tc" over the tcgen05 kernels, where it reports the cp.async.bulk re-fill of a ring stage as
 # a WAW hazard: the issuing thread is ordered after the previous fill by full[] -> MMA warp -> tcgen05.commit -> empty[],
 # a chain through the tensor-core proxy that the tool does not track (DESIGN.md "Sanitizer evidence").
-NON_TC="tests/test_pn2_ops_gpu.py::test_fps_every_cluster_size_and_temp_writeback tests/test_pn2_ops_gpu.py::test_fps_vs_oracle tests/test_pn2_ops_gpu.py::test_ball_query_vs_oracle tests/test_pn2_ops_gpu.py::test_ball_query_culled_vs_oracle tests/test_pn2_ops_gpu.py::test_three_nn_and_interpolate_vs_oracle tests/test_iou3d_roipool_gpu.py"
-TC="tests/test_linear_tc_gpu.py::test_sa_fused_t_skips_padded_duplicates_exactly tests/test_linear_tc_gpu.py::test_linear_pre_two_layers_in_one_launch"
+# (racecheck instruments every shared-memory access: the 4095-round FPS cases of test_fps_vs_oracle alone exceed the budget;
+# the cluster-size test covers every fps_kernel<*,{1,2,4,8}> instantiation on small clouds)
+NON_TC="tests/test_pn2_ops_gpu.py::test_fps_every_cluster_size_and_temp_writeback tests/test_pn2_ops_gpu.py::test_ball_query_vs_oracle tests/test_iou3d_roipool_gpu.py tests/test_glue_gpu.py::test_proposal_layer_kernels_match_torch_flow tests/test_glue_gpu.py::test_postprocess_kernels_match_torch tests/test_glue_gpu.py::test_rcnn_input_stage_one_launch_matches_torch_flow"
+TC="tests/test_linear_tc_gpu.py::test_linear_pre_two_layers_in_one_launch tests/test_linear_tc_gpu.py::test_rcnn_front_chain_in_one_launch"
 ALL="$SUBSET"
 for tool in memcheck synccheck racecheck racecheck_tc; do
     extra=""
