@@ -29,7 +29,24 @@ def _bin_and_residual(pred, bin_lo, n_bins, res_lo):
 
 def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size,
                        get_xz_fine=True, get_y_by_bin=False, loc_y_scope=0.5, loc_y_bin_size=0.25, get_ry_fine=False):
-    """roi_box3d (N,3) point xyz or (N,7) roi; pred_reg (N,C) -> (N,7) [x,y,z,h,w,l,ry]."""
+    """roi_box3d (N,3) point xyz or (N,7) roi; pred_reg (N,C) -> (N,7) [x,y,z,h,w,l,ry].
+    CUDA float32 inputs go through ONE kernel (glue.decode_bbox = pn2_decode_bbox_f32, bit-identical to the torch statements:
+    tests/test_glue_gpu.py) -- this is also what the unmodified eval_rcnn.py reaches through lib.utils.bbox_transform;
+    anything else runs decode_bbox_target_torch, the reference's statements."""
+    if (roi_box3d.is_cuda and pred_reg.is_cuda and roi_box3d.dtype == torch.float32 and pred_reg.dtype == torch.float32
+            and roi_box3d.dim() == 2 and roi_box3d.shape[1] in (3, 7) and pred_reg.shape[0] > 0):
+        from . import glue
+        if glue.ENABLED:
+            return glue.decode_bbox(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size, get_xz_fine=get_xz_fine,
+                                    get_y_by_bin=get_y_by_bin, loc_y_scope=loc_y_scope, loc_y_bin_size=loc_y_bin_size,
+                                    get_ry_fine=get_ry_fine)
+    return decode_bbox_target_torch(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size, get_xz_fine,
+                                    get_y_by_bin, loc_y_scope, loc_y_bin_size, get_ry_fine)
+
+
+def decode_bbox_target_torch(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size,
+                             get_xz_fine=True, get_y_by_bin=False, loc_y_scope=0.5, loc_y_bin_size=0.25, get_ry_fine=False):
+    """decode_bbox_target as the reference's torch statements, in the reference's operation order."""
     anchor_size = anchor_size.to(roi_box3d.device)
     nb = int(loc_scope / loc_bin_size) * 2
     nby = int(loc_y_scope / loc_y_bin_size) * 2

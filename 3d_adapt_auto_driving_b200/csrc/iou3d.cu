@@ -201,6 +201,46 @@ __global__ void __launch_bounds__(256) pairwise_kernel(int na, const float *__re
     out[(size_t)ia * nb + ib] = IOU ? rot_iou(sa[threadIdx.y], sb[threadIdx.x]) : rot_overlap(sa[threadIdx.y], sb[threadIdx.x]);
 }
 
+// boxes_iou3d_gpu (lib/utils/iou3d/iou3d_utils.py:21-53) in ONE launch: BEV boxes (kitti_utils.py:134-147), rotated
+// intersection area, height overlap, volumes and the ratio -- the reference (and the mirror's torch path) spends one kernel
+// + ~14 elementwise launches on it, twice per scene in the recall bookkeeping of eval_rcnn.py:541-609.  Float operations
+// are torch's, in torch's order: half extents are l / 2 = l * 0.5, clamp(min(a_max, b_max) - max(a_min, b_min), 0),
+// (h * w) * l, overlap / clamp(vol_a + vol_b - overlap, 1e-7).
+__global__ void __launch_bounds__(256) iou3d_pairs_kernel(int na, const float *__restrict__ a, int nb,
+                                                         const float *__restrict__ b, float *__restrict__ out) {
+    const int ia = blockIdx.y * 16 + threadIdx.y;
+    const int ib = blockIdx.x * 16 + threadIdx.x;
+    __shared__ float sa[16][7], sb[16][7];
+    const int t = threadIdx.y * 16 + threadIdx.x;
+    if (t < 112) {
+        const int r = t / 7, c = t % 7;
+        const int ga = blockIdx.y * 16 + r;
+        sa[r][c] = ga < na ? a[ga * 7 + c] : 0.f;
+    } else if (t < 224) {
+        const int r = (t - 112) / 7, c = (t - 112) % 7;
+        const int gb = blockIdx.x * 16 + r;
+        sb[r][c] = gb < nb ? b[gb * 7 + c] : 0.f;
+    }
+    __syncthreads();
+    if (ia >= na || ib >= nb) return;
+    const float *pa = sa[threadIdx.y], *pb = sb[threadIdx.x];      // [x, y, z, h, w, l, ry]
+    float ba[5], bb[5];
+    {
+        const float hl = __fmul_rn(pa[5], 0.5f), hw = __fmul_rn(pa[4], 0.5f);
+        ba[0] = __fsub_rn(pa[0], hl); ba[1] = __fsub_rn(pa[2], hw); ba[2] = __fadd_rn(pa[0], hl); ba[3] = __fadd_rn(pa[2], hw); ba[4] = pa[6];
+    }
+    {
+        const float hl = __fmul_rn(pb[5], 0.5f), hw = __fmul_rn(pb[4], 0.5f);
+        bb[0] = __fsub_rn(pb[0], hl); bb[1] = __fsub_rn(pb[2], hw); bb[2] = __fadd_rn(pb[0], hl); bb[3] = __fadd_rn(pb[2], hw); bb[4] = pb[6];
+    }
+    const float bev = rot_overlap(ba, bb);
+    const float a_min = __fsub_rn(pa[1], pa[3]), b_min = __fsub_rn(pb[1], pb[3]);
+    const float oh = fmaxf(__fsub_rn(fminf(pa[1], pb[1]), fmaxf(a_min, b_min)), 0.f);
+    const float o3 = __fmul_rn(bev, oh);
+    const float va = __fmul_rn(__fmul_rn(pa[3], pa[4]), pa[5]), vb = __fmul_rn(__fmul_rn(pb[3], pb[4]), pb[5]);
+    out[(size_t)ia * nb + ib] = __fdiv_rn(o3, fmaxf(__fsub_rn(__fadd_rn(va, vb), o3), 1e-7f));
+}
+
 constexpr int kNmsMaxWords = 1024;       // up to 32768 boxes per problem
 constexpr int kNmsDense = 128;           // rotated problems up to this size evaluate all pairs up front
 constexpr int kNmsStageBytes = 192 * 1024;   // shared-memory budget for the staged boxes of a problem
@@ -356,6 +396,16 @@ PN2_API int pn2_boxes_iou_bev_f32(const float *a, int na, const float *b, int nb
     if (na == 0 || nb == 0) return PN2_OK;
     dim3 grid(pn2_divup(nb, 16), pn2_divup(na, 16)), block(16, 16);
     pairwise_kernel<true><<<grid, block, 0, stream>>>(na, a, nb, b, out);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
+
+// boxes_iou3d_gpu (lib/utils/iou3d/iou3d_utils.py:21-53): a (na,7), b (nb,7) [x,y,z,h,w,l,ry] -> out (na,nb) 3-D IoU.
+PN2_API int pn2_boxes_iou3d_f32(const float *a, int na, const float *b, int nb, float *out, cudaStream_t stream) {
+    if (na < 0 || nb < 0 || (na > 0 && nb > 0 && (!a || !b || !out))) { pn2_set_last_error("pn2_boxes_iou3d_f32: bad argument"); return PN2_ERR_INVALID; }
+    if (na == 0 || nb == 0) return PN2_OK;
+    dim3 grid(pn2_divup(nb, 16), pn2_divup(na, 16)), block(16, 16);
+    iou3d_pairs_kernel<<<grid, block, 0, stream>>>(na, a, nb, b, out);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -59,6 +59,7 @@ struct SatParams {
     const int32_t *cmap; const int32_t *jmap; const long long *rows_dev;
     int cmap_align;                               // 1, or 8: every aligned group of eight list rows has one centre
     unsigned long long *prof;                     // optional stopwatch buffer (32 u64 per CTA, tools/prof_sat.py) or nullptr
+    int dbg;                                      // stopwatch build only: bit0 = the pooling epilogue only releases the accumulator (garbage results)
 };
 
 struct SmemLayout {
@@ -419,7 +420,12 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             const long long te0 = PROF ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t t3 = lane_addr + col_acc3 + (uint32_t)(half * 64);     // this warp: columns half*64 .. +63
-            if constexpr (COMPACT == 8) {
+            if (PROF && (p.dbg & 1)) {
+                // what-if experiment (tools/prof_sat.py): a free pooling epilogue
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc3_empty);
+            } else if constexpr (COMPACT == 8) {
                 // compact rows in groups of eight (group_compact.cu, align 8): an aligned group of eight columns belongs to
                 // one centre, so its maximum is four static 3-input maxima and the run logic (warp-uniform) runs once per
                 // GROUP: bit 4g of run_e says whether column 8g opens a new centre.  Per warp and pass: 8 groups instead
@@ -629,8 +635,12 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
 }
 
 unsigned long long *g_prof = nullptr;
+int g_dbg = 0;
 
 }  // namespace
+
+// what-if switches of the stopwatch build (tools/prof_sat.py; results are garbage): bit0 = free pooling epilogue
+PN2_API void pn2_sa_fused_t_set_debug(int bits) { g_dbg = bits; }
 
 // stopwatch buffer for tools/prof_sat.py: 32 u64 per CTA (device memory) or NULL to disable (never used by the product)
 PN2_API void pn2_sa_fused_t_set_profile(void *buf) { g_prof = static_cast<unsigned long long *>(buf); }
@@ -690,6 +700,7 @@ PN2_API int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, c
     }
     p.stages = stages;
     p.prof = g_prof;
+    p.dbg = g_dbg;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

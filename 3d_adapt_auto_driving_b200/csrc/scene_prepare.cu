@@ -175,3 +175,88 @@ PN2_API int pn2_scene_gather_f32(const float *valid, const int32_t *near_list, c
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same per-point pipeline as a HOST function, for the DataLoader workers of the unmodified eval_rcnn.py: the script
+// owns the loop and the worker processes (tools/eval_rcnn.py:851-866), so the data path stays on the CPU there -- but it
+// need not be ten numpy passes over a 120 000-point sweep (10-13 ms per scene, the bound of the whole script at 204
+// scenes/s: profiles/r2_config5_n1.json).  One pass, the arithmetic of scene_filter_kernel (= numpy's, bit for bit):
+//   rect = [x y z 1] . M,  image = [rect 1] . P,  u = hx / z, v = hy / z (z == 0 -> 1e-9f),  depth = hz - P[3][2],
+//   valid = in the image, depth >= 0, (optionally) inside PC_AREA_SCOPE in float64.
+// Outputs the compacted valid points (rect x, y, z, intensity) in input order and the positions of the near (z < near_z)
+// and far ones among them, the three counts the np.random draws depend on.  FMAs are hardware FMAs when the CPU has them
+// (every x86-64 server of the last decade; __builtin_cpu_supports), libm's fmaf otherwise: identical results.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// the loop body; __builtin_fmaf becomes a vfmadd instruction inside the target("fma") wrapper and a libm call in the other
+static inline __attribute__((always_inline))
+long long scene_filter_host(const float *raw, long long n, const float *m, const float *p, float width, float height,
+                            int reduce_by_range, const double *scope, float near_z, float *valid, int32_t *near_list,
+                            int32_t *far_list, long long *n_near_out) {
+    long long nv = 0, nn = 0;
+    const float p11 = p[11];
+    for (long long i = 0; i < n; ++i) {
+        const float x = raw[4 * i], y = raw[4 * i + 1], z = raw[4 * i + 2];
+        float r[3], h[3];
+        for (int j = 0; j < 3; ++j) {
+            float t = x * m[j];
+            t = __builtin_fmaf(y, m[3 + j], t);
+            t = __builtin_fmaf(z, m[6 + j], t);
+            r[j] = __builtin_fmaf(1.0f, m[9 + j], t);
+        }
+        for (int j = 0; j < 3; ++j) {
+            float t = r[0] * p[j];
+            t = __builtin_fmaf(r[1], p[3 + j], t);
+            t = __builtin_fmaf(r[2], p[6 + j], t);
+            h[j] = __builtin_fmaf(1.0f, p[9 + j], t);
+        }
+        const float zd = r[2] == 0.f ? 1e-9f : r[2];
+        const float u = h[0] / zd, v = h[1] / zd;
+        const float depth = h[2] - p11;
+        bool ok = u >= 0.f && u < width && v >= 0.f && v < height && depth >= 0.f;
+        if (ok && reduce_by_range)
+            ok = (double)r[0] >= scope[0] && (double)r[0] <= scope[1] && (double)r[1] >= scope[2] && (double)r[1] <= scope[3] &&
+                 (double)r[2] >= scope[4] && (double)r[2] <= scope[5];
+        if (!ok) continue;
+        valid[4 * nv] = r[0]; valid[4 * nv + 1] = r[1]; valid[4 * nv + 2] = r[2]; valid[4 * nv + 3] = raw[4 * i + 3];
+        if (r[2] < near_z) near_list[nn++] = (int32_t)nv;
+        else far_list[nv - nn] = (int32_t)nv;
+        ++nv;
+    }
+    *n_near_out = nn;
+    return nv;
+}
+
+__attribute__((target("fma"))) long long scene_filter_host_fma(const float *raw, long long n, const float *m, const float *p,
+                                                              float width, float height, int reduce_by_range, const double *scope,
+                                                              float near_z, float *valid, int32_t *near_list, int32_t *far_list,
+                                                              long long *n_near_out) {
+    return scene_filter_host(raw, n, m, p, width, height, reduce_by_range, scope, near_z, valid, near_list, far_list, n_near_out);
+}
+long long scene_filter_host_libm(const float *raw, long long n, const float *m, const float *p, float width, float height,
+                                 int reduce_by_range, const double *scope, float near_z, float *valid, int32_t *near_list,
+                                 int32_t *far_list, long long *n_near_out) {
+    return scene_filter_host(raw, n, m, p, width, height, reduce_by_range, scope, near_z, valid, near_list, far_list, n_near_out);
+}
+
+}  // namespace
+
+// HOST function (no device work, no stream): raw (n, 4) f32 sweep, m / p the (4, 3) row-major float32 matrices of
+// calibration.Calibration (_velo_to_rect, P2.T), scope 6 doubles {x0, x1, y0, y1, z0, z1} -> valid (n, 4) f32 capacity,
+// near_list / far_list (n) int32 capacity, counts[3] = {n_valid, n_near, n_far}.
+PN2_API int pn2_scene_filter_host_f32(const float *raw, long long n, const float *m, const float *p, float width, float height,
+                                      int reduce_by_range, const double *scope, float near_z, float *valid,
+                                      int32_t *near_list, int32_t *far_list, long long *counts) {
+    if (n < 0 || (n > 0 && (!raw || !valid || !near_list || !far_list)) || !m || !p || !counts || (reduce_by_range && !scope)) {
+        pn2_set_last_error("pn2_scene_filter_host_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    long long nn = 0, nv;
+    // contraction of `x * m[j]` + ... into FMAs would change the first product's rounding: the expressions above are
+    // written so that only the explicit fma calls fuse (a lone product feeding an fma is not contractible further)
+    if (__builtin_cpu_supports("fma")) nv = scene_filter_host_fma(raw, n, m, p, width, height, reduce_by_range, scope, near_z, valid, near_list, far_list, &nn);
+    else nv = scene_filter_host_libm(raw, n, m, p, width, height, reduce_by_range, scope, near_z, valid, near_list, far_list, &nn);
+    counts[0] = nv; counts[1] = nn; counts[2] = nv - nn;
+    return PN2_OK;
+}

@@ -33,8 +33,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Wait on an mbarrier phase.  try_wait carries a suspend-time hint so the hardware parks the warp
 // until the phase flips instead of spinning: a polling loop of 22 warps saturates the four
 // schedulers of the SM and starves the warps that have real work (measured: 1.6 G of the 1.7 G
-// warp-instructions of a run were polls before this).  Bounded: after ~4 s of waiting a protocol bug
-// aborts the kernel (launch error on the next sync) rather than hanging the GPU.
+// warp-instructions of a run were polls before this).  Bounded: after ~30 s of waiting a protocol bug
+// aborts the kernel (launch error on the next sync) rather than hanging the GPU (4 s was too tight under
+// compute-sanitizer's racecheck, which slows a tile down by two orders of magnitude).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = pn2_smem_u32(bar);
     uint32_t done = 0;
@@ -42,7 +43,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     // fused SA kernel's 15 k instructions were unrolled polls) and every role pays instruction-cache misses
     // ("no_inst" stalls after each wait) for code that never runs.
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < 4096u; ++spin) {
+    for (uint32_t spin = 0; spin < 32768u; ++spin) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -66,7 +67,7 @@ __device__ __forceinline__ void mbar_wait_lazy(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = pn2_smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 25); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"

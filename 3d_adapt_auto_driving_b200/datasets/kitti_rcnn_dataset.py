@@ -12,10 +12,19 @@ The file is organised around three independent steps instead of the reference's 
                           identically (tests/test_dataset_vs_reference_cpu.py compares samples with the live class).
     stack_samples()       list of per-scene dicts -> batch dict (collate_batch)
 
+Fast path (default, PN2_NATIVE_DATAPATH=0 disables it): the first two steps in native code.  eval_rcnn.py owns the loop and
+its DataLoader worker processes, so the data path of the unmodified script stays on the CPU -- but ten numpy passes over a
+120 000-point sweep cost 10-13 ms per scene and bounded the whole script (204 scenes/s, profiles/r2_config5_n1.json).
+`pn2_scene_filter_host_f32` (csrc/scene_prepare.cu) does the transform, projection and visibility test in one pass with
+numpy's float32 arithmetic, and the np.random draws are replayed on the SAME MT19937 state by csrc/mt_select.cu
+(np.random.get_state -> native draws -> set_state): identical samples, identical generator state afterwards
+(tests/test_dataset_vs_reference_cpu.py against the live reference class, tests/test_gpu_loader_cpu.py).
+
 Two additions the unmodified eval_rcnn.py needs: the constructor accepts `far_points` (eval_rcnn.py:862 passes it
 although the reference constructor names the argument npoints_faraway -- a TypeError upstream), and scene sharding
 for multi-GPU runs lives here because the script has none (PN2_SHARD_RANK / PN2_SHARD_WORLD, tools/eval_sharded.py:
 the data set keeps sample_id_list[rank::world])."""
+import ctypes
 import os
 
 import numpy as np
@@ -33,6 +42,39 @@ CLASS_GROUPS = {
 NEAR_DEPTH = 40.0                 # metres: the near / far split of the point budget (:293)
 BOX_KEYS = ('gt_boxes3d', 'roi_boxes3d')
 SCENE_SEED_BASE = 666 * 1000003   # per-scene seeds of sharded runs: (base + sample_id) mod 2^32
+NATIVE_DATAPATH = os.environ.get("PN2_NATIVE_DATAPATH", "1") != "0"
+SHARED_BATCHES = os.environ.get("PN2_SHARED_BATCHES", "1") != "0"      # worker -> main process through shared memory (_ShmArray)
+_FAR_BASE = 1 << 30               # encoding of pn2_mt_draw_selection's output (datasets/gpu_loader.py)
+
+
+def _native_filter(lidar, calib, img_shape):
+    """visible_points() in one native pass -> (valid (k, 4) float32 [rect x, y, z, intensity], near positions, far
+    positions): the rows, order and float32 values of the numpy chain"""
+    from .. import cabi
+    lib = cabi.lib()
+    if not getattr(lib, "_pn2_filter_host_ready", False):
+        f32p, i32p, f64p, i64p = (ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_longlong))
+        lib.pn2_scene_filter_host_f32.argtypes = [f32p, ctypes.c_longlong, f32p, f32p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                  f64p, ctypes.c_float, f32p, i32p, i32p, i64p]
+        lib._pn2_filter_host_ready = True
+    raw = np.ascontiguousarray(lidar, dtype=np.float32)
+    n = raw.shape[0]
+    m = np.ascontiguousarray(calib._velo_to_rect, dtype=np.float32)
+    p = np.ascontiguousarray(calib._rect_to_image, dtype=np.float32)
+    scope = np.ascontiguousarray(np.asarray(cfg.PC_AREA_SCOPE, dtype=np.float64).reshape(-1))
+    valid = np.empty((max(n, 1), 4), np.float32)
+    near = np.empty((max(n, 1),), np.int32)
+    far = np.empty((max(n, 1),), np.int32)
+    counts = np.zeros((3,), np.int64)
+    fp = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    cabi.check(lib.pn2_scene_filter_host_f32(fp(raw, ctypes.c_float), n, fp(m, ctypes.c_float), fp(p, ctypes.c_float),
+                                             float(img_shape[1]), float(img_shape[0]), 1 if cfg.PC_REDUCE_BY_RANGE else 0,
+                                             fp(scope, ctypes.c_double), NEAR_DEPTH, fp(valid, ctypes.c_float),
+                                             fp(near, ctypes.c_int32), fp(far, ctypes.c_int32), fp(counts, ctypes.c_longlong)),
+               "pn2_scene_filter_host_f32")
+    k, kn = int(counts[0]), int(counts[1])
+    return valid[:k], near[:kn], far[:k - kn]
 
 
 def _inside(values, bounds):
@@ -72,6 +114,30 @@ class PointBudget:
         return picked
 
 
+class _ShmArray(np.ndarray):
+    """A batch array built inside a DataLoader WORKER.  torch's DataLoader moves torch tensors between processes through
+    shared memory but pickles numpy arrays byte by byte through a pipe -- 7 MB per batch of 16 scenes, ~1.5 ms per scene of
+    the main process of eval_rcnn.py, which must hand the script numpy arrays (it calls torch.from_numpy on them,
+    eval_rcnn.py:498).  Pickling an instance sends its buffer as a shared-memory torch tensor instead (one copy into
+    shared memory in the worker, none in the main process) and the main process receives a PLAIN ndarray on that memory."""
+
+    def __reduce__(self):
+        import torch
+        return (_array_from_shared_tensor, (torch.from_numpy(np.ascontiguousarray(self).view(np.ndarray)).share_memory_(),))
+
+
+def _array_from_shared_tensor(tensor):
+    return tensor.numpy()
+
+
+def _in_loader_worker():
+    import torch.utils.data
+    return torch.utils.data.get_worker_info() is not None
+
+
+SHARED_BATCH_MIN_BYTES = 1 << 16     # smaller arrays (sample ids, boxes) travel by value as before
+
+
 def stack_samples(samples):
     """collate_batch (:1125-1158): box lists are zero-padded to the longest of the batch, arrays are stacked, Python
     ints / floats become int32 / float32 vectors, anything else stays a list."""
@@ -85,7 +151,10 @@ def stack_samples(samples):
                 row[:len(boxes)] = boxes
             batch[key] = padded
         elif isinstance(probe, np.ndarray):
-            batch[key] = np.concatenate([a[np.newaxis, ...] for a in column], axis=0)
+            stacked = np.concatenate([a[np.newaxis, ...] for a in column], axis=0)
+            if stacked.nbytes >= SHARED_BATCH_MIN_BYTES and SHARED_BATCHES and _in_loader_worker():
+                stacked = stacked.view(_ShmArray)
+            batch[key] = stacked
         elif isinstance(probe, int):
             batch[key] = np.array(column, dtype=np.int32)
         elif isinstance(probe, float):
@@ -175,10 +244,37 @@ class KittiRCNNDataset(KittiDataset):
     def __getitem__(self, index):
         return self.get_rpn_sample(index)
 
+    def _native_sample(self, sample_id):
+        """visible_points + PointBudget.draw in native code: the same points in the same order, np.random left in the same
+        state.  -> (xyz (npoints, 3), intensity (npoints,))"""
+        from . import gpu_loader as gl
+        valid, near, far = _native_filter(self.get_lidar(sample_id), self.get_calib(sample_id), self.get_image_shape(sample_id))
+        if self.per_scene_seed:
+            state = gl.MTState.seeded((SCENE_SEED_BASE + sample_id) % (2 ** 32))
+        else:
+            state = gl.MTState.from_numpy_global()
+        sel = np.empty((self.npoints,), np.int32)
+        scratch = np.empty((max(len(valid), self.npoints) + self.npoints,), np.int32)   # pn2_mt_draw_selection: population + selection
+        gl.draw_selection_native(state, len(valid), len(near), len(far), self.npoints, self.npoints_faraway, self.with_replace,
+                                 sel, scratch)
+        state.to_numpy_global()
+        picked = np.where(sel < 0, -sel - 1, 0).astype(np.int64)
+        is_near = (sel >= 0) & (sel < _FAR_BASE)
+        is_far = sel >= _FAR_BASE
+        if is_near.any():
+            picked[is_near] = near[sel[is_near]]
+        if is_far.any():
+            picked[is_far] = far[sel[is_far] - _FAR_BASE]
+        chosen = valid[picked]
+        return np.ascontiguousarray(chosen[:, 0:3]), np.ascontiguousarray(chosen[:, 3])
+
     def get_rpn_sample(self, index):
         sample_id = int(self.sample_id_list[index])
-        xyz, intensity = self.visible_points(sample_id)
-        if self.random_select:
+        if self.random_select and NATIVE_DATAPATH:
+            xyz, intensity = self._native_sample(sample_id)
+        else:
+            xyz, intensity = self.visible_points(sample_id)
+        if self.random_select and not NATIVE_DATAPATH:
             if self.per_scene_seed:
                 np.random.seed((SCENE_SEED_BASE + sample_id) % (2 ** 32))
             picked = self._sample_indices(xyz)

@@ -372,10 +372,12 @@ SA_TRANSPOSED = os.environ.get("PN2_SA_TRANSPOSED", "1") != "0"
 # Push only the UNIQUE rows of every ball-query group through the SA MLP (csrc/group_compact.cu): a group that found
 # cnt < nsample neighbours is padded with copies of its first hit, which cannot change the max-pool.
 SA_SKIP_DUPLICATES = os.environ.get("PN2_SA_SKIP_DUPLICATES", "1") != "0"
-# The transposed kernel also handles last layers of fewer than 128 channels (accumulator padded to 128 lanes), but for
-# the two RPN SA1 scales (32 / 64 channels, 16 / 32-channel hidden layers) it measured no faster than the row-major
-# kernel (0.39 vs 0.43 ms per step: those launches are prologue- and producer-bound, not pooling-bound): not routed.
-SA_TRANSPOSED_SMALL = os.environ.get("PN2_SA_TRANSPOSED_SMALL", "0") == "1"
+# The transposed kernel also handles last layers of fewer than 128 channels (accumulator padded to 128 lanes).  For the two
+# RPN SA1 scales (32 / 64 channels, 16 / 32-channel hidden layers) it is no faster than the row-major kernel on DENSE rows
+# (0.39 vs 0.43 ms per step: those launches are prologue- and producer-bound), but it has the duplicate-skipping mode, and
+# only 8-37 % of those groups' rows are unique: 0.40 ms (row-major, dense) -> 0.24 ms + 0.05 ms of compaction launches,
+# +1.5 % scenes/s on the bench (A/B in one call, profiles/r2d_*): routed since round 2.
+SA_TRANSPOSED_SMALL = os.environ.get("PN2_SA_TRANSPOSED_SMALL", "1") == "1"
 SA_SKIP_MIN_ROWS = 1 << 20      # below ~1 M grouped rows the two compaction launches + the zero-fill cost more than they save
 
 

@@ -20,7 +20,7 @@ from . import fused as fz
 from . import glue
 from . import iou3d_cuda
 from . import kitti_utils
-from .bbox_transform import decode_bbox_target
+from .bbox_transform import decode_bbox_target_torch as decode_bbox_target     # postprocess_torch: the torch statements
 from .config import cfg
 
 

@@ -17,8 +17,22 @@ def boxes_iou_bev(boxes_a, boxes_b):
 
 
 def boxes_iou3d_gpu(boxes_a, boxes_b):
-    """(N,7),(M,7) [x,y,z,h,w,l,ry] -> (N,M) 3D IoU = BEV overlap x height overlap / union
-    (iou3d_utils.py:21-53; the elementwise part is torch in the reference too)."""
+    """(N,7),(M,7) [x,y,z,h,w,l,ry] -> (N,M) 3D IoU = BEV overlap x height overlap / union (iou3d_utils.py:21-53).
+    One launch (pn2_boxes_iou3d_f32) for contiguous CUDA float32 boxes -- eval_rcnn.py calls this twice per scene in its
+    recall bookkeeping; boxes_iou3d_torch is the reference's composition (one kernel + ~14 elementwise launches) and what
+    tests/test_iou3d_roipool_gpu.py compares the kernel with."""
+    if (boxes_a.is_cuda and boxes_b.is_cuda and boxes_a.dtype == torch.float32 and boxes_b.dtype == torch.float32
+            and boxes_a.dim() == 2 and boxes_b.dim() == 2 and boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7):
+        from .cabi import call, i32, ptr
+        a, b = boxes_a.contiguous(), boxes_b.contiguous()
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+        call("pn2_boxes_iou3d_f32", ptr(a), i32(a.shape[0]), ptr(b), i32(b.shape[0]), ptr(out))
+        return out
+    return boxes_iou3d_torch(boxes_a, boxes_b)
+
+
+def boxes_iou3d_torch(boxes_a, boxes_b):
+    """boxes_iou3d_gpu as the reference composes it: BEV overlap kernel + torch elementwise statements."""
     boxes_a_bev = kitti_utils.boxes3d_to_bev_torch(boxes_a)
     boxes_b_bev = kitti_utils.boxes3d_to_bev_torch(boxes_b)
     overlaps_bev = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
@@ -38,7 +52,11 @@ def _nms(boxes, scores, thresh, rotated, max_keep=None):
     scores = scores.reshape(-1)      # eval_rcnn.py:626 passes (n, 1) scores; the result is .view(-1)'ed there
     order = scores.sort(0, descending=True)[1]
     sorted_boxes = boxes[order].contiguous()
-    keep, num = iou3d_cuda.nms_device(sorted_boxes, thresh, rotated, max_keep=max_keep)
+    n = sorted_boxes.shape[0]
+    if n == 0:
+        return order
+    from . import glue
+    keep, num = glue.nms_raw(sorted_boxes.view(1, n, 5), None, thresh, rotated, n if max_keep is None else int(max_keep))
     return order[keep[0, :int(num.item())]].contiguous()
 
 

@@ -14,7 +14,7 @@ Two execution paths with identical results:
 import torch
 import torch.nn as nn
 
-from .bbox_transform import decode_bbox_target
+from .bbox_transform import decode_bbox_target_torch as decode_bbox_target     # the non-kernel flows: the torch statements
 from .config import cfg
 from . import kitti_utils
 from . import iou3d_utils

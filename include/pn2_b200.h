@@ -129,6 +129,11 @@ int pn2_roipool3d_split_f32(const float *xyz, const float *boxes3d, const float 
 int pn2_boxes_overlap_bev_f32(const float *a, int na, const float *b, int nb, float *out, void *stream);
 /* boxes_iou_bev_gpu  iou3d.cpp:52-71, iou3d_kernel.cu:236-248. */
 int pn2_boxes_iou_bev_f32(const float *a, int na, const float *b, int nb, float *out, void *stream);
+/* boxes_iou3d_gpu (lib/utils/iou3d/iou3d_utils.py:21-53) in one launch: a (na,7), b (nb,7) [x,y,z,h,w,l,ry] -> out (na,nb)
+ * 3-D IoU = rotated BEV intersection x height overlap / union volume; float operations in the order of the reference's torch
+ * statements. */
+int pn2_boxes_iou3d_f32(const float *a, int na, const float *b, int nb, float *out, void *stream);
+
 /* nms_gpu / nms_normal_gpu (boxes, keep, thresh) -> num  iou3d.cpp:73-169 (mask kernels
  * iou3d_kernel.cu:250-348 + host greedy pass), batched and device-resident: boxes
  * (problems, stride, 5) sorted by descending score, problem p uses its first counts[p] boxes
@@ -213,6 +218,7 @@ int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t
                           int32_t *cmap, int32_t *jmap, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
 void pn2_sa_fused_t_set_profile(void *buf);    /* tools/prof_sat.py: in-kernel stopwatch of pn2_sa_fused_t_tc_f32 */
+void pn2_sa_fused_t_set_debug(int bits);       /* tools/prof_sat.py: what-if switches of the stopwatch build (garbage results) */
 void pn2_rcnn_front_set_profile(void *buf);   /* tools/prof_front.py: in-kernel stopwatch of pn2_rcnn_front_tc_f32 */
 void pn2_rcnn_front_set_mode(int bits);       /* tools/prof_front.py: tuning variants of the same kernel (same results) */
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
@@ -234,6 +240,14 @@ int pn2_scene_filter_f32(const float *raw, const long long *offsets, const float
                          int32_t *near_list, int32_t *far_list, int32_t *counts, int b, long long cap, void *stream);
 int pn2_scene_gather_f32(const float *valid, const int32_t *near_list, const int32_t *far_list, const int32_t *sel,
                          float *pts, float *feat, int b, int npoints, long long cap, void *stream);
+
+/* HOST function: pn2_scene_filter_f32's per-point pipeline for ONE scene on the CPU (the DataLoader workers of the
+ * unmodified eval_rcnn.py): raw (n, 4) f32, m / p = the (4, 3) row-major float32 matrices lidar -> rect and rect -> image,
+ * scope {x0, x1, y0, y1, z0, z1} -> valid (n, 4) capacity [rect x, y, z, intensity] compacted in input order, near_list /
+ * far_list (n) capacity, counts[3] = {n_valid, n_near, n_far}.  Same float32 arithmetic as numpy's (FMA chains). */
+int pn2_scene_filter_host_f32(const float *raw, long long n, const float *m, const float *p, float width, float height,
+                              int reduce_by_range, const double *scope, float near_z, float *valid, int32_t *near_list,
+                              int32_t *far_list, long long *counts);
 
 /* HOST functions (no device work): the np.random draws of KittiRCNNDataset._sample_indices
  * (lib/datasets/kitti_rcnn_dataset.py:291-320) on an explicit MT19937 state, bit for bit numpy's legacy

@@ -1,5 +1,5 @@
 """csrc/glue.cu + pn2_roipool3d_canon_f32: every one-launch stage is BIT-IDENTICAL to the torch composition it replaces
-(bbox_transform.decode_bbox_target, ProposalLayer's torch flow, RCNNNet._pool_rois_padded, Detector.postprocess_torch),
+(bbox_transform.decode_bbox_target_torch, ProposalLayer's torch flow, RCNNNet._pool_rois_padded, Detector.postprocess_torch),
 which are themselves the reference's statements (tests/test_host_utils_cpu.py, test_refnet_vs_port_cpu.py).
 The kernels must reproduce IEEE single precision exactly: decoded boxes feed thresholds and NMS."""
 import numpy as np
@@ -46,7 +46,7 @@ def test_decode_bbox_matches_torch_bitwise(cuda, fine, ybin, ryfine):
     anchor = torch.from_numpy(cfg.CLS_MEAN_SIZE[0]).to(cuda)
     for roi_dim in (3, 7):
         roi = (torch.randn((rows, roi_dim), generator=g) * torch.tensor([20.0, 1.0, 30.0, 0.3, 0.3, 0.5, 2.0][:roi_dim])).to(cuda)
-        want = bt.decode_bbox_target(roi, reg, 3.0, 0.5, 12, anchor, get_xz_fine=fine, get_y_by_bin=ybin, loc_y_scope=0.5,
+        want = bt.decode_bbox_target_torch(roi, reg, 3.0, 0.5, 12, anchor, get_xz_fine=fine, get_y_by_bin=ybin, loc_y_scope=0.5,
                                      loc_y_bin_size=0.25, get_ry_fine=ryfine)
         got = glue.decode_bbox(roi, reg, 3.0, 0.5, 12, cfg.CLS_MEAN_SIZE[0], get_xz_fine=fine, get_y_by_bin=ybin,
                                loc_y_scope=0.5, loc_y_bin_size=0.25, get_ry_fine=ryfine)
@@ -63,7 +63,7 @@ def test_decode_bbox_matches_torch_bitwise(cuda, fine, ybin, ryfine):
         _bits_equal(got, want, "decode roi_dim=%d" % roi_dim)
     # the proposal layer's variant: y moved to the bottom face
     xyz = torch.from_numpy(synthetic.make_clouds("lidar", 1, rows, seed=2)[0]).to(cuda)
-    want = bt.decode_bbox_target(xyz, reg, 3.0, 0.5, 12, anchor, get_xz_fine=fine, get_y_by_bin=ybin, get_ry_fine=ryfine)
+    want = bt.decode_bbox_target_torch(xyz, reg, 3.0, 0.5, 12, anchor, get_xz_fine=fine, get_y_by_bin=ybin, get_ry_fine=ryfine)
     want[:, 1] += want[:, 3] / 2
     got = glue.decode_bbox(xyz, reg, 3.0, 0.5, 12, cfg.CLS_MEAN_SIZE[0], get_xz_fine=fine, get_y_by_bin=ybin,
                            get_ry_fine=ryfine, y_bottom=True)
@@ -188,3 +188,37 @@ def test_detector_with_and_without_glue_kernels_is_identical(cuda, model):
         glue.ENABLED = old
     assert torch.equal(num0, num1)
     _bits_equal(rec1, rec0, "records with / without the glue kernels")
+
+
+def test_whole_forward_graph_replay_equals_eager(cuda):
+    """PointRCNN.graph_forward (what the drop-in tree of the unmodified eval_rcnn.py switches on): replaying the captured
+    forward gives the eager launches' outputs bit for bit, for new data in the same shape, for a second shape, and again
+    after the weights changed (load_state_dict drops the captured graphs)."""
+    inf = load("inference")
+    model = inf.build_model(seed=0, device=cuda)
+    keys = ("rpn_cls", "rpn_reg", "backbone_features", "rois", "roi_scores_raw", "seg_result", "rcnn_cls", "rcnn_reg")
+
+    def both(pts):
+        with torch.no_grad():
+            model.graph_forward = False
+            want = model({"pts_input": pts})
+            model.graph_forward = True
+            got = model({"pts_input": pts})
+            again = model({"pts_input": pts})
+        model.graph_forward = False
+        for k in keys:
+            assert torch.equal(got[k], want[k]), k
+            assert torch.equal(again[k], want[k]) and again[k].data_ptr() != got[k].data_ptr(), k
+        return got
+
+    a = both(torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=5)).to(cuda))
+    b = both(torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=6)).to(cuda))      # same shape: a replay
+    assert not torch.equal(a["rois"], b["rois"])
+    both(torch.from_numpy(synthetic.make_clouds("lidar", 3, 16384, seed=7)).to(cuda))           # another shape
+    assert len(model._graphs) == 2
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    state["rcnn_net.cls_layer.2.conv.bias"] += 1.0
+    model.load_state_dict(state)
+    assert len(model._graphs) == 0
+    c = both(torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=5)).to(cuda))
+    assert not torch.equal(c["rcnn_cls"], a["rcnn_cls"])

@@ -130,8 +130,11 @@ def test_boxes_iou3d_vs_legacy_overlap(cuda, legacy):
     oh = torch.clamp(torch.min(a_max, b_max) - torch.max(a_min, b_min), min=0)
     o3 = ov * oh
     va = (a[:, 3] * a[:, 4] * a[:, 5]).view(-1, 1); vb = (b[:, 3] * b[:, 4] * b[:, 5]).view(1, -1)
-    assert torch.equal(got, o3 / torch.clamp(va + vb - o3, min=1e-7))
+    assert torch.equal(got, o3 / torch.clamp(va + vb - o3, min=1e-7))      # the one-launch kernel == reference composition
+    assert torch.equal(got, iu.boxes_iou3d_torch(a, b))
     assert got.max() > 0.5
+    assert iu.boxes_iou3d_gpu(a[:0], b).shape == (0, 40) and iu.boxes_iou3d_gpu(a, b[:0]).shape == (90, 0)
+    assert torch.equal(iu.boxes_iou3d_gpu(a[3:4], a[3:4]), iu.boxes_iou3d_torch(a[3:4], a[3:4]))
 
 
 def test_roipool3d_matches_reference_golden(cuda):

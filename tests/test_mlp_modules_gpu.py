@@ -254,7 +254,7 @@ def test_proposal_layer_vs_reference_nms_composition(cuda, model, legacy):
     pl = model.rpn.proposal_layer
     rois, roi_scores = pl(scores, reg, xyz)
     assert rois.shape == (B, 100, 7)
-    props = bt.decode_bbox_target(xyz.view(-1, 3), reg.view(-1, 76), anchor_size=pl.MEAN_SIZE, loc_scope=cfg.RPN.LOC_SCOPE,
+    props = bt.decode_bbox_target_torch(xyz.view(-1, 3), reg.view(-1, 76), anchor_size=pl.MEAN_SIZE, loc_scope=cfg.RPN.LOC_SCOPE,
                                   loc_bin_size=cfg.RPN.LOC_BIN_SIZE, num_head_bin=cfg.RPN.NUM_HEAD_BIN,
                                   get_xz_fine=True, get_y_by_bin=False, get_ry_fine=False)
     props[:, 1] += props[:, 3] / 2

@@ -22,7 +22,7 @@ names = {0: "MMA warp total", 1: "MMA wait operand ring", 2: "MMA wait acc2 free
          12: "EPI E2 work", 13: "EPI E3 work", 14: "PROD wait row metadata", 15: "PROD wait free stage", 16: "PROD total"}
 
 
-def run(tag, h, idx, xyz, centres, wxyz, l2, l3, out):
+def run(tag, h, idx, xyz, centres, wxyz, l2, l3, out, dbg=0):
     for _ in range(2):
         fz.sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out)
     torch.cuda.synchronize()
@@ -36,8 +36,10 @@ def run(tag, h, idx, xyz, centres, wxyz, l2, l3, out):
     ncta = 148 * 4
     prof = torch.zeros((ncta * 32,), dtype=torch.int64, device="cuda")
     cabi.lib().pn2_sa_fused_t_set_profile(ctypes.c_void_p(prof.data_ptr()))
+    cabi.lib().pn2_sa_fused_t_set_debug(dbg)
     fz.sa_fused_tc(h, idx, xyz, centres, wxyz, l2, l3, out)
     torch.cuda.synchronize()
+    cabi.lib().pn2_sa_fused_t_set_debug(0)
     cabi.lib().pn2_sa_fused_t_set_profile(ctypes.c_void_p(0))
     pr = prof.view(ncta, 32).double().cpu()
     pr = pr[pr[:, 5] > 0]
@@ -73,9 +75,10 @@ def main():
         uniq = int((idx[:, :, 1:] != idx[:, :, :1]).sum().item()) + R * M
         print("%s: %d grouped rows, %d unique (%.1f %%), %d after 8-row alignment" % (
             tag, R * M * ns, uniq, 100.0 * uniq / (R * M * ns), int(fz.group_compact(idx, align=8)[2].item())))
-        for skip, align in ((True, 8), (True, 1), (False, 8)):
+        for skip, align, dbg in ((True, 8, 0), (True, 8, 1), (True, 1, 0), (False, 8, 0)):
             fz.SA_SKIP_DUPLICATES, fz.SA_COMPACT_ALIGN = skip, align
-            run("%s, %s" % (tag, ("duplicate-skipping, align %d" % align) if skip else "dense"), h, idx, xyz, centres, wxyz, l2, l3, out_t)
+            run("%s, %s%s" % (tag, ("duplicate-skipping, align %d" % align) if skip else "dense", ", WHAT-IF free pooling epilogue (stopwatch pass only)" if dbg else ""),
+                h, idx, xyz, centres, wxyz, l2, l3, out_t, dbg)
     fz.SA_SKIP_DUPLICATES, fz.SA_COMPACT_ALIGN = True, 8
 
 
