@@ -383,6 +383,11 @@ __global__ void __launch_bounds__(256) fps_prefix_check_kernel(const float *__re
 
 }  // namespace
 
+// fps_cells.cu: the pruned one-CTA kernel (clouds of up to 16384 points)
+bool pn2_fps_cells_supported(int n);
+cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
+                                 const int32_t *viol, cudaStream_t stream);
+
 // Block size the reference launcher would have used (cuda_utils.h:10-14); it only matters
 // here because it fixes the tie-break order.  Same double-precision expression.
 PN2_API int pn2_fps_ref_block_size(int n) {
@@ -407,6 +412,18 @@ static int fps_launch(const float *xyz, float *temp, int32_t *idx, int b, int n,
     if (n == 0) {
         pn2_set_last_error("pn2_fps_f32: empty cloud with m > 0");
         return PN2_ERR_INVALID;
+    }
+    // Heuristic launches of mid-sized clouds go to the pruned one-CTA kernel (fps_cells.cu): a shorter round on a quarter
+    // of the SMs.  Below kCellsMinN points the whole cloud is a handful of cells and the plain kernel's round is as short;
+    // with few rounds the Hilbert-sort prepass (~20 us) does not pay.
+    constexpr int kCellsMinN = 2048, kCellsMinM = 128;
+    if (cluster_size == 0 && n > kCellsMinN && m >= kCellsMinM && pn2_fps_cells_supported(n)) {
+        const cudaError_t ec = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, 0, viol, stream);
+        if (ec != cudaSuccess) {
+            pn2_set_last_error(cudaGetErrorString(ec));
+            return PN2_ERR_LAUNCH;
+        }
+        return PN2_OK;
     }
     const int bs = pn2_fps_ref_block_size(n);
     int log2bs = 0;

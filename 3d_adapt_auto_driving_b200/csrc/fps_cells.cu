@@ -1,0 +1,492 @@
+// fps_cells.cu -- furthest point sampling with exact spatial pruning: one CTA per cloud, 2048 < N <= 16384.
+//
+// Replaces pointrcnn/pointnet2_lib/pointnet2/src/sampling_gpu.cu:93-253 like fps.cu does (same result, bit for
+// bit: max d2, then the reference's tree order among equal distances, see the header of fps.cu).
+//
+// Why a second kernel.  fps.cu updates the running min-distance of EVERY point in every round, which costs ~470 cycles of
+// a ~1310-cycle round, and needs a 4-CTA cluster (with a ~840-cycle DSMEM exchange) to hold the cloud in registers.
+// But a new centre c only lowers min-distances inside the ball around c whose radius is the current maximum: after a
+// few hundred rounds that is a small neighbourhood.  Here the cloud is sorted along a Hilbert curve (in-kernel counting
+// sort) and cut into CELLS of 128 consecutive points = 4 register slots x 32 lanes of one warp; a warp owns CPW cells
+// that lie far apart on the curve.  Per cell the warp keeps the bounding box and the exact maximum `cmax` of the cell's
+// running min-distances.  In a round a cell is touched only if
+//      lb(c, box) < cmax ,    lb = sqdist(max(0, lo - c, c - hi))  evaluated with the reference's own float expression.
+// Rounding is monotone, so lb is a true lower bound of the FLOAT distance the reference computes for every point of
+// the cell:  d2(p, c) >= lb >= cmax >= t[p]  =>  min(t[p], d2) == t[p] -- skipping the cell changes nothing, the result is
+// bit-identical.  On KITTI-shaped clouds ~4.6 of the 128 cells are touched per round (tools/sim_fps_cells.py).
+// Everything is on one SM, so the exchange is one __syncthreads per round:
+//   1. every warp tests its CPW boxes (lane i < CPW tests cell i, one ballot);
+//   2. touched cells: 3 x LDS.128 (coordinates live in shared memory, SoA, slot-major per lane) + packed fp32 update of
+//      4 running distances per lane, redux.max -> new cmax; then the warp's record (d2 bits | ~rank | position), where
+//      ties on d2 are resolved exactly by the reference rank (u16 table of point indices in shared memory);
+//      untouched warps copy last round's record (8 bytes);
+//   3. __syncthreads; every warp reduces the WARPS records redundantly (two redux.sync) and reads the next centre's
+//      coordinates from shared memory.
+// Registers hold only the running distances (4 * CPW per lane) -- 16 warps x 8 cells cover 16384 points in ONE CTA:
+// ~4-8x less SM-time than the 4-CTA cluster kernel at a shorter round, which is what counts with several batches in flight.
+#include "spatial_order.cuh"
+#include <cmath>
+#include <type_traits>
+
+namespace {
+
+constexpr int kCellPts = 128;
+
+__device__ __forceinline__ uint32_t cells_rank(uint32_t k, int log2bs, int cnt) {
+    const uint32_t tref = k & ((1u << log2bs) - 1u);
+    const uint32_t rev = log2bs ? (__brev(tref) >> (32 - log2bs)) : 0u;
+    return rev * (uint32_t)cnt + (k >> log2bs);
+}
+
+// explicit shared-memory accesses on 32-bit shared addresses (see the main loop)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+
+// f(integral_constant<ci>) through a binary tree of uniform branches (a switch became an LDC jump table + BRX, ~80 cycles)
+template <int LO, int HI, class F>
+__device__ __forceinline__ void dispatch_cell(int ci, F &&f) {
+    if constexpr (HI - LO == 1) {
+        f(std::integral_constant<int, LO>{});
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if (ci < MID) dispatch_cell<LO, MID>(ci, f);
+        else dispatch_cell<MID, HI>(ci, f);
+    }
+}
+
+template <int WARPS, int CPW>
+struct CellsCfg {
+    static constexpr int T = WARPS * 32;
+    static constexpr int SLOTS = 4 * CPW;
+    static constexpr int NP = WARPS * CPW * kCellPts;
+    // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16) | recs (2 x WARPS u64)
+    static constexpr size_t kMain = (size_t)NP * 14 + 2 * WARPS * 8;
+    // prepass scratch (aliases the image): hist (4096 int) | ord (NP u16) | red (4 x WARPS float) | wsum (WARPS int)
+    static constexpr size_t kPre = (size_t)kOrderCells * 4 + (size_t)NP * 2 + 5 * WARPS * 4;
+    static constexpr size_t kSmem = kMain > kPre ? kMain : kPre;
+};
+
+// PROF: in-kernel stopwatch (tools/prof_fps_cells.py): per warp, cycles spent in each phase of the round
+template <int WARPS, int CPW, bool PROF>
+__global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
+                                                                  int32_t *__restrict__ idx, int n, int m, int log2bs, int cnt,
+                                                                  const int32_t *__restrict__ viol,
+                                                                  unsigned long long *__restrict__ prof) {
+    using Cfg = CellsCfg<WARPS, CPW>;
+    constexpr int T = Cfg::T, SLOTS = Cfg::SLOTS, NP = Cfg::NP;
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *X = reinterpret_cast<float *>(smem), *Y = X + NP, *Z = Y + NP;
+    uint16_t *ktab = reinterpret_cast<uint16_t *>(Z + NP);
+    unsigned long long *recs = reinterpret_cast<unsigned long long *>(ktab + NP);   // [2][WARPS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    xyz += (size_t)cloud * n * 3;
+    idx += (size_t)cloud * m;
+    if (temp) temp += (size_t)cloud * n;
+    if (viol != nullptr && __ldg(viol + cloud) == 0) {       // guarded launch, see fps.cu
+        for (int i = tid; i < m; i += T) idx[i] = i;
+        return;
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // prepass 1: Hilbert order of the cloud (counting sort on a 64 x 64 grid over the (x, z) bounding box).  The order
+    // inside a grid cell is whatever the atomics produce: the sampling result does not depend on which lane owns a point.
+    // ------------------------------------------------------------------------------------------------------------
+    uint16_t kk[SLOTS];
+    {
+        int *hist = reinterpret_cast<int *>(smem);
+        uint16_t *ord = reinterpret_cast<uint16_t *>(smem + (size_t)kOrderCells * 4);
+        float *red = reinterpret_cast<float *>(smem + (size_t)kOrderCells * 4 + (size_t)NP * 2);   // [4][WARPS]
+        int *wsum = reinterpret_cast<int *>(red + 4 * WARPS);
+
+        float xmin = 3.0e38f, xmax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
+        for (int i = tid; i < n; i += T) {
+            const float x = __ldg(xyz + (size_t)i * 3), z = __ldg(xyz + (size_t)i * 3 + 2);
+            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x);
+            zmin = fminf(zmin, z); zmax = fmaxf(zmax, z);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+            zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        }
+        if (lane == 0) { red[0 * WARPS + warp] = xmin; red[1 * WARPS + warp] = xmax; red[2 * WARPS + warp] = zmin; red[3 * WARPS + warp] = zmax; }
+        for (int i = tid; i < kOrderCells; i += T) hist[i] = 0;
+        __syncthreads();
+        for (int w = 0; w < WARPS; ++w) {
+            xmin = fminf(xmin, red[0 * WARPS + w]); xmax = fmaxf(xmax, red[1 * WARPS + w]);
+            zmin = fminf(zmin, red[2 * WARPS + w]); zmax = fmaxf(zmax, red[3 * WARPS + w]);
+        }
+        const float top = (float)((1 << kOrderBits) - 1);
+        const float sx = xmax > xmin ? top / (xmax - xmin) : 0.f;
+        const float sz = zmax > zmin ? top / (zmax - zmin) : 0.f;
+        auto cell_of = [&](int i) -> int {
+            const float x = __ldg(xyz + (size_t)i * 3), z = __ldg(xyz + (size_t)i * 3 + 2);
+            const float fx = fminf(fmaxf((x - xmin) * sx, 0.f), top), fz = fminf(fmaxf((z - zmin) * sz, 0.f), top);
+            const uint32_t gx = (uint32_t)(int)fx & ((1u << kOrderBits) - 1u), gz = (uint32_t)(int)fz & ((1u << kOrderBits) - 1u);
+            return order_hilbert(gx, gz);
+        };
+        for (int i = tid; i < n; i += T) atomicAdd(&hist[cell_of(i)], 1);
+        __syncthreads();
+        constexpr int kPer = kOrderCells / T;
+        int v[kPer], run = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { v[j] = hist[tid * kPer + j]; run += v[j]; }
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane < WARPS ? wsum[lane] : 0;
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            if (lane < WARPS) wsum[lane] = winc - w;
+        }
+        __syncthreads();
+        int excl = wsum[warp] + inc - run;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { hist[tid * kPer + j] = excl; excl += v[j]; }
+        __syncthreads();
+        for (int i = tid; i < n; i += T) ord[atomicAdd(&hist[cell_of(i)], 1)] = (uint16_t)i;
+        __syncthreads();
+        // sorted position e -> cell e / 128 -> warp (cell mod WARPS), cell-in-warp (cell / WARPS); slot q of the cell, lane
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int e = (((s >> 2) * WARPS + warp) * kCellPts) + (s & 3) * 32 + lane;
+            kk[s] = e < n ? ord[e] : (uint16_t)0xFFFFu;
+        }
+        __syncthreads();     // the scratch is dead: the image may be written
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // prepass 2: shared-memory image (coordinates, point indices), running distances, boxes and maxima of my cells
+    // ------------------------------------------------------------------------------------------------------------
+    float pt[SLOTS], lc[CPW];
+    float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f, cmax = 0.f;   // cell `lane` (lane < CPW)
+    const int cb4 = warp * CPW * 32 + lane;                   // float4 index of (my warp, cell 0, my lane)
+    {
+        float4 *X4 = reinterpret_cast<float4 *>(X), *Y4 = reinterpret_cast<float4 *>(Y), *Z4 = reinterpret_cast<float4 *>(Z);
+        uint2 *K4 = reinterpret_cast<uint2 *>(ktab);
+        const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+            float vx[4], vy[4], vz[4];
+            float lo0 = inf, lo1 = inf, lo2 = inf, hi0 = -inf, hi1 = -inf, hi2 = -inf;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t k = kk[4 * ci + q];
+                const bool valid = k != 0xFFFFu;
+                vx[q] = 0.f; vy[q] = 0.f; vz[q] = 0.f;
+                float t = 0.f;       // padding slot: distance 0 and the worst rank, never wins against a real point
+                if (valid) {
+                    vx[q] = __ldg(xyz + (size_t)k * 3 + 0);
+                    vy[q] = __ldg(xyz + (size_t)k * 3 + 1);
+                    vz[q] = __ldg(xyz + (size_t)k * 3 + 2);
+                    t = temp ? temp[k] : 1e10f;
+                    lo0 = fminf(lo0, vx[q]); hi0 = fmaxf(hi0, vx[q]);
+                    lo1 = fminf(lo1, vy[q]); hi1 = fmaxf(hi1, vy[q]);
+                    lo2 = fminf(lo2, vz[q]); hi2 = fmaxf(hi2, vz[q]);
+                }
+                pt[4 * ci + q] = t;
+            }
+            X4[cb4 + ci * 32] = make_float4(vx[0], vx[1], vx[2], vx[3]);
+            Y4[cb4 + ci * 32] = make_float4(vy[0], vy[1], vy[2], vy[3]);
+            Z4[cb4 + ci * 32] = make_float4(vz[0], vz[1], vz[2], vz[3]);
+            K4[cb4 + ci * 32] = make_uint2((uint32_t)kk[4 * ci] | ((uint32_t)kk[4 * ci + 1] << 16),
+                                           (uint32_t)kk[4 * ci + 2] | ((uint32_t)kk[4 * ci + 3] << 16));
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lo0 = fminf(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+                lo1 = fminf(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+                lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+            }
+            lc[ci] = fmaxf(fmaxf(pt[4 * ci], pt[4 * ci + 1]), fmaxf(pt[4 * ci + 2], pt[4 * ci + 3]));
+            const uint32_t cm = __reduce_max_sync(0xffffffffu, __float_as_uint(lc[ci]));
+            if (lane == ci) {
+                blx = lo0; bly = lo1; blz = lo2; bhx = hi0; bhy = hi1; bhz = hi2;   // an all-padding cell keeps +inf / -inf:
+                cmax = __uint_as_float(cm);                                         // lb = +inf, never touched
+            }
+        }
+        if (tid < 2 * WARPS) recs[tid] = 0ull;
+    }
+    float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);   // idx[0] = 0 always
+    if (tid == 0) idx[0] = 0;
+    __syncthreads();
+
+    // Shared-memory addresses as 32-bit registers + explicit ld/st.shared: through generic pointers ptxas rebuilt the
+    // shared window base (S2UR SR_CgaCtaId -> ULEA) in front of every access group, three dependent ~30-cycle detours
+    // per round on the critical path (ncu source page, profiles/r2d_ncu_fps_cells_stalls.txt).
+    const uint32_t sX = pn2_smem_u32(X), sY = pn2_smem_u32(Y), sZ = pn2_smem_u32(Z), sK = pn2_smem_u32(ktab);
+    const uint32_t sRec = pn2_smem_u32(recs);
+    const uint32_t sX4 = sX + (uint32_t)cb4 * 16u, sY4 = sY + (uint32_t)cb4 * 16u, sZ4 = sZ + (uint32_t)cb4 * 16u;
+    const uint32_t pos0 = (uint32_t)cb4 * 4u;                 // position of (my warp, cell 0, my lane, slot 0)
+    // per lane and cell: which of the 4 slots holds the cell maximum (2 bits) and whether several do (1 bit); a nibble
+    // per cell.  Start with "several" everywhere: a cell that wins before its first update takes the exact path.
+    constexpr int NQ = (CPW + 7) / 8;
+    uint32_t lq[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) lq[i] = 0x44444444u;
+
+    auto update_cell = [&](auto CI, const float2 ncx, const float2 ncy, const float2 ncz) {
+        constexpr int ci = decltype(CI)::value;
+        const float4 x4 = lds_f4(sX4 + ci * 512), y4 = lds_f4(sY4 + ci * 512), z4 = lds_f4(sZ4 + ci * 512);
+        // (p - c) == p + (-c) exactly; t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t) as pn2_sqdist
+        const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), ncx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), ncx);
+        const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), ncy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), ncy);
+        const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), ncz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), ncz);
+        float2 t0 = __fmul2_rn(dy0, dy0), t1 = __fmul2_rn(dy1, dy1);
+        t0 = __ffma2_rn(dx0, dx0, t0); t1 = __ffma2_rn(dx1, dx1, t1);
+        t0 = __ffma2_rn(dz0, dz0, t0); t1 = __ffma2_rn(dz1, dz1, t1);
+        const float p0 = fminf(t0.x, pt[4 * ci + 0]), p1 = fminf(t0.y, pt[4 * ci + 1]);
+        const float p2 = fminf(t1.x, pt[4 * ci + 2]), p3 = fminf(t1.y, pt[4 * ci + 3]);
+        pt[4 * ci + 0] = p0; pt[4 * ci + 1] = p1; pt[4 * ci + 2] = p2; pt[4 * ci + 3] = p3;
+        const float mm = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+        lc[ci] = mm;
+        const uint32_t cm = __reduce_max_sync(0xffffffffu, __float_as_uint(mm));
+        const bool e0 = p0 == mm, e1 = p1 == mm, e2 = p2 == mm, e3 = p3 == mm;
+        const uint32_t q = e0 ? 0u : (e1 ? 1u : (e2 ? 2u : 3u));
+        const uint32_t several = ((int)e0 + (int)e1 + (int)e2 + (int)e3) > 1 ? 4u : 0u;
+        lq[ci >> 3] = (lq[ci >> 3] & ~(0xFu << (4 * (ci & 7)))) | ((q | several) << (4 * (ci & 7)));
+        if (lane == ci) cmax = __uint_as_float(cm);
+    };
+
+    unsigned long long p_test = 0, p_upd = 0, p_rec = 0, p_bar_u = 0, p_bar_n = 0, p_red = 0, p_nupd = 0, p_cells = 0;
+    for (int r = 0; r < m - 1; ++r) {
+        const uint32_t rec_w = sRec + (uint32_t)(((r & 1) * WARPS + warp) * 8);        // my record of this round
+        const uint32_t rec_prev = sRec + (uint32_t)((((r & 1) ^ 1) * WARPS + warp) * 8);
+        const uint32_t rec_r = sRec + (uint32_t)(((r & 1) * WARPS + (lane < WARPS ? lane : 0)) * 8);
+        const long long c0 = PROF ? clock64() : 0;
+        long long c3 = 0;
+        // 1. which of my cells can the new centre change?  (same float expression as the distance itself: see the header)
+        const float bx = fmaxf(fmaxf(__fadd_rn(blx, -cx), __fadd_rn(cx, -bhx)), 0.f);
+        const float by = fmaxf(fmaxf(__fadd_rn(bly, -cy), __fadd_rn(cy, -bhy)), 0.f);
+        const float bz = fmaxf(fmaxf(__fadd_rn(blz, -cz), __fadd_rn(cz, -bhz)), 0.f);
+        const float lb = pn2_sqdist(bx, by, bz);
+        const uint32_t mask = __ballot_sync(0xffffffffu, lane < CPW && lb < cmax);
+        const long long c1 = PROF ? clock64() : 0;
+        if (mask) {
+            // 2. update the touched cells (usually one): one dispatch per touched cell instead of CPW tests
+            const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+            uint32_t todo = mask;
+            do {
+                const int ci = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                dispatch_cell<0, CPW>(ci, [&](auto CI) { update_cell(CI, ncx, ncy, ncz); });
+            } while (todo);
+            const long long c2 = PROF ? clock64() : 0;
+            // the warp's record (maximum distance, position).  Common case: one lane, one cell, one slot hold the maximum
+            // -> the position comes from the bookkeeping nibbles, no table look-up.  Any tie inside the warp takes the exact
+            // path: the reference rank decides (however many slots tie).
+            float lmax = lc[0];
+#pragma unroll
+            for (int ci = 1; ci < CPW; ++ci) lmax = fmaxf(lmax, lc[ci]);
+            const uint32_t lb32 = __float_as_uint(lmax);
+            const uint32_t wb = __reduce_max_sync(0xffffffffu, lb32);
+            const bool cand = lb32 == wb;
+            uint32_t em = 0u;
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) em |= (__float_as_uint(lc[ci]) == wb ? 1u : 0u) << ci;
+            const int wci = __ffs(em) - 1;                                   // (garbage in non-candidate lanes)
+            uint32_t nib = 0u;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) nib = (wci >> 3) == i ? lq[i] : nib;
+            nib = (nib >> (4 * (wci & 7))) & 7u;
+            const uint32_t cbal = __ballot_sync(0xffffffffu, cand);
+            const uint32_t amb = __ballot_sync(0xffffffffu, cand && ((em & (em - 1u)) != 0u || (nib & 4u) != 0u));
+            if (amb == 0u && (cbal & (cbal - 1u)) == 0u) {
+                if (cand) sts_u64(rec_w, ((unsigned long long)wb << 32) | (pos0 + (uint32_t)(wci * 128) + (nib & 3u)));
+            } else {
+                uint32_t best = 0u;
+                if (cand) {
+#pragma unroll
+                    for (int ci = 0; ci < CPW; ++ci) {
+                        if (__float_as_uint(lc[ci]) == wb) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (__float_as_uint(pt[4 * ci + q]) == wb) {
+                                    const uint32_t pos = pos0 + (uint32_t)(ci * 128 + q);
+                                    const uint32_t k = lds_u16(sK + pos * 2u);
+                                    const uint32_t rinv = k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
+                                    const uint32_t key = (rinv << 16) | pos;
+                                    best = key > best ? key : best;
+                                }
+                            }
+                        }
+                    }
+                }
+                best = __reduce_max_sync(0xffffffffu, best);
+                if (lane == 0) sts_u64(rec_w, ((unsigned long long)wb << 32) | (best & 0xFFFFu));
+            }
+            if (PROF) { c3 = clock64(); p_upd += c2 - c1; p_rec += c3 - c2; p_nupd += 1; p_cells += __popc(mask); }
+        } else if (lane == 0) {
+            sts_u64(rec_w, lds_u64(rec_prev));
+        }
+        const long long c4 = PROF ? clock64() : 0;
+        __syncthreads();
+        // 3. every warp reduces the WARPS records (redundantly) -> next centre
+        const unsigned long long key = lds_u64(rec_r);
+        const uint32_t hi = lane < WARPS ? (uint32_t)(key >> 32) : 0u, lo = (uint32_t)key;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+        long long c5 = 0;
+        if (PROF) { c5 = clock64() + (mh == 0x12345678u ? 1 : 0); }
+        const bool mine = lane < WARPS && hi == mh;
+        uint32_t who = __ballot_sync(0xffffffffu, mine);
+        if (who & (who - 1u)) {
+            // several warps tie on the distance: the reference rank of their candidates decides
+            uint32_t v = 0u;
+            if (mine) {
+                const uint32_t k = lds_u16(sK + lo * 2u);
+                const uint32_t rinv = k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
+                v = ((rinv << 16) | lo) + 1u;
+            }
+            const uint32_t mv = __reduce_max_sync(0xffffffffu, v);
+            who = __ballot_sync(0xffffffffu, mine && v == mv);
+        }
+        const uint32_t pos = __shfl_sync(0xffffffffu, lo, __ffs(who) - 1) & 0xFFFFu;
+        cx = lds_f32(sX + pos * 4u); cy = lds_f32(sY + pos * 4u); cz = lds_f32(sZ + pos * 4u);
+        if (tid == 0) idx[r + 1] = (int32_t)lds_u16(sK + pos * 2u);
+        if (PROF) {
+            const long long c6 = clock64() + (cz == 1.2345e-30f ? 1 : 0);
+            p_test += c1 - c0;
+            if (mask) p_bar_u += c5 - c4; else p_bar_n += c5 - c4;
+            p_red += c6 - c5;
+        }
+    }
+    if (PROF && lane == 0 && prof) {
+        unsigned long long *o = prof + ((size_t)cloud * WARPS + warp) * 8;
+        o[0] = p_test; o[1] = p_upd; o[2] = p_rec; o[3] = p_bar_u; o[4] = p_bar_n; o[5] = p_red; o[6] = p_nupd; o[7] = p_cells;
+    }
+
+    if (temp) {   // the reference leaves the running min distances in the caller's scratch
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const uint32_t k = ktab[pos0 + (uint32_t)((s >> 2) * 128 + (s & 3))];
+            if (k != 0xFFFFu) temp[k] = pt[s];
+        }
+    }
+}
+
+unsigned long long *g_cells_prof = nullptr;
+
+template <int WARPS, int CPW>
+cudaError_t launch_cells(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
+                         const int32_t *viol, cudaStream_t stream) {
+    using Cfg = CellsCfg<WARPS, CPW>;
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        cudaError_t ea = cudaFuncSetAttribute(fps_cells_kernel<WARPS, CPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)Cfg::kSmem);
+        if constexpr (WARPS * CPW == 128) {
+            if (ea == cudaSuccess)
+                ea = cudaFuncSetAttribute(fps_cells_kernel<WARPS, CPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        }
+        if (ea != cudaSuccess) return ea;
+        attr_done = true;
+    }
+    if constexpr (WARPS * CPW == 128) {      // stopwatch build: the 16384-point shapes only (tools/prof_fps_cells.py)
+        if (g_cells_prof) {
+            fps_cells_kernel<WARPS, CPW, true><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, g_cells_prof);
+            return cudaGetLastError();
+        }
+    }
+    fps_cells_kernel<WARPS, CPW, false><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, nullptr);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int pn2_fps_ref_block_size(int n);
+
+// stopwatch buffer for tools/prof_fps_cells.py: 8 u64 per (cloud, warp) in device memory, or NULL (never used by the product)
+PN2_API void pn2_fps_cells_set_profile(void *buf) { g_cells_prof = static_cast<unsigned long long *>(buf); }
+
+// Does the cell kernel take clouds of n points?  (one CTA's shared memory holds 16384 points)
+bool pn2_fps_cells_supported(int n) { return n >= 1 && n <= 16384; }
+
+// Internal door for fps.cu (pn2_fps_f32's heuristic) and pn2_fps_cells_f32.  warps: 0 = heuristic, or 8 / 16 / 32 to force
+// the number of warps of the CTA (tests, tuning); returns cudaErrorInvalidValue for a combination that is not built.
+cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
+                                 const int32_t *viol, cudaStream_t stream) {
+    const int bs = pn2_fps_ref_block_size(n);
+    int log2bs = 0;
+    while ((1 << log2bs) < bs) ++log2bs;
+    const int cnt = (n + bs - 1) / bs;
+    const int cells = (n + kCellPts - 1) / kCellPts;      // 1 .. 128
+    if (warps == 0) warps = cells > 32 ? 16 : 8;
+#define PN2_CELLS_GO(W, C) return launch_cells<W, C>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream)
+    if (warps == 8) {
+        if (cells <= 8) PN2_CELLS_GO(8, 1);
+        if (cells <= 16) PN2_CELLS_GO(8, 2);
+        if (cells <= 32) PN2_CELLS_GO(8, 4);
+        if (cells <= 64) PN2_CELLS_GO(8, 8);
+        if (cells <= 128) PN2_CELLS_GO(8, 16);
+    } else if (warps == 16) {
+        if (cells <= 16) PN2_CELLS_GO(16, 1);
+        if (cells <= 32) PN2_CELLS_GO(16, 2);
+        if (cells <= 64) PN2_CELLS_GO(16, 4);
+        if (cells <= 128) PN2_CELLS_GO(16, 8);
+    } else if (warps == 32) {
+        if (cells <= 32) PN2_CELLS_GO(32, 1);
+        if (cells <= 64) PN2_CELLS_GO(32, 2);
+        if (cells <= 128) PN2_CELLS_GO(32, 4);
+    }
+#undef PN2_CELLS_GO
+    return cudaErrorInvalidValue;
+}
+
+// pn2_fps_f32 through the pruned one-CTA kernel, whatever the heuristic of pn2_fps_f32 would pick (tests, tuning).
+// n <= 16384; warps = 0 (heuristic), 8, 16 or 32.  Same result as pn2_fps_f32 for every value.
+PN2_API int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
+                              cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0 || (!xyz && b * n > 0) || (!idx && b * m > 0)) {
+        pn2_set_last_error("pn2_fps_cells_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (b == 0 || m == 0) return PN2_OK;
+    if (!pn2_fps_cells_supported(n)) {
+        pn2_set_last_error("pn2_fps_cells_f32: 1 <= N <= 16384 points per cloud");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    const cudaError_t e = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, warps, nullptr, stream);
+    if (e == cudaErrorInvalidValue) {
+        pn2_set_last_error("pn2_fps_cells_f32: warps must be 0, 8, 16 or 32");
+        return PN2_ERR_INVALID;
+    }
+    if (e != cudaSuccess) {
+        pn2_set_last_error(cudaGetErrorString(e));
+        return PN2_ERR_LAUNCH;
+    }
+    return PN2_OK;
+}

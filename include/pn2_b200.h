@@ -46,6 +46,10 @@ int pn2_fps_ref_block_size(int n);
 /* pn2_fps_f32 with the CTAs-per-cloud thread-block-cluster size given explicitly (1, 2, 4, 8; 0 = heuristic): tests and
  * tuning.  Same result for every value; no process-global state. */
 int pn2_fps_cluster_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int cluster_size, void *stream);
+/* pn2_fps_f32 through the pruned one-CTA kernel (csrc/fps_cells.cu: Hilbert-ordered cells of 128 points with bounding
+ * boxes; a round only touches the cells the new centre can change -- an exact test, same indices bit for bit), which is
+ * what pn2_fps_f32 picks by itself for 2048 < N <= 16384.  N <= 16384; warps = CTA size in warps: 0 (heuristic), 8, 16, 32. */
+int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps, void *stream);
 /* Exact parallel test "does furthest_point_sample(xyz, m) return 0, 1, ..., m-1?" (true for every SA level of the
  * backbone after the first: pointnet2_msg.py:131-137 feeds level l the FPS-ordered centres of level l-1, and FPS of a
  * prefix of an FPS ordering is that prefix unless two candidates tie at the maximum).  viol (B) int32 ZEROED by the
@@ -220,6 +224,7 @@ void pn2_sa_fused_tc_set_profile(void *buf);
 void pn2_sa_fused_t_set_profile(void *buf);    /* tools/prof_sat.py: in-kernel stopwatch of pn2_sa_fused_t_tc_f32 */
 void pn2_sa_fused_t_set_debug(int bits);       /* tools/prof_sat.py: what-if switches of the stopwatch build (garbage results) */
 void pn2_rcnn_front_set_profile(void *buf);   /* tools/prof_front.py: in-kernel stopwatch of pn2_rcnn_front_tc_f32 */
+void pn2_fps_cells_set_profile(void *buf);    /* tools/prof_fps_cells.py: in-kernel stopwatch of pn2_fps_cells_f32 (16384-point shapes) */
 void pn2_rcnn_front_set_mode(int bits);       /* tools/prof_front.py: tuning variants of the same kernel (same results) */
 /* profiling experiments only: bit0 / bit1 switch off the TMEM traffic of the pooling / conversion epilogue
  * (results become garbage); 0 restores the product behaviour. */

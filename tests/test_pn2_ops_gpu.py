@@ -42,6 +42,42 @@ def test_fps_every_cluster_size_and_temp_writeback(cuda, oracle, cluster):
     assert np.array_equal(temp.cpu().numpy(), ref_temp)  # caller scratch mutated like the reference
 
 
+@pytest.mark.parametrize("warps", [0, 8, 16, 32])
+@pytest.mark.parametrize("kind,n,m,b", [("lidar", 16384, 1024, 2), ("ties", 16384, 700, 2), ("uniform", 9000, 600, 2),
+                                         ("ties", 4096, 512, 3), ("lidar", 3000, 3000, 1), ("ties", 2049, 300, 2),
+                                         ("lidar", 130, 64, 3), ("ties", 64, 64, 2)])
+def test_fps_cells_kernel_vs_oracle(cuda, oracle, warps, kind, n, m, b):
+    """csrc/fps_cells.cu (exact spatial pruning, one CTA per cloud) for every CTA size: indices AND the running
+    min-distances it leaves in the caller's scratch equal the C restatement of sampling_gpu.cu:93-209."""
+    cabi = load("cabi")
+    xyz_h = synthetic.make_clouds(kind, b, n, seed=77 + n)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    temp = torch.full((b, n), 1e10, device=cuda)
+    idx = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+    cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(temp), cabi.ptr(idx), cabi.i32(b), cabi.i32(n), cabi.i32(m),
+              cabi.i32(warps))
+    ref, ref_temp = oracle.fps(xyz_h, m)
+    assert np.array_equal(idx.cpu().numpy(), ref), (kind, n, m, int((idx.cpu().numpy() != ref).sum()))
+    assert np.array_equal(temp.cpu().numpy(), ref_temp)
+    # without the scratch (the inference path) and through the heuristic of pn2_fps_f32
+    idx2 = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+    cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx2), cabi.i32(b), cabi.i32(n), cabi.i32(m),
+              cabi.i32(warps))
+    assert torch.equal(idx2, idx)
+
+
+def test_fps_cells_rejects_what_it_cannot_hold(cuda):
+    cabi = load("cabi")
+    xyz = torch.zeros((1, 20000, 3), device=cuda)
+    idx = torch.empty((1, 8), dtype=torch.int32, device=cuda)
+    with pytest.raises(RuntimeError):
+        cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(1), cabi.i32(20000), cabi.i32(8),
+                  cabi.i32(0))
+    with pytest.raises(RuntimeError):
+        cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(1), cabi.i32(4096), cabi.i32(8),
+                  cabi.i32(5))
+
+
 def test_fps_edge_cases(cuda, oracle):
     f = p2u().furthest_point_sample
     one = torch.zeros((2, 1, 3), device=cuda)
