@@ -31,6 +31,7 @@
 namespace {
 
 constexpr int kCellPts = 128;
+constexpr int kMaxCells = 128;      // cells per cloud (16384 points); the record arrays always have this many entries
 
 __device__ __forceinline__ uint32_t cells_rank(uint32_t k, int log2bs, int cnt) {
     const uint32_t tref = k & ((1u << log2bs) - 1u);
@@ -54,25 +55,75 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
-    unsigned long long v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// f(integral_constant<ci>) through a binary tree of uniform branches (a switch became an LDC jump table + BRX, ~80 cycles)
+__device__ __forceinline__ void sts_u32_if(bool p, uint32_t a, uint32_t v) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
+}
+
+// ~rank (16 bits, larger is better) of the point at shared-memory position pos; padding slots get 0
+__device__ __forceinline__ uint32_t pos_rinv(uint32_t pos, uint32_t sK, int log2bs, int cnt) {
+    const uint32_t k = lds_u16(sK + pos * 2u);
+    return k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
+}
+
+// Exact paths (ties on the distance; rare, out of line).  Both are called by the whole warp.
+// The slots of one cell that hold its maximum mm, over all candidate lanes: position of the one with the best rank.
+__device__ __noinline__ uint32_t cell_exact_pos(bool cand, float p0, float p1, float p2, float p3, float mm, uint32_t posc,
+                                                uint32_t sK, int log2bs, int cnt) {
+    uint32_t best = 0u;
+    if (cand) {
+        const float p[4] = {p0, p1, p2, p3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (p[q] == mm) {
+                const uint32_t key = (pos_rinv(posc + q, sK, log2bs, cnt) << 16) | (posc + q);
+                best = key > best ? key : best;
+            }
+        }
+    }
+    return __reduce_max_sync(0xffffffffu, best) & 0xFFFFu;
+}
+// The cell records (four per lane) whose distance equals the maximum mh: position of the candidate with the best rank.
+__device__ __noinline__ uint32_t records_exact_pos(uint4 h4, uint4 p4, uint32_t mh, uint32_t sK, int log2bs, int cnt) {
+    const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
+    uint32_t best = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (h[j] == mh) {
+            const uint32_t key = ((pos_rinv(p[j], sK, log2bs, cnt) << 16) | p[j]) + 1u;
+            best = key > best ? key : best;
+        }
+    }
+    return (__reduce_max_sync(0xffffffffu, best) - 1u) & 0xFFFFu;
+}
+
+// f(integral_constant<ci>) through a binary tree of uniform branches (a switch became an LDC jump table + BRX, ~80 cycles).
+// The tree tests single BITS of ci, most significant first, so every level's predicate can be formed as soon as ci exists.
+template <int BASE, int BIT, int N, class F>
+__device__ __forceinline__ void dispatch_bits(uint32_t ci, F &&f) {
+    if constexpr (BIT == 0) {
+        if constexpr (BASE < N) f(std::integral_constant<int, BASE>{});
+    } else {
+        constexpr int HALF = BIT >> 1;
+        if (ci & (uint32_t)BIT) {
+            dispatch_bits<BASE + BIT, HALF, N>(ci, f);
+        } else {
+            dispatch_bits<BASE, HALF, N>(ci, f);
+        }
+    }
+}
 template <int LO, int HI, class F>
 __device__ __forceinline__ void dispatch_cell(int ci, F &&f) {
-    if constexpr (HI - LO == 1) {
-        f(std::integral_constant<int, LO>{});
-    } else {
-        constexpr int MID = (LO + HI) / 2;
-        if (ci < MID) dispatch_cell<LO, MID>(ci, f);
-        else dispatch_cell<MID, HI>(ci, f);
-    }
+    static_assert(LO == 0 && (HI & (HI - 1)) == 0, "power-of-two cell count");
+    dispatch_bits<0, HI / 2, HI>((uint32_t)ci, f);
 }
 
 template <int WARPS, int CPW>
@@ -80,8 +131,8 @@ struct CellsCfg {
     static constexpr int T = WARPS * 32;
     static constexpr int SLOTS = 4 * CPW;
     static constexpr int NP = WARPS * CPW * kCellPts;
-    // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16) | recs (2 x WARPS u64)
-    static constexpr size_t kMain = (size_t)NP * 14 + 2 * WARPS * 8;
+    // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16) | cell records: 2 buffers x (128 distances | 128 positions) u32
+    static constexpr size_t kMain = (size_t)NP * 14 + 2 * 2 * kMaxCells * 4;
     // prepass scratch (aliases the image): hist (4096 int) | ord (NP u16) | red (4 x WARPS float) | wsum (WARPS int)
     static constexpr size_t kPre = (size_t)kOrderCells * 4 + (size_t)NP * 2 + 5 * WARPS * 4;
     static constexpr size_t kSmem = kMain > kPre ? kMain : kPre;
@@ -98,7 +149,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
     extern __shared__ __align__(16) uint8_t smem[];
     float *X = reinterpret_cast<float *>(smem), *Y = X + NP, *Z = Y + NP;
     uint16_t *ktab = reinterpret_cast<uint16_t *>(Z + NP);
-    unsigned long long *recs = reinterpret_cast<unsigned long long *>(ktab + NP);   // [2][WARPS]
+    uint32_t *recs = reinterpret_cast<uint32_t *>(ktab + NP);   // [2 buffers][distance bits | position][kMaxCells]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -193,7 +244,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
     // ------------------------------------------------------------------------------------------------------------
     // prepass 2: shared-memory image (coordinates, point indices), running distances, boxes and maxima of my cells
     // ------------------------------------------------------------------------------------------------------------
-    float pt[SLOTS], lc[CPW];
+    float pt[SLOTS];
     float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f, cmax = 0.f;   // cell `lane` (lane < CPW)
     const int cb4 = warp * CPW * 32 + lane;                   // float4 index of (my warp, cell 0, my lane)
     {
@@ -232,14 +283,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
                 lo1 = fminf(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
                 lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
             }
-            lc[ci] = fmaxf(fmaxf(pt[4 * ci], pt[4 * ci + 1]), fmaxf(pt[4 * ci + 2], pt[4 * ci + 3]));
-            const uint32_t cm = __reduce_max_sync(0xffffffffu, __float_as_uint(lc[ci]));
+            const float lc = fmaxf(fmaxf(pt[4 * ci], pt[4 * ci + 1]), fmaxf(pt[4 * ci + 2], pt[4 * ci + 3]));
+            const uint32_t cm = __reduce_max_sync(0xffffffffu, __float_as_uint(lc));
             if (lane == ci) {
                 blx = lo0; bly = lo1; blz = lo2; bhx = hi0; bhy = hi1; bhz = hi2;   // an all-padding cell keeps +inf / -inf:
                 cmax = __uint_as_float(cm);                                         // lb = +inf, never touched
             }
+            // the cell's initial record (both buffers), exactly: with the usual 1e10 start every slot ties
+            __syncwarp();
+            const uint32_t best = cell_exact_pos(__float_as_uint(lc) == cm, pt[4 * ci], pt[4 * ci + 1], pt[4 * ci + 2], pt[4 * ci + 3],
+                                                 lc, (uint32_t)(cb4 * 4 + ci * 128), pn2_smem_u32(ktab), log2bs, cnt);
+            if (lane == 0) {
+                const int c = warp * CPW + ci;
+                recs[c] = cm; recs[kMaxCells + c] = best; recs[2 * kMaxCells + c] = cm; recs[3 * kMaxCells + c] = best;
+            }
         }
-        if (tid < 2 * WARPS) recs[tid] = 0ull;
+        for (int i = WARPS * CPW + tid; i < kMaxCells; i += T) {     // entries no warp owns: (0, 0) never beats a real record
+            recs[i] = 0u; recs[kMaxCells + i] = 0u; recs[2 * kMaxCells + i] = 0u; recs[3 * kMaxCells + i] = 0u;
+        }
     }
     float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);   // idx[0] = 0 always
     if (tid == 0) idx[0] = 0;
@@ -247,21 +308,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
 
     // Shared-memory addresses as 32-bit registers + explicit ld/st.shared: through generic pointers ptxas rebuilt the
     // shared window base (S2UR SR_CgaCtaId -> ULEA) in front of every access group, three dependent ~30-cycle detours
-    // per round on the critical path (ncu source page, profiles/r2d_ncu_fps_cells_stalls.txt).
-    const uint32_t sX = pn2_smem_u32(X), sY = pn2_smem_u32(Y), sZ = pn2_smem_u32(Z), sK = pn2_smem_u32(ktab);
-    const uint32_t sRec = pn2_smem_u32(recs);
+    // per round on the critical path (ncu source page of the first version).
+    uint32_t sX = pn2_smem_u32(X);
+    asm volatile("" : "+r"(sX));      // opaque: otherwise ptxas re-derives it from SR_CgaCtaId inside the loop
+    const uint32_t sY = sX + (uint32_t)NP * 4u, sZ = sX + (uint32_t)NP * 8u, sK = sX + (uint32_t)NP * 12u;
+    const uint32_t sRec = sX + (uint32_t)NP * 14u;
     const uint32_t sX4 = sX + (uint32_t)cb4 * 16u, sY4 = sY + (uint32_t)cb4 * 16u, sZ4 = sZ + (uint32_t)cb4 * 16u;
     const uint32_t pos0 = (uint32_t)cb4 * 4u;                 // position of (my warp, cell 0, my lane, slot 0)
-    // per lane and cell: which of the 4 slots holds the cell maximum (2 bits) and whether several do (1 bit); a nibble
-    // per cell.  Start with "several" everywhere: a cell that wins before its first update takes the exact path.
-    constexpr int NQ = (CPW + 7) / 8;
-    uint32_t lq[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) lq[i] = 0x44444444u;
+    constexpr uint32_t kBufBytes = 2u * kMaxCells * 4u;       // one record buffer: distances | positions
+    constexpr uint32_t kPosOff = kMaxCells * 4u;
+    const uint32_t rec_mine = sRec + (uint32_t)(warp * CPW) * 4u;            // record of (my warp, cell 0) in buffer 0
+    const uint32_t rec_read = sRec + (uint32_t)lane * 16u;                   // the four records lane `lane` reduces
 
-    auto update_cell = [&](auto CI, const float2 ncx, const float2 ncy, const float2 ncz) {
+    // One touched cell: update its 4 running distances per lane, new cell maximum, and the cell's RECORD (maximum,
+    // position of the point that holds it) for this round.  Common case: one lane and one slot hold the maximum -> that
+    // lane writes the record; any tie takes the exact path (reference rank).
+    uint32_t cpos = 0u;      // lane ci < CPW: position in the record of my cell ci (the record's distance is cmax)
+    auto update_cell = [&](auto CI, const float4 x4, const float4 y4, const float4 z4, const float2 ncx, const float2 ncy,
+                           const float2 ncz, const uint32_t rec_w) {
         constexpr int ci = decltype(CI)::value;
-        const float4 x4 = lds_f4(sX4 + ci * 512), y4 = lds_f4(sY4 + ci * 512), z4 = lds_f4(sZ4 + ci * 512);
         // (p - c) == p + (-c) exactly; t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t) as pn2_sqdist
         const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), ncx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), ncx);
         const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), ncy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), ncy);
@@ -273,110 +338,85 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
         const float p2 = fminf(t1.x, pt[4 * ci + 2]), p3 = fminf(t1.y, pt[4 * ci + 3]);
         pt[4 * ci + 0] = p0; pt[4 * ci + 1] = p1; pt[4 * ci + 2] = p2; pt[4 * ci + 3] = p3;
         const float mm = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
-        lc[ci] = mm;
         const uint32_t cm = __reduce_max_sync(0xffffffffu, __float_as_uint(mm));
         const bool e0 = p0 == mm, e1 = p1 == mm, e2 = p2 == mm, e3 = p3 == mm;
         const uint32_t q = e0 ? 0u : (e1 ? 1u : (e2 ? 2u : 3u));
-        const uint32_t several = ((int)e0 + (int)e1 + (int)e2 + (int)e3) > 1 ? 4u : 0u;
-        lq[ci >> 3] = (lq[ci >> 3] & ~(0xFu << (4 * (ci & 7)))) | ((q | several) << (4 * (ci & 7)));
-        if (lane == ci) cmax = __uint_as_float(cm);
+        const bool several = ((int)e0 + (int)e1 + (int)e2 + (int)e3) > 1;
+        const bool cand = __float_as_uint(mm) == cm;
+        const uint32_t cbal = __ballot_sync(0xffffffffu, cand);
+        const uint32_t amb = __ballot_sync(0xffffffffu, cand && several);
+        const uint32_t posc = pos0 + (uint32_t)(ci * 128);
+        uint32_t wpos;
+        if (amb == 0u && (cbal & (cbal - 1u)) == 0u) {
+            sts_u32_if(cand, rec_w + ci * 4, cm);                        // predicated stores: no divergent branch
+            sts_u32_if(cand, rec_w + ci * 4 + kPosOff, posc + q);
+            wpos = __reduce_max_sync(0xffffffffu, cand ? posc + q : 0u);     // for lane ci; needed only after the barrier
+        } else {
+            wpos = cell_exact_pos(cand, p0, p1, p2, p3, mm, posc, sK, log2bs, cnt);
+            if (lane == 0) { sts_u32(rec_w + ci * 4, cm); sts_u32(rec_w + ci * 4 + kPosOff, wpos); }
+        }
+        if (lane == ci) { cmax = __uint_as_float(cm); cpos = wpos; }
     };
 
+    uint32_t kpend = 0u;
     unsigned long long p_test = 0, p_upd = 0, p_rec = 0, p_bar_u = 0, p_bar_n = 0, p_red = 0, p_nupd = 0, p_cells = 0;
     for (int r = 0; r < m - 1; ++r) {
-        const uint32_t rec_w = sRec + (uint32_t)(((r & 1) * WARPS + warp) * 8);        // my record of this round
-        const uint32_t rec_prev = sRec + (uint32_t)((((r & 1) ^ 1) * WARPS + warp) * 8);
-        const uint32_t rec_r = sRec + (uint32_t)(((r & 1) * WARPS + (lane < WARPS ? lane : 0)) * 8);
+        const uint32_t boff = (uint32_t)(r & 1) * kBufBytes;
         const long long c0 = PROF ? clock64() : 0;
-        long long c3 = 0;
         // 1. which of my cells can the new centre change?  (same float expression as the distance itself: see the header)
         const float bx = fmaxf(fmaxf(__fadd_rn(blx, -cx), __fadd_rn(cx, -bhx)), 0.f);
         const float by = fmaxf(fmaxf(__fadd_rn(bly, -cy), __fadd_rn(cy, -bhy)), 0.f);
         const float bz = fmaxf(fmaxf(__fadd_rn(blz, -cz), __fadd_rn(cz, -bhz)), 0.f);
         const float lb = pn2_sqdist(bx, by, bz);
-        const uint32_t mask = __ballot_sync(0xffffffffu, lane < CPW && lb < cmax);
+        const bool touched = lane < CPW && lb < cmax;
+        const uint32_t mask = __ballot_sync(0xffffffffu, touched);
+        int ci = (int)__reduce_min_sync(0xffffffffu, touched ? (uint32_t)lane : 32u);   // first touched cell (redux: ~15 cycles, BREV + FLO of the mask: ~40)
         const long long c1 = PROF ? clock64() : 0;
         if (mask) {
-            // 2. update the touched cells (usually one): one dispatch per touched cell instead of CPW tests
+            // 2. update the touched cells (usually one) and their records.  The cell's coordinates are requested before the
+            // dispatch (dynamic address), the branch tree that selects the registers of cell ci runs under the load latency.
             const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
             uint32_t todo = mask;
             do {
-                const int ci = __ffs(todo) - 1;
-                todo &= todo - 1u;
-                dispatch_cell<0, CPW>(ci, [&](auto CI) { update_cell(CI, ncx, ncy, ncz); });
+                const float4 x4 = lds_f4(sX4 + ci * 512), y4 = lds_f4(sY4 + ci * 512), z4 = lds_f4(sZ4 + ci * 512);
+                todo &= ~(1u << ci);
+                dispatch_cell<0, CPW>(ci, [&](auto CI) { update_cell(CI, x4, y4, z4, ncx, ncy, ncz, rec_mine + boff); });
+                ci = __ffs(todo) - 1;
             } while (todo);
-            const long long c2 = PROF ? clock64() : 0;
-            // the warp's record (maximum distance, position).  Common case: one lane, one cell, one slot hold the maximum
-            // -> the position comes from the bookkeeping nibbles, no table look-up.  Any tie inside the warp takes the exact
-            // path: the reference rank decides (however many slots tie).
-            float lmax = lc[0];
-#pragma unroll
-            for (int ci = 1; ci < CPW; ++ci) lmax = fmaxf(lmax, lc[ci]);
-            const uint32_t lb32 = __float_as_uint(lmax);
-            const uint32_t wb = __reduce_max_sync(0xffffffffu, lb32);
-            const bool cand = lb32 == wb;
-            uint32_t em = 0u;
-#pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) em |= (__float_as_uint(lc[ci]) == wb ? 1u : 0u) << ci;
-            const int wci = __ffs(em) - 1;                                   // (garbage in non-candidate lanes)
-            uint32_t nib = 0u;
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) nib = (wci >> 3) == i ? lq[i] : nib;
-            nib = (nib >> (4 * (wci & 7))) & 7u;
-            const uint32_t cbal = __ballot_sync(0xffffffffu, cand);
-            const uint32_t amb = __ballot_sync(0xffffffffu, cand && ((em & (em - 1u)) != 0u || (nib & 4u) != 0u));
-            if (amb == 0u && (cbal & (cbal - 1u)) == 0u) {
-                if (cand) sts_u64(rec_w, ((unsigned long long)wb << 32) | (pos0 + (uint32_t)(wci * 128) + (nib & 3u)));
-            } else {
-                uint32_t best = 0u;
-                if (cand) {
-#pragma unroll
-                    for (int ci = 0; ci < CPW; ++ci) {
-                        if (__float_as_uint(lc[ci]) == wb) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (__float_as_uint(pt[4 * ci + q]) == wb) {
-                                    const uint32_t pos = pos0 + (uint32_t)(ci * 128 + q);
-                                    const uint32_t k = lds_u16(sK + pos * 2u);
-                                    const uint32_t rinv = k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
-                                    const uint32_t key = (rinv << 16) | pos;
-                                    best = key > best ? key : best;
-                                }
-                            }
-                        }
-                    }
-                }
-                best = __reduce_max_sync(0xffffffffu, best);
-                if (lane == 0) sts_u64(rec_w, ((unsigned long long)wb << 32) | (best & 0xFFFFu));
-            }
-            if (PROF) { c3 = clock64(); p_upd += c2 - c1; p_rec += c3 - c2; p_nupd += 1; p_cells += __popc(mask); }
-        } else if (lane == 0) {
-            sts_u64(rec_w, lds_u64(rec_prev));
+            if (PROF) { p_upd += clock64() - c1; p_nupd += 1; p_cells += __popc(mask); }
         }
         const long long c4 = PROF ? clock64() : 0;
         __syncthreads();
-        // 3. every warp reduces the WARPS records (redundantly) -> next centre
-        const unsigned long long key = lds_u64(rec_r);
-        const uint32_t hi = lane < WARPS ? (uint32_t)(key >> 32) : 0u, lo = (uint32_t)key;
-        const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+        // 3. every warp reduces the 128 cell records (redundantly, four per lane) -> next centre
+        const uint4 h4 = lds_u4(rec_read + boff), p4 = lds_u4(rec_read + boff + kPosOff);
+        const uint32_t m01 = h4.x > h4.y ? h4.x : h4.y, m23 = h4.z > h4.w ? h4.z : h4.w;
+        const uint32_t lm = m01 > m23 ? m01 : m23;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, lm);
         long long c5 = 0;
         if (PROF) { c5 = clock64() + (mh == 0x12345678u ? 1 : 0); }
-        const bool mine = lane < WARPS && hi == mh;
-        uint32_t who = __ballot_sync(0xffffffffu, mine);
-        if (who & (who - 1u)) {
-            // several warps tie on the distance: the reference rank of their candidates decides
-            uint32_t v = 0u;
-            if (mine) {
-                const uint32_t k = lds_u16(sK + lo * 2u);
-                const uint32_t rinv = k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
-                v = ((rinv << 16) | lo) + 1u;
-            }
-            const uint32_t mv = __reduce_max_sync(0xffffffffu, v);
-            who = __ballot_sync(0xffffffffu, mine && v == mv);
-        }
-        const uint32_t pos = __shfl_sync(0xffffffffu, lo, __ffs(who) - 1) & 0xFFFFu;
+        const bool f0 = h4.x == mh, f1 = h4.y == mh, f2 = h4.z == mh, f3 = h4.w == mh;
+        const bool mine = f0 || f1 || f2 || f3;
+        const bool several = ((int)f0 + (int)f1 + (int)f2 + (int)f3) > 1;
+        const uint32_t who = __ballot_sync(0xffffffffu, mine);
+        const uint32_t amb = __ballot_sync(0xffffffffu, mine && several);
+        // one candidate: its position reaches every lane through a second redux (shorter than FLO + SHFL of the ballot)
+        uint32_t pos = __reduce_max_sync(0xffffffffu, mine ? (f0 ? p4.x : (f1 ? p4.y : (f2 ? p4.z : p4.w))) : 0u);
+        if (amb != 0u || (who & (who - 1u)) != 0u)
+            pos = records_exact_pos(h4, p4, mh, sK, log2bs, cnt);      // several cells tie: the reference rank decides
         cx = lds_f32(sX + pos * 4u); cy = lds_f32(sY + pos * 4u); cz = lds_f32(sZ + pos * 4u);
-        if (tid == 0) idx[r + 1] = (int32_t)lds_u16(sK + pos * 2u);
+        // idx[r + 1]: the table look-up is issued now, the global store waits until the end of the next round (a store right
+        // here stalled every warp on the look-up's scoreboard, predicated off or not)
+        if (tid == 0) {
+            if (r > 0) idx[r] = (int32_t)kpend;
+            kpend = lds_u16(sK + pos * 2u);
+        }
+        // the records written in this round also go into the other buffer (read in the next round): only now is nobody
+        // reading it any more -- every warp has passed this round's barrier
+        if (touched) {
+            const uint32_t o = rec_mine + (boff ^ kBufBytes) + (uint32_t)lane * 4u;
+            sts_u32(o, __float_as_uint(cmax));
+            sts_u32(o + kPosOff, cpos);
+        }
         if (PROF) {
             const long long c6 = clock64() + (cz == 1.2345e-30f ? 1 : 0);
             p_test += c1 - c0;
@@ -384,6 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
             p_red += c6 - c5;
         }
     }
+    if (tid == 0 && m > 1) idx[m - 1] = (int32_t)kpend;
     if (PROF && lane == 0 && prof) {
         unsigned long long *o = prof + ((size_t)cloud * WARPS + warp) * 8;
         o[0] = p_test; o[1] = p_upd; o[2] = p_rec; o[3] = p_bar_u; o[4] = p_bar_n; o[5] = p_red; o[6] = p_nupd; o[7] = p_cells;
@@ -435,7 +476,7 @@ PN2_API void pn2_fps_cells_set_profile(void *buf) { g_cells_prof = static_cast<u
 // Does the cell kernel take clouds of n points?  (one CTA's shared memory holds 16384 points)
 bool pn2_fps_cells_supported(int n) { return n >= 1 && n <= 16384; }
 
-// Internal door for fps.cu (pn2_fps_f32's heuristic) and pn2_fps_cells_f32.  warps: 0 = heuristic, or 8 / 16 / 32 to force
+// Internal door for fps.cu (pn2_fps_f32's heuristic) and pn2_fps_cells_f32.  warps: 0 = heuristic, or 4 / 8 / 16 to force
 // the number of warps of the CTA (tests, tuning); returns cudaErrorInvalidValue for a combination that is not built.
 cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
                                  const int32_t *viol, cudaStream_t stream) {
@@ -444,9 +485,13 @@ cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, in
     while ((1 << log2bs) < bs) ++log2bs;
     const int cnt = (n + bs - 1) / bs;
     const int cells = (n + kCellPts - 1) / kCellPts;      // 1 .. 128
-    if (warps == 0) warps = cells > 32 ? 16 : 8;
+    if (warps == 0) warps = 8;       // measured best at every size (tools/bench_fps_cluster.py): the redundant per-warp work of a round grows with the warp count
 #define PN2_CELLS_GO(W, C) return launch_cells<W, C>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream)
-    if (warps == 8) {
+    if (warps == 4) {
+        if (cells <= 32) PN2_CELLS_GO(4, 8);
+        if (cells <= 64) PN2_CELLS_GO(4, 16);
+        if (cells <= 128) PN2_CELLS_GO(4, 32);
+    } else if (warps == 8) {
         if (cells <= 8) PN2_CELLS_GO(8, 1);
         if (cells <= 16) PN2_CELLS_GO(8, 2);
         if (cells <= 32) PN2_CELLS_GO(8, 4);
@@ -457,17 +502,13 @@ cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, in
         if (cells <= 32) PN2_CELLS_GO(16, 2);
         if (cells <= 64) PN2_CELLS_GO(16, 4);
         if (cells <= 128) PN2_CELLS_GO(16, 8);
-    } else if (warps == 32) {
-        if (cells <= 32) PN2_CELLS_GO(32, 1);
-        if (cells <= 64) PN2_CELLS_GO(32, 2);
-        if (cells <= 128) PN2_CELLS_GO(32, 4);
     }
 #undef PN2_CELLS_GO
     return cudaErrorInvalidValue;
 }
 
 // pn2_fps_f32 through the pruned one-CTA kernel, whatever the heuristic of pn2_fps_f32 would pick (tests, tuning).
-// n <= 16384; warps = 0 (heuristic), 8, 16 or 32.  Same result as pn2_fps_f32 for every value.
+// n <= 16384; warps = 0 (heuristic), 4, 8 or 16.  Same result as pn2_fps_f32 for every value.
 PN2_API int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
                               cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0 || (!xyz && b * n > 0) || (!idx && b * m > 0)) {
@@ -481,7 +522,7 @@ PN2_API int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b
     }
     const cudaError_t e = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, warps, nullptr, stream);
     if (e == cudaErrorInvalidValue) {
-        pn2_set_last_error("pn2_fps_cells_f32: warps must be 0, 8, 16 or 32");
+        pn2_set_last_error("pn2_fps_cells_f32: warps must be 0, 4, 8 or 16");
         return PN2_ERR_INVALID;
     }
     if (e != cudaSuccess) {

@@ -160,10 +160,9 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
 FPS_PREFIX_CHECK = os.environ.get("PN2_FPS_PREFIX_CHECK", "1") != "0"
 
 
-# Thread-block-cluster size of the FPS kernel for clouds above 4096 points (0 = the kernel's latency heuristic, 4 CTAs per
-# cloud).  With several batches in flight (inference.Detector, depth 3) what counts is SM-time, not latency: 2 CTAs per
-# cloud take 3.43 ms instead of 2.91 ms for 16 x (16384 -> 4096) but hold 32 SMs instead of 64 (110 vs 186 SM-ms,
-# tools/bench_fps_cluster.py), and the other streams' tensor-core kernels get the difference.
+# PN2_FPS_CLUSTER = 1 / 2 / 4 / 8 forces the cluster kernel of csrc/fps.cu (every point updated every round) for clouds above
+# 4096 points; 0 (default) lets pn2_fps_f32 choose: the pruned one-CTA kernel of csrc/fps_cells.cu up to 16384 points
+# (16 x (16384 -> 4096): 1.6 ms on 16 SMs against 2.9 ms on 64 / 3.4 ms on 32, tools/bench_fps_cluster.py).
 FPS_CLUSTER = int(os.environ.get("PN2_FPS_CLUSTER", "0"))
 
 

@@ -42,10 +42,9 @@ class Detector:
         # one-CTA-per-scene NMS and the D2H/host turn-around of batch k then overlap with the
         # tensor-core MLPs of batch k+1 instead of leaving most of the chip idle.
         self.depth = max(1, int(depth))
-        if self.depth > 1 and "PN2_FPS_CLUSTER" not in os.environ:
-            # throughput mode: with batches in flight SM-time counts, not latency -- FPS on 2 CTAs per cloud holds half
-            # the SMs for 18 % longer (fused.FPS_CLUSTER; measured +1..5 % scenes/s at depth 3 / 4)
-            fz.FPS_CLUSTER = 2
+        # (Round 2 ran FPS on 2-CTA clusters here when depth > 1 because SM-time, not latency, counts with batches in
+        # flight.  The pruned one-CTA kernel, csrc/fps_cells.cu, is both faster and 4x cheaper in SM-time, and it is what
+        # pn2_fps_f32 picks by itself for these clouds; PN2_FPS_CLUSTER still forces the cluster kernel.)
         self._slots = None
         self._next = 0
 

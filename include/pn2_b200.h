@@ -48,7 +48,7 @@ int pn2_fps_ref_block_size(int n);
 int pn2_fps_cluster_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int cluster_size, void *stream);
 /* pn2_fps_f32 through the pruned one-CTA kernel (csrc/fps_cells.cu: Hilbert-ordered cells of 128 points with bounding
  * boxes; a round only touches the cells the new centre can change -- an exact test, same indices bit for bit), which is
- * what pn2_fps_f32 picks by itself for 2048 < N <= 16384.  N <= 16384; warps = CTA size in warps: 0 (heuristic), 8, 16, 32. */
+ * what pn2_fps_f32 picks by itself for 2048 < N <= 16384.  N <= 16384; warps = CTA size in warps: 0 (heuristic = 8), 4, 8, 16. */
 int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps, void *stream);
 /* Exact parallel test "does furthest_point_sample(xyz, m) return 0, 1, ..., m-1?" (true for every SA level of the
  * backbone after the first: pointnet2_msg.py:131-137 feeds level l the FPS-ordered centres of level l-1, and FPS of a

@@ -1,6 +1,6 @@
 """FPS latency AND SM-time (latency x CTAs, the figure that matters once several batches are in flight) for every kernel
 variant: the cluster kernel of csrc/fps.cu (1 / 2 / 4 / 8 CTAs per cloud, every point updated every round) and the pruned
-one-CTA kernel of csrc/fps_cells.cu (8 / 16 / 32 warps).   python tools/bench_fps_cluster.py"""
+one-CTA kernel of csrc/fps_cells.cu (4 / 8 / 16 warps).   python tools/bench_fps_cluster.py"""
 import importlib
 import os
 import sys
@@ -30,7 +30,7 @@ for kind in ("lidar", "uniform"):
             continue
         xyz = torch.from_numpy(syn.make_clouds(kind, B, N, seed=1024)).cuda()
         ref = None
-        variants = [("cluster", c) for c in ((4, 2, 8) if N > 4096 else (1, 2))] + [("cells", w) for w in (16, 8, 32)]
+        variants = [("cluster", c) for c in ((4, 2, 8) if N > 4096 else (1, 2))] + [("cells", w) for w in (8, 4, 16)]
         for what, arg in variants:
             idx = torch.empty((B, M), dtype=torch.int32, device="cuda")
             name = "pn2_fps_cluster_f32" if what == "cluster" else "pn2_fps_cells_f32"

@@ -16,7 +16,7 @@ syn = importlib.import_module(PKG + ".synthetic")
 B, N, M = 16, 16384, 4096
 kind = sys.argv[1] if len(sys.argv) > 1 else "lidar"
 xyz = torch.from_numpy(syn.make_clouds(kind, B, N, seed=1024)).cuda()
-for warps in (16, 32, 8):
+for warps in (8, 4, 16):
     idx = torch.empty((B, M), dtype=torch.int32, device="cuda")
     prof = torch.zeros((B, warps, 8), dtype=torch.int64, device="cuda")
     call = lambda: cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(B), cabi.i32(N),
@@ -36,8 +36,7 @@ for warps in (16, 32, 8):
               kind, warps, ms, ms * 1e-3 * 1.965e9 / rounds, 100 * float((nupd / rounds).mean()),
               float((p[..., 7].sum() / nupd.sum())), float(p[..., 7].sum() / B / rounds)))
     print("    box test (every round)            %7.0f" % float((p[..., 0] / rounds).mean()))
-    print("    cell updates (touching rounds)    %7.0f" % float((p[..., 1] / nupd).mean()))
-    print("    record (touching rounds)          %7.0f" % float((p[..., 2] / nupd).mean()))
+    print("    cell updates + records (touching) %7.0f" % float((p[..., 1] / nupd).mean()))
     print("    barrier wait, touching rounds     %7.0f" % float((p[..., 3] / nupd).mean()))
     print("    barrier wait, idle rounds         %7.0f" % float((p[..., 4] / (rounds - nupd)).mean()))
     print("    record reduce + next centre       %7.0f" % float((p[..., 5] / rounds).mean()))
