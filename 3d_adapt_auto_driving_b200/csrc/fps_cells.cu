@@ -133,8 +133,8 @@ struct CellsCfg {
     static constexpr int NP = WARPS * CPW * kCellPts;
     // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16) | cell records: 2 buffers x (128 distances | 128 positions) u32
     static constexpr size_t kMain = (size_t)NP * 14 + 2 * 2 * kMaxCells * 4;
-    // prepass scratch (aliases the image): hist (4096 int) | ord (NP u16) | red (4 x WARPS float) | wsum (WARPS int)
-    static constexpr size_t kPre = (size_t)kOrderCells * 4 + (size_t)NP * 2 + 5 * WARPS * 4;
+    // prepass scratch (aliases the image): hist (4096 int) | ord (NP u16) | red (6 x WARPS float) | wsum (WARPS int)
+    static constexpr size_t kPre = (size_t)kOrderCells * 4 + (size_t)NP * 2 + 7 * WARPS * 4;
     static constexpr size_t kSmem = kMain > kPre ? kMain : kPre;
 };
 
@@ -162,44 +162,56 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
     }
 
     // ------------------------------------------------------------------------------------------------------------
-    // prepass 1: Hilbert order of the cloud (counting sort on a 64 x 64 grid over the (x, z) bounding box).  The order
+    // prepass 1: Hilbert order of the cloud (counting sort on a 64 x 64 grid over the two widest axes of the bounding box).  The order
     // inside a grid cell is whatever the atomics produce: the sampling result does not depend on which lane owns a point.
     // ------------------------------------------------------------------------------------------------------------
     uint16_t kk[SLOTS];
     {
         int *hist = reinterpret_cast<int *>(smem);
         uint16_t *ord = reinterpret_cast<uint16_t *>(smem + (size_t)kOrderCells * 4);
-        float *red = reinterpret_cast<float *>(smem + (size_t)kOrderCells * 4 + (size_t)NP * 2);   // [4][WARPS]
-        int *wsum = reinterpret_cast<int *>(red + 4 * WARPS);
+        float *red = reinterpret_cast<float *>(smem + (size_t)kOrderCells * 4 + (size_t)NP * 2);   // [6][WARPS]
+        int *wsum = reinterpret_cast<int *>(red + 6 * WARPS);
 
-        float xmin = 3.0e38f, xmax = -3.0e38f, zmin = 3.0e38f, zmax = -3.0e38f;
+        // bounding box of the cloud; the grid spans the two axes with the largest extent (x and z for a LiDAR sweep)
+        float lo3[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi3[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
         for (int i = tid; i < n; i += T) {
-            const float x = __ldg(xyz + (size_t)i * 3), z = __ldg(xyz + (size_t)i * 3 + 2);
-            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x);
-            zmin = fminf(zmin, z); zmax = fmaxf(zmax, z);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(xyz + (size_t)i * 3 + a);
+                lo3[a] = fminf(lo3[a], v); hi3[a] = fmaxf(hi3[a], v);
+            }
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-            xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-            zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
-            zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lo3[a] = fminf(lo3[a], __shfl_xor_sync(0xffffffffu, lo3[a], o));
+                hi3[a] = fmaxf(hi3[a], __shfl_xor_sync(0xffffffffu, hi3[a], o));
+            }
+            if (lane == 0) { red[(2 * a) * WARPS + warp] = lo3[a]; red[(2 * a + 1) * WARPS + warp] = hi3[a]; }
         }
-        if (lane == 0) { red[0 * WARPS + warp] = xmin; red[1 * WARPS + warp] = xmax; red[2 * WARPS + warp] = zmin; red[3 * WARPS + warp] = zmax; }
         for (int i = tid; i < kOrderCells; i += T) hist[i] = 0;
         __syncthreads();
-        for (int w = 0; w < WARPS; ++w) {
-            xmin = fminf(xmin, red[0 * WARPS + w]); xmax = fmaxf(xmax, red[1 * WARPS + w]);
-            zmin = fminf(zmin, red[2 * WARPS + w]); zmax = fmaxf(zmax, red[3 * WARPS + w]);
-        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            for (int w = 0; w < WARPS; ++w) {
+                lo3[a] = fminf(lo3[a], red[(2 * a) * WARPS + w]); hi3[a] = fmaxf(hi3[a], red[(2 * a + 1) * WARPS + w]);
+            }
+        const float ex = hi3[0] - lo3[0], ey = hi3[1] - lo3[1], ez = hi3[2] - lo3[2];
+        int ax0 = 0, ax1 = 2;                                  // drop the axis with the smallest extent (ties: keep x, z)
+        if (ex < ey && ex <= ez) { ax0 = 1; ax1 = 2; }
+        else if (ez < ey && ez < ex) { ax0 = 0; ax1 = 1; }
+        const float amin = ax0 == 0 ? lo3[0] : lo3[1], amax = ax0 == 0 ? hi3[0] : hi3[1];
+        const float bmin = ax1 == 2 ? lo3[2] : lo3[1], bmax = ax1 == 2 ? hi3[2] : hi3[1];
         const float top = (float)((1 << kOrderBits) - 1);
-        const float sx = xmax > xmin ? top / (xmax - xmin) : 0.f;
-        const float sz = zmax > zmin ? top / (zmax - zmin) : 0.f;
+        const float sa = amax > amin ? top / (amax - amin) : 0.f;
+        const float sb = bmax > bmin ? top / (bmax - bmin) : 0.f;
         auto cell_of = [&](int i) -> int {
-            const float x = __ldg(xyz + (size_t)i * 3), z = __ldg(xyz + (size_t)i * 3 + 2);
-            const float fx = fminf(fmaxf((x - xmin) * sx, 0.f), top), fz = fminf(fmaxf((z - zmin) * sz, 0.f), top);
-            const uint32_t gx = (uint32_t)(int)fx & ((1u << kOrderBits) - 1u), gz = (uint32_t)(int)fz & ((1u << kOrderBits) - 1u);
-            return order_hilbert(gx, gz);
+            const float u = __ldg(xyz + (size_t)i * 3 + ax0), v = __ldg(xyz + (size_t)i * 3 + ax1);
+            // non-finite coordinates land in some cell; only the ORDER depends on it
+            const float fu = fminf(fmaxf((u - amin) * sa, 0.f), top), fv = fminf(fmaxf((v - bmin) * sb, 0.f), top);
+            const uint32_t gu = (uint32_t)(int)fu & ((1u << kOrderBits) - 1u), gv = (uint32_t)(int)fv & ((1u << kOrderBits) - 1u);
+            return order_hilbert(gu, gv);
         };
         for (int i = tid; i < n; i += T) atomicAdd(&hist[cell_of(i)], 1);
         __syncthreads();

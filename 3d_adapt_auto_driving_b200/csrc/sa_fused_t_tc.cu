@@ -174,9 +174,9 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     uint64_t *empty = full + kMaxStages;
     uint64_t *acc2_full = empty + kMaxStages;   // [2]
     uint64_t *acc2_empty = acc2_full + 2;       // [2]
-    uint64_t *a2_full = acc2_empty + 2;
-    uint64_t *a2_empty = a2_full + 1;
-    uint64_t *acc3_full = a2_empty + 1;
+    uint64_t *a2_full = acc2_empty + 2;         // [2]: per K-block of the layer-2 activation tile A2
+    uint64_t *a2_empty = a2_full + 2;           // [2]
+    uint64_t *acc3_full = a2_empty + 2;
     uint64_t *acc3_empty = acc3_full + 1;
     uint64_t *w_full = acc3_empty + 1;          // W2 in shared memory (bulk copy)
     uint64_t *w3_full = w_full + 1;             // W3 in tensor memory (epilogue warps)
@@ -194,8 +194,10 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             mbar_init(&acc2_full[a], 1);
             mbar_init(&acc2_empty[a], kEpiW);
         }
-        mbar_init(a2_full, kEpiW);
-        mbar_init(a2_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a2_full[a], kEpiW);
+            mbar_init(&a2_empty[a], 1);
+        }
         mbar_init(acc3_full, 1);
         mbar_init(acc3_empty, kEpiW);
         mbar_init(w_full, 1);
@@ -258,7 +260,7 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer ===============================
         // All 32 lanes run the loops (uniform operands, tc::elect_one()); one elected lane issues.
-        // Tensor-pipe order  M2(0) | M2(1) M3(0) | M2(2) M3(1) | ...
+        // Tensor-pipe order  M2(0) M2(1) | M2(2).kb0 M3(0) M2(2).kb1 | M2(3).kb0 M3(1) M2(3).kb1 | ...   (M3(0) M2(1) M3(0)' | ... with one acc2 buffer)
         // (a CTA without a tile -- possible in compact mode, where the grid is sized for the upper bound -- still has
         // to see its weight copies land before it may exit)
         mbar_wait(w_full, 0);
@@ -272,13 +274,16 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             uint32_t phase = 0;
             unsigned long long w_ring = 0, w_acc2 = 0, w_a2 = 0, w_acc3 = 0;
             const long long t_begin = PROF ? clock64() : 0;
-            auto issue_m2 = [&](int it) {
+            // K-blocks [kb_lo, kb_hi) of layer 2 of tile `it` (the ring is consumed in tile / K-block order)
+            auto issue_m2 = [&](int it, int kb_lo, int kb_hi) {
                 const int buf = p.nb2 == 2 ? (it & 1) : 0;
                 const int use = p.nb2 == 2 ? (it >> 1) : it;
-                mbar_wait_timed<PROF>(&acc2_empty[buf], (uint32_t)(use & 1) ^ 1, w_acc2);
-                tc_fence_after_sync();
+                if (kb_lo == 0) {
+                    mbar_wait_timed<PROF>(&acc2_empty[buf], (uint32_t)(use & 1) ^ 1, w_acc2);
+                    tc_fence_after_sync();
+                }
                 const uint32_t d = tmem_base + col_acc2 + (uint32_t)(buf * p.n2);
-                for (int kb = 0; kb < p.nkb1; ++kb) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait_timed<PROF>(&full[stage], phase, w_ring);
                     tc_fence_after_sync();
                     const uint32_t sa = pn2_smem_u32(smem + L.off_ring + (size_t)stage * 2 * kABytes);
@@ -311,38 +316,51 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             };
             // one pass of layer 3 (transposed): acc3^T = W3[pass] (TMEM) x A2^T (shared memory, written by the epilogue)
             auto issue_m3 = [&](int it, int j) {
+                // A2 is handed over K-block by K-block (64 channels of the layer-2 activation): layer 3 starts on the first
+                // while the epilogue still converts the second, and -- what shortens the E2 -> M3 -> E2 loop of the
+                // stopwatch -- the epilogue may overwrite a K-block as soon as the MMAs that read it have completed.
                 const int cnt = it * p.nm3 + j;
-                if (j == 0) mbar_wait_timed<PROF>(a2_full, (uint32_t)(it & 1), w_a2);
                 mbar_wait_timed<PROF>(acc3_empty, (uint32_t)(cnt & 1) ^ 1, w_acc3);
-                tc_fence_after_sync();
                 const uint32_t d3 = tmem_base + col_acc3;
                 const uint32_t w3h = tmem_base + col_w3 + (uint32_t)(j * p.c2), w3l = w3h + (uint32_t)half_c2;
                 const int ksteps3 = p.c2 >> 4;
-                if (elect_one()) {
-                    for (int ks = 0; ks < ksteps3; ++ks) {
-                        const uint32_t tb = a2a + (uint32_t)(ks >> 2) * 2u * kABytes;
-                        const uint32_t b_hi = desc_lo(tb) + (uint32_t)((ks & 3) * 2);
-                        const uint32_t b_lo = desc_lo(tb + kABytes) + (uint32_t)((ks & 3) * 2);
-                        mma_ts_lo(d3, w3h + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
-                        mma_ts_lo(d3, w3h + ks * 8, b_lo, idesc3, 1u);
-                        mma_ts_lo(d3, w3l + ks * 8, b_hi, idesc3, 1u);
+                for (int kb = 0; kb < p.nkb2; ++kb) {
+                    if (j == 0) mbar_wait_timed<PROF>(&a2_full[kb], (uint32_t)(it & 1), w_a2);
+                    tc_fence_after_sync();
+                    const uint32_t tb = a2a + (uint32_t)kb * 2u * kABytes;
+                    const int ks_end = min(ksteps3, kb * 4 + 4);
+                    if (elect_one()) {
+                        for (int ks = kb * 4; ks < ks_end; ++ks) {
+                            const uint32_t b_hi = desc_lo(tb) + (uint32_t)((ks & 3) * 2);
+                            const uint32_t b_lo = desc_lo(tb + kABytes) + (uint32_t)((ks & 3) * 2);
+                            mma_ts_lo(d3, w3h + ks * 8, b_hi, idesc3, ks ? 1u : 0u);
+                            mma_ts_lo(d3, w3h + ks * 8, b_lo, idesc3, 1u);
+                            mma_ts_lo(d3, w3l + ks * 8, b_hi, idesc3, 1u);
+                        }
+                        if (kb == p.nkb2 - 1) mma_commit(acc3_full);
+                        if (j == p.nm3 - 1) mma_commit(&a2_empty[kb]);
                     }
-                    mma_commit(acc3_full);
-                    if (j == p.nm3 - 1) mma_commit(a2_empty);
+                    __syncwarp();
                 }
-                __syncwarp();
             };
-            issue_m2(0);
+            issue_m2(0, 0, p.nkb1);
+            if (p.nb2 == 2 && my_tiles > 1) issue_m2(1, 0, p.nkb1);
             for (int it = 0; it < my_tiles; ++it) {
                 if (p.nb2 == 2) {
-                    // double-buffered acc2: layer 2 of the next tile first, it overlaps this tile's conversion epilogue
-                    if (it + 1 < my_tiles) issue_m2(it + 1);
+                    // double-buffered acc2: layer 2 runs TWO tiles ahead.  M3(it) and M2(it + 2) both become possible when the
+                    // conversion epilogue E2(it) ends, but M3(it) also needs the layer-3 accumulator back from the pooling
+                    // epilogue of tile it - 1, which the epilogue warps only start after E2(it): the tensor pipe idled
+                    // through that wait (1.5 k of 7.1 k cycles per tile in the stopwatch).  The FIRST K-block of M2(it + 2)
+                    // (about as long as the wait) goes in front of M3(it), the rest behind it; all of M2(it + 2) in front
+                    // delayed M3(it) and with it the hand-back of A2 (measured: 7.7 k cycles per tile).
+                    if (it + 2 < my_tiles) issue_m2(it + 2, 0, 1);
                     for (int j = 0; j < p.nm3; ++j) issue_m3(it, j);
+                    if (it + 2 < my_tiles && p.nkb1 > 1) issue_m2(it + 2, 1, p.nkb1);
                 } else {
                     // single acc2 (it is free once this tile's conversion is done, which pass 0 waits for anyway):
                     // layer 2 of the next tile sits between the passes and covers the pooling of pass 0
                     issue_m3(it, 0);
-                    if (it + 1 < my_tiles) issue_m2(it + 1);
+                    if (it + 1 < my_tiles) issue_m2(it + 1, 0, p.nkb1);
                     for (int j = 1; j < p.nm3; ++j) issue_m3(it, j);
                 }
             }
@@ -562,9 +580,19 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
             const int use = pipelined ? (it >> 1) : it;
             // ---- E2: acc2[buf] -> bias, ReLU, bf16 hi/lo -> shared-memory operand A2 of layer 3 ----
             mbar_wait_timed<PROF>(&acc2_full[buf], (uint32_t)(use & 1), w_acc2f);
-            mbar_wait_timed<PROF>(a2_empty, (uint32_t)(it & 1) ^ 1, w_a2e);
+            mbar_wait_timed<PROF>(&a2_empty[0], (uint32_t)(it & 1) ^ 1, w_a2e);
             const long long t20 = PROF ? clock64() : 0;
             tc_fence_after_sync();
+            // one K-block of A2 (64 channels: one pass of the loop below over both warp halves) is complete
+            auto kblock_done = [&](int kb) {
+                fence_proxy_async_smem();      // generic-proxy stores -> visible to the MMA's async-proxy operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a2_full[kb]);
+                if (kb + 1 < p.nkb2) {
+                    mbar_wait_timed<PROF>(&a2_empty[kb + 1], (uint32_t)(it & 1) ^ 1, w_a2e);
+                    tc_fence_after_sync();
+                }
+            };
             const uint32_t t_acc2 = lane_addr + col_acc2 + (uint32_t)(buf * p.n2);
             auto convert = [&](const uint32_t (&v)[16], int c0) {
                 // 16 consecutive k of row r: two 16-byte chunks of the row's 128-byte line in K-block c0 / 64
@@ -589,28 +617,28 @@ __global__ void __maxnreg__(72) sa_fused_t_tc_kernel(const SatParams p) {
                 *reinterpret_cast<uint4 *>(tile_hi + kABytes + sw128_offset(r, ci)) = lo[0];
                 *reinterpret_cast<uint4 *>(tile_hi + kABytes + sw128_offset(r, ci + 1)) = lo[1];
             };
-            int c0 = half * 16;
-            for (; c0 + 32 < p.n2; c0 += 64) {
-                uint32_t va[16], vb[16];
-                tmem_ld16(t_acc2 + c0, va);
-                tmem_ld16(t_acc2 + c0 + 32, vb);
-                tmem_ld_wait();
-                convert(va, c0);
-                convert(vb, c0 + 32);
+            // K-block kb of A2 = channels 64 kb .. 64 kb + 63: this warp converts the 16-column chunks at half * 16 and
+            // half * 16 + 32 of it (those below n2); EVERY warp reports every K-block, with or without columns of its own
+            for (int kb = 0; kb < p.nkb2; ++kb) {
+                const int ca = kb * 64 + half * 16;
+                if (ca + 32 < p.n2) {
+                    uint32_t va[16], vb[16];
+                    tmem_ld16(t_acc2 + ca, va);
+                    tmem_ld16(t_acc2 + ca + 32, vb);
+                    tmem_ld_wait();
+                    convert(va, ca);
+                    convert(vb, ca + 32);
+                } else if (ca < p.n2) {
+                    uint32_t va[16];
+                    tmem_ld16(t_acc2 + ca, va);
+                    tmem_ld_wait();
+                    convert(va, ca);
+                }
+                kblock_done(kb);
             }
-            if (c0 < p.n2) {
-                uint32_t va[16];
-                tmem_ld16(t_acc2 + c0, va);
-                tmem_ld_wait();
-                convert(va, c0);
-            }
-            fence_proxy_async_smem();      // generic-proxy stores -> visible to the MMA's async-proxy operand reads
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(a2_full);
-                mbar_arrive(&acc2_empty[buf]);
-            }
+            if (lane == 0) mbar_arrive(&acc2_empty[buf]);
             if (PROF) t_e2 += (unsigned long long)(clock64() - t20);
             if (!pipelined) {
                 for (int j = 0; j < p.nm3; ++j) e3(it, j);

@@ -614,7 +614,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "mirror"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=4,
+    ap.add_argument("--depth", type=int, default=5,
                     help="batches in flight (Detector.submit/collect); 1 = one batch at a time on one stream")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--min-seconds", type=float, default=0.0,

@@ -66,6 +66,24 @@ def test_fps_cells_kernel_vs_oracle(cuda, oracle, warps, kind, n, m, b):
     assert torch.equal(idx2, idx)
 
 
+@pytest.mark.parametrize("perm", [(1, 0, 2), (2, 1, 0), (0, 2, 1)])
+def test_fps_cells_grid_follows_the_widest_axes(cuda, oracle, perm):
+    """The Hilbert grid of csrc/fps_cells.cu spans the two widest axes of the cloud, whichever they are (a sweep whose
+    flat axis is not y, a wall, a line): the pruning changes, the indices never do."""
+    cabi = load("cabi")
+    base = synthetic.make_clouds("lidar", 2, 6000, seed=9)[:, :, list(perm)].copy()
+    line = np.zeros((1, 6000, 3), np.float32)
+    line[0, :, perm[0]] = np.random.RandomState(3).uniform(-5, 5, 6000).astype(np.float32)
+    for xyz_h in (base, np.ascontiguousarray(line)):
+        b, n, m = xyz_h.shape[0], xyz_h.shape[1], 400
+        xyz = torch.from_numpy(xyz_h).to(cuda)
+        idx = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+        cabi.call("pn2_fps_cells_f32", cabi.ptr(xyz), cabi.ptr(None), cabi.ptr(idx), cabi.i32(b), cabi.i32(n), cabi.i32(m),
+                  cabi.i32(0))
+        ref, _ = oracle.fps(xyz_h, m)
+        assert np.array_equal(idx.cpu().numpy(), ref)
+
+
 def test_fps_cells_rejects_what_it_cannot_hold(cuda):
     cabi = load("cabi")
     xyz = torch.zeros((1, 20000, 3), device=cuda)
