@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
                                                                         const int32_t *__restrict__ order,
                                                                         int32_t *__restrict__ idx0,
                                                                         int32_t *__restrict__ idx1, int n, int m,
-                                                                        float radius0, int ns0, float radius1, int ns1) {
+                                                                        float radius0, int ns0, float radius1, int ns1,
+                                                                        int zero_empty) {
     __shared__ float4 cand[kCullWarps][kWarpList];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wfirst = (blockIdx.x * kCullWarps + warp) * 32;
@@ -270,19 +271,21 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
         if (!__shfl_sync(0xffffffffu, (int)active, j)) continue;
         const int cj = __shfl_sync(0xffffffffu, c, j);
         const int n0 = __shfl_sync(0xffffffffu, cnt0, j), f0 = __shfl_sync(0xffffffffu, first0, j);
-        if (n0 > 0)
-            for (int l = n0 + lane; l < ns0; l += 32) idx0[(row_base + cj) * ns0 + l] = f0;
+        // (a centre without any hit keeps what the caller put there -- zeros, pointnet2_utils.py:177 -- unless the caller
+        // asked for the zeros to be written here, which saves it the fill launch)
+        if (n0 > 0 || zero_empty)
+            for (int l = n0 + lane; l < ns0; l += 32) idx0[(row_base + cj) * ns0 + l] = n0 > 0 ? f0 : 0;
         if (DUAL) {
             const int n1 = __shfl_sync(0xffffffffu, cnt1, j), f1 = __shfl_sync(0xffffffffu, first1, j);
-            if (n1 > 0)
-                for (int l = n1 + lane; l < ns1; l += 32) idx1[(row_base + cj) * ns1 + l] = f1;
+            if (n1 > 0 || zero_empty)
+                for (int l = n1 + lane; l < ns1; l += 32) idx1[(row_base + cj) * ns1 + l] = n1 > 0 ? f1 : 0;
         }
     }
 }
 
 template <bool DUAL>
 int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n, int m,
-                  float r0, int ns0, float r1, int ns1, cudaStream_t stream) {
+                  float r0, int ns0, float r1, int ns1, int zero_empty, cudaStream_t stream) {
     // few centres per cloud: the ordering launch costs more than it saves, warps take the centres as they come
     const bool sorted = m >= 256;
     if (sorted && launch_spatial_order(new_xyz, order, b, m, stream) != cudaSuccess) {
@@ -291,7 +294,7 @@ int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t
     }
     if (!sorted) order = nullptr;
     dim3 grid(pn2_divup(m, kCullThreads), b);   // 2 warps x 32 centres per CTA
-    ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1);
+    ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1, zero_empty);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
@@ -331,20 +334,42 @@ PN2_API int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int3
 // The same results as pn2_ball_query_f32 (nsample1 == 0) / pn2_ball_query_dual_f32 through the
 // spatially culled scan.  `order` is caller-provided scratch of b * m int32 (the Hilbert order of
 // the centres is left there when m >= 256); with order == NULL or a tiny cloud the brute-force kernels run.
-PN2_API int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
-                                      int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
-                                      int nsample1, cudaStream_t stream) {
+static int ball_query_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n,
+                             int m, float radius0, int nsample0, float radius1, int nsample1, int zero_empty, cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0 || nsample0 <= 0 || nsample1 < 0 || (nsample1 > 0 && !idx1)) {
         pn2_set_last_error("pn2_ball_query_culled_f32: bad argument");
         return PN2_ERR_INVALID;
     }
-    if (b == 0 || m == 0 || n == 0) return PN2_OK;
-    if (!use_culled(order, n, m)) {
+    if (b == 0 || m == 0) return PN2_OK;
+    if (n == 0 || !use_culled(order, n, m)) {
+        if (zero_empty) {      // the brute-force kernels only write hits: zero the lists on the stream (memset nodes, not launches)
+            if (cudaMemsetAsync(idx0, 0, (size_t)b * m * nsample0 * sizeof(int32_t), stream) != cudaSuccess ||
+                (nsample1 > 0 && cudaMemsetAsync(idx1, 0, (size_t)b * m * nsample1 * sizeof(int32_t), stream) != cudaSuccess)) {
+                pn2_set_last_error("pn2_ball_query_culled_fill_f32: cudaMemsetAsync failed");
+                return PN2_ERR_LAUNCH;
+            }
+        }
+        if (n == 0) return PN2_OK;
         if (nsample1 > 0)
             return pn2_ball_query_dual_f32(new_xyz, xyz, idx0, idx1, b, n, m, radius0, nsample0, radius1, nsample1, stream);
         return pn2_ball_query_f32(new_xyz, xyz, idx0, b, n, m, radius0, nsample0, stream);
     }
     if (nsample1 > 0)
-        return launch_culled<true>(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, stream);
-    return launch_culled<false>(new_xyz, xyz, idx0, nullptr, order, b, n, m, radius0, nsample0, 0.f, 0, stream);
+        return launch_culled<true>(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, zero_empty, stream);
+    return launch_culled<false>(new_xyz, xyz, idx0, nullptr, order, b, n, m, radius0, nsample0, 0.f, 0, zero_empty, stream);
+}
+
+PN2_API int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
+                                      int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
+                                      int nsample1, cudaStream_t stream) {
+    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 0, stream);
+}
+
+// pn2_ball_query_culled_f32 for index lists the caller has NOT zeroed: the lists of centres without any neighbour are
+// written as zeros here (the value the reference's pre-zeroed tensor keeps, pointnet2_utils.py:177), every other list
+// is complete anyway.  Same results as zero-fill + pn2_ball_query_culled_f32, one launch less per list.
+PN2_API int pn2_ball_query_culled_fill_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
+                                           int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
+                                           int nsample1, cudaStream_t stream) {
+    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 1, stream);
 }

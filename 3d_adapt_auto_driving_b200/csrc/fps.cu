@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t fps_rank(int k, int log2bs, int cnt) {
 template <int P, int CLUSTER>
 __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
                                                        int32_t *__restrict__ idx, int n, int m, int log2bs, int cnt,
-                                                       const int32_t *__restrict__ viol) {
+                                                       const int32_t *__restrict__ viol, float *__restrict__ new_xyz) {
     constexpr int S = CLUSTER * kWarps;  // records per round
     constexpr int P2 = (P + 1) / 2;
     extern __shared__ float4 pts_s[];
@@ -122,10 +122,13 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
     xyz += (size_t)cloud * n * 3;
     idx += (size_t)cloud * m;
     if (temp) temp += (size_t)cloud * n;
+    if (new_xyz) new_xyz += (size_t)cloud * m * 3;     // optional: coordinates of the picked points, (B, M, 3)
     // guarded launch (pn2_fps_guarded_f32): pn2_fps_prefix_check_f32 proved that this cloud's answer is 0, 1, ..., m-1.
     // The flag is per cloud, so every CTA of the cluster leaves here, before any cluster-scope operation.
     if (viol != nullptr && __ldg(viol + cloud) == 0) {
         for (int i = (int)crank * kThreads + tid; i < m; i += CLUSTER * kThreads) idx[i] = i;
+        if (new_xyz)
+            for (int i = (int)crank * kThreads + tid; i < 3 * m; i += CLUSTER * kThreads) new_xyz[i] = __ldg(xyz + i);
         return;
     }
 
@@ -186,7 +189,10 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
     }
 
     float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // idx[0] = 0 always
-    if (crank == 0 && tid == 0) idx[0] = 0;
+    if (crank == 0 && tid == 0) {
+        idx[0] = 0;
+        if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
+    }
 
     // cluster addresses of this warp's record slot and of the round barrier in every CTA (parity 0)
     uint32_t rslot[CLUSTER], rbar[CLUSTER];
@@ -269,7 +275,10 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
         const int wslot = __shfl_sync(0xffffffffu, myslot, __ffs(who) - 1);
         const float4 c4 = *reinterpret_cast<const float4 *>(&slots[par][wslot].x);
         cx = c4.x; cy = c4.y; cz = c4.z;
-        if (crank == 0 && tid == 0) idx[r + 1] = slots[par][wslot].k;
+        if (crank == 0 && tid == 0) {
+            idx[r + 1] = slots[par][wslot].k;
+            if (new_xyz) { new_xyz[3 * r + 3] = c4.x; new_xyz[3 * r + 4] = c4.y; new_xyz[3 * r + 5] = c4.z; }
+        }
     }
 
     if (temp) {  // the reference leaves the running min distances in the caller's scratch
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) fps_kernel(const float *__restrict__
 
 template <int P, int CLUSTER>
 cudaError_t launch_fps(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
-                       const int32_t *viol, cudaStream_t stream) {
+                       const int32_t *viol, float *new_xyz, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER, b, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
@@ -306,19 +315,19 @@ cudaError_t launch_fps(const float *xyz, float *temp, int32_t *idx, int b, int n
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, fps_kernel<P, CLUSTER>, xyz, temp, idx, n, m, log2bs, cnt, viol);
+    return cudaLaunchKernelEx(&cfg, fps_kernel<P, CLUSTER>, xyz, temp, idx, n, m, log2bs, cnt, viol, new_xyz);
 }
 
 template <int CLUSTER>
 cudaError_t dispatch_p(int p, const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
-                       const int32_t *viol, cudaStream_t s) {
+                       const int32_t *viol, float *new_xyz, cudaStream_t s) {
     switch (p) {
-        case 1: return launch_fps<1, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
-        case 2: return launch_fps<2, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
-        case 4: return launch_fps<4, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
-        case 8: return launch_fps<8, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
-        case 16: return launch_fps<16, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
-        default: return launch_fps<32, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, s);
+        case 1: return launch_fps<1, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
+        case 2: return launch_fps<2, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
+        case 4: return launch_fps<4, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
+        case 8: return launch_fps<8, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
+        case 16: return launch_fps<16, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
+        default: return launch_fps<32, CLUSTER>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, s);
     }
 }
 
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(256) fps_prefix_check_kernel(const float *__re
 // fps_cells.cu: the pruned one-CTA kernel (clouds of up to 16384 points)
 bool pn2_fps_cells_supported(int n);
 cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
-                                 const int32_t *viol, cudaStream_t stream);
+                                 const int32_t *viol, float *new_xyz, cudaStream_t stream);
 
 // Block size the reference launcher would have used (cuda_utils.h:10-14); it only matters
 // here because it fixes the tie-break order.  Same double-precision expression.
@@ -403,7 +412,7 @@ PN2_API int pn2_fps_ref_block_size(int n) {
 // viol: NULL, or (B) int32 from pn2_fps_prefix_check_f32 -- clouds with viol == 0 get idx = 0..M-1 without the
 // round loop.  Enqueues on `stream`, never synchronises.
 static int fps_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int cluster_size,
-                      const int32_t *viol, cudaStream_t stream) {
+                      const int32_t *viol, float *new_xyz, cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0 || (!xyz && b * n > 0) || (!idx && b * m > 0)) {
         pn2_set_last_error("pn2_fps_f32: bad argument");
         return PN2_ERR_INVALID;
@@ -418,7 +427,7 @@ static int fps_launch(const float *xyz, float *temp, int32_t *idx, int b, int n,
     // with few rounds the Hilbert-sort prepass (~20 us) does not pay.
     constexpr int kCellsMinN = 2048, kCellsMinM = 128;
     if (cluster_size == 0 && n > kCellsMinN && m >= kCellsMinM && pn2_fps_cells_supported(n)) {
-        const cudaError_t ec = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, 0, viol, stream);
+        const cudaError_t ec = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, 0, viol, new_xyz, stream);
         if (ec != cudaSuccess) {
             pn2_set_last_error(cudaGetErrorString(ec));
             return PN2_ERR_LAUNCH;
@@ -449,10 +458,10 @@ static int fps_launch(const float *xyz, float *temp, int32_t *idx, int b, int n,
     while (pp < p) pp *= 2;
     cudaError_t e;
     switch (cluster) {
-        case 1: e = dispatch_p<1>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream); break;
-        case 2: e = dispatch_p<2>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream); break;
-        case 4: e = dispatch_p<4>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream); break;
-        case 8: e = dispatch_p<8>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream); break;
+        case 1: e = dispatch_p<1>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, stream); break;
+        case 2: e = dispatch_p<2>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, stream); break;
+        case 4: e = dispatch_p<4>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, stream); break;
+        case 8: e = dispatch_p<8>(pp, xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, stream); break;
         default: pn2_set_last_error("pn2_fps_f32: cluster must be 1, 2, 4 or 8"); return PN2_ERR_INVALID;
     }
     if (e != cudaSuccess) {
@@ -463,16 +472,16 @@ static int fps_launch(const float *xyz, float *temp, int32_t *idx, int b, int n,
 }
 
 PN2_API int pn2_fps_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, cudaStream_t stream) {
-    return fps_launch(xyz, temp, idx, b, n, m, 0, nullptr, stream);
+    return fps_launch(xyz, temp, idx, b, n, m, 0, nullptr, nullptr, stream);
 }
 
 // pn2_fps_f32 with the CTAs-per-cloud cluster size forced (1, 2, 4 or 8; 0 = heuristic).  Same result for every value.
 PN2_API int pn2_fps_cluster_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int cluster_size,
                                 cudaStream_t stream) {
-    return fps_launch(xyz, temp, idx, b, n, m, cluster_size, nullptr, stream);
+    return fps_launch(xyz, temp, idx, b, n, m, cluster_size, nullptr, nullptr, stream);
 }
 
-// viol (B) int32, ZEROED by the caller; dmin (B, M) f32 scratch.  Afterwards viol[c] == 0 iff furthest point sampling of
+// viol (B) int32 (zeroed here, on the stream); dmin (B, M) f32 scratch.  Afterwards viol[c] == 0 iff furthest point sampling of
 // cloud c provably returns 0, 1, ..., M-1 (see fps_prefix_check_kernel); M <= 4096.
 PN2_API int pn2_fps_prefix_check_f32(const float *xyz, float *dmin, int32_t *viol, int b, int n, int m, cudaStream_t stream) {
     if (b < 0 || n <= 0 || m <= 0 || m > n || !xyz || !dmin || !viol) {
@@ -483,7 +492,12 @@ PN2_API int pn2_fps_prefix_check_f32(const float *xyz, float *dmin, int32_t *vio
         pn2_set_last_error("pn2_fps_prefix_check_f32: m > 4096 is not supported");
         return PN2_ERR_UNSUPPORTED;
     }
-    if (b == 0 || m == 1) return PN2_OK;
+    if (b == 0) return PN2_OK;
+    if (cudaMemsetAsync(viol, 0, (size_t)b * sizeof(int32_t), stream) != cudaSuccess) {   // a memset node, not a launch
+        pn2_set_last_error("pn2_fps_prefix_check_f32: cudaMemsetAsync failed");
+        return PN2_ERR_LAUNCH;
+    }
+    if (m == 1) return PN2_OK;
     fps_prefix_dist_kernel<<<dim3((m - 1 + 7) / 8, b), 256, 0, stream>>>(xyz, dmin, viol, n, m);
     PN2_CHECK_LAUNCH();
     fps_prefix_check_kernel<<<dim3((n + 255) / 256, b), 256, (size_t)m * sizeof(float4), stream>>>(xyz, dmin, viol, n, m);
@@ -498,5 +512,25 @@ PN2_API int pn2_fps_guarded_f32(const float *xyz, int32_t *idx, const int32_t *v
         pn2_set_last_error("pn2_fps_guarded_f32: viol is required");
         return PN2_ERR_INVALID;
     }
-    return fps_launch(xyz, nullptr, idx, b, n, m, 0, viol, stream);
+    return fps_launch(xyz, nullptr, idx, b, n, m, 0, viol, nullptr, stream);
+}
+
+// pn2_fps_f32 (temp = NULL) that also writes the coordinates of the picked points, new_xyz (B, M, 3): what the callers of
+// furthest_point_sample do next with a gather (pointnet2_modules.py:29-33) costs the kernel three stores per round.
+PN2_API int pn2_fps_xyz_f32(const float *xyz, int32_t *idx, float *new_xyz, int b, int n, int m, cudaStream_t stream) {
+    if (!new_xyz && b * m > 0) {
+        pn2_set_last_error("pn2_fps_xyz_f32: new_xyz is required");
+        return PN2_ERR_INVALID;
+    }
+    return fps_launch(xyz, nullptr, idx, b, n, m, 0, nullptr, new_xyz, stream);
+}
+
+// pn2_fps_guarded_f32 + the coordinates of the picked points (clouds with viol == 0: the first M rows of xyz).
+PN2_API int pn2_fps_guarded_xyz_f32(const float *xyz, int32_t *idx, float *new_xyz, const int32_t *viol, int b, int n, int m,
+                                    cudaStream_t stream) {
+    if (!viol || (!new_xyz && b * m > 0)) {
+        pn2_set_last_error("pn2_fps_guarded_xyz_f32: viol and new_xyz are required");
+        return PN2_ERR_INVALID;
+    }
+    return fps_launch(xyz, nullptr, idx, b, n, m, 0, viol, new_xyz, stream);
 }

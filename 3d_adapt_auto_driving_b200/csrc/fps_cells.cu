@@ -142,7 +142,7 @@ struct CellsCfg {
 template <int WARPS, int CPW, bool PROF>
 __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
                                                                   int32_t *__restrict__ idx, int n, int m, int log2bs, int cnt,
-                                                                  const int32_t *__restrict__ viol,
+                                                                  const int32_t *__restrict__ viol, float *__restrict__ new_xyz,
                                                                   unsigned long long *__restrict__ prof) {
     using Cfg = CellsCfg<WARPS, CPW>;
     constexpr int T = Cfg::T, SLOTS = Cfg::SLOTS, NP = Cfg::NP;
@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
     xyz += (size_t)cloud * n * 3;
     idx += (size_t)cloud * m;
     if (temp) temp += (size_t)cloud * n;
+    if (new_xyz) new_xyz += (size_t)cloud * m * 3;           // optional: coordinates of the picked points, (B, M, 3)
     if (viol != nullptr && __ldg(viol + cloud) == 0) {       // guarded launch, see fps.cu
         for (int i = tid; i < m; i += T) idx[i] = i;
+        if (new_xyz)
+            for (int i = tid; i < 3 * m; i += T) new_xyz[i] = __ldg(xyz + i);
         return;
     }
 
@@ -380,6 +383,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
         const float by = fmaxf(fmaxf(__fadd_rn(bly, -cy), __fadd_rn(cy, -bhy)), 0.f);
         const float bz = fmaxf(fmaxf(__fadd_rn(blz, -cz), __fadd_rn(cz, -bhz)), 0.f);
         const float lb = pn2_sqdist(bx, by, bz);
+        if (tid == 0 && new_xyz) {      // pick r (its coordinates were just consumed above: no extra scoreboard wait)
+            new_xyz[3 * r] = cx; new_xyz[3 * r + 1] = cy; new_xyz[3 * r + 2] = cz;
+        }
         const bool touched = lane < CPW && lb < cmax;
         const uint32_t mask = __ballot_sync(0xffffffffu, touched);
         int ci = (int)__reduce_min_sync(0xffffffffu, touched ? (uint32_t)lane : 32u);   // first touched cell (redux: ~15 cycles, BREV + FLO of the mask: ~40)
@@ -437,6 +443,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
         }
     }
     if (tid == 0 && m > 1) idx[m - 1] = (int32_t)kpend;
+    if (tid == 0 && new_xyz) { new_xyz[3 * (m - 1)] = cx; new_xyz[3 * (m - 1) + 1] = cy; new_xyz[3 * (m - 1) + 2] = cz; }
     if (PROF && lane == 0 && prof) {
         unsigned long long *o = prof + ((size_t)cloud * WARPS + warp) * 8;
         o[0] = p_test; o[1] = p_upd; o[2] = p_rec; o[3] = p_bar_u; o[4] = p_bar_n; o[5] = p_red; o[6] = p_nupd; o[7] = p_cells;
@@ -455,7 +462,7 @@ unsigned long long *g_cells_prof = nullptr;
 
 template <int WARPS, int CPW>
 cudaError_t launch_cells(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int log2bs, int cnt,
-                         const int32_t *viol, cudaStream_t stream) {
+                         const int32_t *viol, float *new_xyz, cudaStream_t stream) {
     using Cfg = CellsCfg<WARPS, CPW>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
@@ -470,11 +477,11 @@ cudaError_t launch_cells(const float *xyz, float *temp, int32_t *idx, int b, int
     }
     if constexpr (WARPS * CPW == 128) {      // stopwatch build: the 16384-point shapes only (tools/prof_fps_cells.py)
         if (g_cells_prof) {
-            fps_cells_kernel<WARPS, CPW, true><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, g_cells_prof);
+            fps_cells_kernel<WARPS, CPW, true><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, new_xyz, g_cells_prof);
             return cudaGetLastError();
         }
     }
-    fps_cells_kernel<WARPS, CPW, false><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, nullptr);
+    fps_cells_kernel<WARPS, CPW, false><<<b, Cfg::T, Cfg::kSmem, stream>>>(xyz, temp, idx, n, m, log2bs, cnt, viol, new_xyz, nullptr);
     return cudaGetLastError();
 }
 
@@ -491,14 +498,14 @@ bool pn2_fps_cells_supported(int n) { return n >= 1 && n <= 16384; }
 // Internal door for fps.cu (pn2_fps_f32's heuristic) and pn2_fps_cells_f32.  warps: 0 = heuristic, or 4 / 8 / 16 to force
 // the number of warps of the CTA (tests, tuning); returns cudaErrorInvalidValue for a combination that is not built.
 cudaError_t pn2_fps_cells_launch(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps,
-                                 const int32_t *viol, cudaStream_t stream) {
+                                 const int32_t *viol, float *new_xyz, cudaStream_t stream) {
     const int bs = pn2_fps_ref_block_size(n);
     int log2bs = 0;
     while ((1 << log2bs) < bs) ++log2bs;
     const int cnt = (n + bs - 1) / bs;
     const int cells = (n + kCellPts - 1) / kCellPts;      // 1 .. 128
     if (warps == 0) warps = 8;       // measured best at every size (tools/bench_fps_cluster.py): the redundant per-warp work of a round grows with the warp count
-#define PN2_CELLS_GO(W, C) return launch_cells<W, C>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, stream)
+#define PN2_CELLS_GO(W, C) return launch_cells<W, C>(xyz, temp, idx, b, n, m, log2bs, cnt, viol, new_xyz, stream)
     if (warps == 4) {
         if (cells <= 32) PN2_CELLS_GO(4, 8);
         if (cells <= 64) PN2_CELLS_GO(4, 16);
@@ -532,7 +539,7 @@ PN2_API int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b
         pn2_set_last_error("pn2_fps_cells_f32: 1 <= N <= 16384 points per cloud");
         return PN2_ERR_UNSUPPORTED;
     }
-    const cudaError_t e = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, warps, nullptr, stream);
+    const cudaError_t e = pn2_fps_cells_launch(xyz, temp, idx, b, n, m, warps, nullptr, nullptr, stream);
     if (e == cudaErrorInvalidValue) {
         pn2_set_last_error("pn2_fps_cells_f32: warps must be 0, 4, 8 or 16");
         return PN2_ERR_INVALID;

@@ -330,7 +330,58 @@ __global__ void __launch_bounds__(256) three_interpolate_pm_kernel(const float *
         o[ch] = t;
     }
 }
+
+// The same interpolation with the weights formed in the kernel from the SQUARED distances of three_nn: the statements
+// the FP module runs in torch between the two ops (pointnet2_utils.py:104 sqrt, pointnet2_modules.py:209-211
+// 1 / (dist + 1e-8), sum over the three, division) with the same IEEE operations in the same order.
+__global__ void __launch_bounds__(256) three_interpolate_pm_d2_kernel(const float *__restrict__ feats, int ldf,
+                                                                     const int32_t *__restrict__ idx,
+                                                                     const float *__restrict__ dist2,
+                                                                     float *__restrict__ out, int ldo, int c, int m,
+                                                                     int n, long long total, int sum_order) {
+    const long long pt = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= total) return;
+    const long long cloud = pt / n;
+    const int32_t *id = idx + pt * 3;
+    const float *d = dist2 + pt * 3;
+    const float q0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d)), 1e-8f));
+    const float q1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + 1)), 1e-8f));
+    const float q2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + 2)), 1e-8f));
+    // association of the three-term sum: torch.sum's reduction kernel is not left-to-right (two threads take the even and
+    // the odd elements), so the order is a parameter pinned against torch by the test
+    const float norm = sum_order == 0 ? __fadd_rn(__fadd_rn(q0, q1), q2)
+                     : sum_order == 1 ? __fadd_rn(__fadd_rn(q0, q2), q1) : __fadd_rn(q0, __fadd_rn(q1, q2));
+    const float w0 = __fdiv_rn(q0, norm), w1 = __fdiv_rn(q1, norm), w2 = __fdiv_rn(q2, norm);
+    const float *r0 = feats + (cloud * m + __ldg(id)) * ldf;
+    const float *r1 = feats + (cloud * m + __ldg(id + 1)) * ldf;
+    const float *r2 = feats + (cloud * m + __ldg(id + 2)) * ldf;
+    float *o = out + pt * ldo;
+    for (int ch = lane; ch < c; ch += 32) {
+        float t = __fmul_rn(w1, __ldg(r1 + ch));
+        t = __fmaf_rn(w0, __ldg(r0 + ch), t);
+        t = __fmaf_rn(w2, __ldg(r2 + ch), t);
+        o[ch] = t;
+    }
+}
 }  // namespace
+
+// pn2_three_interpolate_pm_f32 fed with the squared distances of pn2_three_nn_f32 instead of ready-made weights.
+// sum_order: 0 = (r0 + r1) + r2, 1 = (r0 + r2) + r1, 2 = r0 + (r1 + r2) for the normalising sum of the three reciprocals.
+PN2_API int pn2_three_interpolate_pm_d2_f32(const float *feats, int ldf, const int32_t *idx, const float *dist2,
+                                            float *out, int ldo, int b, int c, int m, int n, int sum_order,
+                                            cudaStream_t stream) {
+    if (b < 0 || c < 0 || n < 0 || m < 0 || ldf < c || ldo < c || sum_order < 0 || sum_order > 2) {
+        pn2_set_last_error("pn2_three_interpolate_pm_d2_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    const long long total = (long long)b * n;
+    if (total == 0 || c == 0) return PN2_OK;
+    three_interpolate_pm_d2_kernel<<<pn2_divup(total * 32, 256), 256, 0, stream>>>(feats, ldf, idx, dist2, out, ldo, c, m,
+                                                                                  n, total, sum_order);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
 
 PN2_API int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx, const float *weight,
                                          float *out, int ldo, int b, int c, int m, int n, cudaStream_t stream) {

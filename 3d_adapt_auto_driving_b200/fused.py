@@ -132,6 +132,25 @@ def sa_group_linear(h, idx, xyz, centres, wxyz, layer, out=None, pool=1):
     return out
 
 
+# association torch.sum(dist_recip, dim=2) uses for its three terms (its reduction kernel gives the even and the odd elements
+# to two threads): 1 = (r0 + r2) + r1; pinned bit for bit by tests/test_pn2_ops_gpu.py
+INTERP_SUM_ORDER = 1
+
+
+def three_interpolate_pm_d2(feats_pm, idx, dist2, out, sum_order=None):
+    """three_interpolate_pm with the weights formed in the kernel from three_nn's squared distances (the sqrt, reciprocal,
+    sum and division the FP module otherwise runs as five torch launches; bit-identical weights)."""
+    B, m, C = feats_pm.shape
+    n = idx.shape[1]
+    f2, _, ldf, _ = _rows2d(feats_pm)
+    o2, orows, ldo, oc = _rows2d(out)
+    assert orows == B * n and oc == C
+    cabi.call("pn2_three_interpolate_pm_d2_f32", ptr(f2), i32(ldf), ptr(idx), ptr(dist2), ptr(o2), i32(ldo), i32(B),
+              i32(C), i32(m), i32(n), i32(INTERP_SUM_ORDER if sum_order is None else sum_order),
+              work=4.0 * B * n * C * 4 + 24.0 * B * n)
+    return out
+
+
 def three_interpolate_pm(feats_pm, idx, weight, out):
     """feats (B,m,C) point-major, idx/weight (B,n,3) -> writes out rows (B*n, >=C) cols [0,C)."""
     B, m, C = feats_pm.shape
@@ -147,12 +166,23 @@ def three_interpolate_pm(feats_pm, idx, weight, out):
 def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
-    i0 = torch.zeros((B, M, ns0), dtype=torch.int32, device=xyz.device)
-    i1 = torch.zeros((B, M, ns1), dtype=torch.int32, device=xyz.device)
+    i0 = torch.empty((B, M, ns0), dtype=torch.int32, device=xyz.device)   # no zero fill: the _fill entry point writes the
+    i1 = torch.empty((B, M, ns1), dtype=torch.int32, device=xyz.device)   # zeros of centres without neighbours itself
     order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)    # scratch: Hilbert order of the centres
-    cabi.call("pn2_ball_query_culled_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), ptr(order), i32(B), i32(N), i32(M),
+    cabi.call("pn2_ball_query_culled_fill_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), ptr(order), i32(B), i32(N), i32(M),
               f32(r0), i32(ns0), f32(r1), i32(ns1), work=12.0 * B * M * N)
     return i0, i1
+
+
+def ball_query_single(xyz, new_xyz, radius, nsample):
+    """pointnet2_utils.ball_query without the zero-fill launch (same lists)."""
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
+    order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)
+    cabi.call("pn2_ball_query_culled_fill_f32", ptr(new_xyz), ptr(xyz), ptr(idx), ptr(None), ptr(order), i32(B), i32(N), i32(M),
+              f32(radius), i32(nsample), f32(0.0), i32(0), work=12.0 * B * M * N)
+    return idx
 
 
 # SA levels that sample an already FPS-ordered cloud (every backbone level after the first) first run the exact
@@ -171,19 +201,21 @@ def fps_gather(xyz, npoint, fps_ordered=False):
     the output of a previous furthest point sampling (a hint, never trusted: the prefix test decides per cloud)."""
     B, N, _ = xyz.shape
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    # the sampling kernels write the coordinates of their picks themselves (three stores a round): no cast / gather / copy
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
     if fps_ordered and FPS_PREFIX_CHECK and 1 < npoint <= min(N, 4096):
-        viol = torch.zeros((B,), dtype=torch.int32, device=xyz.device)
+        viol = torch.empty((B,), dtype=torch.int32, device=xyz.device)       # zeroed by the check itself (a memset node)
         dmin = torch.empty((B, npoint), dtype=torch.float32, device=xyz.device)
         cabi.call("pn2_fps_prefix_check_f32", ptr(xyz), ptr(dmin), ptr(viol), i32(B), i32(N), i32(npoint),
                   work=12.0 * B * npoint * N)
-        cabi.call("pn2_fps_guarded_f32", ptr(xyz), ptr(idx), ptr(viol), i32(B), i32(N), i32(npoint), work=0.0)
+        cabi.call("pn2_fps_guarded_xyz_f32", ptr(xyz), ptr(idx), ptr(new_xyz), ptr(viol), i32(B), i32(N), i32(npoint), work=0.0)
     elif FPS_CLUSTER and N > 4096:
         cabi.call("pn2_fps_cluster_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint), i32(FPS_CLUSTER),
                   work=16.0 * B * max(npoint - 1, 0) * N)
+        new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     else:
-        cabi.call("pn2_fps_f32", ptr(xyz), ptr(None), ptr(idx), i32(B), i32(N), i32(npoint),
+        cabi.call("pn2_fps_xyz_f32", ptr(xyz), ptr(idx), ptr(new_xyz), i32(B), i32(N), i32(npoint),
                   work=16.0 * B * max(npoint - 1, 0) * N)
-    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     return idx, new_xyz
 
 

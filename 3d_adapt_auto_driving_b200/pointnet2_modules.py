@@ -93,7 +93,7 @@ class _PointnetSAModuleBase(pt_utils.PackedCacheMixin, nn.Module):
             g0, g1 = self.groupers
             idxs = fz.ball_query_dual(xyz, new_xyz, g0.radius, g0.nsample, g1.radius, g1.nsample)
         else:
-            idxs = [pointnet2_utils.ball_query(g.radius, g.nsample, xyz, new_xyz) for g in self.groupers]
+            idxs = [fz.ball_query_single(xyz, new_xyz, g.radius, g.nsample) for g in self.groupers]
         c_total = sum(e["layers"][-1].cout for e in packed)
         out = torch.empty((B, M, c_total), dtype=torch.float32, device=xyz.device)
         out2 = out.view(B * M, c_total)
@@ -198,11 +198,13 @@ class PointnetFPModule(pt_utils.PackedCacheMixin, nn.Module):
         c1 = unknow_feats_pm.shape[2] if unknow_feats_pm is not None else 0
         x = torch.empty((B, n, c2 + c1), dtype=torch.float32, device=unknown.device)
         x2 = x.view(B * n, c2 + c1)
-        dist, idx = pointnet2_utils.three_nn(unknown, known)
-        dist_recip = 1.0 / (dist + 1e-8)
-        norm = torch.sum(dist_recip, dim=2, keepdim=True)
-        weight = (dist_recip / norm).contiguous()
-        fz.three_interpolate_pm(known_feats_pm, idx, weight, x2[:, :c2])
+        # three_nn's squared distances go straight into the interpolation kernel, which forms the weights
+        # 1 / (sqrt(d2) + 1e-8) / sum like the torch statements of forward() below (bit-identical, one launch for five)
+        m = known.shape[1]
+        dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+        idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+        pointnet2_utils.pointnet2.three_nn_wrapper(B, n, m, unknown, known, dist2, idx)
+        fz.three_interpolate_pm_d2(known_feats_pm, idx, dist2, x2[:, :c2])
         if c1:
             x[:, :, c2:] = unknow_feats_pm
         cur = x2

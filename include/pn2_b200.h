@@ -52,14 +52,20 @@ int pn2_fps_cluster_f32(const float *xyz, float *temp, int32_t *idx, int b, int 
 int pn2_fps_cells_f32(const float *xyz, float *temp, int32_t *idx, int b, int n, int m, int warps, void *stream);
 /* Exact parallel test "does furthest_point_sample(xyz, m) return 0, 1, ..., m-1?" (true for every SA level of the
  * backbone after the first: pointnet2_msg.py:131-137 feeds level l the FPS-ordered centres of level l-1, and FPS of a
- * prefix of an FPS ordering is that prefix unless two candidates tie at the maximum).  viol (B) int32 ZEROED by the
- * caller, dmin (B, m) f32 scratch; afterwards viol[c] == 0 iff at every round the due point is the STRICT arg-max of the
+ * prefix of an FPS ordering is that prefix unless two candidates tie at the maximum).  viol (B) int32 (zeroed by this
+ * call, on the stream), dmin (B, m) f32 scratch; afterwards viol[c] == 0 iff at every round the due point is the STRICT arg-max of the
  * running min-distances, computed with the reference's own float expressions (sampling_gpu.cu:129-138), so the answer
  * does not depend on the reference's tie order.  N * m independent pair evaluations instead of m dependent rounds. */
 int pn2_fps_prefix_check_f32(const float *xyz, float *dmin, int32_t *viol, int b, int n, int m, void *stream);
 /* pn2_fps_f32 (temp = NULL) that writes idx = 0..m-1 for the clouds with viol[c] == 0 and runs the round loop for the
  * others: bit-exact in both cases. */
 int pn2_fps_guarded_f32(const float *xyz, int32_t *idx, const int32_t *viol, int b, int n, int m, void *stream);
+/* pn2_fps_f32 (temp = NULL) / pn2_fps_guarded_f32 that also write new_xyz (B, m, 3) = the coordinates of the picked points:
+ * the gather the callers of furthest_point_sample run next (pointnet2_modules.py:29-33) costs the kernel three stores a
+ * round instead of a cast, a gather and a copy launch. */
+int pn2_fps_xyz_f32(const float *xyz, int32_t *idx, float *new_xyz, int b, int n, int m, void *stream);
+int pn2_fps_guarded_xyz_f32(const float *xyz, int32_t *idx, float *new_xyz, const int32_t *viol, int b, int n, int m,
+                            void *stream);
 
 /* gather_points_wrapper(b,c,n,npoints,points,idx,out)  sampling.cpp:11-21, sampling_gpu.cu:8-44.
  * points (B,C,N), idx (B,M) int32 -> out (B,C,M). */
@@ -83,6 +89,12 @@ int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int32_t *idx
 int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order,
                               int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
                               void *stream);
+/* The same for index lists the caller has NOT zeroed (the reference allocates them zeroed, pointnet2_utils.py:177, and its
+ * kernel leaves the list of a centre without neighbours untouched): such lists are written as zeros here, every other
+ * list is complete anyway.  Same results as a zero fill followed by pn2_ball_query_culled_f32. */
+int pn2_ball_query_culled_fill_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order,
+                                   int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
+                                   void *stream);
 
 /* group_points_wrapper(b,c,n,npoints,nsample,points,idx,out)  group_points.cpp:24-35,
  * group_points_gpu.cu:47-86.  points (B,C,N), idx (B,M,ns) -> out (B,C,M,ns). */
@@ -163,6 +175,12 @@ int pn2_sa_group_linear_f32(const float *h, int ldh, const int32_t *idx, const f
  * pointnet2_modules.py:139-149). */
 int pn2_three_interpolate_pm_f32(const float *feats, int ldf, const int32_t *idx, const float *weight, float *out,
                                  int ldo, int b, int c, int m, int n, void *stream);
+/* The same fed with the SQUARED distances of three_nn_wrapper: sqrt (pointnet2_utils.py:104), 1 / (dist + 1e-8), the sum of
+ * the three and the division (pointnet2_modules.py:209-211) happen in the kernel, with the IEEE operations torch executes
+ * for those statements in the same order (bit-identical weights, tests/test_pn2_ops_gpu.py).
+ * sum_order = association of the three-term sum, 0: (r0 + r1) + r2, 1: (r0 + r2) + r1 (torch.sum's kernel), 2: r0 + (r1 + r2). */
+int pn2_three_interpolate_pm_d2_f32(const float *feats, int ldf, const int32_t *idx, const float *dist2, float *out,
+                                    int ldo, int b, int c, int m, int n, int sum_order, void *stream);
 
 /* ---- the same shared-MLP layers on the tcgen05 tensor cores (BF16x3 split, fp32 accumulation in
  *      TMEM); wblob is the host-packed weight image described in csrc/linear_tc.cu.  When pool (nsample)

@@ -339,3 +339,80 @@ def test_fps_prefix_check_rejects_unordered_and_duplicate_clouds(cuda, oracle):
     idx, _ = fz.fps_gather(xyz, 256, fps_ordered=True)
     ref, _ = oracle.fps(xyz_h, 256)
     assert np.array_equal(idx.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,m,b", [(16384, 512, 2), (3000, 3000, 1), (512, 128, 5), (20000, 64, 2), (1, 1, 3)])
+def test_fps_writes_the_coordinates_of_its_picks(cuda, n, m, b):
+    """pn2_fps_xyz_f32 / pn2_fps_guarded_xyz_f32 (pruned one-CTA kernel, plain kernel, cluster kernel, guarded exit):
+    new_xyz is exactly xyz gathered at the indices, and the indices are those of pn2_fps_f32."""
+    cabi = load("cabi")
+    xyz_h = synthetic.make_clouds("ties" if n == 3000 else "lidar", b, n, seed=5 + n)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    ref = p2u().furthest_point_sample(xyz, m)
+    idx = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+    new_xyz = torch.full((b, m, 3), float("nan"), device=cuda)
+    cabi.call("pn2_fps_xyz_f32", cabi.ptr(xyz), cabi.ptr(idx), cabi.ptr(new_xyz), cabi.i32(b), cabi.i32(n), cabi.i32(m))
+    assert torch.equal(idx, ref)
+    assert torch.equal(new_xyz, torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
+    # guarded: cloud 0 flagged "provably arange" (only true for an FPS-ordered cloud: reorder it first), the others not
+    ordered = torch.gather(xyz, 1, ref.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()       # (b, m, 3), FPS order
+    mm = max(m // 2, 1)
+    viol = torch.empty((b,), dtype=torch.int32, device=cuda)
+    dmin = torch.empty((b, mm), device=cuda)
+    if mm <= 4096:
+        cabi.call("pn2_fps_prefix_check_f32", cabi.ptr(ordered), cabi.ptr(dmin), cabi.ptr(viol), cabi.i32(b), cabi.i32(m), cabi.i32(mm))
+        idx2 = torch.full((b, mm), -1, dtype=torch.int32, device=cuda)
+        new2 = torch.full((b, mm, 3), float("nan"), device=cuda)
+        cabi.call("pn2_fps_guarded_xyz_f32", cabi.ptr(ordered), cabi.ptr(idx2), cabi.ptr(new2), cabi.ptr(viol), cabi.i32(b),
+                  cabi.i32(m), cabi.i32(mm))
+        assert torch.equal(idx2, p2u().furthest_point_sample(ordered, mm))
+        assert torch.equal(new2, torch.gather(ordered, 1, idx2.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
+@pytest.mark.parametrize("n,m", [(16384, 4096), (4096, 1024), (300, 40), (100, 7)])
+def test_ball_query_fill_variant_needs_no_zeroed_lists(cuda, n, m):
+    """pn2_ball_query_culled_fill_f32 on garbage-initialised lists == zero fill + pn2_ball_query_culled_f32, including
+    centres without a single neighbour (single and dual radius, culled and brute-force sizes)."""
+    cabi = load("cabi")
+    xyz_h = synthetic.make_clouds("lidar", 2, n, seed=31)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    new_xyz = xyz[:, :m].clone()
+    new_xyz[:, ::5] += 300.0                                  # every fifth centre has no neighbour at all
+    for r0, ns0, r1, ns1 in ((0.1, 16, 0.5, 32), (0.4, 64, 0.0, 0)):
+        outs = []
+        for name, init in (("pn2_ball_query_culled_f32", 0), ("pn2_ball_query_culled_fill_f32", -7)):
+            i0 = torch.full((2, m, ns0), init, dtype=torch.int32, device=cuda)
+            i1 = torch.full((2, m, max(ns1, 1)), init, dtype=torch.int32, device=cuda)
+            order = torch.empty((2, m), dtype=torch.int32, device=cuda)
+            cabi.call(name, cabi.ptr(new_xyz), cabi.ptr(xyz), cabi.ptr(i0), cabi.ptr(i1 if ns1 else None), cabi.ptr(order),
+                      cabi.i32(2), cabi.i32(n), cabi.i32(m), cabi.f32(r0), cabi.i32(ns0), cabi.f32(r1), cabi.i32(ns1))
+            outs.append((i0, i1 if ns1 else None))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert int((outs[1][0][:, ::5] != 0).sum()) == 0
+        if ns1:
+            assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_three_interpolate_from_squared_distances_is_the_torch_weighting(cuda):
+    """pn2_three_interpolate_pm_d2_f32 == sqrt / reciprocal / sum / divide in torch (pointnet2_utils.py:104,
+    pointnet2_modules.py:209-211) + pn2_three_interpolate_pm_f32, bit for bit -- including coincident points (d2 = 0)."""
+    fz = load("fused")
+    b, n, m, c = 2, 5000, 1200, 96
+    unknown = torch.from_numpy(synthetic.make_clouds("lidar", b, n, seed=2)).to(cuda)
+    known = unknown[:, :m].contiguous()                      # the first m unknown points coincide with a known one
+    feats = torch.randn((b, m, c), device=cuda)
+    dist, idx = p2u().three_nn(unknown, known)
+    dist_recip = 1.0 / (dist + 1e-8)
+    weight = (dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)).contiguous()
+    ref = torch.empty((b * n, c), device=cuda)
+    fz.three_interpolate_pm(feats, idx, weight, ref)
+    dist2 = torch.empty((b, n, 3), device=cuda)
+    idx2 = torch.empty((b, n, 3), dtype=torch.int32, device=cuda)
+    load("pointnet2_cuda").three_nn_wrapper(b, n, m, unknown, known, dist2, idx2)
+    assert torch.equal(idx, idx2)
+    same = []
+    for order in (0, 1, 2):
+        out = torch.empty((b * n, c), device=cuda)
+        fz.three_interpolate_pm_d2(feats, idx2, dist2, out, sum_order=order)
+        same.append(bool(torch.equal(out, ref)))
+    assert same[fz.INTERP_SUM_ORDER], ("association that matches torch.sum: %s, configured: %d" % (same, fz.INTERP_SUM_ORDER))
