@@ -443,3 +443,112 @@ PN2_API int pn2_rcnn_post_assemble_f32(const float *boxes_sorted, const float *s
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Descending argsort of the per-scene RPN scores (lib/rpn/proposal_layer.py:26: torch.sort(scores, dim=1, descending=True)).
+// torch runs it as a segmented radix sort, eleven launches; here one CTA sorts one row in shared memory: bitonic network
+// over 64-bit keys (~sortable score bits | index), i.e. descending score, ascending index among equal scores -- the stable
+// order the radix sort produces (-0 and +0 are one key, as in its key transform).  N <= 16384.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kSortThreads = 512;
+
+// position of key i in shared memory: one padding word per 16 keys, so that the 16-key register blocks of a warp's lanes
+// (128 bytes apart without it) fall into different banks
+__device__ __forceinline__ int sort_pos(int i) { return i + (i >> 4); }
+
+// Substeps of one bitonic stage `size` with strides 2^(lo + NSUB - 1) .. 2^lo, in registers: a thread loads the 2^NSUB keys
+// whose indices differ only in bits [lo, lo + NSUB), runs the NSUB compare-exchange substeps and stores them back --
+// one shared-memory round trip for up to four substeps (the plain network is bound by shared-memory bandwidth:
+// 105 round trips of 128 KB for 16384 keys; this way 32).
+template <int NSUB>
+__device__ __forceinline__ void sort_block_steps(unsigned long long *keys, int npow2, int size, int lo, int tid) {
+    constexpr int E = 1 << NSUB;
+    const int nblocks = npow2 >> NSUB;
+    for (int blk = tid; blk < nblocks; blk += kSortThreads) {
+        const int low = blk & ((1 << lo) - 1), high = blk >> lo;
+        const int base = (high << (lo + NSUB)) | low;
+        const bool up = (base & size) == 0;
+        unsigned long long r[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) r[j] = keys[sort_pos(base + (j << lo))];
+#pragma unroll
+        for (int bit = NSUB - 1; bit >= 0; --bit) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                if ((j >> bit) & 1) continue;
+                const unsigned long long a = r[j], c = r[j | (1 << bit)];
+                const bool sw = (a > c) == up;
+                r[j] = sw ? c : a;
+                r[j | (1 << bit)] = sw ? a : c;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) keys[sort_pos(base + (j << lo))] = r[j];
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) argsort_desc_kernel(const float *__restrict__ scores, long long *__restrict__ order,
+                                                                   int n, int npow2) {
+    extern __shared__ unsigned long long keys[];
+    const float *row = scores + (size_t)blockIdx.x * n;
+    long long *out = order + (size_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < npow2; i += kSortThreads) {
+        unsigned long long k = 0xFFFFFFFFFFFFFFFFull;             // padding sorts last
+        if (i < n) {
+            uint32_t u = __float_as_uint(__ldg(row + i));
+            if (u == 0x80000000u) u = 0u;                         // -0 == +0, as for the radix sort's key transform
+            const uint32_t asc = u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);   // monotone in the float order
+            k = ((unsigned long long)(~asc) << 32) | (uint32_t)i;
+        }
+        keys[sort_pos(i)] = k;
+    }
+    __syncthreads();
+    int s = 1;
+    for (int size = 2; size <= npow2; size <<= 1, ++s) {
+        // stride exponents s-1 .. 0: a first group of ((s - 1) % 4) + 1 substeps, then groups of four
+        int hi = s;                                   // exponents [hi - g, hi) are done next
+        const int g0 = ((s - 1) & 3) + 1;
+        switch (g0) {
+            case 1: sort_block_steps<1>(keys, npow2, size, hi - 1, threadIdx.x); break;
+            case 2: sort_block_steps<2>(keys, npow2, size, hi - 2, threadIdx.x); break;
+            case 3: sort_block_steps<3>(keys, npow2, size, hi - 3, threadIdx.x); break;
+            default: sort_block_steps<4>(keys, npow2, size, hi - 4, threadIdx.x); break;
+        }
+        hi -= g0;
+        __syncthreads();
+        for (; hi > 0; hi -= 4) {
+            sort_block_steps<4>(keys, npow2, size, hi - 4, threadIdx.x);
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += kSortThreads) out[i] = (long long)(uint32_t)keys[sort_pos(i)];
+}
+}  // namespace
+
+// scores (B, N) f32 -> order (B, N) int64: indices by descending score, ties by ascending index.  N <= 16384.
+PN2_API int pn2_argsort_desc_f32(const float *scores, long long *order, int b, int n, cudaStream_t stream) {
+    if (b < 0 || n < 0 || (b * (long long)n > 0 && (!scores || !order))) {
+        pn2_set_last_error("pn2_argsort_desc_f32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    if (n > 16384) {
+        pn2_set_last_error("pn2_argsort_desc_f32: rows of more than 16384 scores are not supported");
+        return PN2_ERR_UNSUPPORTED;
+    }
+    if (b == 0 || n == 0) return PN2_OK;
+    int npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
+    const size_t smem = (size_t)(npow2 + (npow2 >> 4) + 1) * sizeof(unsigned long long);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(argsort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 1024 + 1) * 8) != cudaSuccess) {
+            pn2_set_last_error("pn2_argsort_desc_f32: cudaFuncSetAttribute failed");
+            return PN2_ERR_LAUNCH;
+        }
+        attr_done = true;
+    }
+    argsort_desc_kernel<<<b, kSortThreads, smem, stream>>>(scores, order, n, npow2);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}

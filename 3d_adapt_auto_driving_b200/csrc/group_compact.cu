@@ -63,7 +63,120 @@ __global__ void __launch_bounds__(256) compact_kernel(const int32_t *__restrict_
     }
 }
 
+// ---- the whole compaction in two launches (count + block sums | offsets + lists) instead of count, a two-launch
+//      device scan, a subtraction and the list kernel: a CTA takes kBlockGroups consecutive groups, the exclusive offset of
+//      its first group is the sum of the block totals before it (at most a few hundred values) ----
+constexpr int kBlockGroups = 256;       // 8 warps x 32 groups
+
+__global__ void __launch_bounds__(256) unique_count_blocks_kernel(const int32_t *__restrict__ idx, long long g, int ns, int align,
+                                                                 int32_t *__restrict__ cnt, int32_t *__restrict__ block_sum) {
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long g0 = (long long)blockIdx.x * kBlockGroups + warp * 32;
+    int mine = 0;                        // lane i keeps the count of group g0 + i
+    for (int i = 0; i < 32; ++i) {
+        const long long grp = g0 + i;
+        if (grp >= g) break;             // warp-uniform
+        const int32_t *row = idx + grp * ns;
+        const int32_t first = __ldg(row);
+        int c = 0;
+        for (int k = lane; k < ns; k += 32) c += (k == 0 || __ldg(row + k) != first) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        c = (c + align - 1) / align * align;
+        if (lane == i) mine = c;
+    }
+    if (g0 + lane < g) cnt[g0 + lane] = mine;
+    int s = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__restrict__ idx, long long g, int ns,
+                                                            const int32_t *__restrict__ cnt, const int32_t *__restrict__ block_sum,
+                                                            int32_t *__restrict__ cmap, int32_t *__restrict__ jmap,
+                                                            long long *__restrict__ total) {
+    __shared__ long long red[8];
+    __shared__ long long offs_s[kBlockGroups];
+    __shared__ int wtot[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // exclusive offset of this CTA's first group
+    long long base = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += 256) base += __ldg(block_sum + j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    if (lane == 0) red[warp] = base;
+    // exclusive scan of the CTA's counts (thread t <-> group blockIdx.x * 256 + t)
+    const long long gt = (long long)blockIdx.x * kBlockGroups + threadIdx.x;
+    const int c = gt < g ? __ldg(cnt + gt) : 0;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    base = 0;
+    for (int w = 0; w < 8; ++w) base += red[w];
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += wtot[w];
+    offs_s[threadIdx.x] = base + wbase + inc - c;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) *total = base + wbase + inc;      // sum of all counts
+    __syncthreads();
+    // the lists of the warp's 32 groups (compact_kernel, one group at a time)
+    for (int i = 0; i < 32; ++i) {
+        const long long grp = (long long)blockIdx.x * kBlockGroups + warp * 32 + i;
+        if (grp >= g) break;
+        const long long o = offs_s[warp * 32 + i];
+        const int32_t *row = idx + grp * ns;
+        const int32_t first = __ldg(row);
+        int nb = 0;
+        for (int k0 = 0; k0 < ns; k0 += 32) {
+            const int k = k0 + lane;
+            const int32_t v = k < ns ? __ldg(row + k) : first;
+            const bool keep = k < ns && (k == 0 || v != first);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const long long pos = o + nb + __popc(bal & ((1u << lane) - 1u));
+                cmap[pos] = (int32_t)grp;
+                jmap[pos] = v;
+            }
+            nb += __popc(bal);
+        }
+        const int cg = __shfl_sync(0xffffffffu, c, i);            // this group's (aligned) count lives in lane i
+        for (int k = nb + lane; k < cg; k += 32) {
+            cmap[o + k] = (int32_t)grp;
+            jmap[o + k] = first;
+        }
+    }
+}
+
 }  // namespace
+
+// pn2_group_unique_count_i32 + exclusive scan + pn2_group_compact_i32 in two launches.  cnt (G) int32 and block_sum
+// (ceil(G / 256)) int32 are scratch; cmap / jmap: capacity >= G * ns; *total (device, int64) = number of list rows.
+PN2_API int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, int32_t *block_sum,
+                                        int32_t *cmap, int32_t *jmap, long long *total, cudaStream_t stream) {
+    if (g <= 0 || ns <= 0 || !idx || !cnt || !block_sum || !cmap || !jmap || !total || g > 2147483647LL || align < 1 ||
+        align > 16 || (align & (align - 1)) || ns % align) {
+        pn2_set_last_error("pn2_group_compact_lists_i32: bad argument");
+        return PN2_ERR_INVALID;
+    }
+    const unsigned blocks = (unsigned)((g + kBlockGroups - 1) / kBlockGroups);
+    unique_count_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, align, cnt, block_sum);
+    PN2_CHECK_LAUNCH();
+    compact_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, cnt, block_sum, cmap, jmap, total);
+    PN2_CHECK_LAUNCH();
+    return PN2_OK;
+}
 
 PN2_API int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt,
                                        cudaStream_t stream) {

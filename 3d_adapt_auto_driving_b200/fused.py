@@ -415,6 +415,9 @@ SA_SKIP_MIN_ROWS = 1 << 20      # below ~1 M grouped rows the two compaction lau
 SA_COMPACT_ALIGN = int(os.environ.get("PN2_SA_COMPACT_ALIGN", "8"))
 
 
+COMPACT_TWO_LAUNCHES = os.environ.get("PN2_COMPACT_TWO_LAUNCHES", "1") != "0"   # 0: count, torch.cumsum, subtraction, lists
+
+
 def group_compact(idx, align=None):
     """idx (B, M, ns) int32 from ball_query -> (cmap, jmap int32 lists of the unique rows, device int64 row count);
     no host synchronisation (the count stays on the device).  align: every group is topped up to a multiple of `align`
@@ -423,11 +426,18 @@ def group_compact(idx, align=None):
     B, M, ns = idx.shape
     G = B * M
     cnt = torch.empty((G,), dtype=torch.int32, device=idx.device)
+    cmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
+    jmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
+    total = torch.empty((1,), dtype=torch.int64, device=idx.device)
+    if COMPACT_TWO_LAUNCHES:
+        # count + block sums | offsets + lists: the prefix sum between the two steps happens inside the second kernel
+        block_sum = torch.empty(((G + 255) // 256,), dtype=torch.int32, device=idx.device)
+        cabi.call("pn2_group_compact_lists_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(cnt), ptr(block_sum), ptr(cmap),
+                  ptr(jmap), ptr(total))
+        return cmap, jmap, total
     cabi.call("pn2_group_unique_count_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(cnt))
     incl = torch.cumsum(cnt, dim=0, dtype=torch.int64)
     offs = incl - cnt
-    cmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
-    jmap = torch.empty((G * ns + 128,), dtype=torch.int32, device=idx.device)
     cabi.call("pn2_group_compact_i32", ptr(idx), _i64(G), i32(ns), ptr(cnt), ptr(offs), ptr(cmap), ptr(jmap))
     return cmap, jmap, incl[G - 1:G]
 

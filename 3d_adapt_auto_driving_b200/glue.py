@@ -65,6 +65,14 @@ def decode_bbox(roi, reg, loc_scope, loc_bin_size, num_head_bin, anchor_size, ge
     return out
 
 
+def argsort_desc(scores):
+    """torch.sort(scores, dim=1, descending=True)[1] in one launch (csrc/glue.cu); rows of up to 16384 scores."""
+    B, N = scores.shape
+    order = torch.empty((B, N), dtype=torch.int64, device=scores.device)
+    cabi.call("pn2_argsort_desc_f32", ptr(scores.contiguous()), ptr(order), i32(B), i32(N))
+    return order
+
+
 def proposal_select(order, props, pre0, pre1):
     """order (B, N) int64 descending-score order, props (B, N, 7) -> cidx0, cidx1, bev0, bev1, cnt (2, B)."""
     B, N = order.shape

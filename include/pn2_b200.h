@@ -238,6 +238,10 @@ int pn2_sa_fused_t_tc_f32(const float *h, int ldh, const int32_t *idx, const flo
 int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, void *stream);
 int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
                           int32_t *cmap, int32_t *jmap, void *stream);
+/* Both steps and the exclusive scan between them in two launches: cnt (G) and block_sum (ceil(G / 256)) int32 scratch,
+ * *total (device int64) = number of list rows.  Same lists as count -> prefix sum -> pn2_group_compact_i32. */
+int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, int32_t *block_sum,
+                                int32_t *cmap, int32_t *jmap, long long *total, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
 void pn2_sa_fused_t_set_profile(void *buf);    /* tools/prof_sat.py: in-kernel stopwatch of pn2_sa_fused_t_tc_f32 */
 void pn2_sa_fused_t_set_debug(int bits);       /* tools/prof_sat.py: what-if switches of the stopwatch build (garbage results) */
@@ -348,6 +352,9 @@ int pn2_decode_bbox_f32(const float *roi, int roi_dim, const float *reg, int c, 
                         double loc_scope, double loc_bin_size, int num_head_bin, const float *h_anchor, int get_xz_fine,
                         int get_y_by_bin, double loc_y_scope, double loc_y_bin_size, int get_ry_fine, int y_bottom,
                         int rot_mode, void *stream);
+/* torch.sort(scores, dim=1, descending=True)[1] of lib/rpn/proposal_layer.py:26 as one launch (one CTA per row, bitonic
+ * network in shared memory): order (B, N) int64, descending score, ascending index among equal scores; N <= 16384. */
+int pn2_argsort_desc_f32(const float *scores, long long *order, int b, int n, void *stream);
 int pn2_proposal_select_f32(const long long *order, const float *props, int b, int n, int pre0, int pre1, int32_t *cidx0,
                             int32_t *cidx1, float *bev0, float *bev1, int32_t *cnt, void *stream);
 int pn2_proposal_assemble_f32(const float *props, const float *scores, int b, int n, const int32_t *cidx0,

@@ -222,3 +222,21 @@ def test_whole_forward_graph_replay_equals_eager(cuda):
     assert len(model._graphs) == 0
     c = both(torch.from_numpy(synthetic.make_clouds("lidar", 2, 16384, seed=5)).to(cuda))
     assert not torch.equal(c["rcnn_cls"], a["rcnn_cls"])
+
+
+@pytest.mark.parametrize("b,n", [(16, 16384), (3, 5000), (2, 1), (1, 2), (4, 777)])
+def test_argsort_desc_is_torch_sort(cuda, b, n):
+    """pn2_argsort_desc_f32 == torch.sort(scores, dim=1, descending=True)[1] (proposal_layer.py:26), with many exactly
+    equal scores (ties go to the lower index, as the stable radix sort of torch leaves them)."""
+    glue = load("glue")
+    g = torch.Generator(device="cpu").manual_seed(b * 1000 + n)
+    scores = torch.randn((b, n), generator=g)
+    scores[:, ::3] = torch.round(scores[:, ::3] * 2) / 2            # a third of the scores on a 0.5 lattice: lots of ties
+    scores = scores.to(cuda)
+    want = torch.sort(scores, dim=1, descending=True, stable=True)[1]
+    got = glue.argsort_desc(scores)
+    assert got.dtype == torch.int64
+    assert torch.equal(torch.gather(scores, 1, got), torch.gather(scores, 1, want))       # a descending order of the scores
+    assert torch.equal(torch.sort(got, dim=1)[0], torch.arange(n, device=cuda).expand(b, n))   # a permutation
+    assert torch.equal(got, want), "ties: %d positions differ from the stable order" % int((got != want).sum())
+    assert torch.equal(got, torch.sort(scores, dim=1, descending=True)[1])      # the call the reference makes

@@ -222,6 +222,14 @@ def test_sa_fused_t_skips_padded_duplicates_exactly(cuda, c1, c2, c3, ns, B, N, 
     k8 = k.expand(B, M, ns)
     want8 = torch.where(k8 < cnt, idx_pad.cpu(), idx_pad.cpu()[:, :, :1].expand(B, M, ns))[k8 < cnt8]
     assert torch.equal(jm8[:u8].cpu(), want8)
+    # the two-launch compaction (prefix sum inside the list kernel) and the count / torch.cumsum / list path agree
+    two = fz.COMPACT_TWO_LAUNCHES
+    try:
+        fz.COMPACT_TWO_LAUNCHES = not two
+        cmo, jmo, nro = fz.group_compact(idx_pad, align=8)
+    finally:
+        fz.COMPACT_TWO_LAUNCHES = two
+    assert int(nro.item()) == u8 and torch.equal(cmo[:u8], cm8[:u8]) and torch.equal(jmo[:u8], jm8[:u8])
     saved = (fz.SA_SKIP_DUPLICATES, fz.SA_SKIP_MIN_ROWS, fz.SA_TRANSPOSED_SMALL, fz.SA_COMPACT_ALIGN)
     try:
         fz.SA_SKIP_MIN_ROWS = 0
