@@ -340,10 +340,11 @@ cudaError_t dispatch_p(int p, const float *xyz, float *temp, int32_t *idx, int b
 // any input and in parallel instead of in sequence:
 //     D[k]   = min_{i<k} d2(p_k, p_i)                       (running min-distance of point k when it is due)
 //     R_j(k) = min(1e10, min_{i<k} d2(p_j, p_i))  <  D[k]    for all k < m, j > k;   D[k] > 0 covers the picked j < k
-// with d2 the reference's own expression (pn2_sqdist) -- the same floats the sequential kernel would compare.  If every
-// inequality is strict the arg-max of round k-1 is k whatever the tie order, so idx = arange(m) is the reference's
-// answer bit for bit; any violation (ties, duplicates, NaNs) bumps viol[cloud] and the guarded launch runs the real
-// kernel for that cloud.  N * m pair evaluations, no dependence between them: ~20 us instead of 0.5 ms for 16 x (4096 -> 1024).
+// with d2 the reference's own expression (pn2_sqdist) -- the same floats the sequential kernel would compare.  Where the
+// inequality is strict the arg-max of round k-1 is k whatever the tie order; an exact tie R_j(k) == D[k] is decided like the
+// reference decides it, by the rank of the header of this file (k must have the lower rank).  Then idx = arange(m) is the
+// reference's answer bit for bit; any violation (a lost tie, a larger candidate, duplicates of picked points, NaNs) bumps
+// viol[cloud] and the guarded launch runs the real kernel for that cloud.  N * m pair evaluations, no dependence between them: ~20 us instead of 0.5 ms for 16 x (4096 -> 1024).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fps_prefix_dist_kernel(const float *__restrict__ xyz, float *__restrict__ dmin,
                                                               int32_t *__restrict__ viol, int n, int m) {
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) fps_prefix_dist_kernel(const float *__res
 }
 
 __global__ void __launch_bounds__(256) fps_prefix_check_kernel(const float *__restrict__ xyz, const float *__restrict__ dmin,
-                                                               int32_t *__restrict__ viol, int n, int m) {
+                                                               int32_t *__restrict__ viol, int n, int m, int log2bs, int cnt) {
     extern __shared__ float4 cen[];          // entry i < m-1: (p_i, D[i+1])
     const int cloud = blockIdx.y;
     const float *p = xyz + (size_t)cloud * n * 3;
@@ -381,10 +382,13 @@ __global__ void __launch_bounds__(256) fps_prefix_check_kernel(const float *__re
         const float jx = __ldg(p + 3 * j), jy = __ldg(p + 3 * j + 1), jz = __ldg(p + 3 * j + 2);
         const int last = min(j - 1, m - 1);          // rounds i = 0 .. last-1: the pick due after round i is i+1 < j
         float r = 1e10f;
+        const uint32_t rank_j = fps_rank(j, log2bs, cnt);
         for (int i = 0; i < last; ++i) {
             const float4 c = cen[i];
             r = fminf(pn2_sqdist(__fadd_rn(jx, -c.x), __fadd_rn(jy, -c.y), __fadd_rn(jz, -c.z)), r);
-            bad |= !(r < c.w);
+            // an exact tie with the due point i + 1 is decided by the reference's rank (header of this file): only a tie
+            // that j wins breaks the prefix
+            bad |= !(r < c.w) && !(r == c.w && rank_j > fps_rank(i + 1, log2bs, cnt));
         }
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(viol + cloud, 1);
@@ -500,7 +504,11 @@ PN2_API int pn2_fps_prefix_check_f32(const float *xyz, float *dmin, int32_t *vio
     if (m == 1) return PN2_OK;
     fps_prefix_dist_kernel<<<dim3((m - 1 + 7) / 8, b), 256, 0, stream>>>(xyz, dmin, viol, n, m);
     PN2_CHECK_LAUNCH();
-    fps_prefix_check_kernel<<<dim3((n + 255) / 256, b), 256, (size_t)m * sizeof(float4), stream>>>(xyz, dmin, viol, n, m);
+    const int bs = pn2_fps_ref_block_size(n);
+    int log2bs = 0;
+    while ((1 << log2bs) < bs) ++log2bs;
+    fps_prefix_check_kernel<<<dim3((n + 255) / 256, b), 256, (size_t)m * sizeof(float4), stream>>>(xyz, dmin, viol, n, m, log2bs,
+                                                                                                  (n + bs - 1) / bs);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
             sts_u32(o, __float_as_uint(cmax));
             sts_u32(o + kPosOff, cpos);
         }
+        __syncwarp();      // orders these stores before the record another lane of this warp may write to the same slot next round
         if (PROF) {
             const long long c6 = clock64() + (cz == 1.2345e-30f ? 1 : 0);
             p_test += c1 - c0;

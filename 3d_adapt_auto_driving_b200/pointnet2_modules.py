@@ -196,8 +196,11 @@ class PointnetFPModule(pt_utils.PackedCacheMixin, nn.Module):
         B, n, _ = unknown.shape
         c2 = known_feats_pm.shape[2]
         c1 = unknow_feats_pm.shape[2] if unknow_feats_pm is not None else 0
-        x = torch.empty((B, n, c2 + c1), dtype=torch.float32, device=unknown.device)
-        x2 = x.view(B * n, c2 + c1)
+        # skip connection: when both halves are whole 64-channel K-blocks the first layer reads cat[interpolated, skip] from
+        # its two sources (fused.linear_cat) and the copy of the skip features into a concatenation buffer disappears
+        two_src = c1 > 0 and c1 % 64 == 0 and c2 % 64 == 0 and fz.MLP_ENGINE == "tc"
+        x = torch.empty((B, n, c2 if two_src else c2 + c1), dtype=torch.float32, device=unknown.device)
+        x2 = x.view(B * n, -1)
         # three_nn's squared distances go straight into the interpolation kernel, which forms the weights
         # 1 / (sqrt(d2) + 1e-8) / sum like the torch statements of forward() below (bit-identical, one launch for five)
         m = known.shape[1]
@@ -205,10 +208,14 @@ class PointnetFPModule(pt_utils.PackedCacheMixin, nn.Module):
         idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
         pointnet2_utils.pointnet2.three_nn_wrapper(B, n, m, unknown, known, dist2, idx)
         fz.three_interpolate_pm_d2(known_feats_pm, idx, dist2, x2[:, :c2])
-        if c1:
-            x[:, :, c2:] = unknow_feats_pm
-        cur = x2
-        for layer in self._packed:
+        if two_src:
+            cur = fz.linear_cat(x2, unknow_feats_pm.reshape(B * n, c1), self._packed[0])
+            rest = self._packed[1:]
+        else:
+            if c1:
+                x[:, :, c2:] = unknow_feats_pm
+            cur, rest = x2, self._packed
+        for layer in rest:
             cur = fz.linear(cur, layer)
         return cur.view(B, n, -1)
 

@@ -385,18 +385,20 @@ def run_b200(args):
         "roofline": roof,
         "kernel_breakdown_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
         "kernel_ms_per_step_sum": round(step_kernel_ms, 3),
-        # FPS against the HBM roofline (north_star): scan bytes are SURVEY 8(d)'s 16 B per point and round, not DRAM traffic
-        # (the cloud lives in registers); it forms every pair, so the figure is comparable with a streaming kernel's.
+        # FPS against the HBM roofline (north_star): scan bytes are SURVEY 8(d)'s 16 B per point and round of the reference's
+        # scan, not DRAM traffic (the cloud lives on chip; since round 2 the pruned kernel does not even form most pairs:
+        # the figure says how fast the reference's scan work is disposed of, like `culled_search` below).
         "scan_roofline": {k: {"ms": round(v["ms"], 4), "scan_GBps": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1),
                               "frac_of_hbm_peak": round(v["work"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
-                          for k, v in breakdown.items() if k in ("pn2_fps_f32", "pn2_fps_cluster_f32") and v["ms"] > 0},
+                          for k, v in breakdown.items()
+                          if k in ("pn2_fps_f32", "pn2_fps_xyz_f32", "pn2_fps_cluster_f32") and v["ms"] > 0},
         # The culled neighbour searches never form most centre-point pairs, so a bandwidth fraction over the reference's
         # scan bytes says nothing about them (it came out at 2.7 / 6.7 of the HBM peak).  Reported instead: the rate at
         # which the REFERENCE's pair tests are disposed of (B * M * N pairs of the brute-force kernels per second); the
         # limiter is occupancy / tail imbalance, not bandwidth (ncu: profiles/*_ncu_full_summary.csv, warps_active_pct).
         "culled_search": {k: {"ms": round(v["ms"], 4), "reference_pairs_per_s": round(v["work"] / 12.0 / (v["ms"] * 1e-3), 0)}
                           for k, v in breakdown.items()
-                          if k in ("pn2_ball_query_culled_f32", "pn2_ball_query_f32", "pn2_ball_query_dual_f32",
+                          if k in ("pn2_ball_query_culled_f32", "pn2_ball_query_culled_fill_f32", "pn2_ball_query_f32", "pn2_ball_query_dual_f32",
                                    "pn2_three_nn_culled_f32", "pn2_three_nn_f32") and v["ms"] > 0},
         "mlp_tflops_effective": FLOPS_PER_SCENE * scenes / (ms_total * 1e-3) / 1e12,
     }

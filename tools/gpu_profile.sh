@@ -24,7 +24,7 @@ for name in ("prof_mlp", "prof_scan"):
             w.writerow([r[i] for i in keep if i < len(r)])
     print(name, len(rows) - 2, "launches,", len(keep), "columns")
 PY
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fps_kernel|fps_prefix|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise|gather_rows|spatial_order|unique_count_kernel|compact_kernel|decode_kernel|proposal_select|proposal_assemble|rcnn_post" --profile-from-start off -f -o /tmp/ncu/prof_scan \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fps_kernel|fps_cells_kernel|argsort_desc|unique_count_blocks|compact_blocks|fps_prefix|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise|gather_rows|spatial_order|unique_count_kernel|compact_kernel|decode_kernel|proposal_select|proposal_assemble|rcnn_post" --profile-from-start off -f -o /tmp/ncu/prof_scan \
     python bench.py --steps 1 --warmup 3 --minimal --no-graph --depth 1 > gpurun_out/bench_ncu3.log 2>&1; echo "ncu scan exit $?"
 ncu -i /tmp/ncu/prof_scan.ncu-rep --page raw --csv > /tmp/ncu/prof_scan_raw.csv 2>/dev/null
 python - <<'PY'

@@ -18,7 +18,7 @@ from collections import OrderedDict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-OWN = re.compile(r"fps_kernel|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise_kernel|gather_rows|"
+OWN = re.compile(r"fps_kernel|fps_cells_kernel|argsort_desc|unique_count_blocks|compact_blocks|ball_query|three_nn|three_interpolate|nms_kernel|roipool3d|pairwise_kernel|gather_rows|"
                  r"scatter_rows|spatial_order|unique_count_kernel|compact_kernel|scene_filter|scene_gather|stat_rescale|d3_overlap|linear_tc_kernel|sa_fused_tc_kernel|sa_fused_t_tc_kernel|linear_kernel|rotate_iou|"
                  r"rcnn_front_tc_kernel|decode_kernel|proposal_select_kernel|proposal_assemble_kernel|rcnn_post_prepare_kernel|rcnn_post_assemble_kernel|roipool3d_canon_kernel|fps_prefix")
 MLP = re.compile(r"linear_tc_kernel|sa_fused_tc_kernel|sa_fused_t_tc_kernel|linear_kernel|rcnn_front_tc_kernel")
