@@ -68,23 +68,29 @@ __device__ __forceinline__ void sts_u32_if(bool p, uint32_t a, uint32_t v) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
 }
 
-// ~rank (16 bits, larger is better) of the point at shared-memory position pos; padding slots get 0
-__device__ __forceinline__ uint32_t pos_rinv(uint32_t pos, uint32_t sK, int log2bs, int cnt) {
-    const uint32_t k = lds_u16(sK + pos * 2u);
-    return k == 0xFFFFu ? 0u : (~cells_rank(k, log2bs, cnt) & 0xFFFFu);
+// The u16 table of the main loop holds, per shared-memory position, the INVERTED reference rank of the point (~rank & 0xFFFF,
+// larger is better; 0 = padding slot; real ranks are < N + 1024 <= 17408, so real entries are >= 48128).  A tie costs one
+// table read per tied candidate; the point index, needed only for the output, is recovered from the rank.
+__device__ __forceinline__ uint32_t rinv_of(uint32_t k, int log2bs, int cnt) { return ~cells_rank(k, log2bs, cnt) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t k_of_rinv(uint32_t rinv, int log2bs, int cnt) {
+    const uint32_t rank = ~rinv & 0xFFFFu;
+    if (log2bs == 0) return rank;
+    const uint32_t rev = rank / (uint32_t)cnt, kd = rank - rev * (uint32_t)cnt;
+    return (kd << log2bs) | (__brev(rev) >> (32 - log2bs));
 }
 
-// Exact paths (ties on the distance; rare, out of line).  Both are called by the whole warp.
+// Exact paths (ties on the distance): called by the whole warp.  Out of line: inlined into the sixteen cell bodies they grew the
+// round loop enough to slow EVERY phase of it by ~10 % (instruction fetch), ties or not.
 // The slots of one cell that hold its maximum mm, over all candidate lanes: position of the one with the best rank.
 __device__ __noinline__ uint32_t cell_exact_pos(bool cand, float p0, float p1, float p2, float p3, float mm, uint32_t posc,
-                                                uint32_t sK, int log2bs, int cnt) {
+                                                   uint32_t sK) {
     uint32_t best = 0u;
     if (cand) {
         const float p[4] = {p0, p1, p2, p3};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (p[q] == mm) {
-                const uint32_t key = (pos_rinv(posc + q, sK, log2bs, cnt) << 16) | (posc + q);
+                const uint32_t key = (lds_u16(sK + (posc + q) * 2u) << 16) | (posc + q);
                 best = key > best ? key : best;
             }
         }
@@ -92,13 +98,13 @@ __device__ __noinline__ uint32_t cell_exact_pos(bool cand, float p0, float p1, f
     return __reduce_max_sync(0xffffffffu, best) & 0xFFFFu;
 }
 // The cell records (four per lane) whose distance equals the maximum mh: position of the candidate with the best rank.
-__device__ __noinline__ uint32_t records_exact_pos(uint4 h4, uint4 p4, uint32_t mh, uint32_t sK, int log2bs, int cnt) {
+__device__ __noinline__ uint32_t records_exact_pos(uint4 h4, uint4 p4, uint32_t mh, uint32_t sK) {
     const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
     uint32_t best = 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (h[j] == mh) {
-            const uint32_t key = ((pos_rinv(p[j], sK, log2bs, cnt) << 16) | p[j]) + 1u;
+            const uint32_t key = ((lds_u16(sK + p[j] * 2u) << 16) | p[j]) + 1u;
             best = key > best ? key : best;
         }
     }
@@ -131,7 +137,7 @@ struct CellsCfg {
     static constexpr int T = WARPS * 32;
     static constexpr int SLOTS = 4 * CPW;
     static constexpr int NP = WARPS * CPW * kCellPts;
-    // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16) | cell records: 2 buffers x (128 distances | 128 positions) u32
+    // main-loop image: X | Y | Z (NP floats each) | ktab (NP u16: inverted ranks) | cell records: 2 buffers x (128 distances | 128 positions) u32
     static constexpr size_t kMain = (size_t)NP * 14 + 2 * 2 * kMaxCells * 4;
     // prepass scratch (aliases the image): hist (4096 int) | ord (NP u16) | red (6 x WARPS float) | wsum (WARPS int)
     static constexpr size_t kPre = (size_t)kOrderCells * 4 + (size_t)NP * 2 + 7 * WARPS * 4;
@@ -290,8 +296,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
             X4[cb4 + ci * 32] = make_float4(vx[0], vx[1], vx[2], vx[3]);
             Y4[cb4 + ci * 32] = make_float4(vy[0], vy[1], vy[2], vy[3]);
             Z4[cb4 + ci * 32] = make_float4(vz[0], vz[1], vz[2], vz[3]);
-            K4[cb4 + ci * 32] = make_uint2((uint32_t)kk[4 * ci] | ((uint32_t)kk[4 * ci + 1] << 16),
-                                           (uint32_t)kk[4 * ci + 2] | ((uint32_t)kk[4 * ci + 3] << 16));
+            {
+                uint32_t ri[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ri[q] = kk[4 * ci + q] == 0xFFFFu ? 0u : rinv_of(kk[4 * ci + q], log2bs, cnt);
+                K4[cb4 + ci * 32] = make_uint2(ri[0] | (ri[1] << 16), ri[2] | (ri[3] << 16));
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 lo0 = fminf(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
             // the cell's initial record (both buffers), exactly: with the usual 1e10 start every slot ties
             __syncwarp();
             const uint32_t best = cell_exact_pos(__float_as_uint(lc) == cm, pt[4 * ci], pt[4 * ci + 1], pt[4 * ci + 2], pt[4 * ci + 3],
-                                                 lc, (uint32_t)(cb4 * 4 + ci * 128), pn2_smem_u32(ktab), log2bs, cnt);
+                                                 lc, (uint32_t)(cb4 * 4 + ci * 128), pn2_smem_u32(ktab));
             if (lane == 0) {
                 const int c = warp * CPW + ci;
                 recs[c] = cm; recs[kMaxCells + c] = best; recs[2 * kMaxCells + c] = cm; recs[3 * kMaxCells + c] = best;
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
             sts_u32_if(cand, rec_w + ci * 4 + kPosOff, posc + q);
             wpos = __reduce_max_sync(0xffffffffu, cand ? posc + q : 0u);     // for lane ci; needed only after the barrier
         } else {
-            wpos = cell_exact_pos(cand, p0, p1, p2, p3, mm, posc, sK, log2bs, cnt);
+            wpos = cell_exact_pos(cand, p0, p1, p2, p3, mm, posc, sK);
             if (lane == 0) { sts_u32(rec_w + ci * 4, cm); sts_u32(rec_w + ci * 4 + kPosOff, wpos); }
         }
         if (lane == ci) { cmax = __uint_as_float(cm); cpos = wpos; }
@@ -420,12 +430,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
         // one candidate: its position reaches every lane through a second redux (shorter than FLO + SHFL of the ballot)
         uint32_t pos = __reduce_max_sync(0xffffffffu, mine ? (f0 ? p4.x : (f1 ? p4.y : (f2 ? p4.z : p4.w))) : 0u);
         if (amb != 0u || (who & (who - 1u)) != 0u)
-            pos = records_exact_pos(h4, p4, mh, sK, log2bs, cnt);      // several cells tie: the reference rank decides
+            pos = records_exact_pos(h4, p4, mh, sK);      // several cells tie: the reference rank decides
         cx = lds_f32(sX + pos * 4u); cy = lds_f32(sY + pos * 4u); cz = lds_f32(sZ + pos * 4u);
         // idx[r + 1]: the table look-up is issued now, the global store waits until the end of the next round (a store right
         // here stalled every warp on the look-up's scoreboard, predicated off or not)
         if (tid == 0) {
-            if (r > 0) idx[r] = (int32_t)kpend;
+            if (r > 0) idx[r] = (int32_t)kpend;      // the table entry (inverted rank); turned into point indices after the loop
             kpend = lds_u16(sK + pos * 2u);
         }
         // the records written in this round also go into the other buffer (read in the next round): only now is nobody
@@ -444,6 +454,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
         }
     }
     if (tid == 0 && m > 1) idx[m - 1] = (int32_t)kpend;
+    // idx[1 .. m-1] hold inverted ranks (the division that recovers the point index would sit in every warp's round, predicated
+    // off or not): converted here by the whole CTA
+    __syncthreads();
+    for (int i = 1 + tid; i < m; i += T) idx[i] = (int32_t)k_of_rinv((uint32_t)idx[i], log2bs, cnt);
     if (tid == 0 && new_xyz) { new_xyz[3 * (m - 1)] = cx; new_xyz[3 * (m - 1) + 1] = cy; new_xyz[3 * (m - 1) + 2] = cz; }
     if (PROF && lane == 0 && prof) {
         unsigned long long *o = prof + ((size_t)cloud * WARPS + warp) * 8;
@@ -453,8 +467,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fps_cells_kernel(const float *_
     if (temp) {   // the reference leaves the running min distances in the caller's scratch
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const uint32_t k = ktab[pos0 + (uint32_t)((s >> 2) * 128 + (s & 3))];
-            if (k != 0xFFFFu) temp[k] = pt[s];
+            const uint32_t ri = ktab[pos0 + (uint32_t)((s >> 2) * 128 + (s & 3))];
+            if (ri != 0u) temp[k_of_rinv(ri, log2bs, cnt)] = pt[s];
         }
     }
 }

@@ -55,11 +55,25 @@ class RPN(pt_utils.PackedCacheMixin, nn.Module):
         if self.backbone_net.can_fuse(pts_input):
             backbone_xyz, feats_pm = self.backbone_net.forward_pm(pts_input)          # (B,N,3), (B,N,C)
             if not self._packed_valid():
-                self._store_packed((fz.pack_sequential(self.rpn_cls_layer), fz.pack_sequential(self.rpn_reg_layer)))
+                cls_l, reg_l = fz.pack_sequential(self.rpn_cls_layer), fz.pack_sequential(self.rpn_reg_layer)
+                # the first layers of the two heads read the same (B*N, C) features: one launch with their output channels side
+                # by side reads them once (every output element is the same dot product in the same order: bit-identical)
+                both = None
+                a, b = cls_l[0], reg_l[0]
+                if (len(cls_l) > 1 and len(reg_l) > 1 and a.cin == b.cin and a.relu == b.relu and a.cout % 4 == 0
+                        and a.cout + b.cout <= 256):
+                    both = fz.PackedLayer(torch.cat((a.w[:, :a.cin], b.w[:, :b.cin]), dim=0), torch.cat((a.b, b.b)), a.relu)
+                self._store_packed((cls_l, reg_l, both))
             B, N, _ = feats_pm.shape
+            cls_l, reg_l, both = self._packed
+            x = feats_pm.view(B * N, -1)
+            if both is not None:
+                h = fz.linear(x, both)                                  # (B*N, c_cls + c_reg)
+                heads = ((h[:, :cls_l[0].cout], cls_l[1:]), (h[:, cls_l[0].cout:], reg_l[1:]))
+            else:
+                heads = ((x, cls_l), (x, reg_l))
             outs = []
-            for layers in self._packed:
-                cur = feats_pm.view(B * N, -1)
+            for cur, layers in heads:
                 for layer in layers:
                     cur = fz.linear(cur, layer)
                 outs.append(cur.view(B, N, -1))
