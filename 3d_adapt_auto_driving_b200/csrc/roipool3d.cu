@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(kThreads) roipool3d_canon_kernel(const float *
                                                                   int32_t *__restrict__ empty, int n, int m, int c2, int off2,
                                                                   int row, int sampled, float extra, float extra2, float thresh,
                                                                   float inv_depth, int rot_mode) {
-    extern __shared__ int32_t list[];
-    __shared__ int warp_cnt[kWarps];
+    extern __shared__ int32_t list[];          // sampled hit list | sampled source ids | sampled x 5 head values
+    __shared__ int warp_cnt[4 * kWarps];
     const int roi = blockIdx.x, cloud = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *bx = rois + ((size_t)cloud * m + roi) * 7;
@@ -165,69 +165,109 @@ __global__ void __launch_bounds__(kThreads) roipool3d_canon_kernel(const float *
     }
     __syncthreads();
 
+    // ---- phase 1: ordered list of the first `sampled` points inside the box.  kScan points per thread and step, all loads
+    //      issued before the tests (the box test's early exits are shortcuts, evaluating every condition gives the same
+    //      boolean): a step costs one load latency and two barriers for 1024 points.  (First version: one point per thread
+    //      with the x / y / z loads serialised behind the early exits -- 64 steps of three dependent L2 round trips.) ----
+    constexpr int kScan = 4;
+    int32_t *srcs = list + sampled;                                      // phase 2: source point of every pooled row
+    float *head = reinterpret_cast<float *>(list + 2 * sampled);         // phase 2: 5 head values per pooled row
     int cnt = 0;
-    for (int base = 0; base < n && cnt < sampled; base += kThreads) {
-        const int k = base + tid;
-        bool hit = false;
-        if (k < n) hit = in_box(b, __ldg(xyz + (size_t)k * 3), __ldg(xyz + (size_t)k * 3 + 1), __ldg(xyz + (size_t)k * 3 + 2));
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
+    for (int base = 0; base < n && cnt < sampled; base += kThreads * kScan) {
+        float px[kScan], py[kScan], pz[kScan];
+#pragma unroll
+        for (int u = 0; u < kScan; ++u) {
+            const int k = min(base + u * kThreads + tid, n - 1);
+            px[u] = __ldg(xyz + (size_t)k * 3); py[u] = __ldg(xyz + (size_t)k * 3 + 1); pz[u] = __ldg(xyz + (size_t)k * 3 + 2);
+        }
+        unsigned bal[kScan];
+        int mine = 0;                       // lane u < kScan of every warp publishes the warp's hit count of sub-step u
+#pragma unroll
+        for (int u = 0; u < kScan; ++u) {
+            const bool hit = base + u * kThreads + tid < n && in_box(b, px[u], py[u], pz[u]);
+            bal[u] = __ballot_sync(0xffffffffu, hit);
+            if (lane == u) mine = __popc(bal[u]);
+        }
+        if (lane < kScan) warp_cnt[lane * kWarps + warp] = mine;
         __syncthreads();
+        // hits are ordered by point index: sub-step u (points base + u * 256 ..), then warp, then lane
         int off = cnt;
 #pragma unroll
-        for (int wv = 0; wv < kWarps; ++wv) {
-            const int cw = warp_cnt[wv];
-            if (wv < warp) off += cw;
-            cnt += cw;
+        for (int u = 0; u < kScan; ++u) {
+            int before = 0, total = 0;
+#pragma unroll
+            for (int wv = 0; wv < kWarps; ++wv) {
+                const int cw = warp_cnt[u * kWarps + wv];
+                if (wv < warp) before += cw;
+                total += cw;
+            }
+            if ((bal[u] >> lane) & 1u) {
+                const int pos = off + before + __popc(bal[u] & ((1u << lane) - 1u));
+                if (pos < sampled) list[pos] = base + u * kThreads + tid;
+            }
+            off += total;
         }
-        if (hit) {
-            const int pos = off + __popc(bal & ((1u << lane) - 1u));
-            if (pos < sampled) list[pos] = k;
-        }
+        cnt = off;
         __syncthreads();
     }
     if (cnt == 0 && tid == 0) empty[(size_t)cloud * m + roi] = 1;
     const int have = min(cnt, sampled);
+
+    // ---- phase 2: the five head values of every pooled row, one THREAD per row (uniform code; in the first version every
+    //      warp walked through the lane-0..4 branches of each of its rows: ~150 instructions a row) ----
     // rotation of the canonical transform: the same cos / sin of the roi angle (torch.cos / torch.sin of a float tensor)
     const float cosa = b.cosa, sina = b.sina, nsina = -sina;
-    float *dst_base = pooled + ((size_t)cloud * m + roi) * (size_t)sampled * row;
-    for (int s = warp; s < sampled; s += kWarps) {
-        float *dst = dst_base + (size_t)s * row;
+    for (int s2 = tid; s2 < sampled; s2 += kThreads) {
         float px = 0.f, py = 0.f, pz = 0.f, mk = 0.f, dp = 0.f;
         int src = -1;
         if (have > 0) {
-            src = list[s < have ? s : s % have];
+            src = list[s2 < have ? s2 : s2 % have];
             px = __ldg(xyz + (size_t)src * 3);
             py = __ldg(xyz + (size_t)src * 3 + 1);
             pz = __ldg(xyz + (size_t)src * 3 + 2);
+            const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__ldg(score + src))));
+            mk = sg > thresh ? 1.0f : 0.0f;
+            dp = __fadd_rn(__fmul_rn(__ldg(depth + src), inv_depth), -0.5f);
         }
-        if (lane < off2) {
-            float v = 0.f;
-            if (lane < 3) {
-                const float x = __fadd_rn(px, -rx), z = __fadd_rn(pz, -rz);
-                if (lane == 0) v = rp_dot2(x, cosa, z, nsina, rot_mode);
-                else if (lane == 1) v = __fadd_rn(py, -ry);
-                else v = rp_dot2(x, sina, z, cosa, rot_mode);
-            } else if (lane == 3) {
-                if (src >= 0) {
-                    const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__ldg(score + src))));
-                    mk = sg > thresh ? 1.0f : 0.0f;
-                }
-                v = mk;
-            } else if (lane == 4) {
-                if (src >= 0) dp = __fadd_rn(__fmul_rn(__ldg(depth + src), inv_depth), -0.5f);
-                v = dp;
-            }
-            dst[lane] = v;
+        const float x = __fadd_rn(px, -rx), z = __fadd_rn(pz, -rz);
+        float *hd = head + s2 * 5;
+        hd[0] = rp_dot2(x, cosa, z, nsina, rot_mode);
+        hd[1] = __fadd_rn(py, -ry);
+        hd[2] = rp_dot2(x, sina, z, cosa, rot_mode);
+        hd[3] = mk;
+        hd[4] = dp;
+        srcs[s2] = src;
+    }
+    __syncthreads();
+
+    // ---- phase 3: the rows, one warp per row, four rows in flight per warp ----
+    float *dst_base = pooled + ((size_t)cloud * m + roi) * (size_t)sampled * row;
+    const int nv = c2 >> 2;
+    constexpr int kRows = 4;
+    for (int s0 = warp * kRows; s0 < sampled; s0 += kWarps * kRows) {
+        float4 v[kRows];
+        float hv[kRows];
+        int src[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            const int sr = min(s0 + u, sampled - 1);
+            src[u] = srcs[sr];
+            hv[u] = lane < 5 ? head[sr * 5 + lane] : 0.f;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[u] >= 0 && lane < nv) v[u] = __ldg(reinterpret_cast<const float4 *>(feat2 + (size_t)src[u] * c2) + lane);
         }
-        float4 *d2 = reinterpret_cast<float4 *>(dst + off2);
-        if (src >= 0) {
-            const float4 *f2 = reinterpret_cast<const float4 *>(feat2 + (size_t)src * c2);
-            for (int j = lane; j < (c2 >> 2); j += 32) d2[j] = __ldg(f2 + j);
-        } else {
-            for (int j = lane; j < (c2 >> 2); j += 32) d2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            if (s0 + u >= sampled) break;
+            float *dst = dst_base + (size_t)(s0 + u) * row;
+            if (lane < off2) dst[lane] = hv[u];
+            float4 *d2 = reinterpret_cast<float4 *>(dst + off2);
+            if (lane < nv) d2[lane] = v[u];
+            for (int j = lane + 32; j < nv; j += 32)          // feature blocks wider than 128 channels
+                d2[j] = src[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(feat2 + (size_t)src[u] * c2) + j)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = off2 + c2 + lane; j < row; j += 32) dst[j] = 0.f;
         }
-        for (int j = off2 + c2 + lane; j < row; j += 32) dst[j] = 0.f;
     }
 }
 
@@ -295,11 +335,15 @@ PN2_API int pn2_roipool3d_canon_f32(const float *xyz, const float *rois, double 
         pn2_set_last_error("pn2_roipool3d_canon_f32: feat2 block must be 16-byte aligned");
         return PN2_ERR_UNSUPPORTED;
     }
+    if (sampled > 1024) {
+        pn2_set_last_error("pn2_roipool3d_canon_f32: more than 1024 sampled points per roi are not supported (28 bytes of shared memory each)");
+        return PN2_ERR_UNSUPPORTED;
+    }
     if (b == 0 || m == 0) return PN2_OK;
     dim3 grid(m, b);
     // ATen divides by a CPU scalar as a multiplication by the reciprocal formed in float
     const float inv = 1.0f / (float)depth_norm;
-    roipool3d_canon_kernel<<<grid, kThreads, sampled * sizeof(int32_t), stream>>>(
+    roipool3d_canon_kernel<<<grid, kThreads, (size_t)sampled * 7 * sizeof(int32_t), stream>>>(
         xyz, rois, score, depth, feat2, pooled, empty, n, m, c2, off2, ld_out, sampled, (float)extra_width,
         (float)(extra_width * 2), (float)score_thresh, inv, rot_mode);
     PN2_CHECK_LAUNCH();
