@@ -96,6 +96,22 @@ def test_fps_cells_rejects_what_it_cannot_hold(cuda):
                   cabi.i32(5))
 
 
+@pytest.mark.parametrize("kind,n,m", [("lidar", 512, 128), ("ties", 512, 128), ("uniform", 128, 32), ("ties", 1000, 100),
+                                      ("lidar", 65, 65)])
+def test_fps_many_small_clouds_take_the_two_warp_kernel(cuda, oracle, kind, n, m):
+    """b >= 256 clouds of at most 1024 points (the RCNN stage: 1600 ROI clouds) run fps_kernel<P, 1, 64>: indices and the
+    scratch left behind equal the oracle's, like every other launch shape."""
+    b = 300
+    xyz_h = synthetic.make_clouds(kind, b, n, seed=n + m)
+    xyz = torch.from_numpy(xyz_h).to(cuda)
+    temp = torch.full((b, n), 1e10, device=cuda)
+    idx = torch.full((b, m), -1, dtype=torch.int32, device=cuda)
+    load("pointnet2_cuda").furthest_point_sampling_wrapper(b, n, m, xyz, temp, idx)
+    ref, ref_temp = oracle.fps(xyz_h, m)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(temp.cpu().numpy(), ref_temp)
+
+
 def test_fps_edge_cases(cuda, oracle):
     f = p2u().furthest_point_sample
     one = torch.zeros((2, 1, 3), device=cuda)
