@@ -28,7 +28,8 @@ template <bool DUAL>
 __global__ void __launch_bounds__(kThreads) ball_query_kernel(const float *__restrict__ new_xyz,
                                                              const float *__restrict__ xyz, int32_t *__restrict__ idx0,
                                                              int32_t *__restrict__ idx1, int n, int m, float radius0,
-                                                             int ns0, float radius1, int ns1) {
+                                                             int ns0, float radius1, int ns1, int32_t *__restrict__ hits0,
+                                                             int32_t *__restrict__ hits1) {
     __shared__ float4 tile[kTile];
     const int cloud = blockIdx.y;
     const int c = blockIdx.x * kThreads + threadIdx.x;
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(kThreads) ball_query_kernel(const float *__res
             }
         }
     }
+    // optional: number of neighbours found (capped at nsample), for the duplicate-skipping SA kernels
+    if (active && hits0) hits0[(size_t)cloud * m + c] = min(cnt0, ns0);
+    if (DUAL && active && hits1) hits1[(size_t)cloud * m + c] = min(cnt1, ns1);
 }
 
 
@@ -198,7 +202,8 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
                                                                         int32_t *__restrict__ idx0,
                                                                         int32_t *__restrict__ idx1, int n, int m,
                                                                         float radius0, int ns0, float radius1, int ns1,
-                                                                        int zero_empty) {
+                                                                        int zero_empty, int32_t *__restrict__ hits0,
+                                                                        int32_t *__restrict__ hits1) {
     __shared__ float4 cand[kCullWarps][kWarpList];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wfirst = (blockIdx.x * kCullWarps + warp) * 32;
@@ -266,6 +271,8 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
             if (__all_sync(0xffffffffu, done)) break;
         }
     }
+    if (active && hits0) hits0[row_base + c] = cnt0;          // neighbours found, capped at nsample (0: none)
+    if (DUAL && active && hits1) hits1[row_base + c] = cnt1;
     // ---- fill rule of the reference: the first hit occupies every slot a later hit did not take ----
     for (int j = 0; j < 32; ++j) {
         if (!__shfl_sync(0xffffffffu, (int)active, j)) continue;
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
 
 template <bool DUAL>
 int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n, int m,
-                  float r0, int ns0, float r1, int ns1, int zero_empty, cudaStream_t stream) {
+                  float r0, int ns0, float r1, int ns1, int zero_empty, int32_t *hits0, int32_t *hits1, cudaStream_t stream) {
     // few centres per cloud: the ordering launch costs more than it saves, warps take the centres as they come
     const bool sorted = m >= 256;
     if (sorted && launch_spatial_order(new_xyz, order, b, m, stream) != cudaSuccess) {
@@ -294,7 +301,8 @@ int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t
     }
     if (!sorted) order = nullptr;
     dim3 grid(pn2_divup(m, kCullThreads), b);   // 2 warps x 32 centres per CTA
-    ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1, zero_empty);
+    ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1, zero_empty,
+                                                                      hits0, hits1);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
@@ -311,7 +319,7 @@ PN2_API int pn2_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *
     }
     if (b == 0 || m == 0 || n == 0 || nsample == 0) return PN2_OK;
     dim3 grid(pn2_divup(m, kThreads), b);
-    ball_query_kernel<false><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, idx, nullptr, n, m, radius, nsample, 0.f, 0);
+    ball_query_kernel<false><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, idx, nullptr, n, m, radius, nsample, 0.f, 0, nullptr, nullptr);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
@@ -326,7 +334,7 @@ PN2_API int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int3
     if (b == 0 || m == 0 || n == 0) return PN2_OK;
     dim3 grid(pn2_divup(m, kThreads), b);
     ball_query_kernel<true><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, idx0, idx1, n, m, radius0, nsample0, radius1,
-                                                           nsample1);
+                                                           nsample1, nullptr, nullptr);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
@@ -335,7 +343,8 @@ PN2_API int pn2_ball_query_dual_f32(const float *new_xyz, const float *xyz, int3
 // spatially culled scan.  `order` is caller-provided scratch of b * m int32 (the Hilbert order of
 // the centres is left there when m >= 256); with order == NULL or a tiny cloud the brute-force kernels run.
 static int ball_query_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order, int b, int n,
-                             int m, float radius0, int nsample0, float radius1, int nsample1, int zero_empty, cudaStream_t stream) {
+                             int m, float radius0, int nsample0, float radius1, int nsample1, int zero_empty, int32_t *hits0,
+                             int32_t *hits1, cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0 || nsample0 <= 0 || nsample1 < 0 || (nsample1 > 0 && !idx1)) {
         pn2_set_last_error("pn2_ball_query_culled_f32: bad argument");
         return PN2_ERR_INVALID;
@@ -349,27 +358,45 @@ static int ball_query_culled(const float *new_xyz, const float *xyz, int32_t *id
                 return PN2_ERR_LAUNCH;
             }
         }
-        if (n == 0) return PN2_OK;
+        if (n == 0) {
+            if ((hits0 && cudaMemsetAsync(hits0, 0, (size_t)b * m * sizeof(int32_t), stream) != cudaSuccess) ||
+                (hits1 && cudaMemsetAsync(hits1, 0, (size_t)b * m * sizeof(int32_t), stream) != cudaSuccess)) {
+                pn2_set_last_error("pn2_ball_query_culled_fill_f32: cudaMemsetAsync failed");
+                return PN2_ERR_LAUNCH;
+            }
+            return PN2_OK;
+        }
+        dim3 grid(pn2_divup(m, kThreads), b);
         if (nsample1 > 0)
-            return pn2_ball_query_dual_f32(new_xyz, xyz, idx0, idx1, b, n, m, radius0, nsample0, radius1, nsample1, stream);
-        return pn2_ball_query_f32(new_xyz, xyz, idx0, b, n, m, radius0, nsample0, stream);
+            ball_query_kernel<true><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, idx0, idx1, n, m, radius0, nsample0, radius1,
+                                                                   nsample1, hits0, hits1);
+        else
+            ball_query_kernel<false><<<grid, kThreads, 0, stream>>>(new_xyz, xyz, idx0, nullptr, n, m, radius0, nsample0, 0.f, 0,
+                                                                    hits0, nullptr);
+        PN2_CHECK_LAUNCH();
+        return PN2_OK;
     }
     if (nsample1 > 0)
-        return launch_culled<true>(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, zero_empty, stream);
-    return launch_culled<false>(new_xyz, xyz, idx0, nullptr, order, b, n, m, radius0, nsample0, 0.f, 0, zero_empty, stream);
+        return launch_culled<true>(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, zero_empty,
+                                   hits0, hits1, stream);
+    return launch_culled<false>(new_xyz, xyz, idx0, nullptr, order, b, n, m, radius0, nsample0, 0.f, 0, zero_empty, hits0, nullptr,
+                                stream);
 }
 
 PN2_API int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
                                       int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
                                       int nsample1, cudaStream_t stream) {
-    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 0, stream);
+    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 0, nullptr, nullptr, stream);
 }
 
 // pn2_ball_query_culled_f32 for index lists the caller has NOT zeroed: the lists of centres without any neighbour are
 // written as zeros here (the value the reference's pre-zeroed tensor keeps, pointnet2_utils.py:177), every other list
 // is complete anyway.  Same results as zero-fill + pn2_ball_query_culled_f32, one launch less per list.
+// hits0 / hits1 (B, M) int32 or NULL: the number of neighbours each centre found, capped at nsample (0 = none) -- what the
+// duplicate-skipping SA kernels otherwise re-derive from the lists with a launch of their own (csrc/group_compact.cu).
 PN2_API int pn2_ball_query_culled_fill_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1,
                                            int32_t *order, int b, int n, int m, float radius0, int nsample0, float radius1,
-                                           int nsample1, cudaStream_t stream) {
-    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 1, stream);
+                                           int nsample1, int32_t *hits0, int32_t *hits1, cudaStream_t stream) {
+    return ball_query_culled(new_xyz, xyz, idx0, idx1, order, b, n, m, radius0, nsample0, radius1, nsample1, 1, hits0, hits1,
+                             stream);
 }

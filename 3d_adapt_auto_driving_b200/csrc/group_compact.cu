@@ -99,6 +99,29 @@ __global__ void __launch_bounds__(256) unique_count_blocks_kernel(const int32_t 
     }
 }
 
+// the same counts from the ball query's own hit counts (pn2_ball_query_culled_fill_f32): unique rows = max(hits, 1) -- a group
+// without a neighbour keeps its single zero row -- rounded up to the alignment; reads 4 bytes per group instead of the lists
+__global__ void __launch_bounds__(256) counts_from_hits_kernel(const int32_t *__restrict__ hits, long long g, int align,
+                                                              int32_t *__restrict__ cnt, int32_t *__restrict__ block_sum) {
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long grp = (long long)blockIdx.x * kBlockGroups + threadIdx.x;
+    int c = 0;
+    if (grp < g) {
+        c = (max(__ldg(hits + grp), 1) + align - 1) / align * align;
+        cnt[grp] = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
 __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__restrict__ idx, long long g, int ns,
                                                             const int32_t *__restrict__ cnt, const int32_t *__restrict__ block_sum,
                                                             int32_t *__restrict__ cmap, int32_t *__restrict__ jmap,
@@ -163,15 +186,17 @@ __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__re
 
 // pn2_group_unique_count_i32 + exclusive scan + pn2_group_compact_i32 in two launches.  cnt (G) int32 and block_sum
 // (ceil(G / 256)) int32 are scratch; cmap / jmap: capacity >= G * ns; *total (device, int64) = number of list rows.
-PN2_API int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, int32_t *block_sum,
-                                        int32_t *cmap, int32_t *jmap, long long *total, cudaStream_t stream) {
+// hits (G) int32 or NULL: the ball query's hit counts; with them the count pass reads 4 bytes per group, not the lists.
+PN2_API int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, const int32_t *hits, int32_t *cnt,
+                                        int32_t *block_sum, int32_t *cmap, int32_t *jmap, long long *total, cudaStream_t stream) {
     if (g <= 0 || ns <= 0 || !idx || !cnt || !block_sum || !cmap || !jmap || !total || g > 2147483647LL || align < 1 ||
         align > 16 || (align & (align - 1)) || ns % align) {
         pn2_set_last_error("pn2_group_compact_lists_i32: bad argument");
         return PN2_ERR_INVALID;
     }
     const unsigned blocks = (unsigned)((g + kBlockGroups - 1) / kBlockGroups);
-    unique_count_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, align, cnt, block_sum);
+    if (hits) counts_from_hits_kernel<<<blocks, 256, 0, stream>>>(hits, g, align, cnt, block_sum);
+    else unique_count_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, align, cnt, block_sum);
     PN2_CHECK_LAUNCH();
     compact_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, cnt, block_sum, cmap, jmap, total);
     PN2_CHECK_LAUNCH();

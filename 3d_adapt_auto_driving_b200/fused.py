@@ -169,8 +169,10 @@ def ball_query_dual(xyz, new_xyz, r0, ns0, r1, ns1):
     i0 = torch.empty((B, M, ns0), dtype=torch.int32, device=xyz.device)   # no zero fill: the _fill entry point writes the
     i1 = torch.empty((B, M, ns1), dtype=torch.int32, device=xyz.device)   # zeros of centres without neighbours itself
     order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)    # scratch: Hilbert order of the centres
+    hits = torch.empty((2, B, M), dtype=torch.int32, device=xyz.device)  # neighbours found per centre (group_compact)
     cabi.call("pn2_ball_query_culled_fill_f32", ptr(new_xyz), ptr(xyz), ptr(i0), ptr(i1), ptr(order), i32(B), i32(N), i32(M),
-              f32(r0), i32(ns0), f32(r1), i32(ns1), work=12.0 * B * M * N)
+              f32(r0), i32(ns0), f32(r1), i32(ns1), ptr(hits[0]), ptr(hits[1]), work=12.0 * B * M * N)
+    i0._pn2_hits, i1._pn2_hits = hits[0], hits[1]
     return i0, i1
 
 
@@ -180,8 +182,10 @@ def ball_query_single(xyz, new_xyz, radius, nsample):
     M = new_xyz.shape[1]
     idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
     order = torch.empty((B, M), dtype=torch.int32, device=xyz.device)
+    hits = torch.empty((B, M), dtype=torch.int32, device=xyz.device)
     cabi.call("pn2_ball_query_culled_fill_f32", ptr(new_xyz), ptr(xyz), ptr(idx), ptr(None), ptr(order), i32(B), i32(N), i32(M),
-              f32(radius), i32(nsample), f32(0.0), i32(0), work=12.0 * B * M * N)
+              f32(radius), i32(nsample), f32(0.0), i32(0), ptr(hits), ptr(None), work=12.0 * B * M * N)
+    idx._pn2_hits = hits      # rides along with the lists: group_compact() then skips its counting pass over them
     return idx
 
 
@@ -416,6 +420,7 @@ SA_COMPACT_ALIGN = int(os.environ.get("PN2_SA_COMPACT_ALIGN", "8"))
 
 
 COMPACT_TWO_LAUNCHES = os.environ.get("PN2_COMPACT_TWO_LAUNCHES", "1") != "0"   # 0: count, torch.cumsum, subtraction, lists
+COMPACT_USE_HITS = os.environ.get("PN2_COMPACT_USE_HITS", "1") != "0"           # 0: always count the unique rows from the lists
 
 
 def group_compact(idx, align=None):
@@ -432,8 +437,11 @@ def group_compact(idx, align=None):
     if COMPACT_TWO_LAUNCHES:
         # count + block sums | offsets + lists: the prefix sum between the two steps happens inside the second kernel
         block_sum = torch.empty(((G + 255) // 256,), dtype=torch.int32, device=idx.device)
-        cabi.call("pn2_group_compact_lists_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(cnt), ptr(block_sum), ptr(cmap),
-                  ptr(jmap), ptr(total))
+        hits = getattr(idx, "_pn2_hits", None) if COMPACT_USE_HITS else None      # the ball query's own hit counts, if it left them
+        if hits is not None and (hits.numel() != G or not hits.is_contiguous()):
+            hits = None
+        cabi.call("pn2_group_compact_lists_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(hits), ptr(cnt), ptr(block_sum),
+                  ptr(cmap), ptr(jmap), ptr(total))
         return cmap, jmap, total
     cabi.call("pn2_group_unique_count_i32", ptr(idx), _i64(G), i32(ns), i32(align), ptr(cnt))
     incl = torch.cumsum(cnt, dim=0, dtype=torch.int64)

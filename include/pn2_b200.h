@@ -91,10 +91,11 @@ int pn2_ball_query_culled_f32(const float *new_xyz, const float *xyz, int32_t *i
                               void *stream);
 /* The same for index lists the caller has NOT zeroed (the reference allocates them zeroed, pointnet2_utils.py:177, and its
  * kernel leaves the list of a centre without neighbours untouched): such lists are written as zeros here, every other
- * list is complete anyway.  Same results as a zero fill followed by pn2_ball_query_culled_f32. */
+ * list is complete anyway.  Same results as a zero fill followed by pn2_ball_query_culled_f32.
+ * hits0 / hits1 (B, M) int32 or NULL: neighbours found per centre, capped at nsample (input of pn2_group_compact_lists_i32). */
 int pn2_ball_query_culled_fill_f32(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t *idx1, int32_t *order,
                                    int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
-                                   void *stream);
+                                   int32_t *hits0, int32_t *hits1, void *stream);
 
 /* group_points_wrapper(b,c,n,npoints,nsample,points,idx,out)  group_points.cpp:24-35,
  * group_points_gpu.cu:47-86.  points (B,C,N), idx (B,M,ns) -> out (B,C,M,ns). */
@@ -239,9 +240,10 @@ int pn2_group_unique_count_i32(const int32_t *idx, long long g, int ns, int alig
 int pn2_group_compact_i32(const int32_t *idx, long long g, int ns, const int32_t *cnt, const long long *offs,
                           int32_t *cmap, int32_t *jmap, void *stream);
 /* Both steps and the exclusive scan between them in two launches: cnt (G) and block_sum (ceil(G / 256)) int32 scratch,
- * *total (device int64) = number of list rows.  Same lists as count -> prefix sum -> pn2_group_compact_i32. */
-int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, int32_t *cnt, int32_t *block_sum,
-                                int32_t *cmap, int32_t *jmap, long long *total, void *stream);
+ * *total (device int64) = number of list rows.  Same lists as count -> prefix sum -> pn2_group_compact_i32.  hits (G) or
+ * NULL: the hit counts of pn2_ball_query_culled_fill_f32 for these lists; the count pass then does not read the lists. */
+int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns, int align, const int32_t *hits, int32_t *cnt,
+                                int32_t *block_sum, int32_t *cmap, int32_t *jmap, long long *total, void *stream);
 void pn2_sa_fused_tc_set_profile(void *buf);
 void pn2_sa_fused_t_set_profile(void *buf);    /* tools/prof_sat.py: in-kernel stopwatch of pn2_sa_fused_t_tc_f32 */
 void pn2_sa_fused_t_set_debug(int bits);       /* tools/prof_sat.py: what-if switches of the stopwatch build (garbage results) */

@@ -400,13 +400,20 @@ def test_ball_query_fill_variant_needs_no_zeroed_lists(cuda, n, m):
             i0 = torch.full((2, m, ns0), init, dtype=torch.int32, device=cuda)
             i1 = torch.full((2, m, max(ns1, 1)), init, dtype=torch.int32, device=cuda)
             order = torch.empty((2, m), dtype=torch.int32, device=cuda)
+            hits = torch.full((2, 2, m), -5, dtype=torch.int32, device=cuda)
+            extra = (cabi.ptr(hits[0]), cabi.ptr(hits[1] if ns1 else None)) if "fill" in name else ()
             cabi.call(name, cabi.ptr(new_xyz), cabi.ptr(xyz), cabi.ptr(i0), cabi.ptr(i1 if ns1 else None), cabi.ptr(order),
-                      cabi.i32(2), cabi.i32(n), cabi.i32(m), cabi.f32(r0), cabi.i32(ns0), cabi.f32(r1), cabi.i32(ns1))
-            outs.append((i0, i1 if ns1 else None))
+                      cabi.i32(2), cabi.i32(n), cabi.i32(m), cabi.f32(r0), cabi.i32(ns0), cabi.f32(r1), cabi.i32(ns1), *extra)
+            outs.append((i0, i1 if ns1 else None, hits))
         assert torch.equal(outs[0][0], outs[1][0])
         assert int((outs[1][0][:, ::5] != 0).sum()) == 0
         if ns1:
             assert torch.equal(outs[0][1], outs[1][1])
+        # hit counts: the neighbours found, capped at nsample = the number of distinct entries of a list (0 for an empty one)
+        for lst, h in ((outs[1][0], outs[1][2][0]),) + (((outs[1][1], outs[1][2][1]),) if ns1 else ()):
+            distinct = (lst[:, :, 1:] != lst[:, :, :1]).sum(dim=2) + 1
+            found = torch.where(new_xyz[:, :, 0] > 200.0, torch.zeros_like(distinct), distinct)      # the shifted centres: none
+            assert torch.equal(h.long(), found)
 
 
 def test_three_interpolate_from_squared_distances_is_the_torch_weighting(cuda):
@@ -432,3 +439,25 @@ def test_three_interpolate_from_squared_distances_is_the_torch_weighting(cuda):
         fz.three_interpolate_pm_d2(feats, idx2, dist2, out, sum_order=order)
         same.append(bool(torch.equal(out, ref)))
     assert same[fz.INTERP_SUM_ORDER], ("association that matches torch.sum: %s, configured: %d" % (same, fz.INTERP_SUM_ORDER))
+
+
+def test_group_compaction_from_the_ball_querys_hit_counts(cuda):
+    """fused.ball_query_single / _dual leave the per-centre hit counts with the lists; group_compact() then skips its counting pass
+    over the lists (pn2_group_compact_lists_i32 with hits): same compact lists and row count as counting from the lists."""
+    fz = load("fused")
+    xyz = torch.from_numpy(synthetic.make_clouds("lidar", 3, 6000, seed=12)).to(cuda)
+    centres = xyz[:, :700].clone()
+    centres[:, ::7] += 300.0                                  # centres without any neighbour
+    lists = list(fz.ball_query_dual(xyz, centres, 0.3, 16, 1.2, 32)) + [fz.ball_query_single(xyz, centres, 0.6, 64)]
+    for idx in lists:
+        assert getattr(idx, "_pn2_hits", None) is not None
+        got = fz.group_compact(idx, align=8)
+        saved = fz.COMPACT_USE_HITS
+        try:
+            fz.COMPACT_USE_HITS = False
+            want = fz.group_compact(idx, align=8)
+        finally:
+            fz.COMPACT_USE_HITS = saved
+        u = int(want[2].item())
+        assert int(got[2].item()) == u
+        assert torch.equal(got[0][:u], want[0][:u]) and torch.equal(got[1][:u], want[1][:u])

@@ -44,7 +44,7 @@ def main():
             order = torch.empty((B, M), dtype=torch.int32, device="cuda") if use_order else None
             fn = lambda: cabi.call("pn2_ball_query_culled_fill_f32", cabi.ptr(centres), cabi.ptr(xyz), cabi.ptr(idx), cabi.ptr(None),
                                    cabi.ptr(order), cabi.i32(B), cabi.i32(N), cabi.i32(M), cabi.f32(radius), cabi.i32(ns),
-                                   cabi.f32(0.0), cabi.i32(0))
+                                   cabi.f32(0.0), cabi.i32(0), cabi.ptr(None), cabi.ptr(None))
             ms = timed(fn)
             res[tag] = idx.clone()
             print("%d clouds of %d points, %d centres, r = %.1f, nsample %d: %-11s %.3f ms" % (B, N, M, radius, ns, tag, ms), flush=True)
