@@ -122,8 +122,12 @@ __global__ void __launch_bounds__(256) counts_from_hits_kernel(const int32_t *__
     }
 }
 
+// HITS: the lists come from ball_query with its hit counts -- the unique rows of a group are its first `hits` slots, so a
+// list row is a plain copy (no ballot compaction), and four groups are in flight per warp
+template <bool HITS>
 __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__restrict__ idx, long long g, int ns,
                                                             const int32_t *__restrict__ cnt, const int32_t *__restrict__ block_sum,
+                                                            const int32_t *__restrict__ hits,
                                                             int32_t *__restrict__ cmap, int32_t *__restrict__ jmap,
                                                             long long *__restrict__ total) {
     __shared__ long long red[8];
@@ -154,6 +158,38 @@ __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__re
     offs_s[threadIdx.x] = base + wbase + inc - c;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) *total = base + wbase + inc;      // sum of all counts
     __syncthreads();
+    if constexpr (HITS) {
+        const long long gw = (long long)blockIdx.x * kBlockGroups + warp * 32;      // first group of this warp
+        const int h = gw + lane < g ? max(__ldg(hits + gw + lane), 1) : 0;           // lane i: unique rows of group i
+        constexpr int kG = 4;
+        for (int i0 = 0; i0 < 32 && gw + i0 < g; i0 += kG) {
+            int32_t v[kG][2], first[kG];
+            int cg[kG], hg[kG];
+            long long o[kG];
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+                const int i = i0 + u;
+                const bool live = gw + i < g;
+                cg[u] = live ? __shfl_sync(0xffffffffu, c, i) : 0;
+                hg[u] = __shfl_sync(0xffffffffu, h, i);
+                o[u] = offs_s[warp * 32 + i];
+                const int32_t *row = idx + (gw + (live ? i : 0)) * ns;
+                first[u] = __ldg(row);
+                v[u][0] = lane < hg[u] ? __ldg(row + lane) : first[u];
+                v[u][1] = lane + 32 < hg[u] ? __ldg(row + lane + 32) : first[u];
+            }
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+                const int32_t grp = (int32_t)(gw + i0 + u);
+                if (lane < cg[u]) { cmap[o[u] + lane] = grp; jmap[o[u] + lane] = v[u][0]; }
+                if (lane + 32 < cg[u]) { cmap[o[u] + lane + 32] = grp; jmap[o[u] + lane + 32] = v[u][1]; }
+                for (int k = lane + 64; k < cg[u]; k += 32) {      // nsample 128
+                    cmap[o[u] + k] = grp;
+                    jmap[o[u] + k] = k < hg[u] ? __ldg(idx + (long long)grp * ns + k) : first[u];
+                }
+            }
+        }
+    } else {
     // the lists of the warp's 32 groups (compact_kernel, one group at a time)
     for (int i = 0; i < 32; ++i) {
         const long long grp = (long long)blockIdx.x * kBlockGroups + warp * 32 + i;
@@ -180,6 +216,7 @@ __global__ void __launch_bounds__(256) compact_blocks_kernel(const int32_t *__re
             jmap[o + k] = first;
         }
     }
+    }
 }
 
 }  // namespace
@@ -198,7 +235,8 @@ PN2_API int pn2_group_compact_lists_i32(const int32_t *idx, long long g, int ns,
     if (hits) counts_from_hits_kernel<<<blocks, 256, 0, stream>>>(hits, g, align, cnt, block_sum);
     else unique_count_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, align, cnt, block_sum);
     PN2_CHECK_LAUNCH();
-    compact_blocks_kernel<<<blocks, 256, 0, stream>>>(idx, g, ns, cnt, block_sum, cmap, jmap, total);
+    if (hits) compact_blocks_kernel<true><<<blocks, 256, 0, stream>>>(idx, g, ns, cnt, block_sum, hits, cmap, jmap, total);
+    else compact_blocks_kernel<false><<<blocks, 256, 0, stream>>>(idx, g, ns, cnt, block_sum, nullptr, cmap, jmap, total);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }

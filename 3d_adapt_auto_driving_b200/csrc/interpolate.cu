@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(256) three_interpolate_pm_kernel(const float *
 // The same interpolation with the weights formed in the kernel from the SQUARED distances of three_nn: the statements
 // the FP module runs in torch between the two ops (pointnet2_utils.py:104 sqrt, pointnet2_modules.py:209-211
 // 1 / (dist + 1e-8), sum over the three, division) with the same IEEE operations in the same order.
+template <bool VEC>
 __global__ void __launch_bounds__(256) three_interpolate_pm_d2_kernel(const float *__restrict__ feats, int ldf,
                                                                      const int32_t *__restrict__ idx,
                                                                      const float *__restrict__ dist2,
@@ -343,25 +344,40 @@ __global__ void __launch_bounds__(256) three_interpolate_pm_d2_kernel(const floa
     const int lane = threadIdx.x & 31;
     if (pt >= total) return;
     const long long cloud = pt / n;
-    const int32_t *id = idx + pt * 3;
-    const float *d = dist2 + pt * 3;
-    const float q0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d)), 1e-8f));
-    const float q1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + 1)), 1e-8f));
-    const float q2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + 2)), 1e-8f));
+    // lanes 0..2 each form one reciprocal and one weight (a square root and two IEEE divisions per LANE instead of three and six
+    // per warp-wide instruction stream: the first version spent two thirds of its instructions on these uniform values)
+    const int l3 = lane < 3 ? lane : 0;
+    const float q = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + pt * 3 + l3)), 1e-8f));
+    const int id = __ldg(idx + pt * 3 + l3);
+    const float q0 = __shfl_sync(0xffffffffu, q, 0), q1 = __shfl_sync(0xffffffffu, q, 1), q2 = __shfl_sync(0xffffffffu, q, 2);
     // association of the three-term sum: torch.sum's reduction kernel is not left-to-right (two threads take the even and
     // the odd elements), so the order is a parameter pinned against torch by the test
     const float norm = sum_order == 0 ? __fadd_rn(__fadd_rn(q0, q1), q2)
                      : sum_order == 1 ? __fadd_rn(__fadd_rn(q0, q2), q1) : __fadd_rn(q0, __fadd_rn(q1, q2));
-    const float w0 = __fdiv_rn(q0, norm), w1 = __fdiv_rn(q1, norm), w2 = __fdiv_rn(q2, norm);
-    const float *r0 = feats + (cloud * m + __ldg(id)) * ldf;
-    const float *r1 = feats + (cloud * m + __ldg(id + 1)) * ldf;
-    const float *r2 = feats + (cloud * m + __ldg(id + 2)) * ldf;
+    const float w = __fdiv_rn(q, norm);
+    const float w0 = __shfl_sync(0xffffffffu, w, 0), w1 = __shfl_sync(0xffffffffu, w, 1), w2 = __shfl_sync(0xffffffffu, w, 2);
+    const float *r0 = feats + (cloud * m + __shfl_sync(0xffffffffu, id, 0)) * ldf;
+    const float *r1 = feats + (cloud * m + __shfl_sync(0xffffffffu, id, 1)) * ldf;
+    const float *r2 = feats + (cloud * m + __shfl_sync(0xffffffffu, id, 2)) * ldf;
     float *o = out + pt * ldo;
-    for (int ch = lane; ch < c; ch += 32) {
-        float t = __fmul_rn(w1, __ldg(r1 + ch));
-        t = __fmaf_rn(w0, __ldg(r0 + ch), t);
-        t = __fmaf_rn(w2, __ldg(r2 + ch), t);
-        o[ch] = t;
+    if (VEC) {
+        for (int ch = lane * 4; ch < c; ch += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(r0 + ch)), b4 = __ldg(reinterpret_cast<const float4 *>(r1 + ch)),
+                         c4 = __ldg(reinterpret_cast<const float4 *>(r2 + ch));
+            float4 t;
+            t.x = __fmaf_rn(w2, c4.x, __fmaf_rn(w0, a.x, __fmul_rn(w1, b4.x)));
+            t.y = __fmaf_rn(w2, c4.y, __fmaf_rn(w0, a.y, __fmul_rn(w1, b4.y)));
+            t.z = __fmaf_rn(w2, c4.z, __fmaf_rn(w0, a.z, __fmul_rn(w1, b4.z)));
+            t.w = __fmaf_rn(w2, c4.w, __fmaf_rn(w0, a.w, __fmul_rn(w1, b4.w)));
+            *reinterpret_cast<float4 *>(o + ch) = t;
+        }
+    } else {
+        for (int ch = lane; ch < c; ch += 32) {
+            float t = __fmul_rn(w1, __ldg(r1 + ch));
+            t = __fmaf_rn(w0, __ldg(r0 + ch), t);
+            t = __fmaf_rn(w2, __ldg(r2 + ch), t);
+            o[ch] = t;
+        }
     }
 }
 }  // namespace
@@ -377,8 +393,14 @@ PN2_API int pn2_three_interpolate_pm_d2_f32(const float *feats, int ldf, const i
     }
     const long long total = (long long)b * n;
     if (total == 0 || c == 0) return PN2_OK;
-    three_interpolate_pm_d2_kernel<<<pn2_divup(total * 32, 256), 256, 0, stream>>>(feats, ldf, idx, dist2, out, ldo, c, m,
-                                                                                  n, total, sum_order);
+    const bool vec = !(c & 3) && !(ldf & 3) && !(ldo & 3) && !(reinterpret_cast<uintptr_t>(feats) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(out) & 15);
+    if (vec)
+        three_interpolate_pm_d2_kernel<true><<<pn2_divup(total * 32, 256), 256, 0, stream>>>(feats, ldf, idx, dist2, out, ldo, c,
+                                                                                            m, n, total, sum_order);
+    else
+        three_interpolate_pm_d2_kernel<false><<<pn2_divup(total * 32, 256), 256, 0, stream>>>(feats, ldf, idx, dist2, out, ldo, c,
+                                                                                             m, n, total, sum_order);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
