@@ -18,6 +18,7 @@
 // survives.  A CTA leaves the tile loop as soon as all its centres are full.
 #include "common.cuh"
 #include "spatial_order.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -203,12 +204,14 @@ __global__ void __launch_bounds__(kCullThreads) ball_query_culled_kernel(const f
                                                                         int32_t *__restrict__ idx1, int n, int m,
                                                                         float radius0, int ns0, float radius1, int ns1,
                                                                         int zero_empty, int32_t *__restrict__ hits0,
-                                                                        int32_t *__restrict__ hits1) {
+                                                                        int32_t *__restrict__ hits1, int cpw) {
     __shared__ float4 cand[kCullWarps][kWarpList];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wfirst = (blockIdx.x * kCullWarps + warp) * 32;
+    // cpw centres per warp (lanes >= cpw stay inactive but help with the cull and the scan): fewer centres mean a smaller
+    // box, shorter candidate lists and more warps to spread the sparse regions' long scans over
+    const int wfirst = (blockIdx.x * kCullWarps + warp) * cpw;
     if (wfirst >= m) return;                      // warps never meet at a CTA barrier
-    const bool active = wfirst + lane < m;
+    const bool active = lane < cpw && wfirst + lane < m;
     // inactive lanes mirror the warp's first centre so they do not widen the box
     const int slot = active ? wfirst + lane : wfirst;
     const int c = order ? __ldg(order + (size_t)cloud * m + slot) : slot;
@@ -300,9 +303,18 @@ int launch_culled(const float *new_xyz, const float *xyz, int32_t *idx0, int32_t
         return PN2_ERR_LAUNCH;
     }
     if (!sorted) order = nullptr;
-    dim3 grid(pn2_divup(m, kCullThreads), b);   // 2 warps x 32 centres per CTA
+    static int cpw_env = -1;                      // PN2_BQ_CPW: centres per warp (tuning; 32, 16 or 8)
+    if (cpw_env < 0) {
+        const char *e = getenv("PN2_BQ_CPW");
+        cpw_env = e ? atoi(e) : 0;
+        if (cpw_env != 8 && cpw_env != 16 && cpw_env != 32) cpw_env = 0;
+    }
+    // measured on the bench clouds (B = 16, profiles/r2l_bench_cpw*.json): 32 centres per warp 0.88 ms of ball query per step, 16:
+    // 0.63, 8: 0.70 (and 3.5 % fewer scenes/s with batches in flight: twice the cull passes); same lists for every value
+    const int cpw = cpw_env ? cpw_env : 16;
+    dim3 grid(pn2_divup(m, kCullWarps * cpw), b);   // 2 warps x cpw centres per CTA
     ball_query_culled_kernel<DUAL><<<grid, kCullThreads, 0, stream>>>(new_xyz, xyz, order, idx0, idx1, n, m, r0, ns0, r1, ns1, zero_empty,
-                                                                      hits0, hits1);
+                                                                      hits0, hits1, cpw);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
