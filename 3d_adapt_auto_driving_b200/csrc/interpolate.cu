@@ -17,6 +17,7 @@
 // the reference expression (interpolate_gpu.cu:96).  One thread per unknown point loops over
 // a block of channels so idx/weight are read once per 8 channels instead of once per channel.
 #include "common.cuh"
+#include <cstdlib>
 #include "spatial_order.cuh"
 #include <math.h>
 
@@ -91,12 +92,13 @@ __global__ void __launch_bounds__(kThreads) three_nn_culled_kernel(const float *
                                                                   const float *__restrict__ known,
                                                                   const int32_t *__restrict__ order,
                                                                   float *__restrict__ dist2, int32_t *__restrict__ idx,
-                                                                  int n, int m) {
+                                                                  int n, int m, int cpw) {
     __shared__ float4 cand[kNnWarps][kNnList];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wfirst = (blockIdx.x * kNnWarps + warp) * 32;
+    // cpw unknown points per warp (lanes >= cpw are inactive but take part in the cull): see ball_query_culled_kernel
+    const int wfirst = (blockIdx.x * kNnWarps + warp) * cpw;
     if (wfirst >= n) return;                     // warps never meet at a CTA barrier
-    const bool active = wfirst + lane < n;
+    const bool active = lane < cpw && wfirst + lane < n;
     // inactive lanes mirror the warp's first point: they neither widen the box nor raise the bound
     const int i = __ldg(order + (size_t)cloud * n + (active ? wfirst + lane : wfirst));
     known += (size_t)cloud * m * 3;
@@ -270,8 +272,15 @@ PN2_API int pn2_three_nn_culled_f32(const float *unknown, const float *known, fl
         pn2_set_last_error("pn2_three_nn_culled_f32: ordering kernel launch failed");
         return PN2_ERR_LAUNCH;
     }
-    dim3 grid(pn2_divup(n, kThreads), b);
-    three_nn_culled_kernel<<<grid, kThreads, 0, stream>>>(unknown, known, order, dist2, idx, n, m);
+    static int cpw_env = -1;                      // PN2_NN_CPW: unknown points per warp (tuning; 32, 16 or 8)
+    if (cpw_env < 0) {
+        const char *e = getenv("PN2_NN_CPW");
+        cpw_env = e ? atoi(e) : 0;
+        if (cpw_env != 8 && cpw_env != 16 && cpw_env != 32) cpw_env = 0;
+    }
+    const int cpw = cpw_env ? cpw_env : 32;
+    dim3 grid(pn2_divup(n, kNnWarps * cpw), b);
+    three_nn_culled_kernel<<<grid, kThreads, 0, stream>>>(unknown, known, order, dist2, idx, n, m, cpw);
     PN2_CHECK_LAUNCH();
     return PN2_OK;
 }
