@@ -44,6 +44,7 @@ def test_fps_every_cluster_size_and_temp_writeback(cuda, oracle, cluster):
 
 @pytest.mark.parametrize("warps", [0, 4, 8, 16])
 @pytest.mark.parametrize("kind,n,m,b", [("lidar", 16384, 1024, 2), ("ties", 16384, 700, 2), ("uniform", 9000, 600, 2),
+                                         ("lidar", 6000, 500, 2),
                                          ("ties", 4096, 512, 3), ("lidar", 3000, 3000, 1), ("ties", 2049, 300, 2),
                                          ("lidar", 130, 64, 3), ("ties", 64, 64, 2)])
 def test_fps_cells_kernel_vs_oracle(cuda, oracle, warps, kind, n, m, b):
