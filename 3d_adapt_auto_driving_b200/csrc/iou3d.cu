@@ -254,15 +254,13 @@ constexpr int kNmsStageBytes = 192 * 1024;   // shared-memory budget for the sta
 //    rotated IoU is ~50x the cost of the axis-aligned one, and the lazy row of a 100-box problem
 //    keeps 3 of 8 warps busy for one IoU at a time.
 template <bool ROTATED, int THREADS>
-__global__ void __launch_bounds__(THREADS) nms_kernel(const float *__restrict__ boxes, int stride, int n_fixed,
-                                                     const int32_t *__restrict__ counts, float thresh, int max_keep,
-                                                     long long *__restrict__ keep, int32_t *__restrict__ num_out,
-                                                     int stage_cap) {
+__device__ __forceinline__ void nms_body(const int prob, const float *__restrict__ boxes, int stride, int n_fixed,
+                                         const int32_t *__restrict__ counts, float thresh, int max_keep,
+                                         long long *__restrict__ keep, int32_t *__restrict__ num_out, int stage_cap) {
     extern __shared__ float staged[];     // stage_cap boxes x 5
     __shared__ uint32_t remv[kNmsMaxWords];
     __shared__ int cur;
     __shared__ float cur_box[5];
-    const int prob = blockIdx.x;
     const int n = counts ? counts[prob] : n_fixed;
     boxes += (size_t)prob * stride * 5;
     keep += (size_t)prob * max_keep;
@@ -363,6 +361,28 @@ __global__ void __launch_bounds__(THREADS) nms_kernel(const float *__restrict__ 
 static_assert(kNmsDense * (kNmsDense / 32) <= kNmsMaxWords, "dense bit matrix must fit in remv[]");
 
 template <bool ROTATED, int THREADS>
+__global__ void __launch_bounds__(THREADS) nms_kernel(const float *__restrict__ boxes, int stride, int n_fixed,
+                                                     const int32_t *__restrict__ counts, float thresh, int max_keep,
+                                                     long long *__restrict__ keep, int32_t *__restrict__ num_out,
+                                                     int stage_cap) {
+    nms_body<ROTATED, THREADS>(blockIdx.x, boxes, stride, n_fixed, counts, thresh, max_keep, keep, num_out, stage_cap);
+}
+
+// Two independent sets of problems in one launch (the near and the far band of the proposal layer, lib/rpn/proposal_layer.py:
+// 58-119: different candidate counts and keep limits): CTAs [0, pa) take set a, the rest set b.  As two launches the second
+// band waited for the first although each keeps only 16 SMs busy.
+struct NmsSet {
+    const float *boxes; int stride; int n; const int32_t *counts; int max_keep; long long *keep; int32_t *num; int cap;
+};
+template <bool ROTATED, int THREADS>
+__global__ void __launch_bounds__(THREADS) nms_pair_kernel(const NmsSet a, const NmsSet b, int pa, float thresh) {
+    const bool first = (int)blockIdx.x < pa;
+    const NmsSet &s = first ? a : b;
+    nms_body<ROTATED, THREADS>(first ? (int)blockIdx.x : (int)blockIdx.x - pa, s.boxes, s.stride, s.n, s.counts, thresh, s.max_keep,
+                               s.keep, s.num, s.cap);
+}
+
+template <bool ROTATED, int THREADS>
 cudaError_t launch_nms(const float *boxes, int problems, int stride, int n, const int32_t *counts, float thresh, int max_keep,
                        long long *keep, int32_t *num, cudaStream_t stream) {
     static bool attr_done = false;
@@ -374,6 +394,19 @@ cudaError_t launch_nms(const float *boxes, int problems, int stride, int n, cons
     if (cap > stride) cap = stride;
     nms_kernel<ROTATED, THREADS><<<problems, THREADS, (size_t)cap * 20, stream>>>(boxes, stride, n, counts, thresh, max_keep,
                                                                                keep, num, cap);
+    return cudaGetLastError();
+}
+
+template <bool ROTATED, int THREADS>
+cudaError_t launch_nms_pair(NmsSet a, int pa, NmsSet b, int pb, float thresh, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(nms_pair_kernel<ROTATED, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsStageBytes);
+        attr_done = true;
+    }
+    a.cap = min(kNmsStageBytes / 20, a.stride);
+    b.cap = min(kNmsStageBytes / 20, b.stride);
+    nms_pair_kernel<ROTATED, THREADS><<<pa + pb, THREADS, (size_t)max(a.cap, b.cap) * 20, stream>>>(a, b, pa, thresh);
     return cudaGetLastError();
 }
 
@@ -424,6 +457,29 @@ PN2_API int pn2_nms_bev_f32(const float *boxes, int problems, int stride, int n,
     if (problems == 0) return PN2_OK;
     const cudaError_t e = rotated ? launch_nms<true, 256>(boxes, problems, stride, n, counts, thresh, max_keep, keep, num, stream)
                                   : launch_nms<false, 1024>(boxes, problems, stride, n, counts, thresh, max_keep, keep, num, stream);
+    if (e != cudaSuccess) {
+        pn2_set_last_error(cudaGetErrorString(e));
+        return PN2_ERR_LAUNCH;
+    }
+    return PN2_OK;
+}
+
+// pn2_nms_bev_f32 for two sets of problems in ONE launch (same results as two calls): set 0 = problems0 x (stride0, n0,
+// counts0, max_keep0) -> keep0 / num0, set 1 likewise; one threshold and one NMS type for both.
+PN2_API int pn2_nms_bev_pair_f32(const float *boxes0, int problems0, int stride0, int n0, const int32_t *counts0, int max_keep0,
+                                 long long *keep0, int32_t *num0, const float *boxes1, int problems1, int stride1, int n1,
+                                 const int32_t *counts1, int max_keep1, long long *keep1, int32_t *num1, float thresh,
+                                 int rotated, cudaStream_t stream) {
+    if (problems0 < 0 || problems1 < 0 || stride0 < 0 || stride1 < 0 || n0 < 0 || n1 < 0 || n0 > stride0 || n1 > stride1 ||
+        max_keep0 < 0 || max_keep1 < 0 || stride0 > kNmsMaxWords * 32 || stride1 > kNmsMaxWords * 32) {
+        pn2_set_last_error("pn2_nms_bev_pair_f32: bad argument (at most 32768 boxes per problem)");
+        return PN2_ERR_INVALID;
+    }
+    if (problems0 + problems1 == 0) return PN2_OK;
+    const NmsSet a = {boxes0, stride0, n0, counts0, max_keep0, keep0, num0, 0};
+    const NmsSet b = {boxes1, stride1, n1, counts1, max_keep1, keep1, num1, 0};
+    const cudaError_t e = rotated ? launch_nms_pair<true, 256>(a, problems0, b, problems1, thresh, stream)
+                                  : launch_nms_pair<false, 1024>(a, problems0, b, problems1, thresh, stream);
     if (e != cudaSuccess) {
         pn2_set_last_error(cudaGetErrorString(e));
         return PN2_ERR_LAUNCH;

@@ -97,6 +97,20 @@ def nms_raw(bev, counts, thresh, rotated, max_keep):
     return keep, num
 
 
+def nms_raw_pair(bev0, counts0, max_keep0, bev1, counts1, max_keep1, thresh, rotated):
+    """nms_raw for two sets of problems in one launch (pn2_nms_bev_pair_f32) -> (keep0, num0, keep1, num1)."""
+    P0, n0, _ = bev0.shape
+    P1, n1, _ = bev1.shape
+    keep0 = torch.empty((P0, max(max_keep0, 1)), dtype=torch.int64, device=bev0.device)
+    keep1 = torch.empty((P1, max(max_keep1, 1)), dtype=torch.int64, device=bev0.device)
+    num0 = torch.empty((P0,), dtype=torch.int32, device=bev0.device)
+    num1 = torch.empty((P1,), dtype=torch.int32, device=bev0.device)
+    cabi.call("pn2_nms_bev_pair_f32", ptr(bev0), i32(P0), i32(n0), i32(n0), ptr(counts0), i32(max_keep0), ptr(keep0), ptr(num0),
+              ptr(bev1), i32(P1), i32(n1), i32(n1), ptr(counts1), i32(max_keep1), ptr(keep1), ptr(num1), cabi.f32(thresh),
+              i32(1 if rotated else 0))
+    return keep0, num0, keep1, num1
+
+
 def proposal_assemble(props, scores, cidx0, cidx1, keep0, keep1, num0, num1, post0, post1):
     B, N = scores.shape
     rois = torch.empty((B, post0 + post1, 7), dtype=torch.float32, device=props.device)

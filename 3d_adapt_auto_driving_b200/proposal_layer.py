@@ -67,7 +67,7 @@ class ProposalLayer(nn.Module):
         return ([int(pre_tot * 0.7), pre_tot - int(pre_tot * 0.7)], [int(post_tot * 0.7), post_tot - int(post_tot * 0.7)])
 
     def _forward_kernels(self, scores, rpn_reg, xyz):
-        """The whole layer in seven launches (csrc/glue.cu): decode, score order, band selection with the BEV
+        """The whole layer in six launches (csrc/glue.cu): decode, score order, band selection with the BEV
         boxes of the candidates, one batched device NMS per band, assembly of the zero-padded (B, 100, 7) ROIs.
         Bit-identical to _forward_batched and to the per-scene reference flow (tests/test_glue_gpu.py)."""
         B, N = scores.shape
@@ -81,8 +81,8 @@ class ProposalLayer(nn.Module):
         cidx0, cidx1, bev0, bev1, cnt = glue.proposal_select(order, props, pre_n[0], pre_n[1])
         thresh = cfg[self.mode].RPN_NMS_THRESH
         rotated = cfg.RPN.NMS_TYPE == 'rotate'
-        keep0, num0 = glue.nms_raw(bev0, cnt[0], thresh, rotated, post_n[0])
-        keep1, num1 = glue.nms_raw(bev1, cnt[1], thresh, rotated, post_n[1])
+        # both distance bands in one launch (each keeps only B SMs busy; as two launches the second waited for the first)
+        keep0, num0, keep1, num1 = glue.nms_raw_pair(bev0, cnt[0], post_n[0], bev1, cnt[1], post_n[1], thresh, rotated)
         return glue.proposal_assemble(props, scores, cidx0, cidx1, keep0, keep1, num0, num1, post_n[0], post_n[1])
 
     def _forward_batched(self, scores, proposals, order):

@@ -158,6 +158,12 @@ int pn2_boxes_iou3d_f32(const float *a, int na, const float *b, int nb, float *o
  * max_keep = n gives the reference's full keep list; keep indices are bit-exact. */
 int pn2_nms_bev_f32(const float *boxes, int problems, int stride, int n, const int32_t *counts, float thresh,
                     int rotated, int max_keep, long long *keep, int32_t *num, void *stream);
+/* The same for TWO sets of problems in one launch (the near and the far band of the proposal layer,
+ * lib/rpn/proposal_layer.py:58-119, differ in candidate count and keep limit): same results as two calls. */
+int pn2_nms_bev_pair_f32(const float *boxes0, int problems0, int stride0, int n0, const int32_t *counts0, int max_keep0,
+                         long long *keep0, int32_t *num0, const float *boxes1, int problems1, int stride1, int n1,
+                         const int32_t *counts1, int max_keep1, long long *keep1, int32_t *num1, float thresh, int rotated,
+                         void *stream);
 
 /* ---- shared-MLP layers (pointnet2_lib/pointnet2/pytorch_utils.py:5-101 SharedMLP/Conv1d/Conv2d,
  *      pointnet2_modules.py:37-48 group -> MLP -> max_pool2d), point-major activations ---- */

@@ -240,3 +240,28 @@ def test_argsort_desc_is_torch_sort(cuda, b, n):
     assert torch.equal(torch.sort(got, dim=1)[0], torch.arange(n, device=cuda).expand(b, n))   # a permutation
     assert torch.equal(got, want), "ties: %d positions differ from the stable order" % int((got != want).sum())
     assert torch.equal(got, torch.sort(scores, dim=1, descending=True)[1])      # the call the reference makes
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_nms_pair_launch_equals_two_launches(cuda, rotated):
+    """pn2_nms_bev_pair_f32 (both distance bands of the proposal layer in one launch) == two pn2_nms_bev_f32 calls."""
+    glue = load("glue")
+    g = torch.Generator(device="cpu").manual_seed(11)
+
+    def problems(p, n):
+        c = torch.rand((p, n, 2), generator=g) * 20.0
+        wl = torch.rand((p, n, 2), generator=g) * 3.0 + 0.5
+        ry = (torch.rand((p, n, 1), generator=g) - 0.5) * 6.0
+        bev = torch.cat((c - wl / 2, c + wl / 2, ry), dim=2).contiguous().to(cuda)        # x1, y1, x2, y2, ry
+        cnt = torch.randint(n // 2, n + 1, (p,), generator=g, dtype=torch.int32).to(cuda)
+        return bev, cnt
+
+    bev0, cnt0 = problems(5, 300 if rotated else 900)
+    bev1, cnt1 = problems(3, 100 if rotated else 400)
+    k0, n0 = glue.nms_raw(bev0, cnt0, 0.4, rotated, 40)
+    k1, n1 = glue.nms_raw(bev1, cnt1, 0.4, rotated, 17)
+    pk0, pn0, pk1, pn1 = glue.nms_raw_pair(bev0, cnt0, 40, bev1, cnt1, 17, 0.4, rotated)
+    assert torch.equal(pn0, n0) and torch.equal(pn1, n1)
+    for k, pk, n in ((k0, pk0, n0), (k1, pk1, n1)):
+        for i in range(k.shape[0]):
+            assert torch.equal(pk[i, :int(n[i])], k[i, :int(n[i])])
