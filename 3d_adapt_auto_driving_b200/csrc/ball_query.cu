@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kThreads) ball_query_kernel(const float *__res
 // =================================================================================================
 constexpr int kCullThreads = 64;                  // 2 autonomous warps per CTA
 constexpr int kCullWarps = kCullThreads / 32;
-constexpr int kWarpList = 1024;                   // capacity of a warp's candidate list (16 KB)
+constexpr int kWarpList = 1024;                   // capacity of a warp's candidate list (16 KB; 8 KB lists, twice the resident
+                                                  // warps, measured slower: 0.66 vs 0.62 ms of ball query per step)
 constexpr int kScanUnroll = 8;                    // groups of 32 list entries evaluated per scan step
 constexpr int kCullBatch = 8;                     // rounds of 32 candidates whose loads are in flight together
 
