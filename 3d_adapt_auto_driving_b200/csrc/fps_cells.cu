@@ -13,17 +13,22 @@
 //      lb(c, box) < cmax ,    lb = sqdist(max(0, lo - c, c - hi))  evaluated with the reference's own float expression.
 // Rounding is monotone, so lb is a true lower bound of the FLOAT distance the reference computes for every point of
 // the cell:  d2(p, c) >= lb >= cmax >= t[p]  =>  min(t[p], d2) == t[p] -- skipping the cell changes nothing, the result is
-// bit-identical.  On KITTI-shaped clouds ~4.6 of the 128 cells are touched per round (tools/sim_fps_cells.py).
+// bit-identical.  On KITTI-shaped clouds ~3 of the 128 cells are touched per round (in-kernel stopwatch, tools/prof_fps_cells.py;
+// the numpy model written before the kernel, tools/sim_fps_cells.py, said 3-5).
 // Everything is on one SM, so the exchange is one __syncthreads per round:
-//   1. every warp tests its CPW boxes (lane i < CPW tests cell i, one ballot);
-//   2. touched cells: 3 x LDS.128 (coordinates live in shared memory, SoA, slot-major per lane) + packed fp32 update of
-//      4 running distances per lane, redux.max -> new cmax; then the warp's record (d2 bits | ~rank | position), where
-//      ties on d2 are resolved exactly by the reference rank (u16 table of point indices in shared memory);
-//      untouched warps copy last round's record (8 bytes);
-//   3. __syncthreads; every warp reduces the WARPS records redundantly (two redux.sync) and reads the next centre's
-//      coordinates from shared memory.
-// Registers hold only the running distances (4 * CPW per lane) -- 16 warps x 8 cells cover 16384 points in ONE CTA:
-// ~4-8x less SM-time than the 4-CTA cluster kernel at a shorter round, which is what counts with several batches in flight.
+//   1. every warp tests its CPW boxes (lane i < CPW tests cell i; one ballot, one redux for the first touched cell);
+//   2. a touched cell: 3 x LDS.128 (coordinates live in shared memory, SoA, slot-major per lane; requested before the branch
+//      tree that selects the cell's registers) + packed fp32 update of 4 running distances per lane, redux.max -> new cmax,
+//      and the cell's RECORD (maximum distance bits, shared-memory position of the point that holds it) written to the
+//      record buffer of this round; after the barrier the lane that owns the cell copies it into the other buffer too
+//      (untouched cells therefore need no per-round work at all);
+//   3. __syncthreads; every warp reduces the 128 cell records redundantly (four per lane, two redux.sync) and reads the next
+//      centre's coordinates from shared memory.
+// An exact tie on the distance -- inside a cell or between cells -- leaves these fast paths: the reference's rank decides, read
+// from a u16 table of inverted ranks per shared-memory position (the point index, needed only for the output, is recovered
+// from the rank after the loop).
+// Registers hold only the running distances (4 * CPW per lane) -- 8 warps x 16 cells cover 16384 points in ONE CTA: 1.6 ms and
+// 16 SMs for 16 x (16384 -> 4096) against 2.9 ms on 64 SMs for the 4-CTA cluster kernel (tools/bench_fps_cluster.py).
 #include "spatial_order.cuh"
 #include <cmath>
 #include <type_traits>
