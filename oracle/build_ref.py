@@ -35,7 +35,8 @@ def _newer(dst, srcs):
 
 
 def build_oracle(verbose=False):
-    src = [os.path.join(HERE, "pn2_oracle.c"), os.path.join(HERE, "geom_oracle.c"), os.path.join(HERE, "datapath_oracle.c")]
+    src = [os.path.join(HERE, "pn2_oracle.c"), os.path.join(HERE, "geom_oracle.c"), os.path.join(HERE, "datapath_oracle.c"),
+           os.path.join(HERE, "fps_pruned_model.c")]
     src = [s for s in src if os.path.exists(s)]
     dst = os.path.join(HERE, "libpn2_oracle.so")
     if _newer(dst, src):

@@ -48,6 +48,21 @@ def fps(xyz, npoint, temp=None):
     return idx, temp
 
 
+def fps_pruned_model(xyz, npoint, order, cell=128, temp=None):
+    """CPU model of the algorithm of csrc/fps_cells.cu (oracle/fps_pruned_model.c) for ONE cloud: xyz (N,3), order (N) a
+    permutation -> idx (npoint) int32, temp (N) after the call, number of touched (round, cell) pairs."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    order = np.ascontiguousarray(order, np.int32)
+    N = xyz.shape[0]
+    temp = np.full((N,), 1e10, np.float32) if temp is None else np.array(temp, np.float32, copy=True)
+    idx = np.zeros((npoint,), np.int32)
+    fn = lib().orc_fps_pruned_model
+    fn.restype = ctypes.c_longlong
+    touched = fn(xyz.ctypes.data_as(ctypes.c_void_p), order.ctypes.data_as(ctypes.c_void_p), N, int(npoint), int(cell),
+                 temp.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p))
+    return idx, temp, int(touched)
+
+
 def gather_points(points, idx):
     points, pp = _f(points); idx, pi = _i(idx)
     B, C, N = points.shape
