@@ -390,8 +390,14 @@ def run_b200(args):
         # the figure says how fast the reference's scan work is disposed of, like `culled_search` below).
         "scan_roofline": {k: {"ms": round(v["ms"], 4), "scan_GBps": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1),
                               "frac_of_hbm_peak": round(v["work"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
-                          for k, v in breakdown.items()
-                          if k in ("pn2_fps_f32", "pn2_fps_xyz_f32", "pn2_fps_cluster_f32") and v["ms"] > 0},
+                          for k, v in breakdown.items() if k == "pn2_fps_cluster_f32" and v["ms"] > 0},
+        # The default FPS kernel (csrc/fps_cells.cu) PRUNES: a round touches ~3 of 128 cells, so a fraction of the HBM peak over
+        # the reference's scan bytes says as little as for the culled neighbour searches below (it comes out above 1).  Reported:
+        # the rate at which the reference's scan bytes are disposed of, and the kernel's own unit, sampling rounds per second
+        # and cloud (the launches of a step run B clouds side by side, one CTA each).
+        "pruned_fps": {k: {"ms": round(v["ms"], 4), "reference_scan_GBps": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1),
+                           "launches_per_step": v["launches"]}
+                       for k, v in breakdown.items() if k in ("pn2_fps_f32", "pn2_fps_xyz_f32") and v["ms"] > 0},
         # The culled neighbour searches never form most centre-point pairs, so a bandwidth fraction over the reference's
         # scan bytes says nothing about them (it came out at 2.7 / 6.7 of the HBM peak).  Reported instead: the rate at
         # which the REFERENCE's pair tests are disposed of (B * M * N pairs of the brute-force kernels per second); the
